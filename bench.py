@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- RoIRotate forward throughput on B200 (BASELINE.json metric: RoIRotate Mfeat-px/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                  # product arm (default)
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # reference CPU arm
+
+One STEP = one RoIRotate forward over one batch of synthetic input in BASELINE.json configs[1]
+("cfg1"): a single 1280x720 image's shared feature map (180x320 at 1/4 scale), 64 random rotated
+RoIs, 8x64 pooled output, fp32.  `value` = output feature pixels (N*C*PH*PW, zero tail included)
+per second, whole job (all ranks), inputs resident in HBM.  Between steps the working set rotates over
+--sets independent (feature map, RoIs, output) buffer sets whose total size exceeds the 126 MB L2,
+so every step reads its features from HBM.  The K timed steps are replayed from CUDA graphs and
+timed with CUDA events on the launching stream, bracketed by barrier + synchronize; max over ranks.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "roirotate_fwd_mfeat_px_per_s"
+UNIT = "Mfeat-px/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--channels", type=int, default=64, help="64 = the reference's focr map; 256 = FPN map")
+    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"])
+    ap.add_argument("--images", type=int, default=1, help="images per step (cfg1 = 1)")
+    ap.add_argument("--rois-per-image", type=int, default=64)
+    ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough to exceed 3x L2)")
+    ap.add_argument("--graph-chunk", type=int, default=500)
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- helpers
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def sample(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:  # pragma: no cover
+            pass
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def finish(self):
+        self.sample()
+        self.stop_flag.set()
+        self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/roofline_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------- workload
+
+class Workload:
+    """`sets` independent (features, rois, pooled) buffer sets of the cfg1 shape, resident on the device."""
+
+    def __init__(self, args, device, torch):
+        import workloads as WL
+        self.WL = WL
+        self.C, self.H, self.W, self.PH, self.PW, self.scale = args.channels, 180, 320, 8, 64, 0.25
+        self.B = args.images
+        self.N = args.images * args.rois_per_image
+        self.layout = args.layout
+        per_set = 4 * (self.B * self.C * self.H * self.W + self.N * self.C * self.PH * self.PW)
+        self.sets = args.sets if args.sets > 0 else max(4, int(np.ceil(3 * 126e6 / per_set)) + 1)
+        self.working_set_mb = per_set * self.sets / 1e6
+        fmt = torch.channels_last if self.layout == "nhwc" else torch.contiguous_format
+        gen = torch.Generator(device=device).manual_seed(1234)
+        self.feats, self.rois, self.rois_np, self.alg_bytes = [], [], [], []
+        for s in range(self.sets):
+            f = torch.randn(self.B, self.C, self.H, self.W, device=device, generator=gen)
+            self.feats.append(f.contiguous(memory_format=fmt))
+            r = WL.batch_rois(self.B, args.rois_per_image, seed0=s * self.B)
+            self.rois_np.append(r)
+            self.rois.append(torch.from_numpy(r).to(device))
+            self.alg_bytes.append(WL.algorithmic_bytes_fwd(r, self.C, self.PH, self.PW))
+        self.feat_px_per_step = self.N * self.C * self.PH * self.PW
+        self.out = [torch.empty((self.N, self.C, self.PH, self.PW), device=device, memory_format=fmt)
+                    for _ in range(self.sets)]
+
+    def launch(self, s, lib, cabi, stream):
+        """One step on buffer set s: exactly one kernel launch through the C ABI (rroi_b200_forward)."""
+        st = lib.rroi_b200_forward(self.feats[s].data_ptr(), self.rois[s].data_ptr(), self.out[s].data_ptr(),
+                                   None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
+                                   self.scale, cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW,
+                                   stream)
+        if st != 0:
+            raise RuntimeError("rroi_b200_forward -> %d" % st)
+
+
+def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier):
+    """W untimed warm-up steps, then exactly K steps replayed from CUDA graphs; returns elapsed ms."""
+    stream = torch.cuda.Stream()
+    graphs = {}
+
+    def graph_for(n, first):
+        key = (n, first % wl.sets)
+        if key not in graphs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(n):
+                    wl.launch((first + i) % wl.sets, lib, cabi, torch.cuda.current_stream().cuda_stream)
+            graphs[key] = g
+        return graphs[key]
+
+    def plan(total):
+        seq, done = [], 0
+        while done < total:
+            n = min(chunk, total - done)
+            seq.append(graph_for(n, done))
+            done += n
+        return seq
+
+    with torch.cuda.stream(stream):
+        for i in range(3):   # lazy module load etc. outside any capture
+            wl.launch(i % wl.sets, lib, cabi, stream.cuda_stream)
+    stream.synchronize()
+    warm_seq, timed_seq = plan(max(warmup, 3)), plan(steps)
+    # clock ramp (untimed, before the W warm-up steps): ~0.3 s of the same work
+    t_end = time.time() + 0.3
+    with torch.cuda.stream(stream):
+        while time.time() < t_end:
+            for g in timed_seq[:4]:
+                g.replay()
+            stream.synchronize()
+        for g in warm_seq:
+            g.replay()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for g in timed_seq:
+            g.replay()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def e2e_leg(args, wl, torch, device, steps):
+    """Same metric end to end through the public module API with HOST buffers: per step a pinned-host ->
+    device copy of the step's features + RoIs, _RRoiAlign.forward, and a device -> pinned-host read of the
+    pooled result.  Two streams alternate so the H2D of step i+1 overlaps the D2H of step i."""
+    from fots.pytorch_b200 import _RRoiAlign
+    fmt = torch.channels_last if wl.layout == "nhwc" else torch.contiguous_format
+    nbuf = 2
+    mod = _RRoiAlign(wl.PH, wl.PW, wl.scale)
+    h_feat = [wl.feats[i % wl.sets].cpu().contiguous(memory_format=fmt).pin_memory() for i in range(nbuf)]
+    h_rois = [wl.rois[i % wl.sets].cpu().pin_memory() for i in range(nbuf)]
+    d_feat = [torch.empty_like(wl.feats[0]) for _ in range(nbuf)]
+    d_rois = [torch.empty_like(wl.rois[0]) for _ in range(nbuf)]
+    h_out = [torch.empty((wl.N, wl.C, wl.PH, wl.PW), memory_format=fmt).pin_memory() for _ in range(nbuf)]
+    streams = [torch.cuda.Stream() for _ in range(nbuf)]
+
+    def step(i):
+        b = i % nbuf
+        with torch.cuda.stream(streams[b]):
+            d_feat[b].copy_(h_feat[b], non_blocking=True)
+            d_rois[b].copy_(h_rois[b], non_blocking=True)
+            y = mod(d_feat[b], d_rois[b])
+            h_out[b].copy_(y, non_blocking=True)
+
+    for i in range(6):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    h2d = h_feat[0].numel() * 4 + h_rois[0].numel() * 4
+    d2h = h_out[0].numel() * 4
+    return dt, h2d, d2h
+
+
+def cpu_baseline_leg(wl, seconds):
+    """The CPU oracle (a port: the reference has no CPU RoIRotate) on the same cfg1 step, all host threads."""
+    from oracle import rroi_oracle as O
+    feats = wl.feats[0].cpu().contiguous().numpy()
+    rois = wl.rois_np[0]
+    threads = O.max_threads()
+    O.forward(feats, rois, wl.PH, wl.PW, wl.scale, threads=0)
+    t0, reps = time.perf_counter(), 0
+    while True:
+        O.forward(feats, rois, wl.PH, wl.PW, wl.scale, threads=0)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds or reps >= 2000:
+            break
+    return {"value": wl.feat_px_per_step * reps / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d full cfg1 forward passes (%d RoIs, C=%d, NCHW) in %.1f s, OpenMP over (RoI,channel) planes"
+                      % (reps, wl.N, wl.C, dt)}
+
+
+# ----------------------------------------------------------------------------------------- arms
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this metric.  The reference ships no CPU RoIRotate
+    (rroi_align/functions/rroi_align.py:22-25 is dead code), so this is the oracle port of
+    rroi_align_kernel.cu:28-162 with all host threads.  Each step is a bounded sample of the cfg1 step."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import workloads as WL
+    from oracle import rroi_oracle as O
+    C, PH, PW, scale = args.channels, 8, 64, 0.25
+    steps = args.steps if args.steps is not None else 50
+    warmup = args.warmup if args.warmup is not None else 3
+    feats = WL.features(0, args.images, C, 180, 320)
+    rois = WL.batch_rois(args.images, args.rois_per_image)
+    threads = O.max_threads()
+    O.forward(feats, rois, PH, PW, scale, threads=0)           # page in, spin up the OpenMP team
+    t0 = time.perf_counter()
+    O.forward(feats, rois, PH, PW, scale, threads=0)
+    t_full = time.perf_counter() - t0
+    # bounded sample: the first n RoIs x first c channels of the step, sized so K+W steps fit the budget
+    budget = 60.0
+    frac = min(1.0, budget / max((steps + warmup) * t_full, 1e-9))
+    n = max(1, min(len(rois), int(round(len(rois) * frac))))
+    c = C if n > 1 or frac * len(rois) >= 1 else max(1, int(C * frac * len(rois)))
+    sample, fsample = rois[:n], np.ascontiguousarray(feats[:, :c])
+    for _ in range(warmup):
+        O.forward(fsample, sample, PH, PW, scale, threads=0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.forward(fsample, sample, PH, PW, scale, threads=0)
+    dt = time.perf_counter() - t0
+    px = n * c * PH * PW
+    value = px * steps / dt / 1e6
+    desc = "first %d of %d RoIs x first %d of %d channels of the cfg1 step per step (NCHW fp32), %d OpenMP threads" % (
+        n, len(rois), c, C, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg1: 1x%dx180x320 fp32 map, %d rotated RoIs, 8x64 pooled, forward" % (C, len(rois)),
+                   "sample": desc, "note": "reference has no CPU RoIRotate; oracle port of rroi_align_kernel.cu:28-162"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_b200(args):
+    import torch
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        barrier = lambda: dist.barrier(device_ids=[local])
+    else:
+        dist = None
+        barrier = lambda: None
+    from fots.pytorch_b200 import _cabi
+    lib = _cabi.lib()
+    _cabi.set_tuning(_cabi.TUNE_USE_PDL, args.pdl)
+
+    steps = args.steps if args.steps is not None else 100000
+    warmup = args.warmup if args.warmup is not None else 1000
+    wl = Workload(args, device, torch)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_steps(wl, steps, warmup, args.graph_chunk, torch, lib, _cabi, barrier)
+    clocks = sampler.finish()
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = wl.feat_px_per_step * steps * world / (ms_max * 1e-3) / 1e6
+
+    peak, peak_src = measured_peak_gbs()
+    alg = float(np.mean(wl.alg_bytes))
+    launch_us = ms / steps * 1e3
+    achieved = alg / (launch_us * 1e-6) / 1e9
+    kname = "rroi_fwd_%s_kernel" % wl.layout
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg1 (BASELINE.json configs[1]): %dx%dx180x320 fp32 feature map per step, %d random rotated RoIs, "
+                               "8x64 pooled output, RoIRotate forward only" % (wl.B, wl.C, wl.N),
+                   "layout": "channels_last (NHWC in HBM)" if wl.layout == "nhwc" else "NCHW (reference layout)",
+                   "images_per_step": wl.B, "rois_per_step": wl.N, "channels": wl.C,
+                   "l2": "inputs larger than L2: %d rotating buffer sets, %.0f MB working set vs 126 MB L2" % (wl.sets, wl.working_set_mb),
+                   "launch": "CUDA graphs of %d steps, PDL=%d" % (min(args.graph_chunk, steps), args.pdl),
+                   "parallelism": "image-sharded, %d rank(s), no data-path collective in RoIRotate" % world},
+        "gpu_launches": steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic("%s_c%d" % (wl.layout, wl.C)),
+                     "algorithmic_bytes_per_launch": alg, "avg_launch_us": launch_us, "peak_source": peak_src},
+    }
+    if rank == 0 and not args.no_extras:
+        dt, h2d, d2h = e2e_leg(args, wl, torch, device, args.e2e_steps)
+        line["e2e"] = {"value": wl.feat_px_per_step * args.e2e_steps / dt / 1e6, "unit": UNIT,
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                       "api": "fots.pytorch_b200._RRoiAlign(8,64,0.25)(features, rois) with pinned host buffers, 2 streams"}
+        line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_seconds)
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,99 @@
+"""ctypes binding of include/rroi_align_b200.h (fots/pytorch_b200/lib/librroi_b200.so).
+
+The library is plain C ABI (device pointers + sizes + cudaStream_t); torch only supplies the device
+memory and the current stream.  Loading fails loudly when the .so has not been built -- there is no
+fallback implementation.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librroi_b200.so")
+
+OK = 0
+ERR_INVALID_ARG = -1
+ERR_TOO_LARGE = -2
+ERR_CUDA = -3
+
+LAYOUT_NCHW = 0
+LAYOUT_NHWC = 1
+
+TUNE_NCHW_CG = 0
+TUNE_NHWC_UNROLL = 1
+TUNE_USE_PDL = 2
+TUNE_BWD_DEDUPE = 3
+
+ABI_VERSION = 1
+
+# every symbol include/rroi_align_b200.h declares
+EXPORTS = (
+    "RROIAlignForwardLaucher", "RROIAlignBackwardLaucher",
+    "rroi_b200_forward", "rroi_b200_backward", "rroi_b200_expand_idx",
+    "rroi_b200_set_tuning", "rroi_b200_get_tuning", "rroi_b200_last_cuda_error",
+    "rroi_b200_strerror", "rroi_b200_abi_version", "rroi_b200_build_info",
+)
+
+_lib = None
+
+
+class RRoiAlignError(RuntimeError):
+    """A non-success status from the C ABI."""
+
+
+def lib():
+    """Load (once) and return the ctypes handle with argtypes set."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "fots.pytorch_b200: %s is missing -- build it with `make -C fots/pytorch_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`).  There is no CPU/PyTorch "
+            "fallback for RoIRotate." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+    L.RROIAlignForwardLaucher.restype = i
+    L.RROIAlignForwardLaucher.argtypes = [vp, f, i, i, i, i, i, i, vp, vp, vp, vp, vp]
+    L.RROIAlignBackwardLaucher.restype = i
+    L.RROIAlignBackwardLaucher.argtypes = [vp, f, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
+    L.rroi_b200_forward.restype = i
+    L.rroi_b200_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, vp]
+    L.rroi_b200_backward.restype = i
+    L.rroi_b200_backward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, i, vp]
+    L.rroi_b200_expand_idx.restype = i
+    L.rroi_b200_expand_idx.argtypes = [vp, vp, i, i, i, i, vp]
+    L.rroi_b200_set_tuning.restype = i
+    L.rroi_b200_set_tuning.argtypes = [i, i]
+    L.rroi_b200_get_tuning.restype = i
+    L.rroi_b200_get_tuning.argtypes = [i]
+    L.rroi_b200_last_cuda_error.restype = i
+    L.rroi_b200_strerror.restype = ctypes.c_char_p
+    L.rroi_b200_strerror.argtypes = [i]
+    L.rroi_b200_abi_version.restype = i
+    L.rroi_b200_build_info.restype = ctypes.c_char_p
+    if L.rroi_b200_abi_version() != ABI_VERSION:
+        raise ImportError("librroi_b200.so ABI version %d != binding %d: rebuild the library"
+                          % (L.rroi_b200_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status != OK:
+        L = lib()
+        msg = L.rroi_b200_strerror(status).decode()
+        if status == ERR_CUDA:
+            msg += " [cudaError_t=%d]" % L.rroi_b200_last_cuda_error()
+        raise RRoiAlignError("%s failed: %s" % (what, msg))
+
+
+def set_tuning(key, value):
+    check(lib().rroi_b200_set_tuning(int(key), int(value)), "rroi_b200_set_tuning(%d,%d)" % (key, value))
+
+
+def get_tuning(key):
+    return lib().rroi_b200_get_tuning(int(key))
+
+
+def build_info():
+    return lib().rroi_b200_build_info().decode()

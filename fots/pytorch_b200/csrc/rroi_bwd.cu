@@ -1,0 +1,317 @@
+// rroi_bwd.cu -- RoIRotate backward for sm_100a.  Replaces RROIAlignBackward
+// (/root/reference/rroi_align/src/rroi_align_kernel.cu:193-278): every valid output element scatters
+// top_diff * {wlt, wrt, wrb, wlb} to the <=4 pixels around its saved sample centre, each only if
+// 0 < y < H-1 and 0 < x < W-1 (kernel.cu:267-274 -- stricter than the forward's border test).
+//
+// What changed relative to the reference's four float atomics per output element:
+//   * bin geometry once per (n,ph,pw), reused over channels; centres read from the compact
+//     [N,PH,PW] tensor the forward saved, or recomputed from the RoI row when none was kept;
+//   * NCHW: lanes of a warp hold consecutive bins along pw; neighbours that landed on the same
+//     sample centre (bin pitch < 1 feature pixel) are summed with a segmented warp-shuffle
+//     reduction and only the run head issues RED.ADD -- fewer, less contended L2 atomics;
+//   * zero-weight taps (rx == 0 or ry == 0: the reference adds 0.0 to the same pixel) are skipped;
+//   * channels-last: one 128-bit vector reduction (red.global.add.v4.f32, sm_90+) per tap and
+//     4-channel group instead of four scalar atomics.
+// fp32 accumulation order is unspecified exactly as in the reference, so parity is to 1e-4 rel.
+#include "rroi_geom.cuh"
+#include "rroi_kernels.cuh"
+
+namespace rroi {
+
+// What a thread needs to scatter one bin.
+struct ScatterGeom {
+    float wlt, wrt, wrb, wlb;
+    int   l, t, r, b;
+    bool  in;         // bin inside the RoI (kernel.cu:238: skipped only if rpw < pw)
+    bool  p_lt, p_rt, p_rb, p_lb;
+    float cx, cy;
+};
+
+// kernel.cu:236-274 for one (n, ph, pw), centre either loaded or recomputed.
+template <bool kF64Weights>
+__device__ __forceinline__ ScatterGeom scatter_geom(float cx, float cy, bool in, int H, int W) {
+    ScatterGeom g;
+    g.cx = cx; g.cy = cy; g.in = in;
+    if (kF64Weights) weights_f64(cx, cy, g.wlt, g.wrt, g.wrb, g.wlb);
+    else             weights_half_grid(cx, cy, g.wlt, g.wrt, g.wrb, g.wlb);
+    g.l = __float2int_rz(floorf(cx)); g.r = __float2int_rz(ceilf(cx));
+    g.t = __float2int_rz(floorf(cy)); g.b = __float2int_rz(ceilf(cy));
+    const bool xl = (g.l > 0) & (g.l < W - 1), xr = (g.r > 0) & (g.r < W - 1);
+    const bool yt = (g.t > 0) & (g.t < H - 1), yb = (g.b > 0) & (g.b < H - 1);
+    g.p_lt = in & xl & yt;
+    g.p_rt = in & xr & yt;
+    g.p_rb = in & xr & yb;
+    g.p_lb = in & xl & yb;
+    return g;
+}
+
+__device__ __forceinline__ void red_add(float* addr, float v) { atomicAdd(addr, v); }
+
+// ------------------------------------------------------------------------------------------ NCHW
+constexpr int kBlock = 256;
+
+template <int CG, bool kDedupe>
+__global__ void __launch_bounds__(kBlock) rroi_bwd_nchw_kernel(const BwdParams p) {
+    __shared__ RoiXform sX;
+    int item = blockIdx.x;
+    const int tile = item % p.tiles;  item /= p.tiles;
+    const int cg = item % p.cgroups;
+    const int n = item / p.cgroups;
+    const int bins = p.PH * p.PW;
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x < 32) {
+        RoiXform X;
+        if (p.idx_mode == IDX_NONE) {
+            X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        } else {  // centres are loaded: only the batch index and the width mask are needed
+            const float* roi = p.rois + (size_t)n * 6;
+            X.batch = __float2int_rz(__ldg(roi));
+            X.rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
+        }
+        if (threadIdx.x == 0) sX = X;
+    }
+    __syncthreads();
+    const RoiXform X = sX;
+
+    const int bin = tile * kBlock + threadIdx.x;
+    const bool live = bin < bins;
+    const int ph = live ? bin / p.PW : 0, pw = live ? bin - ph * p.PW : 0;
+    const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+    float cx = 0.f, cy = 0.f;
+    if (live) {
+        if (p.idx_mode == IDX_NONE) bin_center(X, ph, pw, (float)(p.W - 1), (float)(p.H - 1), cx, cy);
+        else { cx = __ldg(p.idx_x + (size_t)n * bins + bin); cy = __ldg(p.idx_y + (size_t)n * bins + bin); }
+    }
+    const bool in = live & batch_ok & !(X.rpw < (float)pw);
+    const ScatterGeom g = scatter_geom<false>(cx, cy, in, p.H, p.W);
+
+    // Segmented-reduction plan over the warp: runs of consecutive lanes with the same centre.
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned step_mask = 0;   // bit k: lane + 2^k is in my run
+    bool head = in;
+    if (kDedupe) {
+        const unsigned kx = __float_as_uint(cx), ky = __float_as_uint(cy);
+        const unsigned px = __shfl_up_sync(0xffffffffu, kx, 1), py = __shfl_up_sync(0xffffffffu, ky, 1);
+        const bool pin = __shfl_up_sync(0xffffffffu, (int)in, 1);
+        const bool same_prev = (lane > 0) & in & pin & (px == kx) & (py == ky);
+        if (__ballot_sync(0xffffffffu, same_prev) != 0u) {       // warp-uniform: any run longer than 1?
+            const unsigned breaks = __ballot_sync(0xffffffffu, !same_prev);
+            const int run = __popc(breaks & (0xffffffffu >> (31u - lane)));
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int other = __shfl_down_sync(0xffffffffu, run, 1 << k);
+                if ((lane + (1u << k)) < 32u && other == run) step_mask |= 1u << k;
+            }
+            head = in & !same_prev;
+        }
+    }
+    const bool any_merge = kDedupe && (__ballot_sync(0xffffffffu, step_mask != 0u) != 0u);
+
+    const int c0 = cg * CG;
+    const size_t HW = (size_t)p.H * p.W;
+    const float* gsrc = p.top_diff + ((size_t)n * p.C + c0) * bins + bin;
+    float* dst = p.bottom_diff + ((size_t)(batch_ok ? X.batch : 0) * p.C + c0) * HW;
+    const unsigned o_lt = (unsigned)g.t * (unsigned)p.W + (unsigned)g.l;
+    const unsigned o_rt = (unsigned)g.t * (unsigned)p.W + (unsigned)g.r;
+    const unsigned o_rb = (unsigned)g.b * (unsigned)p.W + (unsigned)g.r;
+    const unsigned o_lb = (unsigned)g.b * (unsigned)p.W + (unsigned)g.l;
+    const bool s_lt = head & g.p_lt & (g.wlt != 0.0f);
+    const bool s_rt = head & g.p_rt & (g.wrt != 0.0f);
+    const bool s_rb = head & g.p_rb & (g.wrb != 0.0f);
+    const bool s_lb = head & g.p_lb & (g.wlb != 0.0f);
+
+    float gv[CG];
+#pragma unroll
+    for (int k = 0; k < CG; ++k)
+        gv[k] = (in && (c0 + k) < p.C) ? __ldg(gsrc + (size_t)k * bins) : 0.0f;
+    if (any_merge) {
+#pragma unroll
+        for (int k = 0; k < CG; ++k) {
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const float o = __shfl_down_sync(0xffffffffu, gv[k], 1 << s);
+                if (step_mask & (1u << s)) gv[k] += o;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CG; ++k) {
+        if ((c0 + k) < p.C) {
+            float* d = dst + (size_t)k * HW;
+            if (s_lt) red_add(d + o_lt, __fmul_rn(g.wlt, gv[k]));
+            if (s_rt) red_add(d + o_rt, __fmul_rn(g.wrt, gv[k]));
+            if (s_rb) red_add(d + o_rb, __fmul_rn(g.wrb, gv[k]));
+            if (s_lb) red_add(d + o_lb, __fmul_rn(g.wlb, gv[k]));
+        }
+    }
+}
+
+template <bool kDedupe>
+static cudaError_t launch_bwd_nchw_cg(const BwdParams& p, int cg, long long grid, cudaStream_t s, bool pdl) {
+    switch (cg) {
+        case 1:  return launch_1d(rroi_bwd_nchw_kernel<1, kDedupe>, grid, kBlock, p, s, pdl);
+        case 2:  return launch_1d(rroi_bwd_nchw_kernel<2, kDedupe>, grid, kBlock, p, s, pdl);
+        case 4:  return launch_1d(rroi_bwd_nchw_kernel<4, kDedupe>, grid, kBlock, p, s, pdl);
+        case 16: return launch_1d(rroi_bwd_nchw_kernel<16, kDedupe>, grid, kBlock, p, s, pdl);
+        default: return launch_1d(rroi_bwd_nchw_kernel<8, kDedupe>, grid, kBlock, p, s, pdl);
+    }
+}
+
+static int pick_cg(int want, int C) {
+    int cg = (want == 1 || want == 2 || want == 4 || want == 8 || want == 16) ? want : 8;
+    while (cg > 1 && cg / 2 >= C) cg /= 2;
+    return cg;
+}
+
+cudaError_t launch_bwd_nchw(const BwdParams& p0, cudaStream_t s) {
+    BwdParams p = p0;
+    const int cg = pick_cg(g_tuning.nchw_cg, p.C);
+    const int bins = p.PH * p.PW;
+    p.tiles = (bins + kBlock - 1) / kBlock;
+    p.cgroups = (p.C + cg - 1) / cg;
+    const long long grid = (long long)p.N * p.cgroups * p.tiles;
+    const bool pdl = g_tuning.use_pdl != 0;
+    return g_tuning.bwd_dedupe ? launch_bwd_nchw_cg<true>(p, cg, grid, s, pdl)
+                               : launch_bwd_nchw_cg<false>(p, cg, grid, s, pdl);
+}
+
+// ------------------------------------------------------------------------------------------ legacy
+// Reference-layout backward that, like kernel.cu:232-233, reads the centre of EVERY (n,c,ph,pw)
+// element from caller-supplied [N,C,PH,PW] tensors (fp64 weight products, all four adds issued).
+// One thread per output element, pw fastest; only used by RROIAlignBackwardLaucher.
+__global__ void __launch_bounds__(kBlock) rroi_bwd_legacy_kernel(const BwdParams p) {
+    const size_t bins = (size_t)p.PH * p.PW;
+    const size_t total = (size_t)p.N * p.C * bins;
+    pdl_wait();
+    pdl_launch_dependents();
+    for (size_t index = (size_t)blockIdx.x * kBlock + threadIdx.x; index < total;
+         index += (size_t)gridDim.x * kBlock) {
+        const int pw = (int)(index % p.PW);
+        const size_t nc = index / bins;
+        const int c = (int)(nc % p.C);
+        const size_t n = nc / p.C;
+        const float* roi = p.rois + n * 6;
+        const int batch = __float2int_rz(__ldg(roi));
+        const float rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
+        if (rpw < (float)pw) continue;
+        if (batch < 0 || batch >= p.B) continue;
+        const ScatterGeom g = scatter_geom<true>(__ldg(p.idx_x + index), __ldg(p.idx_y + index), true, p.H, p.W);
+        const float gv = __ldg(p.top_diff + index);
+        float* d = p.bottom_diff + ((size_t)batch * p.C + c) * p.H * p.W;
+        if (g.p_lt) red_add(d + (size_t)g.t * p.W + g.l, __fmul_rn(g.wlt, gv));
+        if (g.p_rt) red_add(d + (size_t)g.t * p.W + g.r, __fmul_rn(g.wrt, gv));
+        if (g.p_rb) red_add(d + (size_t)g.b * p.W + g.r, __fmul_rn(g.wrb, gv));
+        if (g.p_lb) red_add(d + (size_t)g.b * p.W + g.l, __fmul_rn(g.wlb, gv));
+    }
+}
+
+cudaError_t launch_bwd_legacy(const BwdParams& p, cudaStream_t s) {
+    const size_t total = (size_t)p.N * p.C * p.PH * p.PW;
+    long long grid = (long long)((total + kBlock - 1) / kBlock);
+    if (grid > (1LL << 30)) grid = 1LL << 30;
+    return launch_1d(rroi_bwd_legacy_kernel, grid, kBlock, p, s, g_tuning.use_pdl != 0);
+}
+
+// ------------------------------------------------------------------------------------------ NHWC
+// top_diff [N,PH,PW,C], bottom_diff [B,H,W,C].  Same two-phase shape as the NHWC forward.
+constexpr int kTilePix = 64;
+
+struct __align__(16) PixScatter {
+    long long base;                 // (batch*H)*W pixel index of the image origin
+    int l, t, r, b;
+    float wlt, wrt, wrb, wlb;
+    uint32_t pred;                  // bit0 lt, bit1 rt, bit2 rb, bit3 lb (border test & weight != 0)
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float w, const float4& g) {
+    const float a = __fmul_rn(w, g.x), b = __fmul_rn(w, g.y), c = __fmul_rn(w, g.z), d = __fmul_rn(w, g.w);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kBlock) rroi_bwd_nhwc_kernel(const BwdParams p) {
+    __shared__ RoiXform sX;
+    __shared__ PixScatter rec[kTilePix];
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int bins = p.PH * p.PW;
+    const int bin0 = tile * kTilePix;
+    const int npix = min(kTilePix, bins - bin0);
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x < 32) {
+        RoiXform X;
+        if (p.idx_mode == IDX_NONE) {
+            X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        } else {
+            const float* roi = p.rois + (size_t)n * 6;
+            X.batch = __float2int_rz(__ldg(roi));
+            X.rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
+        }
+        if (threadIdx.x == 0) sX = X;
+    }
+    __syncthreads();
+    if (threadIdx.x < npix) {
+        const RoiXform X = sX;
+        const int bin = bin0 + threadIdx.x;
+        const int ph = bin / p.PW, pw = bin - ph * p.PW;
+        const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+        float cx, cy;
+        if (p.idx_mode == IDX_NONE) bin_center(X, ph, pw, (float)(p.W - 1), (float)(p.H - 1), cx, cy);
+        else { cx = __ldg(p.idx_x + (size_t)n * bins + bin); cy = __ldg(p.idx_y + (size_t)n * bins + bin); }
+        const bool in = batch_ok & !(X.rpw < (float)pw);
+        const ScatterGeom g = scatter_geom<false>(cx, cy, in, p.H, p.W);
+        PixScatter r;
+        r.base = (long long)(batch_ok ? X.batch : 0) * p.H * p.W;
+        r.l = g.l; r.t = g.t; r.r = g.r; r.b = g.b;
+        r.wlt = g.wlt; r.wrt = g.wrt; r.wrb = g.wrb; r.wlb = g.wlb;
+        r.pred = ((g.p_lt & (g.wlt != 0.f)) ? 1u : 0u) | ((g.p_rt & (g.wrt != 0.f)) ? 2u : 0u) |
+                 ((g.p_rb & (g.wrb != 0.f)) ? 4u : 0u) | ((g.p_lb & (g.wlb != 0.f)) ? 8u : 0u);
+        rec[threadIdx.x] = r;
+    }
+    __syncthreads();
+
+    constexpr int VN = kVec ? 4 : 1;
+    const int CV = p.C / VN;
+    const int units = npix * CV;
+    const float* gsrc = p.top_diff + ((size_t)n * bins + bin0) * p.C;
+    for (int u = threadIdx.x; u < units; u += kBlock) {
+        const int px = u / CV, v = u - px * CV;
+        const PixScatter r = rec[px];
+        if (r.pred == 0u) continue;
+        float* base = p.bottom_diff + (size_t)r.base * p.C + (size_t)v * VN;
+        const size_t o_lt = ((size_t)r.t * p.W + r.l) * p.C, o_rt = ((size_t)r.t * p.W + r.r) * p.C;
+        const size_t o_rb = ((size_t)r.b * p.W + r.r) * p.C, o_lb = ((size_t)r.b * p.W + r.l) * p.C;
+        if (kVec) {
+            const float4 gq = __ldg(reinterpret_cast<const float4*>(gsrc + (size_t)u * 4));
+            if (r.pred & 1u) red_add_v4(base + o_lt, r.wlt, gq);
+            if (r.pred & 2u) red_add_v4(base + o_rt, r.wrt, gq);
+            if (r.pred & 4u) red_add_v4(base + o_rb, r.wrb, gq);
+            if (r.pred & 8u) red_add_v4(base + o_lb, r.wlb, gq);
+        } else {
+            const float gq = __ldg(gsrc + u);
+            if (r.pred & 1u) red_add(base + o_lt, __fmul_rn(r.wlt, gq));
+            if (r.pred & 2u) red_add(base + o_rt, __fmul_rn(r.wrt, gq));
+            if (r.pred & 4u) red_add(base + o_rb, __fmul_rn(r.wrb, gq));
+            if (r.pred & 8u) red_add(base + o_lb, __fmul_rn(r.wlb, gq));
+        }
+    }
+}
+
+cudaError_t launch_bwd_nhwc(const BwdParams& p0, cudaStream_t s) {
+    BwdParams p = p0;
+    const int bins = p.PH * p.PW;
+    p.tiles = (bins + kTilePix - 1) / kTilePix;
+    p.cgroups = 1;
+    const long long grid = (long long)p.N * p.tiles;
+    const bool pdl = g_tuning.use_pdl != 0;
+    const bool vec = (p.C % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.top_diff) | reinterpret_cast<uintptr_t>(p.bottom_diff)) % 16 == 0);
+    return vec ? launch_1d(rroi_bwd_nhwc_kernel<true>, grid, kBlock, p, s, pdl)
+               : launch_1d(rroi_bwd_nhwc_kernel<false>, grid, kBlock, p, s, pdl);
+}
+
+}  // namespace rroi

@@ -1,0 +1,311 @@
+"""GPU parity tests (the parity tests proper): the sm_100a kernels, called through the Python host
+API -> C ABI, against
+  (1) the CPU oracle (oracle/rroi_oracle.c, restating rroi_align_kernel.cu:28-162 / :193-278) and
+  (2) the reference CUDA kernel itself, compiled unmodified for sm_100a (oracle/_ref), when present.
+Bar: sample centres (index work) and sampled values bit-exact in the forward -- the weights are
+{0,1/4,1/2,1} so only the sum order matters and it is reproduced; backward within 1e-4 relative
+(fp32 atomics: the reference's own sum order is unspecified).
+"""
+import numpy as np
+import pytest
+
+import helpers as Hh
+import workloads as WL
+
+pytestmark = pytest.mark.gpu
+
+REL_BWD = 1e-4   # north_star tolerance for sampled / accumulated fp32 values
+
+
+def _ref_gpu(oracle, feats, rois, ph, pw, scale, device):
+    f, r = Hh.to_cuda(feats, device), Hh.to_cuda(rois, device)
+    out, ix, iy = oracle.ref_gpu_forward(f, r, ph, pw, scale)
+    return out.cpu().numpy(), ix.cpu().numpy(), iy.cpu().numpy()
+
+
+def _check_forward_all_paths(oracle, feats, rois, ph, pw, scale, device, vs_cpu=True, vs_ref=True):
+    C = feats.shape[1]
+    got = {}
+    got["nchw"] = Hh.run_new_forward(feats, rois, ph, pw, scale, device, channels_last=False)
+    got["nhwc"] = Hh.run_new_forward(feats, rois, ph, pw, scale, device, channels_last=True)
+    lo, lx, ly = Hh.run_legacy_forward(feats, rois, ph, pw, scale, device)
+    # legacy idx is [N,C,PH,PW]; all channels must agree with the compact centres
+    Hh.assert_bit_equal(lx, Hh.expand_idx(got["nchw"][1], C), "legacy idx_x vs compact")
+    Hh.assert_bit_equal(ly, Hh.expand_idx(got["nchw"][2], C), "legacy idx_y vs compact")
+    Hh.assert_bit_equal(lo, got["nchw"][0], "legacy launcher vs v2 NCHW")
+    Hh.assert_bit_equal(got["nhwc"][0], got["nchw"][0], "NHWC vs NCHW values")
+    Hh.assert_bit_equal(got["nhwc"][1], got["nchw"][1], "NHWC vs NCHW idx_x")
+    Hh.assert_bit_equal(got["nhwc"][2], got["nchw"][2], "NHWC vs NCHW idx_y")
+    out, ix, iy = got["nchw"]
+    if vs_cpu:
+        eo, ex, ey = oracle.forward(feats, rois, ph, pw, scale, threads=0)
+        Hh.assert_bit_equal(Hh.expand_idx(ix, C), ex, "idx_x vs CPU oracle")
+        Hh.assert_bit_equal(Hh.expand_idx(iy, C), ey, "idx_y vs CPU oracle")
+        Hh.assert_bit_equal(out, eo, "values vs CPU oracle")
+    if vs_ref and oracle.ref_gpu_available():
+        ro, rx, ry = _ref_gpu(oracle, feats, rois, ph, pw, scale, device)
+        Hh.assert_bit_equal(Hh.expand_idx(ix, C), rx, "idx_x vs reference kernel")
+        Hh.assert_bit_equal(Hh.expand_idx(iy, C), ry, "idx_y vs reference kernel")
+        Hh.assert_bit_equal(out, ro, "values vs reference kernel")
+    return out, ix, iy
+
+
+def test_library_is_the_cuda_one(cuda):
+    from fots.pytorch_b200 import _cabi
+    assert "sm_100a" in _cabi.build_info()
+
+
+def test_cfg0_forward_backward(oracle, cuda):
+    """BASELINE.json configs[0]: 1x3x64x64, 4 axis-aligned RoIs (one overhanging), fwd + bwd."""
+    feats, rois, ph, pw, scale = WL.cfg0()
+    assert (ph, pw) == (8, 32)
+    out, ix, iy = _check_forward_all_paths(oracle, feats, rois, ph, pw, scale, cuda)
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal(out.shape, dtype=np.float32)
+    C = feats.shape[1]
+    want = oracle.backward(g, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), feats.shape, scale)
+    for cl in (False, True):
+        for idx in ((ix, iy), None):
+            got = Hh.run_new_backward(g, rois, idx, feats.shape, scale, cuda, channels_last=cl)
+            Hh.assert_close_rel(got, want, REL_BWD, "cfg0 backward cl=%s idx=%s" % (cl, idx is not None))
+    got = Hh.run_legacy_backward(g, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), feats.shape, scale, cuda)
+    Hh.assert_close_rel(got, want, REL_BWD, "cfg0 legacy backward")
+    if oracle.ref_gpu_available():
+        import torch
+        r = oracle.ref_gpu_backward(Hh.to_cuda(g, cuda), Hh.to_cuda(rois, cuda),
+                                    Hh.to_cuda(Hh.expand_idx(ix, C), cuda), Hh.to_cuda(Hh.expand_idx(iy, C), cuda),
+                                    feats.shape, scale).cpu().numpy()
+        Hh.assert_close_rel(got, r, REL_BWD, "cfg0 backward vs reference kernel")
+        Hh.assert_close_rel(want, r, REL_BWD, "cfg0 CPU-oracle backward vs reference kernel")
+
+
+@pytest.mark.parametrize("channels", [64, 256])
+def test_cfg1_forward(oracle, cuda, channels):
+    """BASELINE.json configs[1]: 180x320 map (1280x720 / 4), 64 random rotated RoIs, 8x64 output."""
+    feats, rois, ph, pw, scale = WL.cfg1(channels)
+    _check_forward_all_paths(oracle, feats, rois, ph, pw, scale, cuda, vs_cpu=(channels == 64))
+
+
+def test_test2_scenario_forward_backward(oracle, cuda):
+    """rroi_align/test2.py:22-77 replayed on the committed image: 3 rotated RoIs, PH=44, scale 1,
+    loss = pooled.pow(2).sum(); forward against the reference's res*.jpg and both oracles."""
+    import torch
+    from fots.pytorch_b200 import _RRoiAlign
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ref_test2_jpeg.npz"))
+    img = g["timg"].astype(np.float32).transpose(2, 0, 1)[None]
+    rois, ph, pw = WL.test2_rois()
+    out, ix, iy = _check_forward_all_paths(oracle, img, rois, ph, pw, 1.0, cuda)
+    for i in range(3):
+        crop = out[i].transpose(1, 2, 0).astype(np.uint8).astype(np.float64)
+        mse = ((crop - g["res%d" % i]) ** 2).mean()
+        assert 10 * np.log10(255 ** 2 / mse) > 40.0
+    # autograd through the module, as test2.py:72-77 does
+    x = Hh.to_cuda(img, cuda).requires_grad_(True)
+    pooled = _RRoiAlign(ph, pw, 1.0)(x, Hh.to_cuda(rois, cuda).view(-1, 6))
+    pooled.pow(2).sum().backward()
+    C = img.shape[1]
+    want = oracle.backward(2 * out, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), img.shape, 1.0)
+    Hh.assert_close_rel(x.grad.cpu().numpy(), want, REL_BWD, "test2 autograd backward")
+
+
+@pytest.mark.parametrize("seed,B,C,H,W,N,ph,pw,scale", [
+    (1, 2, 5, 45, 80, 96, 8, 64, 0.25),      # odd C -> scalar NHWC path
+    (2, 3, 8, 45, 80, 64, 11, 37, 0.25),     # PH=11 as src/ocr_process.py:260; ragged PW
+    (3, 1, 3, 72, 128, 40, 32, 100, 1.0),    # CRNN variant: raw image, PH=32 (src/utils.py:430-436)
+    (4, 4, 16, 23, 31, 128, 4, 9, 0.125),    # tiny map
+    (5, 2, 1, 64, 64, 33, 8, 300, 0.5),      # C=1, PW > 256 (several bin tiles per plane)
+    (6, 2, 12, 50, 70, 80, 1, 1, 0.25),      # 1x1 pooling
+])
+def test_stress_forward_backward(oracle, cuda, seed, B, C, H, W, N, ph, pw, scale):
+    feats = WL.features(seed, B, C, H, W)
+    rois = WL.stress_rois(seed, N, B, int(W / scale), int(H / scale))
+    out, ix, iy = _check_forward_all_paths(oracle, feats, rois, ph, pw, scale, cuda)
+    g = np.random.default_rng(seed).standard_normal(out.shape, dtype=np.float32)
+    want = oracle.backward(g, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), feats.shape, scale, threads=0)
+    for cl in (False, True):
+        for idx in ((ix, iy), None):
+            got = Hh.run_new_backward(g, rois, idx, feats.shape, scale, cuda, channels_last=cl)
+            Hh.assert_close_rel(got, want, REL_BWD, "stress backward cl=%s saved_idx=%s" % (cl, idx is not None))
+    got = Hh.run_legacy_backward(g, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), feats.shape, scale, cuda)
+    Hh.assert_close_rel(got, want, REL_BWD, "stress legacy backward")
+
+
+def test_degenerate_rois_match_reference_kernel(oracle, cuda):
+    """h=0, w=0, negative sizes, NaN/inf parameters: whatever the reference kernel produces (zeros,
+    the image centre, NaN) must come out bit-identically -- no special cases of our own."""
+    if not oracle.ref_gpu_available():
+        pytest.skip("oracle/_ref not built")
+    feats = WL.features(9, 1, 4, 40, 60)
+    inf, nan = np.inf, np.nan
+    rois = np.array([[0, 100, 80, 0, 50, 10], [0, 100, 80, 20, 0, 10], [0, 100, 80, 0, 0, 0],
+                     [0, 100, 80, -20, 60, 30], [0, 100, 80, 20, -60, 30], [0, inf, 80, 20, 60, 30],
+                     [0, 100, -inf, 20, 60, 30], [0, 100, 80, 20, 60, inf], [0, 100, 80, 20, 60, nan],
+                     [0, nan, 80, 20, 60, 0], [0, 100, 80, inf, 60, 0], [0, 100, 80, 20, inf, 0],
+                     [0, 1e30, 1e30, 20, 60, 45], [0, 100, 80, 1e-30, 1e-30, 45], [0, 100, 80, 1e20, 1e25, 45]],
+                    dtype=np.float32)
+    _check_forward_all_paths(oracle, feats, rois, 8, 24, 0.25, cuda, vs_cpu=True, vs_ref=True)
+
+
+def test_ten_million_bins_index_parity_vs_reference_kernel(oracle, cuda):
+    """>= 1e7 random (RoI, bin) pairs: sample centres bit-identical to the reference kernel (GPU vs GPU)."""
+    if not oracle.ref_gpu_available():
+        pytest.skip("oracle/_ref not built")
+    N, ph, pw = 20000, 8, 64       # 10.24 M bins
+    feats = WL.features(11, 2, 1, 180, 320)
+    rois = np.concatenate([WL.stress_rois(21, N // 2, 2, 1280, 720),
+                           np.concatenate([WL.random_rois(100 + i, 64, i % 2) for i in range(N // 2 // 64 + 1)])[:N // 2]])
+    out, ix, iy = Hh.run_new_forward(feats, rois, ph, pw, 0.25, cuda)
+    ro, rx, ry = _ref_gpu(oracle, feats, rois, ph, pw, 0.25, cuda)
+    Hh.assert_bit_equal(ix[:, None], rx, "10M-bin idx_x")
+    Hh.assert_bit_equal(iy[:, None], ry, "10M-bin idx_y")
+    Hh.assert_bit_equal(out, ro, "10M-bin values")
+
+
+def test_full_size_properties(cuda):
+    """cfg4 per-GPU size (32 images x 64 RoIs, C=64, 180x320): size-independent properties.
+      * zero tail: every element with pw > rpw is exactly 0, and nothing else was left unwritten;
+      * layout invariance: NHWC result == NCHW result bitwise;
+      * linearity: f(a + b) ~= f(a) + f(b), f(2a) == 2 f(a) exactly (power-of-two scaling commutes);
+      * adjointness for RoIs away from the border: <f(x), g> ~= <x, f^T(g)>."""
+    import torch
+    from fots.pytorch_b200.rroi_align.functions.rroi_align import forward_raw, backward_raw
+    from fots.pytorch_b200 import _cabi
+    B, C, H, W, ph, pw, scale = 32, 64, 180, 320, 8, 64, 0.25
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    a = torch.randn(B, C, H, W, device=cuda, generator=gen)
+    b = torch.randn(B, C, H, W, device=cuda, generator=gen)
+    rois_np = WL.batch_rois(B, 64)
+    rois = Hh.to_cuda(rois_np, cuda)
+    fa, ix, iy, _ = forward_raw(a, rois, ph, pw, scale)
+    fa_cl, _, _, _ = forward_raw(a.contiguous(memory_format=torch.channels_last), rois, ph, pw, scale)
+    assert torch.equal(fa, fa_cl.contiguous())
+    rpw = (rois[:, 4] * ph) / rois[:, 3]
+    tail = torch.arange(pw, device=cuda)[None, :] > rpw[:, None]            # [N,PW]
+    assert (fa.permute(0, 3, 1, 2)[tail] == 0).all()
+    assert (ix.permute(0, 2, 1)[tail] == 0).all() and (iy.permute(0, 2, 1)[tail] == 0).all()
+    poisoned = torch.full_like(fa, float("nan"))                             # every element is written
+    st = _cabi.lib().rroi_b200_forward(a.data_ptr(), rois.data_ptr(), poisoned.data_ptr(), None, None,
+                                       rois.shape[0], B, C, H, W, ph, pw, scale, _cabi.LAYOUT_NCHW,
+                                       torch.cuda.current_stream(cuda).cuda_stream)
+    assert st == 0 and torch.equal(poisoned, fa)
+    f2a, _, _, _ = forward_raw(2 * a, rois, ph, pw, scale)
+    assert torch.equal(f2a, 2 * fa)
+    fb, _, _, _ = forward_raw(b, rois, ph, pw, scale)
+    fab, _, _, _ = forward_raw(a + b, rois, ph, pw, scale)
+    assert torch.allclose(fab, fa + fb, rtol=1e-4, atol=1e-5)
+    # adjointness on interior RoIs (the backward's border rule is stricter than the forward's)
+    inner = WL.batch_rois(B, 64)
+    inner[:, 1] = np.clip(inner[:, 1], 500, 780)
+    inner[:, 2] = np.clip(inner[:, 2], 300, 420)
+    inner[:, 3] = np.minimum(inner[:, 3], 40)
+    inner[:, 4] = np.minimum(inner[:, 4], 160)
+    ri = Hh.to_cuda(inner, cuda)
+    fx, jx, jy, lay = forward_raw(a, ri, ph, pw, scale)
+    g = torch.randn(fx.shape, device=cuda, generator=gen)
+    gt = backward_raw(g, ri, jx, jy, (B, C, H, W), scale, lay)
+    lhs = (fx.double() * g.double()).sum().item()
+    rhs = (a.double() * gt.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+    # recomputed centres == saved centres
+    gt2 = backward_raw(g, ri, None, None, (B, C, H, W), scale, lay)
+    assert torch.allclose(gt, gt2, rtol=1e-4, atol=1e-5)
+
+
+def test_backward_dedupe_on_off_agree(cuda):
+    import torch
+    from fots.pytorch_b200 import _cabi
+    feats = WL.features(3, 2, 16, 90, 160)
+    rois = WL.stress_rois(33, 200, 2, 640, 360)
+    rois[:, 3] = np.minimum(rois[:, 3], 6)          # bin pitch < 1 px -> long runs of equal centres
+    out, ix, iy = Hh.run_new_forward(feats, rois, 8, 64, 0.25, cuda)
+    g = np.random.default_rng(0).standard_normal(out.shape, dtype=np.float32)
+    try:
+        _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, 1)
+        a = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda)
+        _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, 0)
+        b = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda)
+    finally:
+        _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, 1)
+    Hh.assert_close_rel(a, b, REL_BWD, "dedupe on vs off")
+
+
+@pytest.mark.parametrize("cg", [1, 2, 4, 8, 16])
+def test_tuning_variants_bit_exact(cuda, cg):
+    from fots.pytorch_b200 import _cabi
+    feats, rois, ph, pw, scale = WL.cfg1(24)
+    base = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda)
+    try:
+        _cabi.set_tuning(_cabi.TUNE_NCHW_CG, cg)
+        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, {1: 1, 2: 2, 4: 4, 8: 1, 16: 2}[cg])
+        _cabi.set_tuning(_cabi.TUNE_USE_PDL, cg % 4 == 0)
+        a = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda)
+        b = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda, channels_last=True)
+    finally:
+        _cabi.set_tuning(_cabi.TUNE_NCHW_CG, 0)
+        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, 0)
+        _cabi.set_tuning(_cabi.TUNE_USE_PDL, 0)
+    for x, y in zip(a, base):
+        Hh.assert_bit_equal(x, y, "NCHW cg=%d" % cg)
+    for x, y in zip(b, base):
+        Hh.assert_bit_equal(x, y, "NHWC variant")
+
+
+def test_module_api_and_function_attributes(oracle, cuda):
+    """Drop-in surface: rroi_align.modules.rroi_align._RRoiAlign / rroi_align.functions.rroi_align.RRoiAlignFunction."""
+    import torch
+    from rroi_align.modules.rroi_align import _RRoiAlign
+    from rroi_align.functions.rroi_align import RRoiAlignFunction
+    feats, rois, ph, pw, scale = WL.cfg0()
+    f = Hh.to_cuda(feats, cuda).requires_grad_(True)
+    r = Hh.to_cuda(rois, cuda)
+    eo, ex, ey = oracle.forward(feats, rois, ph, pw, scale)
+    m = _RRoiAlign(ph, pw, scale)
+    assert (m.pooled_height, m.pooled_width, m.spatial_scale) == (8, 32, 1.0)
+    y = m(f, r)
+    assert y.shape == (4, 3, 8, 32) and y.requires_grad
+    Hh.assert_bit_equal(y.detach().cpu().numpy(), eo, "module forward")
+    fn = RRoiAlignFunction(ph, pw, scale)
+    y2 = fn(f, r)
+    Hh.assert_bit_equal(y2.detach().cpu().numpy(), eo, "function forward")
+    assert tuple(fn.feature_size) == (1, 3, 64, 64) and fn.rois is r
+    Hh.assert_bit_equal(fn.idx_x.cpu().numpy(), ex, "fn.idx_x")     # [N,C,PH,PW] like the reference's ctx.idx_x
+    Hh.assert_bit_equal(fn.idx_y.cpu().numpy(), ey, "fn.idx_y")
+    g = torch.randn_like(y2)
+    y2.backward(g)
+    want = oracle.backward(g.cpu().numpy(), rois, ex, ey, feats.shape, scale)
+    Hh.assert_close_rel(f.grad.cpu().numpy(), want, REL_BWD, "autograd backward")
+    # legacy direct forward()/backward() pair returns (grad_input, None) like functions/rroi_align.py:40
+    fn2 = RRoiAlignFunction(ph, pw, scale)
+    y3 = fn2.forward(f.detach(), r)
+    gi, none = fn2.backward(g)
+    assert none is None
+    Hh.assert_bit_equal(y3.cpu().numpy(), eo, "legacy forward()")
+    Hh.assert_close_rel(gi.cpu().numpy(), want, REL_BWD, "legacy backward()")
+    # channels_last features -> channels_last result, same logical values
+    fcl = f.detach().contiguous(memory_format=torch.channels_last)
+    ycl = m(fcl, r)
+    assert ycl.is_contiguous(memory_format=torch.channels_last)
+    Hh.assert_bit_equal(ycl.cpu().numpy(), eo, "channels_last forward")
+    # empty RoI set
+    y0 = m(f, r[:0])
+    assert y0.shape == (0, 3, 8, 32)
+    y0.sum().backward()
+
+
+def test_error_behaviour(cuda):
+    import torch
+    from fots.pytorch_b200 import _RRoiAlign, _cabi
+    m = _RRoiAlign(8, 32, 1.0)
+    f = torch.zeros(1, 3, 16, 16, device=cuda)
+    with pytest.raises(ValueError):
+        m(f, torch.zeros(4, 5, device=cuda))                 # reference: wrapper returns 0, silently
+    with pytest.raises(RuntimeError):
+        m(f.cpu(), torch.zeros(4, 6))                        # reference: NameError on the CPU branch
+    with pytest.raises(TypeError):
+        m(f.double(), torch.zeros(4, 6, device=cuda))
+    # out-of-range batch index: zeros instead of the reference's out-of-bounds read
+    r = torch.tensor([[3, 8, 8, 4, 8, 0], [-1, 8, 8, 4, 8, 0]], device=cuda, dtype=torch.float32)
+    y = m(f + 1, r)
+    assert (y == 0).all()
+    assert _cabi.lib().rroi_b200_forward(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1.0, 0, None) == _cabi.ERR_INVALID_ARG
+    assert _cabi.lib().rroi_b200_forward(f.data_ptr(), r.data_ptr(), y.data_ptr(), None, None, 2, 1, 3, 16, 16, 8, 32, 1.0, 7, None) == _cabi.ERR_INVALID_ARG
