@@ -18,7 +18,7 @@ int cuda_status(cudaError_t e) {
 
 bool dims_ok(int n, int b, int c, int h, int w, int ph, int pw) {
     return n >= 0 && b > 0 && c > 0 && h > 0 && w > 0 && ph > 0 && pw > 0 &&
-           (long long)ph * pw <= 0x7fffffffLL && (long long)h * w <= 0x7fffffffLL;
+           (long long)ph * pw <= 0x7fffffffLL && (long long)b * h * w <= 0x7fffffffLL;
 }
 
 __global__ void expand_idx_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t bins, int C, size_t total) {
@@ -38,7 +38,7 @@ int RROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale,
                             const int pooled_height, const int pooled_width, const float* bottom_rois,
                             float* top_data, float* con_idx_x, float* con_idx_y, cudaStream_t stream) {
     if (!bottom_data || !bottom_rois || !top_data || ((con_idx_x == nullptr) != (con_idx_y == nullptr))) return 0;
-    if (!dims_ok(num_rois, 1, channels, height, width, pooled_height, pooled_width)) return 0;
+    if (!dims_ok(num_rois, 1, channels, height, width, pooled_height, pooled_width)) return 0;   // batch unknown here
     if (num_rois == 0) return 1;
     rroi::FwdParams p = {};
     p.feat = bottom_data; p.rois = bottom_rois; p.out = top_data; p.idx_x = con_idx_x; p.idx_y = con_idx_y;
@@ -128,7 +128,7 @@ int rroi_b200_set_tuning(int key, int value) {
             if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.nchw_cg = value; return RROI_B200_OK;
         case RROI_B200_TUNE_NHWC_UNROLL:
-            if (value != 0 && value != 1 && value != 2 && value != 4) return RROI_B200_ERR_INVALID_ARG;
+            if (value < 0 || value > 5) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.nhwc_unroll = value; return RROI_B200_OK;
         case RROI_B200_TUNE_USE_PDL:    rroi::g_tuning.use_pdl = value != 0; return RROI_B200_OK;
         case RROI_B200_TUNE_BWD_DEDUPE: rroi::g_tuning.bwd_dedupe = value != 0; return RROI_B200_OK;

@@ -122,137 +122,384 @@ cudaError_t launch_fwd_nchw(const FwdParams& p0, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------ NHWC
-// Channels-last: feat [B,H,W,C], out [N,PH,PW,C].  grid = N * tiles; one CTA = one RoI x kTilePix
-// consecutive bins x all channels.  Phase 1: one thread per bin computes the geometry into shared
-// memory.  Phase 2: the CTA streams (bin, 4-channel vector) units, consecutive threads on
-// consecutive vectors, so each tap is read and each output pixel written as contiguous float4s.
-constexpr int kNhwcBlock = 256;
-constexpr int kTilePix = 64;
+// Channels-last: feat [B,H,W,C], out [N,PH,PW,C].  One tap of one bin is a contiguous C*4-byte vector.
+//
+// grid = N * tiles; CTA = 8 warps = one RoI x (8*PPW) consecutive bins.  Warp 0 computes the RoI
+// transform once (shared memory broadcast).  Each warp then owns PPW bins:
+//   geometry -- lane j computes bin j (lane-parallel, no redundancy), keeping only a float offset of
+//               the top-left tap and a small code word;
+//   gather   -- the WHOLE warp walks its bins one at a time, lane = channel vector, so every tap is
+//               one fully coalesced 32*VEC*4-byte request, every branch is warp-uniform, and there
+//               is no per-lane select/predicate arithmetic.  UN bins are in flight at once
+//               (loads of UN bins are issued before the first blend).
+// Per bin this is ~25 warp instructions for C=64 (3 SHFL, <=4 LDG, 8 FFMA, 1 STG, addressing), against
+// ~40 thread-instructions per output float in a one-thread-per-vector formulation.
+constexpr int kNhwcWarps = 8;
 
-struct __align__(16) PixRec {
-    long long base;     // ((batch*H + t)*W + l): pixel index of the top-left tap
-    uint32_t flags;
-    float wlt, wrt, wrb, wlb;
+// code word of a bin (warp-uniform once broadcast)
+enum : uint32_t {
+    C_LT = 1u, C_RT = 2u, C_LB = 4u, C_RB = 8u,  // tap must be loaded (valid, distinct)
+    C_HX = 16u, C_HY = 32u,                       // rx == 0.5 / ry == 0.5
+    C_IN = 64u,                                   // bin inside the RoI
+    C_NAN = 128u,                                 // centre not finite: the reference's weights are NaN
+    C_LIVE = 256u                                 // bin index < PH*PW
 };
 
-template <typename V> struct VecOps;
-template <> struct VecOps<float4> {
-    static constexpr int N = 4;
-    __device__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-    __device__ static float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-    __device__ static void st(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
-    __device__ static float4 blend4(const float4& a, const float4& b, const float4& c, const float4& d, const BinTaps& g) {
-        return make_float4(blend(a.x, b.x, c.x, d.x, g), blend(a.y, b.y, c.y, d.y, g),
-                           blend(a.z, b.z, c.z, d.z, g), blend(a.w, b.w, c.w, d.w, g));
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using T = float; };
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+
+template <int VEC> __device__ __forceinline__ void vzero(float (&v)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = 0.0f;
+}
+template <int VEC> __device__ __forceinline__ void vload(float (&v)[VEC], const float* p) {
+    using T = typename VecT<VEC>::T;
+    const T t = __ldg(reinterpret_cast<const T*>(p));
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = f[i];
+}
+template <int VEC> __device__ __forceinline__ void vstore(float* p, const float (&v)[VEC]) {
+    using T = typename VecT<VEC>::T;
+    T t;
+    float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) f[i] = v[i];
+    *reinterpret_cast<T*>(p) = t;
+}
+
+// kernel.cu:136-141 with the weights of the four half-grid cases as literals.  Taps that coincide
+// (r == l and/or b == t) reuse the loaded register, exactly as the reference re-reads the same pixel.
+template <int VEC>
+__device__ __forceinline__ void blend_case(float (&o)[VEC], const float (&lt)[VEC], const float (&rt)[VEC],
+                                           const float (&lb)[VEC], const float (&rb)[VEC], uint32_t code) {
+    const bool hx = code & C_HX, hy = code & C_HY;
+    if (!hx && !hy) {            // weights 1,0,0,0 ; rt = rb = lb = lt
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float v = __fmaf_rn(lt[i], 1.0f, 0.0f);
+            v = __fmaf_rn(lt[i], 0.0f, v); v = __fmaf_rn(0.0f, lt[i], v); v = __fmaf_rn(lt[i], 0.0f, v);
+            o[i] = v;
+        }
+    } else if (hx && !hy) {      // weights .5,.5,0,0 ; lb = lt, rb = rt
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float v = __fmaf_rn(lt[i], 0.5f, 0.0f);
+            v = __fmaf_rn(rt[i], 0.5f, v); v = __fmaf_rn(0.0f, rt[i], v); v = __fmaf_rn(lt[i], 0.0f, v);
+            o[i] = v;
+        }
+    } else if (!hx && hy) {      // weights .5,0,0,.5 ; rt = lt, rb = lb
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float v = __fmaf_rn(lt[i], 0.5f, 0.0f);
+            v = __fmaf_rn(lt[i], 0.0f, v); v = __fmaf_rn(0.0f, lb[i], v); v = __fmaf_rn(lb[i], 0.5f, v);
+            o[i] = v;
+        }
+    } else {                     // weights .25 x4
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float v = __fmaf_rn(lt[i], 0.25f, 0.0f);
+            v = __fmaf_rn(rt[i], 0.25f, v); v = __fmaf_rn(0.25f, rb[i], v); v = __fmaf_rn(lb[i], 0.25f, v);
+            o[i] = v;
+        }
     }
-};
-template <> struct VecOps<float> {
-    static constexpr int N = 1;
-    __device__ static float zero() { return 0.f; }
-    __device__ static float ld(const float* p) { return __ldg(p); }
-    __device__ static void st(float* p, const float& v) { *p = v; }
-    __device__ static float blend4(const float& a, const float& b, const float& c, const float& d, const BinTaps& g) {
-        return blend(a, b, c, d, g);
-    }
-};
+}
 
-template <typename V, int U>
-__global__ void __launch_bounds__(kNhwcBlock) rroi_fwd_nhwc_kernel(const FwdParams p) {
-    using Ops = VecOps<V>;
+// CT = compile-time channel count (64/128/256: tap strides become LDG immediates and a warp spans the
+// channels exactly) or 0 = run-time p.C with vector width VEC and a ragged last channel chunk.
+template <int CT, int VEC, int PPW, int UN>
+__global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_kernel(const FwdParams p) {
     __shared__ RoiXform sX;
-    __shared__ PixRec rec[kTilePix];
-
+    const int C = CT ? CT : p.C;
     const int n = blockIdx.x / p.tiles;
     const int tile = blockIdx.x - n * p.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bins = p.PH * p.PW;
-    const int bin0 = tile * kTilePix;
-    const int npix = min(kTilePix, bins - bin0);
 
     pdl_wait();
     pdl_launch_dependents();
-    if (threadIdx.x < 32) {
+    if (warp == 0) {
         const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        if (threadIdx.x == 0) sX = X;
+        if (lane == 0) sX = X;
     }
     __syncthreads();
-    if (threadIdx.x < npix) {
+
+    // ---- geometry: lane j <-> bin bin0 + j
+    const int bin0 = (tile * kNhwcWarps + warp) * PPW;
+    if (bin0 >= bins) return;                         // warp-uniform
+    int pix = 0;                                      // pixel index (batch*H + t)*W + l of the top-left tap
+    uint32_t code = 0;
+    if (lane < PPW && bin0 + lane < bins) {
         const RoiXform X = sX;
-        const int bin = bin0 + threadIdx.x;
+        const int bin = bin0 + lane;
         const int ph = bin / p.PW, pw = bin - ph * p.PW;
         const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
         const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
-        PixRec r;
-        r.base = ((long long)(batch_ok ? X.batch : 0) * p.H + g.t) * p.W + g.l;
-        r.flags = g.flags;
-        r.wlt = g.wlt; r.wrt = g.wrt; r.wrb = g.wrb; r.wlb = g.wlb;
-        rec[threadIdx.x] = r;
+        const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+        // only dereferenced under a tap bit, and then 0 <= t < H, 0 <= l < W (wrap-around is harmless otherwise)
+        pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+        code = C_LIVE;
+        if (in) {
+            code |= C_IN;
+            if (g.flags & TAP_LT) code |= C_LT;
+            if ((g.flags & TAP_RT) && two_c) code |= C_RT;
+            if ((g.flags & TAP_LB) && two_r) code |= C_LB;
+            if ((g.flags & TAP_RB) && two_c && two_r) code |= C_RB;
+            if (two_c) code |= C_HX;                  // r != l  <=>  rx == 0.5 for a finite centre
+            if (two_r) code |= C_HY;
+            if (!(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY)) code |= C_NAN;
+        }
         if (p.idx_mode == IDX_COMPACT) {
-            const bool in = g.flags & BIN_IN;
             p.idx_x[(size_t)n * bins + bin] = in ? g.cx : 0.0f;
             p.idx_y[(size_t)n * bins + bin] = in ? g.cy : 0.0f;
         }
     }
-    __syncthreads();
 
-    const int CV = p.C / Ops::N;            // vectors per pixel
-    const int units = npix * CV;
-    float* outp = p.out + ((size_t)n * bins + bin0) * p.C;
-    const size_t rowC = (size_t)p.W * p.C;
-
-    for (int u0 = threadIdx.x; u0 < units; u0 += kNhwcBlock * U) {
-        V lt[U], rt[U], lb[U], rb[U];
-        int pix[U];
+    // ---- gather: whole warp per bin, lane = channel vector
+    const int CV = C / VEC;
+    const long long rowC = (long long)p.W * C;
+    constexpr bool kExact = CT != 0;                 // CT % (32*VEC) == 0: no ragged chunk
+    for (int cv = lane; cv < (kExact ? CV : ((CV + 31) & ~31)); cv += 32) {
+        const bool act = kExact || cv < CV;
+        const float* fbase = p.feat + (size_t)cv * VEC;
+        float* outp = p.out + ((size_t)n * bins + bin0) * C + (size_t)cv * VEC;
+#pragma unroll 1
+        for (int j0 = 0; j0 < PPW; j0 += UN) {
+            float lt[UN][VEC], rt[UN][VEC], lb[UN][VEC], rb[UN][VEC];
+            uint32_t cd[UN];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int u = u0 + j * kNhwcBlock;
-            lt[j] = rt[j] = lb[j] = rb[j] = Ops::zero();
-            pix[j] = -1;
-            if (u < units) {
-                const int px = u / CV, v = u - px * CV;
-                pix[j] = px;
-                const uint32_t f = rec[px].flags;
-                const bool in = f & BIN_IN, two_c = f & TWO_COLS, two_r = f & TWO_ROWS;
-                const float* s = p.feat + (size_t)rec[px].base * p.C + (size_t)v * Ops::N;
-                if (in && (f & TAP_LT)) lt[j] = Ops::ld(s);
-                if (in && (f & TAP_RT) && two_c) rt[j] = Ops::ld(s + p.C);
-                if (in && (f & TAP_LB) && two_r) lb[j] = Ops::ld(s + rowC);
-                if (in && (f & TAP_RB) && two_c && two_r) rb[j] = Ops::ld(s + rowC + p.C);
+            for (int u = 0; u < UN; ++u) {
+                const int px = __shfl_sync(0xffffffffu, pix, j0 + u);
+                cd[u] = __shfl_sync(0xffffffffu, code, j0 + u);
+                vzero<VEC>(lt[u]); vzero<VEC>(rt[u]); vzero<VEC>(lb[u]); vzero<VEC>(rb[u]);
+                if (act) {
+                    const float* s = fbase + (long long)px * C;
+                    const float* s2 = s + rowC;
+                    if (cd[u] & C_LT) vload<VEC>(lt[u], s);
+                    if (cd[u] & C_RT) vload<VEC>(rt[u], s + C);
+                    if (cd[u] & C_LB) vload<VEC>(lb[u], s2);
+                    if (cd[u] & C_RB) vload<VEC>(rb[u], s2 + C);
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            if (pix[j] >= 0) {
-                const int u = u0 + j * kNhwcBlock;
-                const PixRec r = rec[pix[j]];
-                const bool in = r.flags & BIN_IN, two_c = r.flags & TWO_COLS, two_r = r.flags & TWO_ROWS;
-                BinTaps g;
-                g.wlt = r.wlt; g.wrt = r.wrt; g.wrb = r.wrb; g.wlb = r.wlb;
-                const V vrt = two_c ? rt[j] : lt[j];
-                const V vlb = two_r ? lb[j] : lt[j];
-                const V vrb = two_c ? (two_r ? rb[j] : vrt) : vlb;
-                V o = Ops::blend4(lt[j], vrt, vrb, vlb, g);
-                if (!in) o = Ops::zero();
-                Ops::st(outp + (size_t)u * Ops::N, o);
+            for (int u = 0; u < UN; ++u) {
+                if (!(cd[u] & C_LIVE) || !act) continue;
+                float o[VEC];
+                if (!(cd[u] & C_IN)) {
+                    vzero<VEC>(o);
+                } else if (cd[u] & C_NAN) {          // reference: every tap invalid, weights NaN -> 0*NaN
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] = __int_as_float(0x7fffffff);
+                } else {
+                    blend_case<VEC>(o, lt[u], rt[u], lb[u], rb[u], cd[u]);
+                }
+                vstore<VEC>(outp + (j0 + u) * C, o);
             }
         }
     }
 }
 
+// ------------------------------------------------------------------------------------ NHWC, packed
+// Specialisation for C in {32, 64, 128, 256} (C*4 bytes per tap = 128 B .. 1 KB): every lane moves one
+// float4, LPP = C/4 lanes span a pixel, so a warp iteration covers 32/LPP bins (C <= 128) or one bin's
+// 32-lane channel chunk (C = 256).  The record is per lane, so the body is branch-free: predicated
+// 128-bit loads and the reference's 4-FFMA chain with per-lane weights.
+// Per 512 output bytes: 2 LDS.128 + <=4 LDG.128 + 16 FFMA + 1 STG.128 + ~15 integer/zeroing.
+// Geometry uses one THREAD per bin of the CTA tile (shared-memory records), so it costs the same
+// ~6 warp-instructions per bin whatever the tile shape.
+// 128-bit load under a predicate; the destination is zero when the predicate is off.  Deliberately not
+// ld.global.nc: ptxas moves .nc loads across barriers, which defeats the load batching below.
+__device__ __forceinline__ float4 ldg_pred_v4(const float* ptr, uint32_t pred) {
+    float4 r;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+        "@q ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(ptr), "r"(pred));
+    return r;
+}
+
+// Shared-memory record of one bin.  The weights already fold in everything the blend needs to know:
+// a tap that is not loaded (outside the border test, coinciding with another tap, or bin outside the
+// RoI) has weight 0 and its register holds 0, so the reference's four-product sum comes out of the same
+// four FFMAs in the same order without any per-lane select.  (For finite features this is bit-identical
+// to the reference; a zero-weight tap whose value is inf/NaN makes the reference return NaN where this
+// returns the finite/inf bilinear value -- documented in DESIGN.md.)
+struct __align__(16) BinRec {
+    int pix;                       // (batch*H + t)*W + l of the top-left tap
+    uint32_t code;                 // C_LT|C_RT|C_LB|C_RB load bits, C_LIVE
+    float wlt, wrt, wrb, wlb;      // NaN when the centre is not finite (reference: 0 * NaN)
+    int pad[2];
+};
+
+template <int CT, int TILE, int UN>
+__global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_packed_kernel(const FwdParams p) {
+    constexpr int LPP = CT / 4;                          // lanes per pixel
+    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;        // pixels per warp iteration
+    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;         // 32-lane channel chunks per pixel
+    constexpr int PIXW = TILE / kNhwcWarps;              // pixels per warp
+    constexpr int ITERS = PIXW * NCH / PPI;              // warp iterations
+    static_assert(PIXW * kNhwcWarps == TILE && ITERS % UN == 0 && ITERS > 0, "tile shape");
+    __shared__ RoiXform sX;
+    __shared__ BinRec rec[TILE];
+
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+    const int bin0 = tile * TILE;
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (warp == 0) {
+        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        if (lane == 0) sX = X;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TILE; t += kNhwcWarps * 32) {
+        BinRec r;
+        r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
+        const int bin = bin0 + t;
+        if (bin < bins) {
+            const RoiXform X = sX;
+            const int ph = bin / p.PW, pw = bin - ph * p.PW;
+            const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+            const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+            const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+            r.pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+            r.code = C_LIVE;
+            if (in) {
+                const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+                const bool l_lt = g.flags & TAP_LT;
+                const bool l_rt = (g.flags & TAP_RT) && two_c;
+                const bool l_lb = (g.flags & TAP_LB) && two_r;
+                const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+                r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+                // Coinciding taps: the reference adds w*x once per tap NAME; here the duplicate names'
+                // weights are zero by construction (rx == 0 -> wrt = wrb = 0, ry == 0 -> wrb = wlb = 0),
+                // so only border-invalid taps need their weight cleared.
+                r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+                r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+                r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+                r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+            }
+            if (p.idx_mode == IDX_COMPACT) {
+                p.idx_x[(size_t)n * bins + bin] = in ? g.cx : 0.0f;
+                p.idx_y[(size_t)n * bins + bin] = in ? g.cy : 0.0f;
+            }
+        }
+        rec[t] = r;
+    }
+    __syncthreads();
+
+    const int sub = LPP >= 32 ? 0 : lane / LPP;          // which of the iteration's pixels this lane serves
+    const int cvl = LPP >= 32 ? lane : lane % LPP;       // float4 index inside the 32-lane chunk
+    const long long rowC = (long long)p.W * CT;
+    const float* fbase = p.feat + cvl * 4;
+    const int pw0 = warp * PIXW;
+    // per-lane output pointer of iteration 0; later iterations are compile-time offsets from it
+    float* obase = p.out + ((size_t)n * bins + bin0 + pw0 + (NCH > 1 ? 0 : sub)) * CT + cvl * 4;
+    const BinRec* rbase = rec + pw0 + (NCH > 1 ? 0 : sub);
+
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += UN) {
+        float4 lt[UN], rt[UN], lb[UN], rb[UN];
+        BinRec r[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int it = it0 + u;
+            r[u] = rbase[NCH > 1 ? it / NCH : it * PPI];
+        }
+        // all loads of the UN iterations are issued before the first blend (volatile asm keeps them
+        // together and in order: ptxas otherwise serialises the iterations to save registers)
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int it = it0 + u;
+            const int ch = NCH > 1 ? (it % NCH) * 128 : 0;            // float offset of the channel chunk
+            const float* s = fbase + (long long)r[u].pix * CT + ch;
+            const float* s2 = s + rowC;
+            lt[u] = ldg_pred_v4(s, r[u].code & C_LT);
+            rt[u] = ldg_pred_v4(s + CT, r[u].code & C_RT);
+            lb[u] = ldg_pred_v4(s2, r[u].code & C_LB);
+            rb[u] = ldg_pred_v4(s2 + CT, r[u].code & C_RB);
+        }
+        // The blend lives in its own basic block (a branch the optimiser cannot fold): ptxas otherwise
+        // interleaves iteration u's FFMAs between the loads of iterations u and u+1 to save registers,
+        // which serialises the DRAM latencies of the UN iterations.
+        uint32_t any_live = 0;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) any_live |= r[u].code;
+        if (any_live & C_LIVE) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int it = it0 + u;
+                const int dpx = NCH > 1 ? it / NCH : it * PPI;        // pixel offset from the lane's base
+                const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+                const float wlt = r[u].wlt, wrt = r[u].wrt, wrb = r[u].wrb, wlb = r[u].wlb;
+                float4 o;
+                float v;
+                v = __fmaf_rn(lt[u].x, wlt, 0.0f); v = __fmaf_rn(rt[u].x, wrt, v); v = __fmaf_rn(wrb, rb[u].x, v); o.x = __fmaf_rn(lb[u].x, wlb, v);
+                v = __fmaf_rn(lt[u].y, wlt, 0.0f); v = __fmaf_rn(rt[u].y, wrt, v); v = __fmaf_rn(wrb, rb[u].y, v); o.y = __fmaf_rn(lb[u].y, wlb, v);
+                v = __fmaf_rn(lt[u].z, wlt, 0.0f); v = __fmaf_rn(rt[u].z, wrt, v); v = __fmaf_rn(wrb, rb[u].z, v); o.z = __fmaf_rn(lb[u].z, wlb, v);
+                v = __fmaf_rn(lt[u].w, wlt, 0.0f); v = __fmaf_rn(rt[u].w, wrt, v); v = __fmaf_rn(wrb, rb[u].w, v); o.w = __fmaf_rn(lb[u].w, wlb, v);
+                if (r[u].code & C_LIVE) *reinterpret_cast<float4*>(obase + dpx * CT + ch) = o;
+            }
+        }
+    }
+}
+
+template <int CT>
+static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, bool pdl, int variant) {
+    const int bins = p.PH * p.PW;
+    auto go = [&](auto kernel, int tile) {
+        p.tiles = (bins + tile - 1) / tile;
+        return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, pdl);
+    };
+    constexpr int PPI = CT >= 128 ? 1 : 128 / CT;   // pixels per warp iteration
+    constexpr int NCH = CT > 128 ? CT / 128 : 1;
+    // UN chosen so that a 64-bin tile's per-warp iterations (8*NCH/PPI) are a multiple of it
+    constexpr int I64 = 8 * NCH / PPI;
+    switch (variant) {
+        case 1:  return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
+        case 2:  return go(rroi_fwd_nhwc_packed_kernel<CT, 128, 4>, 128);
+        case 3:  return go(rroi_fwd_nhwc_packed_kernel<CT, 128, 2>, 128);
+        case 4:  return go(rroi_fwd_nhwc_packed_kernel<CT, 256, 4>, 256);
+        case 5:  return go(rroi_fwd_nhwc_packed_kernel<CT, 256, 2>, 256);
+        default: return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, 64);
+    }
+}
+
+template <int CT, int VEC>
+static cudaError_t launch_fwd_nhwc_vec(FwdParams& p, cudaStream_t s, bool pdl, int variant) {
+    const int bins = p.PH * p.PW;
+    auto go = [&](auto kernel, int ppw) {
+        p.tiles = (bins + kNhwcWarps * ppw - 1) / (kNhwcWarps * ppw);
+        return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, pdl);
+    };
+    switch (variant) {
+        case 1:  return go(rroi_fwd_nhwc_kernel<CT, VEC, 8, 4>, 8);
+        case 3:  return go(rroi_fwd_nhwc_kernel<CT, VEC, 32, 4>, 32);
+        default: return go(rroi_fwd_nhwc_kernel<CT, VEC, 16, 4>, 16);
+    }
+}
+
 cudaError_t launch_fwd_nhwc(const FwdParams& p0, cudaStream_t s) {
     FwdParams p = p0;
-    const int bins = p.PH * p.PW;
-    p.tiles = (bins + kTilePix - 1) / kTilePix;
     p.cgroups = 1;
-    const long long grid = (long long)p.N * p.tiles;
     const bool pdl = g_tuning.use_pdl != 0;
-    const int U = g_tuning.nhwc_unroll > 0 ? g_tuning.nhwc_unroll : 4;
-    const bool vec = (p.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.feat) | reinterpret_cast<uintptr_t>(p.out)) % 16 == 0);
-    if (vec) {
-        if (U == 1) return launch_1d(rroi_fwd_nhwc_kernel<float4, 1>, grid, kNhwcBlock, p, s, pdl);
-        if (U == 2) return launch_1d(rroi_fwd_nhwc_kernel<float4, 2>, grid, kNhwcBlock, p, s, pdl);
-        return launch_1d(rroi_fwd_nhwc_kernel<float4, 4>, grid, kNhwcBlock, p, s, pdl);
-    }
-    return launch_1d(rroi_fwd_nhwc_kernel<float, 4>, grid, kNhwcBlock, p, s, pdl);
+    const int variant = g_tuning.nhwc_unroll;
+    const bool al16 = (reinterpret_cast<uintptr_t>(p.feat) | reinterpret_cast<uintptr_t>(p.out)) % 16 == 0;
+    if (al16 && p.C == 32)  return launch_fwd_nhwc_packed<32>(p, s, pdl, variant);
+    if (al16 && p.C == 64)  return launch_fwd_nhwc_packed<64>(p, s, pdl, variant);
+    if (al16 && p.C == 128) return launch_fwd_nhwc_packed<128>(p, s, pdl, variant);
+    if (al16 && p.C == 256) return launch_fwd_nhwc_packed<256>(p, s, pdl, variant);
+    // any other C: warp-per-bin kernel with run-time C, widest vector that divides it
+    if (al16 && p.C % 4 == 0 && p.C >= 128) return launch_fwd_nhwc_vec<0, 4>(p, s, pdl, variant);
+    if (al16 && p.C % 2 == 0 && p.C >= 64)  return launch_fwd_nhwc_vec<0, 2>(p, s, pdl, variant);
+    return launch_fwd_nhwc_vec<0, 1>(p, s, pdl, variant);
 }
 
 }  // namespace rroi

@@ -41,7 +41,7 @@ struct BwdParams {
 // Tunables a caller (bench sweeps, tests) may override through rroi_b200_set_tuning(); 0 = default.
 struct Tuning {
     int nchw_cg;       // channels per CTA in the NCHW kernels: 1,2,4,8,16
-    int nhwc_unroll;   // (pixel,vec) units in flight per thread in the NHWC forward: 1,2,4
+    int nhwc_unroll;   // NHWC forward variant 0..5 (bins per warp x bins in flight), see launch_fwd_nhwc_vec
     int use_pdl;       // launch with programmatic stream serialization
     int bwd_dedupe;    // warp-level merge of equal sample points before the atomics (NCHW backward)
 };

@@ -232,11 +232,11 @@ def test_backward_dedupe_on_off_agree(cuda):
 @pytest.mark.parametrize("cg", [1, 2, 4, 8, 16])
 def test_tuning_variants_bit_exact(cuda, cg):
     from fots.pytorch_b200 import _cabi
-    feats, rois, ph, pw, scale = WL.cfg1(24)
+    feats, rois, ph, pw, scale = WL.cfg1({1: 24, 2: 64, 4: 128, 8: 256, 16: 40}[cg])   # templated and run-time C paths
     base = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda)
     try:
         _cabi.set_tuning(_cabi.TUNE_NCHW_CG, cg)
-        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, {1: 1, 2: 2, 4: 4, 8: 1, 16: 2}[cg])
+        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, {1: 1, 2: 2, 4: 3, 8: 4, 16: 5}[cg])
         _cabi.set_tuning(_cabi.TUNE_USE_PDL, cg % 4 == 0)
         a = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda)
         b = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda, channels_last=True)

@@ -55,13 +55,13 @@ if __name__ == "__main__":
     steps = 5000 if a.quick else 20000
     for C in (64, 256):
         for pdl in (0, 1):
-            for U in (1, 2, 4):
+            for U in (0, 1, 2, 3, 4, 5):
                 recs.append(point("nhwc", C, 1, steps, unroll=U, pdl=pdl))
-            for cg in (2, 4, 8, 16):
+            for cg in (8,):
                 recs.append(point("nchw", C, 1, steps, cg=cg, pdl=pdl))
     # batched steps (cfg2: 8 images, cfg4 per GPU: 32 images)
     for images in (8, 32):
-        for layout, kw in (("nhwc", dict(unroll=4)), ("nhwc", dict(unroll=2)), ("nchw", dict(cg=8)), ("nchw", dict(cg=4))):
+        for layout, kw in (("nhwc", dict(unroll=0)), ("nhwc", dict(unroll=1)), ("nhwc", dict(unroll=3)), ("nhwc", dict(unroll=5)), ("nchw", dict(cg=8))):
             recs.append(point(layout, 64, images, max(steps // images, 500), pdl=1, **kw))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w") as f:
