@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough to exceed 3x L2)")
     ap.add_argument("--graph-chunk", type=int, default=500)
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=1,
+                    help="independent steps (different images) are issued round-robin on this many streams")
+    ap.add_argument("--variant", type=int, default=-1, help="NHWC kernel variant override (tuning)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -154,8 +157,24 @@ class Workload:
         self.out = [torch.empty((self.N, self.C, self.PH, self.PW), device=device, memory_format=fmt)
                     for _ in range(self.sets)]
 
+    def enable_backward(self, torch):
+        """Allocate top_diff / bottom_diff per buffer set (tools/sweep.py --backward, not the headline)."""
+        self.gtop = [torch.randn_like(o) for o in self.out]
+        self.gbot = [torch.empty_like(f) for f in self.feats]
+        self.backward = True
+
+    def launch_bwd(self, s, lib, cabi, stream):
+        st = lib.rroi_b200_backward(self.gtop[s].data_ptr(), self.rois[s].data_ptr(), None, None,
+                                    self.gbot[s].data_ptr(), self.N, self.B, self.C, self.H, self.W, self.PH,
+                                    self.PW, self.scale,
+                                    cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW, 1, stream)
+        if st != 0:
+            raise RuntimeError("rroi_b200_backward -> %d" % st)
+
     def launch(self, s, lib, cabi, stream):
         """One step on buffer set s: exactly one kernel launch through the C ABI (rroi_b200_forward)."""
+        if getattr(self, "backward", False):
+            return self.launch_bwd(s, lib, cabi, stream)
         st = lib.rroi_b200_forward(self.feats[s].data_ptr(), self.rois[s].data_ptr(), self.out[s].data_ptr(),
                                    None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
                                    self.scale, cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW,
@@ -164,9 +183,13 @@ class Workload:
             raise RuntimeError("rroi_b200_forward -> %d" % st)
 
 
-def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier):
-    """W untimed warm-up steps, then exactly K steps replayed from CUDA graphs; returns elapsed ms."""
+def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier, nstreams=1):
+    """W untimed warm-up steps, then exactly K steps replayed from CUDA graphs; returns elapsed ms.
+
+    With nstreams > 1 consecutive steps (independent images: different buffer sets) are captured on
+    parallel branches of the graph, the way a serving pipeline keeps several requests in flight."""
     stream = torch.cuda.Stream()
+    side = [torch.cuda.Stream() for _ in range(max(nstreams - 1, 0))]
     graphs = {}
 
     def graph_for(n, first):
@@ -174,8 +197,18 @@ def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier):
         if key not in graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
+                cap = torch.cuda.current_stream()
+                lanes = [cap] + side
+                fork = torch.cuda.Event()
+                fork.record(cap)
+                for sd in side:
+                    sd.wait_event(fork)
                 for i in range(n):
-                    wl.launch((first + i) % wl.sets, lib, cabi, torch.cuda.current_stream().cuda_stream)
+                    wl.launch((first + i) % wl.sets, lib, cabi, lanes[i % len(lanes)].cuda_stream)
+                for sd in side:
+                    join = torch.cuda.Event()
+                    join.record(sd)
+                    cap.wait_event(join)
             graphs[key] = g
         return graphs[key]
 
@@ -341,7 +374,9 @@ def run_b200(args):
     wl = Workload(args, device, torch)
     sampler = ClockSampler(local)
     sampler.start()
-    ms = timed_steps(wl, steps, warmup, args.graph_chunk, torch, lib, _cabi, barrier)
+    if args.variant >= 0:
+        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, args.variant)
+    ms = timed_steps(wl, steps, warmup, args.graph_chunk, torch, lib, _cabi, barrier, args.streams)
     clocks = sampler.finish()
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if dist is not None:
@@ -363,7 +398,7 @@ def run_b200(args):
                    "layout": "channels_last (NHWC in HBM)" if wl.layout == "nhwc" else "NCHW (reference layout)",
                    "images_per_step": wl.B, "rois_per_step": wl.N, "channels": wl.C,
                    "l2": "inputs larger than L2: %d rotating buffer sets, %.0f MB working set vs 126 MB L2" % (wl.sets, wl.working_set_mb),
-                   "launch": "CUDA graphs of %d steps, PDL=%d" % (min(args.graph_chunk, steps), args.pdl),
+                   "launch": "CUDA graphs of %d steps, PDL=%d, %d stream(s)" % (min(args.graph_chunk, steps), args.pdl, args.streams),
                    "parallelism": "image-sharded, %d rank(s), no data-path collective in RoIRotate" % world},
         "gpu_launches": steps,
         "clocks": clocks,

@@ -21,103 +21,155 @@ namespace rroi {
 
 Tuning g_tuning = {0, 0, 0, 1};
 
-// ------------------------------------------------------------------------------------------ NCHW
-// grid = N * cgroups * tiles; one CTA = one RoI x CG channels x 256 consecutive bins (pw fastest).
-// Thread = one bin: geometry once, then CG planes: <=4 predicated loads each, one coalesced store.
-constexpr int kNchwBlock = 256;
+// code word of a bin
+enum : uint32_t {
+    C_LT = 1u, C_RT = 2u, C_LB = 4u, C_RB = 8u,  // tap must be loaded (valid, distinct)
+    C_HX = 16u, C_HY = 32u,                       // rx == 0.5 / ry == 0.5
+    C_IN = 64u,                                   // bin inside the RoI
+    C_NAN = 128u,                                 // centre not finite: the reference's weights are NaN
+    C_LIVE = 256u                                 // bin index < PH*PW
+};
 
-template <int CG>
+// ------------------------------------------------------------------------------------------ NCHW
+// Reference layout: feat [B,C,H,W], out [N,C,PH,PW].  A tap is one 4-byte word of plane (b,c); the 32
+// lanes of a warp are 32 BINS and the warp walks the channels, so stores are coalesced along pw and the
+// loads are a 32-lane gather inside one plane.
+//
+// grid = N * tiles; CTA = 8 warps = one RoI x an 8x8 patch of bins (8 ph x 8 pw) x all channels.  The 2-D
+// patch keeps the CTA's footprint in the feature plane compact for any rotation, so the 32-byte sectors
+// a gather touches are reused out of L1 by the neighbouring bins of the same CTA instead of being
+// re-fetched from L2 by another CTA.  Warp w owns half of the patch (4 ph x 8 pw: four full 32-byte
+// sectors per store) and every 4th channel; its lanes keep their bin's record in registers.
+// Bin geometry: one thread per bin, once per CTA (the reference recomputes it per channel).
+constexpr int kNchwBlock = 256;
+constexpr int kPatch = 8;                 // patch edge in bins
+
+// 32-bit load under a predicate, zero otherwise (not .nc: see ldg_pred_v4)
+template <int kByteOff>
+__device__ __forceinline__ float ldg_pred_f32(const float* ptr, uint32_t pred) {
+    float r;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.f32 %0, [%1+%3];\n\t}"
+        : "=f"(r) : "l"(ptr), "r"(pred), "n"(kByteOff));
+    return r;
+}
+
+struct __align__(16) BinRecP {
+    int off;                       // t*W + l inside the plane
+    uint32_t code;                 // C_LT|C_RT|C_LB|C_RB load bits, C_LIVE
+    float wlt, wrt, wrb, wlb;
+    float cx, cy;                  // for the reference's [N,C,PH,PW] centre tensors (IDX_FULL)
+};
+
+template <int UN>
 __global__ void __launch_bounds__(kNchwBlock) rroi_fwd_nchw_kernel(const FwdParams p) {
     __shared__ RoiXform sX;
-    int item = blockIdx.x;
-    const int tile = item % p.tiles;  item /= p.tiles;
-    const int cg = item % p.cgroups;
-    const int n = item / p.cgroups;
+    __shared__ BinRecP rec[kPatch * kPatch];
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int tiles_w = (p.PW + kPatch - 1) / kPatch;
+    const int ph0 = (tile / tiles_w) * kPatch, pw0 = (tile % tiles_w) * kPatch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
 
     pdl_wait();
     pdl_launch_dependents();
-    if (threadIdx.x < 32) {
+    if (warp == 0) {
         const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        if (threadIdx.x == 0) sX = X;
+        if (lane == 0) sX = X;
     }
     __syncthreads();
     const RoiXform X = sX;
-
-    const int bins = p.PH * p.PW;
-    const int bin = tile * kNchwBlock + threadIdx.x;
-    if (bin >= bins) return;
-    const int ph = bin / p.PW, pw = bin - ph * p.PW;
     const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
-    const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
-
-    const int c0 = cg * CG;
-    const size_t HW = (size_t)p.H * p.W;
-    const float* src = p.feat + ((size_t)(batch_ok ? X.batch : 0) * p.C + c0) * HW;
-    float* dst = p.out + ((size_t)n * p.C + c0) * bins + bin;
-
-    const bool in = g.flags & BIN_IN;
-    const bool two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
-    const bool p_lt = in && (g.flags & TAP_LT);
-    const bool p_rt = in && (g.flags & TAP_RT) && two_c;
-    const bool p_lb = in && (g.flags & TAP_LB) && two_r;
-    const bool p_rb = in && (g.flags & TAP_RB) && two_c && two_r;
-    // offsets are only dereferenced under the predicates above (then 0 < l,t and l < W, t < H)
-    const unsigned o_lt = (unsigned)g.t * (unsigned)p.W + (unsigned)g.l;
-    const unsigned o_rt = o_lt + 1u, o_lb = o_lt + (unsigned)p.W, o_rb = o_lb + 1u;
-
-    float lt[CG], rt[CG], lb[CG], rb[CG];
-#pragma unroll
-    for (int k = 0; k < CG; ++k) {
-        const bool ck = (c0 + k) < p.C;
-        const float* s = src + (size_t)k * HW;
-        lt[k] = (ck && p_lt) ? __ldg(s + o_lt) : 0.0f;
-        rt[k] = (ck && p_rt) ? __ldg(s + o_rt) : 0.0f;
-        lb[k] = (ck && p_lb) ? __ldg(s + o_lb) : 0.0f;
-        rb[k] = (ck && p_rb) ? __ldg(s + o_rb) : 0.0f;
+    if (threadIdx.x < kPatch * kPatch) {
+        BinRecP r;
+        r.off = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.cx = r.cy = 0.0f;
+        const int ph = ph0 + (int)threadIdx.x / kPatch, pw = pw0 + (int)threadIdx.x % kPatch;
+        if (ph < p.PH && pw < p.PW) {
+            const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+            const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+            r.off = (int)((unsigned)g.t * (unsigned)p.W + (unsigned)g.l);
+            r.code = C_LIVE;
+            if (in) {
+                const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+                const bool l_lt = g.flags & TAP_LT;
+                const bool l_rt = (g.flags & TAP_RT) && two_c;
+                const bool l_lb = (g.flags & TAP_LB) && two_r;
+                const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+                r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+                r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+                r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+                r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+                r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+                r.cx = g.cx; r.cy = g.cy;
+            }
+            if (p.idx_mode == IDX_COMPACT) {
+                p.idx_x[(size_t)n * bins + ph * p.PW + pw] = r.cx;
+                p.idx_y[(size_t)n * bins + ph * p.PW + pw] = r.cy;
+            }
+        }
+        rec[threadIdx.x] = r;
     }
-    const float ox = in ? g.cx : 0.0f, oy = in ? g.cy : 0.0f;
+    __syncthreads();
+
+    // lane -> bin of this warp's half patch; warp -> channel phase
+    const int half = warp & 1, cq = warp >> 1;                  // 2 halves x 4 channel phases
+    const int slot = half * 32 + lane;                          // row-major inside the 8x8 patch
+    const BinRecP r = rec[slot];
+    if (!(r.code & C_LIVE)) return;
+    const int ph = ph0 + slot / kPatch, pw = pw0 + slot % kPatch;
+    const size_t HW = (size_t)p.H * p.W;
+    const float* top = p.feat + ((size_t)(batch_ok ? X.batch : 0) * p.C) * HW + r.off;   // lt; rt = top + 1
+    const float* bot = top + p.W;                                                         // lb; rb = bot + 1
+    const size_t obin = (size_t)ph * p.PW + pw;
+    float* dst = p.out + (size_t)n * p.C * bins + obin;
+    const bool full_idx = p.idx_mode == IDX_FULL;
+
+#pragma unroll 1
+    for (int c0 = cq; c0 < p.C; c0 += 4 * UN) {
+        float lt[UN], rt[UN], lb[UN], rb[UN];
 #pragma unroll
-    for (int k = 0; k < CG; ++k) {
-        if ((c0 + k) < p.C) {
-            // r == l (b == t): the reference reads the same pixel twice -- reuse the register
-            const float vrt = two_c ? rt[k] : lt[k];
-            const float vlb = two_r ? lb[k] : lt[k];
-            const float vrb = two_c ? (two_r ? rb[k] : vrt) : vlb;
-            const float v = in ? blend(lt[k], vrt, vrb, vlb, g) : 0.0f;
-            dst[(size_t)k * bins] = v;
-            if (p.idx_mode == IDX_FULL) {
-                const size_t o = ((size_t)n * p.C + c0 + k) * bins + bin;
-                p.idx_x[o] = ox;
-                p.idx_y[o] = oy;
+        for (int u = 0; u < UN; ++u) {
+            const int c = c0 + 4 * u;
+            const uint32_t ok = c < p.C;
+            const size_t po = (size_t)c * HW;
+            lt[u] = ldg_pred_f32<0>(top + po, ok ? (r.code & C_LT) : 0u);
+            rt[u] = ldg_pred_f32<4>(top + po, ok ? (r.code & C_RT) : 0u);
+            lb[u] = ldg_pred_f32<0>(bot + po, ok ? (r.code & C_LB) : 0u);
+            rb[u] = ldg_pred_f32<4>(bot + po, ok ? (r.code & C_RB) : 0u);
+        }
+        if (r.code & C_LIVE) {     // own basic block: keeps the UN channels' loads batched (see NHWC kernel)
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int c = c0 + 4 * u;
+                if (c < p.C) {
+                    float v = __fmaf_rn(lt[u], r.wlt, 0.0f);
+                    v = __fmaf_rn(rt[u], r.wrt, v);
+                    v = __fmaf_rn(r.wrb, rb[u], v);
+                    v = __fmaf_rn(lb[u], r.wlb, v);
+                    dst[(size_t)c * bins] = v;
+                    if (full_idx) {
+                        p.idx_x[((size_t)n * p.C + c) * bins + obin] = r.cx;
+                        p.idx_y[((size_t)n * p.C + c) * bins + obin] = r.cy;
+                    }
+                }
             }
         }
     }
-    if (p.idx_mode == IDX_COMPACT && cg == 0) {
-        p.idx_x[(size_t)n * bins + bin] = ox;
-        p.idx_y[(size_t)n * bins + bin] = oy;
-    }
-}
-
-static int pick_cg(int want, int C) {
-    int cg = (want == 1 || want == 2 || want == 4 || want == 8 || want == 16) ? want : 8;
-    while (cg > 1 && cg / 2 >= C) cg /= 2;
-    return cg;
 }
 
 cudaError_t launch_fwd_nchw(const FwdParams& p0, cudaStream_t s) {
     FwdParams p = p0;
-    const int cg = pick_cg(g_tuning.nchw_cg, p.C);
-    const int bins = p.PH * p.PW;
-    p.tiles = (bins + kNchwBlock - 1) / kNchwBlock;
-    p.cgroups = (p.C + cg - 1) / cg;
-    const long long grid = (long long)p.N * p.cgroups * p.tiles;
+    p.tiles = ((p.PH + kPatch - 1) / kPatch) * ((p.PW + kPatch - 1) / kPatch);
+    p.cgroups = 1;
+    const long long grid = (long long)p.N * p.tiles;
     const bool pdl = g_tuning.use_pdl != 0;
-    switch (cg) {
+    switch (g_tuning.nchw_cg) {     // channels in flight per lane
         case 1:  return launch_1d(rroi_fwd_nchw_kernel<1>, grid, kNchwBlock, p, s, pdl);
         case 2:  return launch_1d(rroi_fwd_nchw_kernel<2>, grid, kNchwBlock, p, s, pdl);
-        case 4:  return launch_1d(rroi_fwd_nchw_kernel<4>, grid, kNchwBlock, p, s, pdl);
+        case 8:  return launch_1d(rroi_fwd_nchw_kernel<8>, grid, kNchwBlock, p, s, pdl);
         case 16: return launch_1d(rroi_fwd_nchw_kernel<16>, grid, kNchwBlock, p, s, pdl);
-        default: return launch_1d(rroi_fwd_nchw_kernel<8>, grid, kNchwBlock, p, s, pdl);
+        default: return launch_1d(rroi_fwd_nchw_kernel<4>, grid, kNchwBlock, p, s, pdl);
     }
 }
 
@@ -136,14 +188,6 @@ cudaError_t launch_fwd_nchw(const FwdParams& p0, cudaStream_t s) {
 // ~40 thread-instructions per output float in a one-thread-per-vector formulation.
 constexpr int kNhwcWarps = 8;
 
-// code word of a bin (warp-uniform once broadcast)
-enum : uint32_t {
-    C_LT = 1u, C_RT = 2u, C_LB = 4u, C_RB = 8u,  // tap must be loaded (valid, distinct)
-    C_HX = 16u, C_HY = 32u,                       // rx == 0.5 / ry == 0.5
-    C_IN = 64u,                                   // bin inside the RoI
-    C_NAN = 128u,                                 // centre not finite: the reference's weights are NaN
-    C_LIVE = 256u                                 // bin index < PH*PW
-};
 
 template <int VEC> struct VecT;
 template <> struct VecT<1> { using T = float; };
@@ -462,13 +506,21 @@ static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, bool pdl
     constexpr int NCH = CT > 128 ? CT / 128 : 1;
     // UN chosen so that a 64-bin tile's per-warp iterations (8*NCH/PPI) are a multiple of it
     constexpr int I64 = 8 * NCH / PPI;
+    if (variant == 0) {
+        // auto: small launches (about one wave of 64-bin CTAs or less) want many small CTAs; large ones
+        // amortise the per-CTA prologue (RoI transform, two barriers) over 256 bins.  Measured on B200:
+        // cfg1 (N=64) 5.2 us with 64-bin tiles vs 8.9 us with 256; N=2048 75.7 us with 256 vs 96.7 with 64.
+        const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
+        variant = ctas256 >= 148 * 4 ? 5 : 1;
+    }
     switch (variant) {
         case 1:  return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
         case 2:  return go(rroi_fwd_nhwc_packed_kernel<CT, 128, 4>, 128);
         case 3:  return go(rroi_fwd_nhwc_packed_kernel<CT, 128, 2>, 128);
         case 4:  return go(rroi_fwd_nhwc_packed_kernel<CT, 256, 4>, 256);
         case 5:  return go(rroi_fwd_nhwc_packed_kernel<CT, 256, 2>, 256);
-        default: return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, 64);
+        case 6:  return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, 64);
+        default: return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
     }
 }
 

@@ -37,7 +37,7 @@ typedef struct CUstream_st* cudaStream_t;   /* same definition as the CUDA runti
 
 /* ---- tuning keys for rroi_b200_set_tuning / rroi_b200_get_tuning ---- */
 #define RROI_B200_TUNE_NCHW_CG      0   /* channels per CTA in the NCHW kernels: 1,2,4,8,16 (0 = default 8) */
-#define RROI_B200_TUNE_NHWC_UNROLL  1   /* NHWC forward variant 0..5: bins per warp x bins in flight (0 = default 8x8) */
+#define RROI_B200_TUNE_NHWC_UNROLL  1   /* NHWC forward variant: 0 = auto, 1..6 = fixed tile size x loads in flight  */
 #define RROI_B200_TUNE_USE_PDL      2   /* 1: launch with programmatic dependent launch                       */
 #define RROI_B200_TUNE_BWD_DEDUPE   3   /* 1 (default): warp-merge equal sample points before the atomics     */
 

@@ -32,6 +32,8 @@ if __name__ == "__main__":
                                  sets=0, graph_chunk=1, pdl=a.pdl)
     dev = torch.device("cuda:0")
     wl = bench.Workload(args, dev, torch)
+    if a.backward:
+        wl.enable_backward(torch)
     _cabi.set_tuning(_cabi.TUNE_NCHW_CG, a.cg)
     _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, a.variant)
     _cabi.set_tuning(_cabi.TUNE_USE_PDL, a.pdl)
