@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough to exceed 3x L2)")
     ap.add_argument("--graph-chunk", type=int, default=500)
     ap.add_argument("--pdl", type=int, default=1)
-    ap.add_argument("--streams", type=int, default=1,
+    ap.add_argument("--streams", type=int, default=4,
                     help="independent steps (different images) are issued round-robin on this many streams")
     ap.add_argument("--variant", type=int, default=-1, help="NHWC kernel variant override (tuning)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
@@ -284,6 +284,32 @@ def e2e_leg(args, wl, torch, device, steps):
     return dt, h2d, d2h
 
 
+def variants_leg(args, torch, device, lib, cabi, peak):
+    """Same harness on neighbouring configurations (not the headline): one stream, the reference NCHW layout,
+    the 256-channel FPN map, and cfg4's per-GPU batch.  Each entry: us per launch, Mfeat-px/s, roofline frac."""
+    import types
+    out = {}
+    grid = [("serial_1stream", dict(channels=args.channels, layout=args.layout, images=1, streams=1)),
+            ("nchw_reference_layout", dict(channels=args.channels, layout="nchw", images=1, streams=args.streams)),
+            ("fpn_c256", dict(channels=256, layout=args.layout, images=1, streams=args.streams)),
+            ("cfg4_per_gpu_32img_2048rois", dict(channels=args.channels, layout=args.layout, images=32, streams=1)),
+            ("cfg4_per_gpu_nchw", dict(channels=args.channels, layout="nchw", images=32, streams=1))]
+    for name, kw in grid:
+        a = types.SimpleNamespace(channels=kw["channels"], layout=kw["layout"], images=kw["images"],
+                                  rois_per_image=args.rois_per_image, sets=0)
+        w = Workload(a, device, torch)
+        steps = max(200, 20000 // kw["images"])
+        ms = timed_steps(w, steps, 20, args.graph_chunk, torch, lib, cabi, lambda: None, kw["streams"])
+        us = ms / steps * 1e3
+        alg = float(np.mean(w.alg_bytes))
+        out[name] = {"us_per_launch": us, "mfeat_px_per_s": w.feat_px_per_step / us, "alg_mb": alg / 1e6,
+                     "achieved_gbs": alg / us / 1e3, "frac": alg / us / 1e3 / peak, "streams": kw["streams"],
+                     "layout": kw["layout"], "channels": kw["channels"], "rois": w.N}
+        del w
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline_leg(wl, seconds):
     """The CPU oracle (a port: the reference has no CPU RoIRotate) on the same cfg1 step, all host threads."""
     from oracle import rroi_oracle as O
@@ -407,6 +433,8 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": alg, "avg_launch_us": launch_us, "peak_source": peak_src},
     }
     if rank == 0 and not args.no_extras:
+        line["variants"] = variants_leg(args, torch, device, lib, _cabi, peak)
+        _cabi.set_tuning(_cabi.TUNE_USE_PDL, args.pdl)
         dt, h2d, d2h = e2e_leg(args, wl, torch, device, args.e2e_steps)
         line["e2e"] = {"value": wl.feat_px_per_step * args.e2e_steps / dt / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
