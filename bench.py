@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
+    ap.add_argument("--pipeline-steps", type=int, default=4)
+    ap.add_argument("--no-pipeline", action="store_true")
     return ap.parse_args()
 
 
@@ -310,6 +313,50 @@ def variants_leg(args, torch, device, lib, cabi, peak):
     return out
 
 
+def pipeline_leg(args, torch, device, dist, world, rank):
+    """End-to-end images/s (BASELINE.json configs[2]/[4]): random-init FOTSNet in bf16 channels-last, 1280x720
+    synthetic images, 64 planted boxes per image, backbone + heads -> RoI rows -> RoIRotate (fp32) -> forward_ocr ->
+    greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 8) with ONE all_gather of the
+    per-image records per step.  Images start on the device; timed with CUDA events, max over ranks."""
+    from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
+    from fots.pytorch_b200.pipeline.infer import planted_quads
+    from fots.pytorch_b200.pipeline.shard import all_gather_records
+    torch.manual_seed(0)
+    net = FOTSNet(attention=True, nclass=89).to_b200(device)
+    pipe = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=torch.bfloat16)
+    per_gpu, micro = args.pipeline_images, 8
+    batch = per_gpu * world
+    gen = torch.Generator(device=device).manual_seed(100 + rank)
+    images = torch.randn(per_gpu, 3, 720, 1280, device=device, generator=gen)
+    quads = torch.from_numpy(planted_quads(per_gpu, 64, seed0=rank * per_gpu)).to(device)
+
+    def step():
+        recs = [pipe.step_local(images[i:i + micro], quads[i:i + micro])[0] for i in range(0, per_gpu, micro)]
+        return all_gather_records(torch.cat(recs, 0), batch)
+
+    for _ in range(2):
+        out = step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier(device_ids=[device.index])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.pipeline_steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.pipeline_steps
+    assert out.shape[0] == batch
+    return {"images_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "images_per_step": batch, "images_per_gpu": per_gpu,
+            "rois_per_image": 64, "dtype": "bf16 convolutions (cuDNN via torch), fp32 RoIRotate",
+            "collective": "one all_gather of int32 [images, 64, 74] records per step" if world > 1 else "none (1 rank)",
+            "boxes": "planted (seeded) -- reference NMS is pathological on random-init maps, SURVEY 8d",
+            "flop_per_image": 221.7e9}
+
+
 def cpu_baseline_leg(wl, seconds):
     """The CPU oracle (a port: the reference has no CPU RoIRotate) on the same cfg1 step, all host threads."""
     from oracle import rroi_oracle as O
@@ -440,6 +487,13 @@ def run_b200(args):
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                        "api": "fots.pytorch_b200._RRoiAlign(8,64,0.25)(features, rois) with pinned host buffers, 2 streams"}
         line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_seconds)
+    if not args.no_pipeline and not args.no_extras:
+        del wl
+        torch.cuda.empty_cache()
+        try:
+            line["pipeline"] = pipeline_leg(args, torch, device, dist, world, rank)
+        except Exception as e:   # the headline line must survive a failure of the secondary leg
+            line["pipeline"] = {"error": repr(e)}
     if dist is not None:
         dist.barrier(device_ids=[local])
         dist.destroy_process_group()

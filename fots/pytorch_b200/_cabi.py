@@ -25,12 +25,14 @@ TUNE_BWD_DEDUPE = 3
 
 ABI_VERSION = 1
 
-# every symbol include/rroi_align_b200.h declares
+# every symbol include/*.h declares
 EXPORTS = (
     "RROIAlignForwardLaucher", "RROIAlignBackwardLaucher",
     "rroi_b200_forward", "rroi_b200_backward", "rroi_b200_expand_idx",
     "rroi_b200_set_tuning", "rroi_b200_get_tuning", "rroi_b200_last_cuda_error",
     "rroi_b200_strerror", "rroi_b200_abi_version", "rroi_b200_build_info",
+    # include/fots_b200_pipeline.h
+    "fots_b200_boxes_to_rois", "fots_b200_ctc_greedy",
 )
 
 _lib = None

@@ -1,0 +1,81 @@
+"""End-to-end inference step (BASELINE.json configs[2] and [4]): backbone -> detection heads -> boxes ->
+RoIRotate -> recogniser -> greedy decode [-> one all_gather], image-sharded across ranks.
+
+Mirrors the reference's test.py:75-127 / tools/ocr_utils.py:131-199 flow, with its per-box loop (one RoIRotate
+launch, one batch-1 recogniser pass and one D2H per box) replaced by one batched launch of each stage and no
+host synchronisation inside the step.
+
+Boxes: with random-init weights the reference's NMS is pathological (~half of all pixels
+pass the threshold, 188 s per image), and the Clipper NMS itself is out of scope for the CUDA path.  The step
+therefore takes the boxes as an input -- `planted_quads()` builds the seeded 64-box set of the measurement
+protocol -- while the backbone and the detection heads are still computed for real every step.
+"""
+import numpy as np
+import torch
+
+from ..rroi_align.functions.rroi_align import rroi_align
+from .decode import greedy_ctc_decode
+from .rois import boxes_to_rois
+from .shard import all_gather_records, pack_records, shard_range
+
+
+def planted_quads(batch, per_image=64, seed0=0, img_w=1280, img_h=720):
+    """Seeded rotated boxes (the cfg1 generator of SURVEY 8d: h~U(16,64), w=h*U(1,8), centre uniform, angle
+    U(-90,90)) as quads [batch, per_image, 9] = x0,y0..x3,y3,score in the corner order nms/adaptor.cpp emits
+    (p0->p1 is the height edge, p1->p2 the width edge, as tools/ocr_utils.py:137-142 assumes)."""
+    out = np.zeros((batch, per_image, 9), np.float32)
+    for b in range(batch):
+        rng = np.random.default_rng(seed0 + b)
+        h = rng.uniform(16, 64, per_image)
+        w = h * rng.uniform(1, 8, per_image)
+        cx = rng.uniform(0, img_w, per_image)
+        cy = rng.uniform(0, img_h, per_image)
+        a = np.deg2rad(rng.uniform(-90, 90, per_image))
+        ux, uy = np.cos(a), np.sin(a)              # width direction
+        vx, vy = -np.sin(a), np.cos(a)             # height direction
+        p1 = np.stack([cx - ux * w / 2 - vx * h / 2, cy - uy * w / 2 - vy * h / 2], 1)
+        p2 = p1 + np.stack([ux * w, uy * w], 1)
+        p3 = p2 + np.stack([vx * h, vy * h], 1)
+        p0 = p1 + np.stack([vx * h, vy * h], 1)
+        out[b, :, 0:2], out[b, :, 2:4], out[b, :, 4:6], out[b, :, 6:8] = p0, p1, p2, p3
+        out[b, :, 8] = 0.9
+    return out
+
+
+class FOTSPipeline:
+    """net: a pipeline.nets.FOTSNet placed with .to_b200(); rank/world from torch.distributed when initialised."""
+
+    def __init__(self, net, pooled_height=8, pooled_width=64, spatial_scale=0.25, amp_dtype=torch.bfloat16):
+        self.net = net.eval()
+        self.ph, self.pw, self.scale = int(pooled_height), int(pooled_width), float(spatial_scale)
+        self.amp_dtype = amp_dtype
+
+    @torch.no_grad()
+    def step_local(self, images, quads):
+        """images [b,3,H,W] (this rank's shard, CUDA, any float dtype), quads [b,R,9] fp32 CUDA.
+        Returns the packed per-image records int32 [b, R, 9 + T + 1] and the detection maps."""
+        b, R, _ = quads.shape
+        x = images.contiguous(memory_format=torch.channels_last)
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            seg, rbox, angle, feats = self.net(x)
+        focr = feats[1].float().contiguous(memory_format=torch.channels_last)     # fp32 sampler input
+        bidx = torch.arange(b, device=quads.device, dtype=torch.int32).repeat_interleave(R)
+        rois = boxes_to_rois(quads.reshape(b * R, 9), bidx)
+        pooled = rroi_align(focr, rois, self.ph, self.pw, self.scale)             # [b*R, 64, PH, PW] channels-last
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            logp = self.net.forward_ocr(pooled)                                   # [b*R, nclass, T]
+        ids, lens = greedy_ctc_decode(logp)
+        T = ids.size(1)
+        rec = pack_records(quads, ids.view(b, R, T), lens.view(b, R))
+        return rec, (seg[0], rbox[0], angle[0])
+
+    @torch.no_grad()
+    def step(self, images, quads, batch=None, group=None):
+        """Full step on this rank's shard + the single all_gather.  Returns records for the whole batch."""
+        rec, _ = self.step_local(images, quads)
+        return all_gather_records(rec, batch if batch is not None else rec.size(0), group)
+
+
+def shard_inputs(images, quads, world, rank):
+    lo, hi = shard_range(images.size(0), world, rank)
+    return images[lo:hi], quads[lo:hi]

@@ -1,0 +1,213 @@
+"""Feature extractor + recognition heads, architecture-compatible with the reference's
+`ModelResNetSep2` (tools/models.py:237-457; forward_ocr :334-379) and `CRNN` (:853-909).
+
+Written from the layer inventory in SURVEY.md section 2 (#7-#9), not from the reference's code: the layer
+tables below are declarative and the parameter names match the reference's `state_dict()` key for key
+(tests/test_pipeline_nets.py checks names, shapes and -- when /root/reference is importable -- outputs), so a
+reference checkpoint (`tools/net_utils.py:16-43`) loads unchanged.
+
+B200 notes: convolutions are cuDNN through torch; run the module under `torch.autocast("cuda", torch.bfloat16)`
+with channels-last activations (`FOTSNet.to_b200()`), InstanceNorm statistics stay fp32 inside autocast, and the
+map handed to RoIRotate (`focr`) is returned as an fp32 channels-last tensor -- the layout the sampler wants.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+def _inorm(ch, affine=True):
+    return nn.InstanceNorm2d(ch, eps=1e-5, momentum=0.1, affine=affine)
+
+
+class _CReLUNorm(nn.Module):
+    """concat(x, -x) -> affine InstanceNorm -> leaky ReLU (the stem's channel-doubling activation)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.bn = _inorm(2 * ch)
+
+    def forward(self, x):
+        return F.leaky_relu(self.bn(torch.cat((x, -x), 1)), 0.01)
+
+
+def _conv(cin, cout, k, stride=1, pad=0, groups=1, bias=False, dilation=1):
+    return nn.Conv2d(cin, cout, k, stride, pad, dilation=dilation, groups=groups, bias=bias)
+
+
+class _ResIN(nn.Module):
+    """3x3 conv - IN - ReLU - 3x3 conv - IN, residual add, ReLU (stages 1 and 2)."""
+
+    def __init__(self, cin, cout, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _conv(cin, cout, 3, stride, 1)
+        self.bn1 = _inorm(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = _conv(cout, cout, 3, 1, 1)
+        self.bn2 = _inorm(cout)
+        self.downsample = downsample
+
+    def forward(self, x):
+        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+class _ResSepIN(nn.Module):
+    """Depthwise-separable residual block with InstanceNorm (stages 3 and 4)."""
+
+    def __init__(self, cin, cout, stride=1, downsample=None):
+        super().__init__()
+        self.conv_sep1 = nn.Sequential(
+            _conv(cin, cin, 3, stride, 1, groups=cin), _conv(cin, cout, 1),
+            _inorm(cout, affine=False), nn.LeakyReLU(0.01, inplace=True))
+        self.conv2 = nn.Sequential(
+            _conv(cout, cout, 3, 1, 1, groups=cout), _inorm(cout), nn.LeakyReLU(0.01, inplace=True),
+            _conv(cout, cout, 1), _inorm(cout))
+        self.downsample = downsample
+        self.relu = nn.LeakyReLU(0.01, inplace=True)
+
+    def forward(self, x):
+        y = self.conv2(self.conv_sep1(x))
+        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+def _up(x, like):
+    return F.interpolate(x, size=like.shape[2:], mode="bilinear", align_corners=True)
+
+
+class FOTSNet(nn.Module):
+    """Shared convolutions + EAST-style heads + fully-convolutional recogniser.
+
+    forward(x[B,3,H,W]) -> ([seg, seg2], [rbox, rbox2], [angle, angle2], [fpn256, focr64])   (tools/models.py:387-457)
+    forward_features(x) -> focr64 only                                                        (:381-385)
+    forward_ocr(pooled[N,64,PH,PW]) -> log-softmax [N, nclass, T=PW]                          (:334-379)
+    """
+
+    STAGES = ((_ResIN, 64, 3, 1), (_ResIN, 128, 4, 2), (_ResSepIN, 256, 6, 2), (_ResSepIN, 512, 4, 2))
+
+    def __init__(self, attention=False, multi_scale=True, nclass=7500):
+        super().__init__()
+        self.attention, self.multi_scale = attention, multi_scale
+        self.layer0 = nn.Sequential(_conv(3, 16, 3, 1, 1), _CReLUNorm(16), _conv(32, 32, 3, 2, 1), _CReLUNorm(32))
+        self.layer0_1 = nn.Sequential(_conv(64, 64, 3, 1, 1), nn.ReLU(), _conv(64, 64, 3, 2, 1), nn.ReLU(inplace=True))
+        # recogniser (conv6/8/9 are applied twice with shared weights; batch6/8/9 exist in checkpoints but are unused)
+        self.conv5, self.conv6 = _conv(64, 128, 3, 1, 1), _conv(128, 128, 3, 1, 1)
+        self.conv7, self.conv8, self.conv9 = _conv(128, 256, 3, 1, 1), _conv(256, 256, 3, 1, 1), _conv(256, 256, 3, 1, 1)
+        self.conv10_s = _conv(256, 256, (2, 3), 1, (0, 1))
+        self.conv11 = _conv(256, nclass, 1, bias=True)
+        for name, ch in (("batch5", 128), ("batch6", 128), ("batch7", 256), ("batch8", 256), ("batch9", 256), ("batch10_s", 256)):
+            setattr(self, name, _inorm(ch))
+        self.max2 = nn.MaxPool2d((2, 1), stride=(2, 1))
+        self.leaky = nn.LeakyReLU(0.01, inplace=True)
+        # residual stages
+        cin = 64
+        for i, (block, ch, depth, stride) in enumerate(self.STAGES, start=1):
+            down = None
+            if stride != 1 or cin != ch:
+                down = nn.Sequential(_conv(cin, ch, 1, stride), nn.BatchNorm2d(ch))
+            setattr(self, "layer%d" % i, nn.Sequential(block(cin, ch, stride, down), *[block(ch, ch) for _ in range(depth - 1)]))
+            cin = ch
+        # top-down merge to 256 channels at 1/4 scale
+        self.feature4, self.feature3, self.feature2 = _conv(512, 256, 1), _conv(256, 256, 1), _conv(128, 256, 1)
+        self.upconv2 = nn.Sequential(_conv(256, 256, 3, 1, 1, groups=256), _conv(256, 256, 1))
+        self.upconv1 = nn.Sequential(_conv(256, 256, 3, 1, 1, groups=256), _conv(256, 256, 1))
+        self.feature1 = _conv(64, 256, 1)
+        self.act, self.rbox, self.angle = _conv(256, 1, 1, bias=True), _conv(256, 4, 1, bias=True), _conv(256, 2, 1, bias=True)
+        self.drop1 = nn.Dropout2d(p=0.2)
+        if attention:
+            self.conv_attenton = _conv(256, 1, 1, bias=True)     # (sic) the reference's spelling is a checkpoint key
+
+    # ---- feeder -------------------------------------------------------------------------------
+    def forward_features(self, x):
+        return self.layer0_1(self.layer0(x))
+
+    def _gate(self, x, like):
+        return _up(torch.sigmoid(self.conv_attenton(x)), like)
+
+    def _heads(self, x):
+        seg = torch.sigmoid(self.act(x))
+        rbox = torch.sigmoid(self.rbox(x)) * 128
+        ang = torch.sigmoid(self.angle(x)) * 2 - 1
+        ang = ang / torch.sqrt((ang * ang).sum(1, keepdim=True))
+        return seg, rbox, ang
+
+    def forward(self, x):
+        focr = self.forward_features(x)
+        s3 = self.layer1(self.drop1(focr))
+        s2 = self.layer2(s3)
+        s1 = self.layer3(s2)
+        f1, f2, f3 = self.feature1(s3), self.feature2(s2), self.feature3(s1)
+        f4 = self.feature4(self.drop1(self.layer4(s1)))
+        if self.attention:
+            x = _up(f4, f3) + f3 * _up(torch.sigmoid(self.conv_attenton(f4)).expand_as(f4), f3)
+            gate = self._gate(x, f2)
+            f2 = self.upconv1(_up(x, f2)) + f2 * gate
+            gate = self._gate(f2, f1)
+            x = self.upconv2(_up(f2, f1)) + f1 * gate
+        else:
+            x = _up(f4, f3) + f3
+            f2 = self.upconv1(_up(x, f2)) + f2
+            x = self.upconv2(_up(f2, f1)) + f1
+        seg2, rbox2, ang2 = self._heads(f2)
+        x = self.drop1(x)
+        seg, rbox, ang = self._heads(x)
+        return [seg, seg2], [rbox, rbox2], [ang, ang2], [x, focr]
+
+    # ---- consumer A ---------------------------------------------------------------------------
+    def forward_ocr(self, x):
+        a = self.leaky
+        x = a(self.batch5(self.conv5(x)))
+        x = a(self.conv6(a(self.conv6(x))))
+        x = a(self.batch7(self.conv7(self.max2(x))))
+        x = a(self.conv8(a(self.conv8(x))))
+        x = a(self.conv9(a(self.conv9(x))))
+        x = a(self.batch10_s(self.conv10_s(self.max2(x))))
+        x = self.conv11(self.drop1(x)).squeeze(2)            # [N, nclass, T]
+        return F.log_softmax(x.float(), dim=1)
+
+    # ---- B200 placement ------------------------------------------------------------------------
+    def to_b200(self, device="cuda"):
+        """eval-mode inference placement: weights on the device, channels-last; call under bf16 autocast."""
+        return self.to(device=device, memory_format=torch.channels_last)
+
+
+class _BiLSTM(nn.Module):
+    def __init__(self, nin, hidden, nout):
+        super().__init__()
+        self.rnn = nn.LSTM(nin, hidden, bidirectional=True)
+        self.embedding = nn.Linear(2 * hidden, nout)
+
+    def forward(self, x):                                    # [T, N, nin]
+        y, _ = self.rnn(x)
+        return self.embedding(y)                             # Linear acts on the last dim: same as the view/unview
+
+
+class CRNN(nn.Module):
+    """Consumer B (tools/models.py:853-909): 7-conv CNN collapsing H 32 -> 1, two BiLSTMs.  Input is RoIRotate of
+    the raw image with PH = 32 (src/utils.py:430-436); output [T = W/4 + 1, N, nclass]."""
+
+    #        cout  k  pad  batchnorm  pool-after
+    PLAN = ((64, 3, 1, False, (2, 2, 2, 2, 0, 0)), (128, 3, 1, False, (2, 2, 2, 2, 0, 0)),
+            (256, 3, 1, True, None), (256, 3, 1, False, (2, 2, 2, 1, 0, 1)),
+            (512, 3, 1, True, None), (512, 3, 1, False, (2, 2, 2, 1, 0, 1)), (512, 2, 0, True, None))
+
+    def __init__(self, nclass=7500, hidden=256):
+        super().__init__()
+        cnn, cin, pool_i = nn.Sequential(), 3, 0
+        for i, (cout, k, pad, bn, pool) in enumerate(self.PLAN):
+            cnn.add_module("conv%d" % i, nn.Conv2d(cin, cout, k, 1, pad))
+            if bn:
+                cnn.add_module("batchnorm%d" % i, nn.BatchNorm2d(cout))
+            cnn.add_module("relu%d" % i, nn.ReLU(True))
+            if pool is not None:
+                kh, kw, sh, sw, ph, pw = pool
+                cnn.add_module("pooling%d" % pool_i, nn.MaxPool2d((kh, kw), (sh, sw), (ph, pw)))
+                pool_i += 1
+            cin = cout
+        self.cnn = cnn
+        self.rnn = nn.Sequential(_BiLSTM(512, hidden, hidden), _BiLSTM(hidden, hidden, nclass))
+
+    def forward(self, x):
+        f = self.cnn(x)
+        if f.size(2) != 1:
+            raise ValueError("CRNN: input height must reduce to 1 (use PH = 32)")
+        return self.rnn(f.squeeze(2).permute(2, 0, 1).contiguous())

@@ -1,0 +1,43 @@
+/*
+ * fots_b200_pipeline.h -- C ABI of the two small kernels either side of RoIRotate in the end-to-end path
+ * (SURVEY.md section 8f-1 and 8f-4).  Same library (librroi_b200.so), same conventions as rroi_align_b200.h:
+ * device pointers, enqueue-only on `stream`, 0 = success, negative RROI_B200_ERR_* otherwise.
+ *
+ * Reference code replaced (chenjun2hao/FOTS.pytorch):
+ *   fots_b200_boxes_to_rois   tools/ocr_utils.py:133-145  (per-box Python: quad -> [b, cx, cy, h, w, -angle_deg])
+ *   fots_b200_ctc_greedy      tools/ocr_utils.py:183-186 + src/utils.py:93-97 (argmax over classes, collapse
+ *                             repeats, drop blank 0 -- done per box on the host in the reference)
+ */
+#ifndef FOTS_B200_PIPELINE_H_
+#define FOTS_B200_PIPELINE_H_
+
+#include "rroi_align_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/*
+ * quads      [num_boxes, quad_stride] fp32, the first 8 values of a row are x0,y0,...,x3,y3 in image pixels
+ *            (the row format of nms/adaptor.cpp:13-29 has 9: + score)
+ * batch_idx  [num_boxes] int32 image index of each box, or NULL for all-zero
+ * rois       [num_boxes, 6] fp32 out: [batch_idx, trunc(cx), trunc(cy), h, w, -angle_deg]; arithmetic in fp64 like
+ *            the reference's Python floats, angle = -atan2(y2-y1, x2-x1) / 3.1415926535 * 180
+ */
+int fots_b200_boxes_to_rois(const float* quads, int quad_stride, const int* batch_idx, int num_boxes,
+                            float* rois, cudaStream_t stream);
+
+/*
+ * logp    [num_seq, num_classes, T] fp32 (the layout forward_ocr returns, tools/models.py:370-379)
+ * ids     [num_seq, T] int32 out: decoded class ids, left-aligned, zero-padded
+ * lengths [num_seq] int32 out
+ * Greedy CTC: per time step the arg-max class (lowest index on ties, like torch.max), then drop repeats and
+ * blanks (class 0).  T <= 1024.
+ */
+int fots_b200_ctc_greedy(const float* logp, int num_seq, int num_classes, int T, int* ids, int* lengths,
+                         cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOTS_B200_PIPELINE_H_ */

@@ -13,9 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "rroi_align_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(RROIAlign\w+|rroi_b200_\w+)\s*\(", src)))
+    names = set()
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(RROIAlign\w+|rroi_b200_\w+|fots_b200_\w+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_are_exported():

@@ -1,0 +1,113 @@
+"""GPU tests of the stages either side of RoIRotate and of the end-to-end inference step."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as Hh
+import workloads as WL
+from test_pipeline_host import ref_roi_row
+
+pytestmark = pytest.mark.gpu
+
+
+def test_boxes_to_rois_matches_reference_python(cuda):
+    """fots_b200_boxes_to_rois vs tools/ocr_utils.py:133-145 restated (numpy float32 scalars + Python floats): bit-exact."""
+    from fots.pytorch_b200.pipeline import boxes_to_rois
+    from fots.pytorch_b200.pipeline.infer import planted_quads
+    q = planted_quads(3, 64).reshape(-1, 9)
+    rng = np.random.default_rng(3)
+    q = np.concatenate([q, rng.uniform(-50, 1400, (200, 9)).astype(np.float32)])      # arbitrary (non-rectangular) quads too
+    bidx = rng.integers(0, 3, len(q)).astype(np.int32)
+    got = boxes_to_rois(torch.from_numpy(q).to(cuda), torch.from_numpy(bidx).to(cuda)).cpu().numpy()
+    want = np.stack([ref_roi_row(q[i], bidx[i]) for i in range(len(q))])
+    # sqrt/atan2 run in fp64 on both sides; libm vs CUDA may differ in the last fp64 bit, invisible after the fp32 cast
+    # except on an exact fp32 rounding tie
+    same = Hh.bits(got) == Hh.bits(want)
+    assert same[:, :5].all()
+    assert same[:, 5].mean() > 0.995 and np.allclose(got[:, 5], want[:, 5], rtol=1e-6, atol=1e-6)
+    got0 = boxes_to_rois(torch.from_numpy(q).to(cuda)).cpu().numpy()
+    assert (got0[:, 0] == 0).all() and np.array_equal(got0[:, 1:], got[:, 1:])
+    with pytest.raises(ValueError):
+        boxes_to_rois(torch.zeros(4, 6, device=cuda))
+
+
+def _ref_greedy(logp):
+    """tools/ocr_utils.py:183-186 + src/utils.py:93-97: argmax over classes, drop blanks and repeats."""
+    ids = logp.argmax(1)                       # numpy argmax = first maximum, like torch.max
+    out = np.zeros(ids.shape, np.int32)
+    lens = np.zeros(len(ids), np.int32)
+    for n, row in enumerate(ids):
+        k = 0
+        for i, t in enumerate(row):
+            if t != 0 and not (i > 0 and row[i - 1] == t):
+                out[n, k] = t
+                k += 1
+        lens[n] = k
+    return out, lens
+
+
+@pytest.mark.parametrize("N,C,T", [(64, 89, 64), (7, 5, 1), (33, 89, 352), (3, 7500, 40), (2, 3, 1024)])
+def test_greedy_ctc_decode_matches_reference_loop(cuda, N, C, T):
+    from fots.pytorch_b200.pipeline import greedy_ctc_decode
+    rng = np.random.default_rng(N * 1000 + T)
+    logits = rng.standard_normal((N, C, T)).astype(np.float32)
+    logits[:, 0] += 1.0                                             # plenty of blanks
+    logits = np.round(logits * 2) / 2                               # and exact ties (lowest index must win)
+    rep = rng.random((N, T)) < 0.4                                  # repeated frames
+    for t in range(1, T):
+        logits[rep[:, t], :, t] = logits[rep[:, t], :, t - 1]
+    ids, lens = greedy_ctc_decode(torch.from_numpy(logits).to(cuda))
+    want_ids, want_lens = _ref_greedy(logits)
+    assert np.array_equal(lens.cpu().numpy(), want_lens)
+    assert np.array_equal(ids.cpu().numpy(), want_ids)
+
+
+def test_inference_step_end_to_end(oracle, cuda):
+    """cfg2-shaped step at reduced size: every stage runs on the GPU; RoIRotate inside the step is checked against
+    the oracle on the features the backbone actually produced; fp32 and bf16 runs agree on the detection maps."""
+    from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
+    from fots.pytorch_b200.pipeline.infer import planted_quads
+    from fots.pytorch_b200.pipeline.rois import boxes_to_rois
+    from fots.pytorch_b200.pipeline.shard import unpack_records
+    torch.manual_seed(0)
+    net = FOTSNet(attention=True, nclass=89).to_b200(cuda)
+    B, R, H, W = 2, 16, 192, 320
+    images = torch.randn(B, 3, H, W, device=cuda)
+    quads = torch.from_numpy(planted_quads(B, R, img_w=W, img_h=H)).to(cuda)
+    pipe32 = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=None)
+    rec, (seg, rbox, ang) = pipe32.step_local(images, quads)
+    assert rec.shape == (B, R, 9 + 64 + 1) and rec.dtype == torch.int32
+    q2, ids, lens = unpack_records(rec, 64)
+    assert torch.equal(q2, quads) and int(lens.max()) <= 64 and int(ids.max()) < 89
+    assert seg.shape == (B, 1, H // 4, W // 4) and torch.isfinite(seg).all()
+    # RoIRotate stage against the oracle, on the real focr map
+    with torch.no_grad():
+        focr = net.forward_features(images.contiguous(memory_format=torch.channels_last)).float()
+    bidx = torch.arange(B, device=cuda, dtype=torch.int32).repeat_interleave(R)
+    rois = boxes_to_rois(quads.reshape(B * R, 9), bidx)
+    from fots.pytorch_b200 import rroi_align
+    pooled = rroi_align(focr.contiguous(memory_format=torch.channels_last), rois, 8, 64, 0.25)
+    want, _, _ = oracle.forward(focr.cpu().numpy(), rois.cpu().numpy(), 8, 64, 0.25, threads=0)
+    Hh.assert_bit_equal(pooled.cpu().numpy(), want, "RoIRotate inside the pipeline")
+    # determinism + bf16 vs fp32
+    rec_b, _ = pipe32.step_local(images, quads)
+    assert torch.equal(rec, rec_b)
+    pipe16 = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=torch.bfloat16)
+    rec16, (seg16, rbox16, ang16) = pipe16.step_local(images, quads)
+    assert rec16.shape == rec.shape
+    assert float((seg16.float() - seg).abs().max()) < 0.08      # sigmoid outputs, bf16 convolutions
+    assert pipe16.step(images, quads).shape == rec.shape        # no process group: the collective is the identity
+
+
+def test_training_step_runs_and_reduces_loss(cuda):
+    from fots.pytorch_b200.pipeline import FOTSNet
+    from fots.pytorch_b200.pipeline.train import TrainStep, synthetic_targets
+    torch.manual_seed(0)
+    net = FOTSNet(attention=True, nclass=89).to_b200(cuda)
+    step = TrainStep(net, lr=1e-3, amp_dtype=torch.bfloat16)
+    B, R, H, W = 2, 8, 128, 192
+    images = torch.randn(B, 3, H, W, device=cuda)
+    tgt = synthetic_targets(B, R, H, W, nclass=89, device=cuda, seed=0)
+    losses = [step(images, tgt)["total"] for _ in range(6)]
+    assert all(np.isfinite(l) for l in losses)
+    assert losses[-1] < losses[0]

@@ -1,0 +1,88 @@
+"""Feeder / consumer networks: checkpoint-key compatibility with the
+reference (fixture tests/golden/ref_model_keys.json), and -- when /root/reference is importable, i.e. in the
+build container -- identical outputs to the reference modules with shared weights (fp32 CPU, 1e-5)."""
+import importlib.util
+import json
+import os
+
+import pytest
+import torch
+
+from fots.pytorch_b200.pipeline.nets import CRNN, FOTSNet
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REF_MODELS = "/root/reference/tools/models.py"
+TOL = 1e-5   # fp32 CPU, same op sequence: differences are summation-order noise only
+
+
+def _ref():
+    spec = importlib.util.spec_from_file_location("ref_models", REF_MODELS)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("name,build", [
+    ("ModelResNetSep2_att_89", lambda: FOTSNet(attention=True, nclass=89)),
+    ("ModelResNetSep2_noatt_89", lambda: FOTSNet(attention=False, nclass=89)),
+    ("CRNN_89", lambda: CRNN(nclass=89)),
+])
+def test_state_dict_keys_match_reference(name, build):
+    want = json.load(open(os.path.join(GOLDEN, "ref_model_keys.json")))[name]
+    got = {k: list(v.shape) for k, v in build().state_dict().items()}
+    assert got == want
+
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_MODELS), reason="reference checkout not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("attention", [True, False])
+def test_fotsnet_matches_reference_outputs(attention):
+    torch.manual_seed(0)
+    ref = _ref().ModelResNetSep2(attention=attention, nclass=89).eval()
+    mine = FOTSNet(attention=attention, nclass=89).eval()
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 3, 96, 160)
+    with torch.no_grad():
+        a, b = ref(x), mine(x)
+    for group_a, group_b in zip(a, b):
+        for ta, tb in zip(group_a, group_b):
+            assert ta.shape == tb.shape
+            assert torch.allclose(ta, tb, rtol=TOL, atol=TOL), float((ta - tb).abs().max())
+    pooled = torch.randn(3, 64, 8, 64)
+    with torch.no_grad():
+        assert torch.allclose(ref.forward_ocr(pooled), mine.forward_ocr(pooled), rtol=TOL, atol=TOL)
+        p11 = torch.randn(2, 64, 11, 96)                                          # PH=11 (src/ocr_process.py:260)
+        assert torch.allclose(ref.forward_ocr(p11), mine.forward_ocr(p11), rtol=TOL, atol=TOL)
+        assert torch.allclose(ref.forward_features(x), mine.forward_features(x), rtol=TOL, atol=TOL)
+
+
+@needs_ref
+def test_crnn_matches_reference_outputs():
+    torch.manual_seed(1)
+    ref = _ref().CRNN(nclass=89).eval()
+    mine = CRNN(nclass=89).eval()
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(3, 3, 32, 120)
+    with torch.no_grad():
+        a, b = ref(x), mine(x)
+    assert a.shape == b.shape == (31, 3, 89)
+    assert torch.allclose(a, b, rtol=TOL, atol=TOL)
+
+
+def test_shapes_and_channels_last():
+    net = FOTSNet(attention=True, nclass=89).eval()
+    x = torch.randn(1, 3, 64, 96).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        seg, rbox, ang, feats = net(x)
+        assert seg[0].shape == (1, 1, 16, 24) and seg[1].shape == (1, 1, 8, 12)
+        assert rbox[0].shape == (1, 4, 16, 24) and ang[0].shape == (1, 2, 16, 24)
+        assert feats[0].shape == (1, 256, 16, 24) and feats[1].shape == (1, 64, 16, 24)
+        assert torch.allclose((ang[0] ** 2).sum(1), torch.ones(1, 16, 24), atol=1e-5)     # unit (sin, cos)
+        for ph in (8, 9, 10, 11):                                                           # SURVEY #8: PH in 8..11
+            assert net.forward_ocr(torch.randn(2, 64, ph, 40)).shape == (2, 89, 40)
+        lp = net.forward_ocr(torch.randn(2, 64, 8, 40))
+        assert torch.allclose(lp.exp().sum(1), torch.ones(2, 40), atol=1e-4)
+    with pytest.raises(ValueError):
+        CRNN(nclass=10)(torch.randn(1, 3, 48, 64))
