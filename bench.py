@@ -316,8 +316,8 @@ def variants_leg(args, torch, device, lib, cabi, peak):
 def pipeline_leg(args, torch, device, dist, world, rank):
     """End-to-end images/s (BASELINE.json configs[2]/[4]): random-init FOTSNet in bf16 channels-last, 1280x720
     synthetic images, 64 planted boxes per image, backbone + heads -> RoI rows -> RoIRotate (fp32) -> forward_ocr ->
-    greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 8) with ONE all_gather of the
-    per-image records per step.  Images start on the device; timed with CUDA events, max over ranks."""
+    greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 8, the rank-local part replayed
+    from one CUDA graph) with ONE all_gather of the per-image records per step.  Images start on the device; timed with CUDA events, max over ranks."""
     from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
     from fots.pytorch_b200.pipeline.infer import planted_quads
     from fots.pytorch_b200.pipeline.shard import all_gather_records
@@ -330,9 +330,10 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     images = torch.randn(per_gpu, 3, 720, 1280, device=device, generator=gen)
     quads = torch.from_numpy(planted_quads(per_gpu, 64, seed0=rank * per_gpu)).to(device)
 
+    local = pipe.capture(images, quads, micro)      # one CUDA graph for the rank-local part of the step
+
     def step():
-        recs = [pipe.step_local(images[i:i + micro], quads[i:i + micro])[0] for i in range(0, per_gpu, micro)]
-        return all_gather_records(torch.cat(recs, 0), batch)
+        return all_gather_records(local(), batch)
 
     for _ in range(2):
         out = step()

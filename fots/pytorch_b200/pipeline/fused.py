@@ -1,0 +1,51 @@
+"""Host side of the fused channels-last InstanceNorm(+affine)(+residual)+leaky-ReLU kernel
+(include/fots_b200_pipeline.h: fots_b200_instnorm_nhwc_bf16).  Used by pipeline.nets on the CUDA bf16
+channels-last inference path; everywhere else (CPU, fp32, training) the networks run torch's own ops, which
+are the definition the fused kernel is tested against."""
+import ctypes
+
+import torch
+
+from .. import _cabi
+
+_ws = {}
+
+
+def _lib():
+    L = _cabi.lib()
+    if not getattr(L, "_instnorm_bound", False):
+        i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+        L.fots_b200_instnorm_nhwc_bf16.restype = i
+        L.fots_b200_instnorm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
+        L._instnorm_bound = True
+    return L
+
+
+def eligible(x, residual=None):
+    ok = (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.size(1) % 8 == 0 and x.size(1) <= 1024
+          and x.is_contiguous(memory_format=torch.channels_last) and not (torch.is_grad_enabled() and x.requires_grad))
+    if ok and residual is not None:
+        ok = (residual.dtype == torch.bfloat16 and residual.shape == x.shape
+              and residual.is_contiguous(memory_format=torch.channels_last))
+    return ok
+
+
+def instnorm_act(x, weight, bias, eps, slope, residual=None, crelu=False):
+    """act(IN(x) * weight + bias [+ residual]); crelu=True: act(IN(concat(x, -x))) with [2C] weight/bias."""
+    B, C, H, W = x.shape
+    cout = 2 * C if crelu else C
+    y = torch.empty((B, cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    key = (x.device, torch.cuda.current_stream(x.device).cuda_stream)
+    ws = _ws.get(key)
+    if ws is None or ws.numel() < B * C * 2:
+        ws = torch.empty(max(B * C * 2, 1 << 16), dtype=torch.float64, device=x.device)
+        _ws[key] = ws
+    w = weight.float().contiguous() if weight is not None else None
+    b = bias.float().contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        st = _lib().fots_b200_instnorm_nhwc_bf16(
+            x.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else None,
+            b.data_ptr() if b is not None else None, residual.data_ptr() if residual is not None else None,
+            ws.data_ptr(), B, H * W, C, float(eps), float(slope), 1 if crelu else 0, key[1])
+    _cabi.check(st, "fots_b200_instnorm_nhwc_bf16")
+    return y

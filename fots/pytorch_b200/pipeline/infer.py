@@ -70,6 +70,36 @@ class FOTSPipeline:
         return rec, (seg[0], rbox[0], angle[0])
 
     @torch.no_grad()
+    def capture(self, images, quads, micro=8):
+        """Capture this rank's whole local step (micro-batches of `micro` images, no host sync inside) into one
+        CUDA graph bound to the given `images` / `quads` buffers.  Returns a callable `replay()` -> records
+        [b, R, 9 + T + 1]; refill the two buffers in place between replays.  The step has ~600 launches per
+        micro-batch, so eager execution is CPU-launch-bound (8.4 ms of CPU for 9.2 ms of GPU at 8 images)."""
+        b = images.size(0)
+
+        def local():
+            recs = [self.step_local(images[i:i + micro], quads[i:i + micro])[0] for i in range(0, b, micro)]
+            return recs[0] if len(recs) == 1 else torch.cat(recs, 0)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                local()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = local()
+
+        def replay():
+            graph.replay()
+            return out
+
+        replay.graph, replay.records = graph, out
+        return replay
+
+    @torch.no_grad()
     def step(self, images, quads, batch=None, group=None):
         """Full step on this rank's shard + the single all_gather.  Returns records for the whole batch."""
         rec, _ = self.step_local(images, quads)

@@ -14,9 +14,22 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import fused
+
 
 def _inorm(ch, affine=True):
     return nn.InstanceNorm2d(ch, eps=1e-5, momentum=0.1, affine=affine)
+
+
+def _in_act(norm, x, slope, residual=None):
+    """act(norm(x) [+ residual]) with leaky slope (0 = ReLU, 1 = none).  On the CUDA bf16 channels-last inference
+    path this is ONE fused pair of kernels (statistics + apply); otherwise torch's ops."""
+    if fused.eligible(x, residual):
+        return fused.instnorm_act(x, norm.weight, norm.bias, norm.eps, slope, residual)
+    y = norm(x)
+    if residual is not None:
+        y = y + residual
+    return y if slope == 1.0 else F.leaky_relu(y, slope)
 
 
 class _CReLUNorm(nn.Module):
@@ -27,6 +40,8 @@ class _CReLUNorm(nn.Module):
         self.bn = _inorm(2 * ch)
 
     def forward(self, x):
+        if fused.eligible(x):
+            return fused.instnorm_act(x, self.bn.weight, self.bn.bias, self.bn.eps, 0.01, crelu=True)
         return F.leaky_relu(self.bn(torch.cat((x, -x), 1)), 0.01)
 
 
@@ -47,8 +62,9 @@ class _ResIN(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
-        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+        res = x if self.downsample is None else self.downsample(x)
+        y = _in_act(self.bn1, self.conv1(x), 0.0)
+        return _in_act(self.bn2, self.conv2(y), 0.0, res)
 
 
 class _ResSepIN(nn.Module):
@@ -66,8 +82,11 @@ class _ResSepIN(nn.Module):
         self.relu = nn.LeakyReLU(0.01, inplace=True)
 
     def forward(self, x):
-        y = self.conv2(self.conv_sep1(x))
-        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+        res = x if self.downsample is None else self.downsample(x)
+        s1, s2 = self.conv_sep1, self.conv2
+        y = _in_act(s1[2], s1[1](s1[0](x)), 0.01)
+        y = _in_act(s2[1], s2[0](y), 0.01)
+        return _in_act(s2[4], s2[3](y), 0.01, res)
 
 
 def _up(x, like):
@@ -124,9 +143,11 @@ class FOTSNet(nn.Module):
         return _up(torch.sigmoid(self.conv_attenton(x)), like)
 
     def _heads(self, x):
-        seg = torch.sigmoid(self.act(x))
-        rbox = torch.sigmoid(self.rbox(x)) * 128
-        ang = torch.sigmoid(self.angle(x)) * 2 - 1
+        # the 1x1 convolutions may run in bf16 under autocast; the squashing and the (sin, cos) normalisation are
+        # done in fp32 (in bf16 both angle components can round to exactly 0 -> 0/0)
+        seg = torch.sigmoid(self.act(x).float())
+        rbox = torch.sigmoid(self.rbox(x).float()) * 128
+        ang = torch.sigmoid(self.angle(x).float()) * 2 - 1
         ang = ang / torch.sqrt((ang * ang).sum(1, keepdim=True))
         return seg, rbox, ang
 
@@ -155,12 +176,12 @@ class FOTSNet(nn.Module):
     # ---- consumer A ---------------------------------------------------------------------------
     def forward_ocr(self, x):
         a = self.leaky
-        x = a(self.batch5(self.conv5(x)))
+        x = _in_act(self.batch5, self.conv5(x), 0.01)
         x = a(self.conv6(a(self.conv6(x))))
-        x = a(self.batch7(self.conv7(self.max2(x))))
+        x = _in_act(self.batch7, self.conv7(self.max2(x)), 0.01)
         x = a(self.conv8(a(self.conv8(x))))
         x = a(self.conv9(a(self.conv9(x))))
-        x = a(self.batch10_s(self.conv10_s(self.max2(x))))
+        x = _in_act(self.batch10_s, self.conv10_s(self.max2(x)), 0.01)
         x = self.conv11(self.drop1(x)).squeeze(2)            # [N, nclass, T]
         return F.log_softmax(x.float(), dim=1)
 

@@ -37,6 +37,23 @@ int fots_b200_boxes_to_rois(const float* quads, int quad_stride, const int* batc
 int fots_b200_ctc_greedy(const float* logp, int num_seq, int num_classes, int T, int* ids, int* lengths,
                          cudaStream_t stream);
 
+/*
+ * Fused channels-last InstanceNorm (+ affine) (+ residual add) + leaky-ReLU for the feeder/consumer networks
+ * (tools/models.py:41-48 CReLU_IN, :142-166 BasicBlockIn, :87-103 conv_dw_*_in, :336-364 forward_ocr).  torch's
+ * instance_norm converts a channels-last tensor to NCHW and back around a batch-norm kernel; this is one
+ * statistics pass and one normalise pass over the NHWC tensor, HBM-bound.
+ *   x         bf16 [B, HW, C]  (channels-last activations, C % 8 == 0, C <= 1024)
+ *   y         bf16 [B, HW, C]  or, with crelu != 0, [B, HW, 2C] = act(IN(concat(x, -x)))  (gamma/beta then [2C])
+ *   gamma/beta fp32 [C] ([2C] with crelu) or both NULL (non-affine)
+ *   residual  optional bf16 [B, HW, C] added after the affine, before the activation (crelu == 0 only)
+ *   workspace fp64 [B, C, 2]; cleared and filled by the call (sum, sum of squares)
+ *   slope     leaky-ReLU negative slope: 0 = ReLU, 1 = no activation
+ * Statistics are accumulated in fp32 per thread and fp64 across the plane; variance is the biased one.
+ */
+int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
+                                 const void* residual, double* workspace, int B, int HW, int C,
+                                 float eps, float slope, int crelu, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

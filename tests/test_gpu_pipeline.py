@@ -97,6 +97,10 @@ def test_inference_step_end_to_end(oracle, cuda):
     assert rec16.shape == rec.shape
     assert float((seg16.float() - seg).abs().max()) < 0.08      # sigmoid outputs, bf16 convolutions
     assert pipe16.step(images, quads).shape == rec.shape        # no process group: the collective is the identity
+    graphed = pipe16.capture(images, quads, micro=1)             # CUDA-graph replay == eager
+    assert torch.equal(graphed(), rec16)
+    images.copy_(torch.randn_like(images))                       # buffers are refilled in place between replays
+    assert torch.equal(graphed(), pipe16.step_local(images, quads)[0])
 
 
 def test_training_step_runs_and_reduces_loss(cuda):
@@ -111,3 +115,62 @@ def test_training_step_runs_and_reduces_loss(cuda):
     losses = [step(images, tgt)["total"] for _ in range(6)]
     assert all(np.isfinite(l) for l in losses)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("B,C,H,W,mode", [
+    (2, 16, 33, 47, "crelu"), (2, 32, 20, 50, "crelu"), (3, 64, 20, 31, "res_relu"), (2, 256, 9, 17, "plain_leaky"),
+    (1, 128, 180, 320, "affine_leaky"), (8, 16, 120, 160, "crelu"), (2, 512, 6, 10, "res_leaky"), (1, 64, 1, 2, "affine_leaky"),
+])
+def test_fused_instnorm_matches_torch_fp32(cuda, B, C, H, W, mode):
+    """fots_b200_instnorm_nhwc_bf16 vs torch's instance_norm evaluated in fp32 on the same bf16 input; the only
+    differences allowed are the bf16 rounding of the output (2^-8 relative) and fp32 statistics noise."""
+    import torch.nn.functional as F
+    from fots.pytorch_b200.pipeline import fused
+    g = torch.Generator(device=cuda).manual_seed(B * 1000 + C)
+    x = (torch.randn(B, C, H, W, device=cuda, generator=g) * 3 + 1.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert fused.eligible(x)
+    xf = x.float()
+    cout = 2 * C if mode == "crelu" else C
+    w = torch.randn(cout, device=cuda, generator=g)
+    b = torch.randn(cout, device=cuda, generator=g)
+    res = None
+    if mode == "crelu":
+        got = fused.instnorm_act(x, w, b, 1e-5, 0.01, crelu=True)
+        want = F.leaky_relu(F.instance_norm(torch.cat((xf, -xf), 1), weight=w, bias=b, eps=1e-5), 0.01)
+    elif mode.startswith("res"):
+        slope = 0.0 if mode == "res_relu" else 0.01
+        res = torch.randn(B, C, H, W, device=cuda, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        got = fused.instnorm_act(x, w, b, 1e-5, slope, residual=res)
+        want = F.leaky_relu(F.instance_norm(xf, weight=w, bias=b, eps=1e-5) + res.float(), slope)
+    elif mode == "plain_leaky":
+        got = fused.instnorm_act(x, None, None, 1e-5, 0.01)
+        want = F.leaky_relu(F.instance_norm(xf, eps=1e-5), 0.01)
+    else:
+        got = fused.instnorm_act(x, w, b, 1e-5, 0.01)
+        want = F.leaky_relu(F.instance_norm(xf, weight=w, bias=b, eps=1e-5), 0.01)
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    err = (got.float() - want).abs()
+    tol = want.abs() * 2.0 ** -7 + 2e-2
+    assert bool((err <= tol).all()), float((err - tol).max())
+
+
+def test_fused_and_torch_paths_agree_on_the_network(cuda):
+    """Same weights, same bf16 input: the network with the fused InstanceNorm kernels vs torch's own ops."""
+    from fots.pytorch_b200.pipeline import FOTSNet, fused
+    torch.manual_seed(0)
+    net = FOTSNet(attention=True, nclass=89).to_b200(cuda).eval()
+    x = torch.randn(2, 3, 128, 192, device=cuda).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        a = net(x)
+        old = fused.eligible
+        fused.eligible = lambda *args, **kw: False
+        try:
+            b = net(x)
+        finally:
+            fused.eligible = old
+    for ga, gb in zip(a, b):
+        for ta, tb in zip(ga, gb):
+            d = (ta.float() - tb.float()).abs()
+            scale = tb.float().abs().mean() + 1e-3
+            assert float(d.mean() / scale) < 0.03, float(d.mean() / scale)
