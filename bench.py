@@ -44,9 +44,11 @@ def parse():
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough to exceed 3x L2)")
     ap.add_argument("--graph-chunk", type=int, default=500)
     ap.add_argument("--pdl", type=int, default=1)
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=8,
                     help="independent steps (different images) are issued round-robin on this many streams")
-    ap.add_argument("--variant", type=int, default=-1, help="NHWC kernel variant override (tuning)")
+    ap.add_argument("--variant", type=int, default=5,
+                    help="NHWC kernel tile variant (rroi_b200_set_tuning): 5 = 256-bin tiles, best when several "
+                         "launches are in flight; 0 = auto (64-bin tiles for one small launch at a time)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -57,6 +59,28 @@ def parse():
 
 
 # ----------------------------------------------------------------------------------------- helpers
+
+def host_threads():
+    """Host cores this process may use; passed explicitly to the oracle (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+class StdoutGuard:
+    """Everything that writes to fd 1 while the benchmark runs (NCCL prints its version banner there) goes to
+    stderr; the ONE JSON line is written to the real stdout at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
 
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
@@ -144,7 +168,9 @@ class Workload:
         self.N = args.images * args.rois_per_image
         self.layout = args.layout
         per_set = 4 * (self.B * self.C * self.H * self.W + self.N * self.C * self.PH * self.PW)
-        self.sets = args.sets if args.sets > 0 else max(4, int(np.ceil(3 * 126e6 / per_set)) + 1)
+        # rotate over ~12x the L2 capacity: with a non-LRU replacement policy a cyclic working set of k x L2 can
+        # still hit ~1/k of the time, so 3x (the first choice) flattered the kernel by up to 30 %
+        self.sets = args.sets if args.sets > 0 else max(4, int(np.ceil(12 * 126e6 / per_set)) + 1)
         self.working_set_mb = per_set * self.sets / 1e6
         fmt = torch.channels_last if self.layout == "nhwc" else torch.contiguous_format
         gen = torch.Generator(device=device).manual_seed(1234)
@@ -194,6 +220,7 @@ def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier, nstreams=1)
     stream = torch.cuda.Stream()
     side = [torch.cuda.Stream() for _ in range(max(nstreams - 1, 0))]
     graphs = {}
+    chunk = max(wl.sets, (chunk // wl.sets) * wl.sets)   # every chunk starts on buffer set 0: one graph is reused
 
     def graph_for(n, first):
         key = (n, first % wl.sets)
@@ -251,6 +278,20 @@ def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier, nstreams=1)
     return e0.elapsed_time(e1)
 
 
+def verify_outputs(wl, torch, cabi):
+    """After the timed region: every buffer set's pooled output (written by the graph replays, on whatever stream)
+    must equal a fresh single-launch result with the default kernel variant, bit for bit."""
+    from fots.pytorch_b200.rroi_align.functions.rroi_align import forward_raw
+    keep = cabi.get_tuning(cabi.TUNE_NHWC_UNROLL)
+    cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, 0)
+    ok = True
+    for s in range(0, wl.sets, max(1, wl.sets // 8)):
+        want, _, _, _ = forward_raw(wl.feats[s], wl.rois[s], wl.PH, wl.PW, wl.scale, want_idx=False)
+        ok = ok and bool(torch.equal(want, wl.out[s]))
+    cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, keep)
+    return ok
+
+
 def e2e_leg(args, wl, torch, device, steps):
     """Same metric end to end through the public module API with HOST buffers: per step a pinned-host ->
     device copy of the step's features + RoIs, _RRoiAlign.forward, and a device -> pinned-host read of the
@@ -298,6 +339,7 @@ def variants_leg(args, torch, device, lib, cabi, peak):
             ("cfg4_per_gpu_32img_2048rois", dict(channels=args.channels, layout=args.layout, images=32, streams=1)),
             ("cfg4_per_gpu_nchw", dict(channels=args.channels, layout="nchw", images=32, streams=1))]
     for name, kw in grid:
+        cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, 0 if kw["streams"] == 1 else max(args.variant, 0))
         a = types.SimpleNamespace(channels=kw["channels"], layout=kw["layout"], images=kw["images"],
                                   rois_per_image=args.rois_per_image, sets=0)
         w = Workload(a, device, torch)
@@ -363,11 +405,11 @@ def cpu_baseline_leg(wl, seconds):
     from oracle import rroi_oracle as O
     feats = wl.feats[0].cpu().contiguous().numpy()
     rois = wl.rois_np[0]
-    threads = O.max_threads()
-    O.forward(feats, rois, wl.PH, wl.PW, wl.scale, threads=0)
+    threads = host_threads()
+    O.forward(feats, rois, wl.PH, wl.PW, wl.scale, threads=threads)
     t0, reps = time.perf_counter(), 0
     while True:
-        O.forward(feats, rois, wl.PH, wl.PW, wl.scale, threads=0)
+        O.forward(feats, rois, wl.PH, wl.PW, wl.scale, threads=threads)
         reps += 1
         dt = time.perf_counter() - t0
         if dt > seconds or reps >= 2000:
@@ -386,6 +428,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    out = StdoutGuard()
     import workloads as WL
     from oracle import rroi_oracle as O
     C, PH, PW, scale = args.channels, 8, 64, 0.25
@@ -393,10 +436,10 @@ def run_reference(args):
     warmup = args.warmup if args.warmup is not None else 3
     feats = WL.features(0, args.images, C, 180, 320)
     rois = WL.batch_rois(args.images, args.rois_per_image)
-    threads = O.max_threads()
-    O.forward(feats, rois, PH, PW, scale, threads=0)           # page in, spin up the OpenMP team
+    threads = host_threads()
+    O.forward(feats, rois, PH, PW, scale, threads=threads)           # page in, spin up the OpenMP team
     t0 = time.perf_counter()
-    O.forward(feats, rois, PH, PW, scale, threads=0)
+    O.forward(feats, rois, PH, PW, scale, threads=threads)
     t_full = time.perf_counter() - t0
     # bounded sample: the first n RoIs x first c channels of the step, sized so K+W steps fit the budget
     budget = 60.0
@@ -405,16 +448,16 @@ def run_reference(args):
     c = C if n > 1 or frac * len(rois) >= 1 else max(1, int(C * frac * len(rois)))
     sample, fsample = rois[:n], np.ascontiguousarray(feats[:, :c])
     for _ in range(warmup):
-        O.forward(fsample, sample, PH, PW, scale, threads=0)
+        O.forward(fsample, sample, PH, PW, scale, threads=threads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.forward(fsample, sample, PH, PW, scale, threads=0)
+        O.forward(fsample, sample, PH, PW, scale, threads=threads)
     dt = time.perf_counter() - t0
     px = n * c * PH * PW
     value = px * steps / dt / 1e6
     desc = "first %d of %d RoIs x first %d of %d channels of the cfg1 step per step (NCHW fp32), %d OpenMP threads" % (
         n, len(rois), c, C, threads)
-    print(json.dumps({
+    out.emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -428,6 +471,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     rank, world, local = dist_env()
+    out = StdoutGuard()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
@@ -448,10 +492,10 @@ def run_b200(args):
     wl = Workload(args, device, torch)
     sampler = ClockSampler(local)
     sampler.start()
-    if args.variant >= 0:
-        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, args.variant)
+    _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, max(args.variant, 0))
     ms = timed_steps(wl, steps, warmup, args.graph_chunk, torch, lib, _cabi, barrier, args.streams)
     clocks = sampler.finish()
+    verified = verify_outputs(wl, torch, _cabi)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -475,6 +519,7 @@ def run_b200(args):
                    "launch": "CUDA graphs of %d steps, PDL=%d, %d stream(s)" % (min(args.graph_chunk, steps), args.pdl, args.streams),
                    "parallelism": "image-sharded, %d rank(s), no data-path collective in RoIRotate" % world},
         "gpu_launches": steps,
+        "verified": verified,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("%s_c%d" % (wl.layout, wl.C)),
@@ -483,6 +528,7 @@ def run_b200(args):
     if rank == 0 and not args.no_extras:
         line["variants"] = variants_leg(args, torch, device, lib, _cabi, peak)
         _cabi.set_tuning(_cabi.TUNE_USE_PDL, args.pdl)
+        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, 0)
         dt, h2d, d2h = e2e_leg(args, wl, torch, device, args.e2e_steps)
         line["e2e"] = {"value": wl.feat_px_per_step * args.e2e_steps / dt / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
@@ -499,7 +545,7 @@ def run_b200(args):
         dist.barrier(device_ids=[local])
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -69,10 +69,12 @@ def detection_loss(seg, rbox, angle, tgt):
 
 
 class TrainStep:
-    def __init__(self, net, lr=1e-3, pooled_height=8, pooled_width=64, spatial_scale=0.25, amp_dtype=torch.bfloat16):
+    def __init__(self, net, lr=1e-3, pooled_height=8, pooled_width=64, spatial_scale=0.25, amp_dtype=torch.bfloat16,
+                 det_weight=1.0):
         self.net = net.train()
         self.opt = torch.optim.Adam(net.parameters(), lr=lr, betas=(0.5, 0.999))      # train.py:40
         self.ph, self.pw, self.scale, self.amp_dtype = pooled_height, pooled_width, spatial_scale, amp_dtype
+        self.det_weight = det_weight
 
     def __call__(self, images, tgt):
         net = self.net
@@ -92,7 +94,7 @@ class TrainStep:
         N, _, T = logp.shape
         ctc = F.ctc_loss(logp.permute(2, 0, 1), tgt["labels"], torch.full((N,), T, dtype=torch.int32, device=logp.device),
                          tgt["label_lens"], blank=0, reduction="sum", zero_infinity=True) / N   # ocr_process.py:300-301
-        total = det_loss + ctc
+        total = self.det_weight * det_loss + ctc
         total.backward()
         self.opt.step()
         return {"total": float(total.detach()), "ctc": float(ctc.detach()), "det": float(det_loss.detach())}
