@@ -364,7 +364,7 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     from fots.pytorch_b200.pipeline.infer import planted_quads
     from fots.pytorch_b200.pipeline.shard import all_gather_records
     torch.manual_seed(0)
-    net = FOTSNet(attention=True, nclass=89).to_b200(device)
+    net = FOTSNet(attention=True, nclass=89).to_b200(device, inference=True)
     pipe = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=torch.bfloat16)
     per_gpu, micro = args.pipeline_images, 8
     batch = per_gpu * world

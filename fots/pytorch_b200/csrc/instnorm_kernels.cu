@@ -123,7 +123,81 @@ __global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __rest
     }
 }
 
+// ---- fused top-down merge: y = (up(a_lo) | c_hi) + b_hi * (up(sigmoid(g_lo)) | 1) --------------------------------
+// thread = one output pixel x 8 channels; consecutive threads on consecutive channel groups (16-byte accesses).
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {   // torch: area_pixel_compute_source_index, align_corners
+    Lerp r;
+    const float s = scale * (float)dst;
+    r.i0 = (int)s;
+    r.i1 = r.i0 + ((r.i0 < in - 1) ? 1 : 0);
+    r.l1 = s - (float)r.i0;
+    r.l0 = 1.0f - r.l1;
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads) fpn_merge_kernel(const Bf16x8* __restrict__ a_lo, const Bf16x8* __restrict__ c_hi,
+                                                              const Bf16x8* __restrict__ b_hi, const __nv_bfloat16* __restrict__ g_lo,
+                                                              Bf16x8* __restrict__ y, int B, int h, int w, int H, int W, int C) {
+    const int G = C / 8;
+    const long long total = (long long)B * H * W * G;
+    const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
+    const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int g = (int)(i % G);
+        long long p = i / G;
+        const int X = (int)(p % W); p /= W;
+        const int Y = (int)(p % H);
+        const int b = (int)(p / H);
+        const Lerp ly = lerp_coord(Y, h, sy), lx = lerp_coord(X, w, sx);
+        const long long lo00 = ((long long)b * h + ly.i0) * w + lx.i0, lo01 = ((long long)b * h + ly.i0) * w + lx.i1;
+        const long long lo10 = ((long long)b * h + ly.i1) * w + lx.i0, lo11 = ((long long)b * h + ly.i1) * w + lx.i1;
+        float o[8];
+        if (a_lo) {
+            float v00[8], v01[8], v10[8], v11[8];
+            unpack8(ld8(a_lo + lo00 * G + g), v00); unpack8(ld8(a_lo + lo01 * G + g), v01);
+            unpack8(ld8(a_lo + lo10 * G + g), v10); unpack8(ld8(a_lo + lo11 * G + g), v11);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                o[k] = ly.l0 * (lx.l0 * v00[k] + lx.l1 * v01[k]) + ly.l1 * (lx.l0 * v10[k] + lx.l1 * v11[k]);
+        } else {
+            unpack8(ld8(c_hi + i), o);
+        }
+        if (b_hi) {
+            float gate = 1.0f;
+            if (g_lo) {
+                const float s00 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo00])));
+                const float s01 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo01])));
+                const float s10 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo10])));
+                const float s11 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo11])));
+                gate = ly.l0 * (lx.l0 * s00 + lx.l1 * s01) + ly.l1 * (lx.l0 * s10 + lx.l1 * s11);
+            }
+            float bb[8];
+            unpack8(ld8(b_hi + i), bb);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(bb[k], gate, o[k]);
+        }
+        y[i] = pack8(o);
+    }
+}
+
 }  // namespace
+
+extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo,
+                                             void* y, int B, int h, int w, int H, int W, int C, cudaStream_t stream) {
+    if (!y || ((a_lo == nullptr) == (c_hi == nullptr)) || (g_lo && !b_hi) || B <= 0 || h <= 0 || w <= 0 || H <= 0 ||
+        W <= 0 || C <= 0 || C % 8 != 0)
+        return RROI_B200_ERR_INVALID_ARG;
+    const long long total = (long long)B * H * W * (C / 8);
+    long long grid = (total + kThreads - 1) / kThreads;
+    if (grid > 148LL * 32) grid = 148LL * 32;
+    fpn_merge_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(static_cast<const Bf16x8*>(a_lo), static_cast<const Bf16x8*>(c_hi),
+                                                              static_cast<const Bf16x8*>(b_hi), static_cast<const __nv_bfloat16*>(g_lo),
+                                                              static_cast<Bf16x8*>(y), B, h, w, H, W, C);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
 
 extern "C" int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
                                             const void* residual, double* workspace, int B, int HW, int C,

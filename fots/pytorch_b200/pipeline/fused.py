@@ -17,6 +17,8 @@ def _lib():
         i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
         L.fots_b200_instnorm_nhwc_bf16.restype = i
         L.fots_b200_instnorm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
+        L.fots_b200_fpn_merge_nhwc_bf16.restype = i
+        L.fots_b200_fpn_merge_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
         L._instnorm_bound = True
     return L
 
@@ -48,4 +50,33 @@ def instnorm_act(x, weight, bias, eps, slope, residual=None, crelu=False):
             b.data_ptr() if b is not None else None, residual.data_ptr() if residual is not None else None,
             ws.data_ptr(), B, H * W, C, float(eps), float(slope), 1 if crelu else 0, key[1])
     _cabi.check(st, "fots_b200_instnorm_nhwc_bf16")
+    return y
+
+
+def _cl_bf16(t):
+    return (t is None) or (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4
+                           and t.is_contiguous(memory_format=torch.channels_last)
+                           and not (torch.is_grad_enabled() and t.requires_grad))
+
+
+def merge_eligible(*tensors):
+    ts = [t for t in tensors if t is not None]
+    return len(ts) > 0 and all(_cl_bf16(t) for t in ts) and ts[0].size(1) % 8 == 0
+
+
+def fpn_merge(a_lo=None, c_hi=None, b_hi=None, gate_logits_lo=None, size=None):
+    """y = (upsample(a_lo) | c_hi) + b_hi * (upsample(sigmoid(gate_logits_lo)) | 1); bilinear, align_corners=True.
+    a_lo [B,C,h,w] / c_hi, b_hi [B,C,H,W] / gate_logits_lo [B,1,h,w]; size=(H, W) when only low-res inputs are given."""
+    hi = c_hi if c_hi is not None else b_hi
+    lo = a_lo if a_lo is not None else gate_logits_lo
+    H, W = (hi.shape[2], hi.shape[3]) if hi is not None else size
+    ref = hi if hi is not None else lo
+    B, C = ref.shape[0], (a_lo if a_lo is not None else hi).shape[1]
+    h, w = (lo.shape[2], lo.shape[3]) if lo is not None else (H, W)
+    y = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=ref.device, memory_format=torch.channels_last)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(ref.device):
+        st = _lib().fots_b200_fpn_merge_nhwc_bf16(ptr(a_lo), ptr(c_hi), ptr(b_hi), ptr(gate_logits_lo), y.data_ptr(),
+                                                  B, h, w, H, W, C, torch.cuda.current_stream(ref.device).cuda_stream)
+    _cabi.check(st, "fots_b200_fpn_merge_nhwc_bf16")
     return y

@@ -90,7 +90,10 @@ class _ResSepIN(nn.Module):
 
 
 def _up(x, like):
-    return F.interpolate(x, size=like.shape[2:], mode="bilinear", align_corners=True)
+    # CUDA autocast lists upsample_bilinear2d as an fp32 op: a 256-channel map at 1/4 scale would be blown up to
+    # fp32 (and every add/mul after it promoted).  Interpolate in the tensor's own dtype instead.
+    with torch.autocast(device_type=x.device.type, enabled=False):
+        return F.interpolate(x, size=like.shape[2:], mode="bilinear", align_corners=True)
 
 
 class FOTSNet(nn.Module):
@@ -158,7 +161,15 @@ class FOTSNet(nn.Module):
         s1 = self.layer3(s2)
         f1, f2, f3 = self.feature1(s3), self.feature2(s2), self.feature3(s1)
         f4 = self.feature4(self.drop1(self.layer4(s1)))
-        if self.attention:
+        if fused.merge_eligible(f1, f2, f3, f4):
+            # inference fast path: each merge step is one fused kernel (upsample + attention gate + add)
+            att = self.conv_attenton if self.attention else (lambda t: None)
+            x = fused.fpn_merge(a_lo=f4, b_hi=f3, gate_logits_lo=att(f4))
+            f2 = fused.fpn_merge(c_hi=self.upconv1(fused.fpn_merge(a_lo=x, size=f2.shape[2:])), b_hi=f2,
+                                 gate_logits_lo=att(x))
+            x = fused.fpn_merge(c_hi=self.upconv2(fused.fpn_merge(a_lo=f2, size=f1.shape[2:])), b_hi=f1,
+                                gate_logits_lo=att(f2))
+        elif self.attention:
             x = _up(f4, f3) + f3 * _up(torch.sigmoid(self.conv_attenton(f4)).expand_as(f4), f3)
             gate = self._gate(x, f2)
             f2 = self.upconv1(_up(x, f2)) + f2 * gate
@@ -186,9 +197,18 @@ class FOTSNet(nn.Module):
         return F.log_softmax(x.float(), dim=1)
 
     # ---- B200 placement ------------------------------------------------------------------------
-    def to_b200(self, device="cuda"):
-        """eval-mode inference placement: weights on the device, channels-last; call under bf16 autocast."""
-        return self.to(device=device, memory_format=torch.channels_last)
+    def to_b200(self, device="cuda", inference=False):
+        """Placement for B200: parameters on the device, convolution weights channels-last; call under bf16
+        autocast.  inference=True additionally stores the convolution weights in bf16 once, so autocast does not
+        re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
+        batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
+        self.to(device=device, memory_format=torch.channels_last)
+        if inference:
+            for m in self.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.to(dtype=torch.bfloat16)
+            self.eval()
+        return self
 
 
 class _BiLSTM(nn.Module):

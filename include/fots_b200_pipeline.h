@@ -54,6 +54,18 @@ int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, con
                                  const void* residual, double* workspace, int B, int HW, int C,
                                  float eps, float slope, int crelu, cudaStream_t stream);
 
+/*
+ * One step of the top-down feature merge of tools/models.py:411-438, fused (channels-last bf16, fp32 arithmetic):
+ *     y = (a_lo ? upsample(a_lo) : c_hi)  +  (b_hi ? b_hi * (g_lo ? upsample(sigmoid(g_lo)) : 1) : 0)
+ * upsample = bilinear, align_corners=True (torch's source-index arithmetic), from [h, w] to [H, W].
+ *   a_lo  bf16 [B, h, w, C] or NULL      c_hi  bf16 [B, H, W, C] or NULL   (exactly one of the two)
+ *   b_hi  bf16 [B, H, W, C] or NULL      g_lo  bf16 [B, h, w, 1] attention LOGITS or NULL (needs b_hi)
+ *   y     bf16 [B, H, W, C];  C % 8 == 0.
+ * torch runs this as upsample + upsample + mul + add (its NHWC bf16 upsample kernel reaches ~0.55 TB/s).
+ */
+int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo, void* y,
+                                  int B, int h, int w, int H, int W, int C, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,22 +161,56 @@ def test_fused_instnorm_matches_torch_fp32(cuda, B, C, H, W, mode):
     assert bool((err <= tol).all()), float((err - tol).max())
 
 
-def test_fused_and_torch_paths_agree_on_the_network(cuda):
-    """Same weights, same bf16 input: the network with the fused InstanceNorm kernels vs torch's own ops."""
+def test_fused_path_is_as_close_to_fp32_as_torch_bf16(cuda):
+    """Same weights, same input.  Reference = the network in fp32 (torch ops).  Two bf16 runs are compared with it:
+    torch's own bf16 ops, and the fused InstanceNorm kernels (fp32 statistics, one bf16 rounding per layer).  The fused
+    path must not be further from fp32 than torch's bf16 path is (25 % slack for noise)."""
     from fots.pytorch_b200.pipeline import FOTSNet, fused
     torch.manual_seed(0)
     net = FOTSNet(attention=True, nclass=89).to_b200(cuda).eval()
     x = torch.randn(2, 3, 128, 192, device=cuda).contiguous(memory_format=torch.channels_last)
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        a = net(x)
-        old = fused.eligible
-        fused.eligible = lambda *args, **kw: False
-        try:
-            b = net(x)
-        finally:
-            fused.eligible = old
-    for ga, gb in zip(a, b):
-        for ta, tb in zip(ga, gb):
-            d = (ta.float() - tb.float()).abs()
-            scale = tb.float().abs().mean() + 1e-3
-            assert float(d.mean() / scale) < 0.03, float(d.mean() / scale)
+    with torch.no_grad():
+        ref = net(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            a = net(x)
+            old = fused.eligible
+            fused.eligible = lambda *args, **kw: False
+            try:
+                b = net(x)
+            finally:
+                fused.eligible = old
+
+    def err(got):
+        out = []
+        for gr, gg in zip(ref, got):
+            for tr, tg in zip(gr, gg):
+                out.append(float((tg.float() - tr).abs().mean() / (tr.abs().mean() + 1e-3)))
+        return np.array(out)
+
+    e_fused, e_torch = err(a), err(b)
+    assert (e_fused <= 1.25 * e_torch + 5e-3).all(), (e_fused, e_torch)
+    assert e_fused.max() < 0.35      # bf16 on a random-init net: the coarse-scale (sin, cos) head is the noisiest
+
+
+@pytest.mark.parametrize("B,C,h,w,H,W", [(2, 256, 6, 10, 12, 20), (1, 64, 5, 7, 9, 13), (3, 8, 1, 1, 4, 4), (2, 256, 23, 40, 45, 80)])
+def test_fused_fpn_merge_matches_torch(cuda, B, C, h, w, H, W):
+    """fots_b200_fpn_merge_nhwc_bf16 vs the torch composition of tools/models.py:411-438 evaluated in fp32."""
+    import torch.nn.functional as F
+    from fots.pytorch_b200.pipeline import fused
+    g = torch.Generator(device=cuda).manual_seed(C + H)
+    mk = lambda *s: torch.randn(*s, device=cuda, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    a_lo, c_hi, b_hi, gl = mk(B, C, h, w), mk(B, C, H, W), mk(B, C, H, W), mk(B, 1, h, w)
+    up = lambda t: F.interpolate(t.float(), size=(H, W), mode="bilinear", align_corners=True)
+    cases = [
+        (dict(a_lo=a_lo, b_hi=b_hi, gate_logits_lo=gl), up(a_lo) + b_hi.float() * up(torch.sigmoid(gl.float()))),
+        (dict(a_lo=a_lo, b_hi=b_hi), up(a_lo) + b_hi.float()),
+        (dict(a_lo=a_lo, size=(H, W)), up(a_lo)),
+        (dict(c_hi=c_hi, b_hi=b_hi, gate_logits_lo=gl), c_hi.float() + b_hi.float() * up(torch.sigmoid(gl.float()))),
+        (dict(c_hi=c_hi, b_hi=b_hi), c_hi.float() + b_hi.float()),
+    ]
+    assert fused.merge_eligible(a_lo, c_hi, b_hi)
+    for kw, want in cases:
+        got = fused.fpn_merge(**kw)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        err = (got.float() - want).abs()
+        assert bool((err <= want.abs() * 2.0 ** -7 + 1e-2).all()), (sorted(kw), float(err.max()))

@@ -14,7 +14,7 @@ from fots.pytorch_b200.pipeline.infer import planted_quads  # noqa: E402
 if __name__ == "__main__":
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    net = FOTSNet(attention=True, nclass=89).to_b200(dev)
+    net = FOTSNet(attention=True, nclass=89).to_b200(dev, inference=True)
     pipe = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=torch.bfloat16)
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     images = torch.randn(B, 3, 720, 1280, device=dev)
