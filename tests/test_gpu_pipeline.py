@@ -214,3 +214,25 @@ def test_fused_fpn_merge_matches_torch(cuda, B, C, h, w, H, W):
         assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
         err = (got.float() - want).abs()
         assert bool((err <= want.abs() * 2.0 ** -7 + 1e-2).all()), (sorted(kw), float(err.max()))
+
+
+def test_crnn_consumer_path(oracle, cuda):
+    """Consumer B (src/utils.py:429-468): RoIRotate of the RAW image (C=3, PH=32, scale 1) -> CRNN -> [T, N, nclass]."""
+    from fots.pytorch_b200 import _RRoiAlign
+    from fots.pytorch_b200.pipeline import CRNN, greedy_ctc_decode
+    from fots.pytorch_b200.pipeline.rois import pooled_width_for
+    torch.manual_seed(0)
+    img = torch.randn(2, 3, 160, 256, device=cuda)
+    rois = np.array([[0, 128, 80, 24, 120, 10], [1, 60, 60, 16, 90, -35], [1, 200, 100, 30, 100, 80]], np.float32)
+    pw = pooled_width_for(rois[:, 3], rois[:, 4], 32, "train")             # ceil(32 * max(w/h)), src/utils.py:430-433
+    r = torch.from_numpy(rois).to(cuda)
+    for x in (img, img.contiguous(memory_format=torch.channels_last)):
+        pooled = _RRoiAlign(32, pw, 1.0)(x, r)
+        want, _, _ = oracle.forward(img.cpu().numpy(), rois, 32, pw, 1.0)
+        Hh.assert_bit_equal(pooled.cpu().numpy(), want, "RoIRotate on the raw image")
+    net = CRNN(nclass=89).to(cuda).eval()
+    with torch.no_grad():
+        y = net(pooled.contiguous())
+    assert y.shape == (pw // 4 + 1, 3, 89) and torch.isfinite(y).all()
+    ids, lens = greedy_ctc_decode(torch.log_softmax(y, 2).permute(1, 2, 0))   # [N, nclass, T]
+    assert ids.shape == (3, pw // 4 + 1) and int(lens.max()) <= pw // 4 + 1
