@@ -434,7 +434,8 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     for _ in range(2):
         step_host()
     ms_host, _ = timed(step_host, args.pipeline_steps)
-    return {"images_per_s": batch / (ms_host * 1e-3), "ms_per_step": ms_host,
+    cpu = pipeline_cpu_baseline(torch) if rank == 0 else None
+    return {"images_per_s": batch / (ms_host * 1e-3), "ms_per_step": ms_host, "cpu_baseline": cpu,
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
             "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
@@ -442,6 +443,46 @@ def pipeline_leg(args, torch, device, dist, world, rank):
             "collective": "one all_gather of int32 [images, 64, 74] records per step" if world > 1 else "none (1 rank)",
             "boxes": "planted (seeded) -- reference NMS is pathological on random-init maps, SURVEY 8d",
             "flop_per_image": 221.7e9}
+
+
+def pipeline_cpu_baseline(torch):
+    """The reference's CPU path for the end-to-end step, on this box's host cores: the same architecture in fp32 on
+    torch CPU (fots.pytorch_b200.pipeline.nets is output-identical to tools/models.py with shared weights) + the
+    oracle's CPU RoIRotate (the reference has none) + forward_ocr + arg-max, one 1280x720 image with 64 RoIs at a time."""
+    from oracle import rroi_oracle as O
+    from fots.pytorch_b200.pipeline import FOTSNet
+    from fots.pytorch_b200.pipeline.infer import planted_quads
+    threads = host_threads()
+    old = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    try:
+        torch.manual_seed(0)
+        net = FOTSNet(attention=True, nclass=89).eval()
+        img = torch.randn(1, 3, 720, 1280)
+        q = planted_quads(1, 64)[0]
+        rois = np.zeros((64, 6), np.float32)
+        for i in range(64):
+            p4 = q[i, :8].reshape(4, 2)
+            dw, dh = p4[2] - p4[1], p4[1] - p4[0]
+            rois[i] = [0, int(p4[:, 0].mean()), int(p4[:, 1].mean()), np.hypot(*dh), np.hypot(*dw),
+                       -np.degrees(np.arctan2(dw[1], dw[0]))]
+
+        def one():
+            with torch.no_grad():
+                _, _, _, feats = net(img)
+                pooled, _, _ = O.forward(feats[1].numpy(), rois, 8, 64, 0.25, threads=threads)
+                return net.forward_ocr(torch.from_numpy(pooled)).argmax(1)
+
+        one()
+        t0, n = time.perf_counter(), 0
+        while n < 3:
+            one()
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+    finally:
+        torch.set_num_threads(old)
+    return {"images_per_s": 1.0 / dt, "cores": threads, "kind": "port",
+            "sample": "%d images, fp32 torch-CPU backbone + heads + forward_ocr, oracle RoIRotate, %d threads" % (n, threads)}
 
 
 def cpu_baseline_leg(wl, seconds):
@@ -550,7 +591,9 @@ def run_b200(args):
     alg = float(np.mean(wl.alg_bytes))
     launch_us = ms / steps * 1e3
     achieved = alg / (launch_us * 1e-6) / 1e9
-    kname = "rroi_fwd_%s_kernel" % wl.layout
+    tile = {5: 256, 4: 256, 3: 128, 2: 128}.get(max(args.variant, 0), 64)
+    kname = ("rroi_fwd_nhwc_packed_kernel<%d,%d,2>" % (wl.C, tile)) if wl.layout == "nhwc" and wl.C in (32, 64, 128, 256) \
+        else "rroi_fwd_%s_kernel" % wl.layout
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -131,7 +131,9 @@ int rroi_b200_set_tuning(int key, int value) {
             if (value < 0 || value > 6) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.nhwc_unroll = value; return RROI_B200_OK;
         case RROI_B200_TUNE_USE_PDL:    rroi::g_tuning.use_pdl = value != 0; return RROI_B200_OK;
-        case RROI_B200_TUNE_BWD_DEDUPE: rroi::g_tuning.bwd_dedupe = value != 0; return RROI_B200_OK;
+        case RROI_B200_TUNE_BWD_DEDUPE:
+            if (value < 0 || value > 2) return RROI_B200_ERR_INVALID_ARG;
+            rroi::g_tuning.bwd_dedupe = value; return RROI_B200_OK;
         default: return RROI_B200_ERR_INVALID_ARG;
     }
 }

@@ -301,6 +301,138 @@ __global__ void __launch_bounds__(kBlock) rroi_bwd_nhwc_kernel(const BwdParams p
     }
 }
 
+// ------------------------------------------------------------------------------------ NHWC, packed
+// Mirror of the packed forward for C in {32, 64, 128, 256}: one thread per bin computes the scatter geometry into
+// a shared record (weights of skipped taps are folded to "not scattered"), then every lane owns one float4 of one
+// bin per iteration: one coalesced 128-bit load of top_diff, <=4 x (4 FMUL + RED.ADD.v4.f32).  UN iterations' loads
+// are issued before the first reduction.
+struct __align__(16) ScatRec {
+    int pix;                       // (batch*H + t)*W + l
+    uint32_t pred;                 // bit0 lt, bit1 rt (pix+1), bit2 rb (pix+W+1), bit3 lb (pix+W); bit4 bin < bins
+    float wlt, wrt, wrb, wlb;
+    int pad[2];
+};
+
+__device__ __forceinline__ float4 ld_v4(const float* ptr, uint32_t pred) {
+    float4 r;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+        "@q ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(ptr), "r"(pred));
+    return r;
+}
+
+constexpr int kPackWarps = 8;
+
+template <int CT, int TILE, int UN>
+__global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(const BwdParams p) {
+    constexpr int LPP = CT / 4;
+    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;
+    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;
+    constexpr int PIXW = TILE / kPackWarps;
+    constexpr int ITERS = PIXW * NCH / PPI;
+    static_assert(PIXW * kPackWarps == TILE && ITERS % UN == 0 && ITERS > 0, "tile shape");
+    __shared__ RoiXform sX;
+    __shared__ ScatRec rec[TILE];
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+    const int bin0 = tile * TILE;
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (warp == 0) {
+        RoiXform X;
+        if (p.idx_mode == IDX_NONE) {
+            X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        } else {
+            const float* roi = p.rois + (size_t)n * 6;
+            X.batch = __float2int_rz(__ldg(roi));
+            X.rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
+        }
+        if (lane == 0) sX = X;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TILE; t += kPackWarps * 32) {
+        ScatRec r;
+        r.pix = 0; r.pred = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
+        const int bin = bin0 + t;
+        if (bin < bins) {
+            const RoiXform X = sX;
+            const int ph = bin / p.PW, pw = bin - ph * p.PW;
+            const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+            float cx, cy;
+            if (p.idx_mode == IDX_NONE) bin_center(X, ph, pw, (float)(p.W - 1), (float)(p.H - 1), cx, cy);
+            else { cx = __ldg(p.idx_x + (size_t)n * bins + bin); cy = __ldg(p.idx_y + (size_t)n * bins + bin); }
+            const bool in = batch_ok & !(X.rpw < (float)pw);
+            const ScatterGeom g = scatter_geom<false>(cx, cy, in, p.H, p.W);
+            r.pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+            // a tap with non-zero weight is a distinct pixel: rt/rb only when r == l + 1, lb/rb only when b == t + 1
+            r.pred = ((g.p_lt & (g.wlt != 0.f)) ? 1u : 0u) | ((g.p_rt & (g.wrt != 0.f) & (g.r == g.l + 1)) ? 2u : 0u) |
+                     ((g.p_rb & (g.wrb != 0.f) & (g.r == g.l + 1) & (g.b == g.t + 1)) ? 4u : 0u) |
+                     ((g.p_lb & (g.wlb != 0.f) & (g.b == g.t + 1)) ? 8u : 0u) | 16u;
+            r.wlt = g.wlt; r.wrt = g.wrt; r.wrb = g.wrb; r.wlb = g.wlb;
+        }
+        rec[t] = r;
+    }
+    __syncthreads();
+
+    const int sub = LPP >= 32 ? 0 : lane / LPP;
+    const int cvl = LPP >= 32 ? lane : lane % LPP;
+    const long long rowC = (long long)p.W * CT;
+    float* gbase = p.bottom_diff + cvl * 4;
+    const int pw0 = warp * PIXW;
+    const float* tbase = p.top_diff + ((size_t)n * bins + bin0 + pw0 + (NCH > 1 ? 0 : sub)) * CT + cvl * 4;
+    const ScatRec* rbase = rec + pw0 + (NCH > 1 ? 0 : sub);
+
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += UN) {
+        float4 gq[UN];
+        ScatRec r[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int it = it0 + u;
+            const int dpx = NCH > 1 ? it / NCH : it * PPI;
+            const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+            r[u] = rbase[dpx];
+            gq[u] = ld_v4(tbase + dpx * CT + ch, r[u].pred & 15u);     // bins that scatter nothing are not even read
+        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) any |= r[u].pred;
+        if (any & 15u) {
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int it = it0 + u;
+                const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+                float* d = gbase + (long long)r[u].pix * CT + ch;
+                if (r[u].pred & 1u) red_add_v4(d, r[u].wlt, gq[u]);
+                if (r[u].pred & 2u) red_add_v4(d + CT, r[u].wrt, gq[u]);
+                if (r[u].pred & 4u) red_add_v4(d + rowC + CT, r[u].wrb, gq[u]);
+                if (r[u].pred & 8u) red_add_v4(d + rowC, r[u].wlb, gq[u]);
+            }
+        }
+    }
+}
+
+template <int CT>
+static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl) {
+    const int bins = p.PH * p.PW;
+    constexpr int PPI = CT >= 128 ? 1 : 128 / CT;
+    constexpr int NCH = CT > 128 ? CT / 128 : 1;
+    constexpr int I64 = 8 * NCH / PPI;
+    const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
+    if (ctas256 >= 148 * 4) {
+        p.tiles = (bins + 255) / 256;
+        return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 256, 4>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
+    }
+    p.tiles = (bins + 63) / 64;
+    return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
+}
+
 cudaError_t launch_bwd_nhwc(const BwdParams& p0, cudaStream_t s) {
     BwdParams p = p0;
     const int bins = p.PH * p.PW;
@@ -310,6 +442,12 @@ cudaError_t launch_bwd_nhwc(const BwdParams& p0, cudaStream_t s) {
     const bool pdl = g_tuning.use_pdl != 0;
     const bool vec = (p.C % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.top_diff) | reinterpret_cast<uintptr_t>(p.bottom_diff)) % 16 == 0);
+    if (vec && g_tuning.bwd_dedupe != 2) {      // TUNE_BWD_DEDUPE = 2 selects the generic kernel (A/B measurements)
+        if (p.C == 32)  return launch_bwd_nhwc_packed<32>(p, s, pdl);
+        if (p.C == 64)  return launch_bwd_nhwc_packed<64>(p, s, pdl);
+        if (p.C == 128) return launch_bwd_nhwc_packed<128>(p, s, pdl);
+        if (p.C == 256) return launch_bwd_nhwc_packed<256>(p, s, pdl);
+    }
     return vec ? launch_1d(rroi_bwd_nhwc_kernel<true>, grid, kBlock, p, s, pdl)
                : launch_1d(rroi_bwd_nhwc_kernel<false>, grid, kBlock, p, s, pdl);
 }

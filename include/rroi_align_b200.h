@@ -39,7 +39,7 @@ typedef struct CUstream_st* cudaStream_t;   /* same definition as the CUDA runti
 #define RROI_B200_TUNE_NCHW_CG      0   /* channels per CTA in the NCHW kernels: 1,2,4,8,16 (0 = default 8) */
 #define RROI_B200_TUNE_NHWC_UNROLL  1   /* NHWC forward variant: 0 = auto, 1..6 = fixed tile size x loads in flight  */
 #define RROI_B200_TUNE_USE_PDL      2   /* 1: launch with programmatic dependent launch                       */
-#define RROI_B200_TUNE_BWD_DEDUPE   3   /* 1 (default): warp-merge equal sample points before the atomics     */
+#define RROI_B200_TUNE_BWD_DEDUPE   3   /* NCHW: 1 (default) warp-merge equal sample points, 0 off; 2 = generic NHWC kernel */
 
 /*
  * Drop-in for rroi_align/src/rroi_align_kernel.h:8-12.  NCHW.  top_data / con_idx_x / con_idx_y are
