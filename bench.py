@@ -434,7 +434,7 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     for _ in range(2):
         step_host()
     ms_host, _ = timed(step_host, args.pipeline_steps)
-    cpu = pipeline_cpu_baseline(torch) if rank == 0 else None
+    cpu = pipeline_cpu_baseline(torch) if (rank == 0 and world == 1) else None      # N=1 only, like cpu_baseline
     return {"images_per_s": batch / (ms_host * 1e-3), "ms_per_step": ms_host, "cpu_baseline": cpu,
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
             "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
