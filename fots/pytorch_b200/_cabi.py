@@ -33,7 +33,7 @@ EXPORTS = (
     "rroi_b200_strerror", "rroi_b200_abi_version", "rroi_b200_build_info",
     # include/fots_b200_pipeline.h
     "fots_b200_boxes_to_rois", "fots_b200_ctc_greedy", "fots_b200_instnorm_nhwc_bf16",
-    "fots_b200_fpn_merge_nhwc_bf16",
+    "fots_b200_fpn_merge_nhwc_bf16", "fots_b200_decode_candidates",
 )
 
 _lib = None

@@ -38,6 +38,27 @@ int fots_b200_ctc_greedy(const float* logp, int num_seq, int num_classes, int T,
                          cudaStream_t stream);
 
 /*
+ * Detection decode: the per-pixel loop of nms/adaptor.cpp:76-117 -- threshold the score
+ * map, build one quadrangle per positive pixel from the four distances and (sin, cos), in x10000 fixed point --
+ * on the GPU, compacted in RASTER ORDER (the reference's row-wise merge nms/nms.h:149-213 depends on that order),
+ * so that the CPU Clipper merge receives a compact candidate list instead of three full maps (test.py:86-96 copies
+ * all three to the host with three synchronisations).
+ *   segm   fp32 [B, h, w]      score map (seg_pred[0] squeezed)
+ *   rbox   fp32 [B, 4, h, w]   distances top, bottom, left, right (NCHW as the network emits them)
+ *   angle  fp32 [B, 2, h, w]   (sin, cos)
+ *   counts int32 [B] out       number of positive pixels per image (may exceed max_per_image; rows beyond it are dropped)
+ *   cand   int32 [B, max_per_image, 16] out, one row per positive pixel in raster order:
+ *            [0..7] x0,y0,..,x3,y3 as cInt(roundf(10000 * coord))   [8] score (fp32 bits)
+ *            [9..12] p_left*p_bt, p_left*p_top, p_right*p_top, p_right*p_bt (fp32 bits)   [13] x  [14] y  [15] 0
+ *   scratch int32 [B * ceil(h*w/256)] per-block counts
+ * fp32 arithmetic in the reference's operation order without fused multiply-adds (its Makefile builds with -O3 on
+ * baseline x86-64), so the fixed-point coordinates are bit-identical; expf() is CUDA's (<= 2 ulp from libm).
+ */
+int fots_b200_decode_candidates(const float* segm, const float* rbox, const float* angle, int B, int h, int w,
+                                float segm_threshold, int max_per_image, int* counts, int* cand, int* scratch,
+                                cudaStream_t stream);
+
+/*
  * Fused channels-last InstanceNorm (+ affine) (+ residual add) + leaky-ReLU for the feeder/consumer networks
  * (tools/models.py:41-48 CReLU_IN, :142-166 BasicBlockIn, :87-103 conv_dw_*_in, :336-364 forward_ocr).  torch's
  * instance_norm converts a channels-last tensor to NCHW and back around a batch-norm kernel; this is one

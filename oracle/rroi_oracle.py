@@ -47,6 +47,9 @@ def cpu_lib():
         lib.rroi_oracle_sinf.restype = ctypes.c_float
         lib.rroi_oracle_sinf.argtypes = [ctypes.c_float]
         lib.rroi_oracle_max_threads.restype = ctypes.c_int
+        lib.detect_oracle_decode.restype = ctypes.c_int
+        lib.detect_oracle_decode.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                             ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
         _cpu = lib
     return _cpu
 
@@ -93,6 +96,16 @@ def backward(top_diff, rois, idx_x, idx_y, feature_size, spatial_scale, threads=
                                         _p(rois), _p(grad), _p(idx_x), _p(idx_y), int(threads))
     assert rc == 1
     return grad
+
+
+def decode_candidates(segm, rbox, angle, segm_threshold, max_rows):
+    """nms/adaptor.cpp:76-117 restated: segm [h,w], rbox [4,h,w], angle [2,h,w] -> (count, cand int32 [max_rows,16])."""
+    segm, rbox, angle = _c32(segm), _c32(rbox), _c32(angle)
+    h, w = segm.shape
+    cand = np.zeros((max_rows, 16), np.int32)
+    n = cpu_lib().detect_oracle_decode(_p(segm), _p(rbox), _p(angle), h, w, float(segm_threshold), int(max_rows),
+                                       cand.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return n, cand
 
 
 def max_threads():

@@ -236,3 +236,28 @@ def test_crnn_consumer_path(oracle, cuda):
     assert y.shape == (pw // 4 + 1, 3, 89) and torch.isfinite(y).all()
     ids, lens = greedy_ctc_decode(torch.log_softmax(y, 2).permute(1, 2, 0))   # [N, nclass, T]
     assert ids.shape == (3, pw // 4 + 1) and int(lens.max()) <= pw // 4 + 1
+
+
+@pytest.mark.parametrize("B,h,w,thr,cap", [(1, 45, 80, 0.5, 4096), (3, 37, 53, 0.7, 4096), (2, 180, 320, 0.9, 2000), (1, 16, 16, 0.5, 10)])
+def test_decode_candidates_matches_adaptor_restatement(oracle, cuda, B, h, w, thr, cap):
+    """fots_b200_decode_candidates vs oracle/detect_oracle.c (nms/adaptor.cpp:76-117): same pixels, raster order,
+    fixed-point coordinates, score and (x, y) bit-exact; the four expf-based edge probabilities to 1e-6."""
+    from fots.pytorch_b200.pipeline.detect import candidates_to_quads, decode_candidates
+    rng = np.random.default_rng(h * 100 + w)
+    seg = rng.random((B, 1, h, w), dtype=np.float32)
+    seg.flat[::17] = thr                                         # exactly on the threshold: NOT a candidate ('>')
+    rbox = (rng.random((B, 4, h, w), dtype=np.float32) * 128).astype(np.float32)
+    a = rng.uniform(-np.pi, np.pi, (B, h, w)).astype(np.float32)
+    angle = np.stack([np.sin(a), np.cos(a)], 1).astype(np.float32)
+    counts, cand = decode_candidates(*(torch.from_numpy(t).to(cuda) for t in (seg, rbox, angle)), thr, cap)
+    counts, cand = counts.cpu().numpy(), cand.cpu().numpy()
+    for b in range(B):
+        n, want = oracle.decode_candidates(seg[b, 0], rbox[b], angle[b], thr, cap)
+        assert counts[b] == n == int((seg[b, 0] > thr).sum())
+        m = min(n, cap)
+        got = cand[b, :m]
+        assert np.array_equal(got[:, :9], want[:m, :9]) and np.array_equal(got[:, 13:], want[:m, 13:])
+        assert np.allclose(got[:, 9:13].view(np.float32), want[:m, 9:13].view(np.float32), rtol=1e-6, atol=0)
+        assert (cand[b, m:] == 0).all()
+    q = candidates_to_quads(torch.from_numpy(cand[0, :min(counts[0], cap)]).to(cuda))
+    assert q.shape[1] == 9 and torch.isfinite(q).all()
