@@ -1,0 +1,380 @@
+// conv_tc.cu -- stride-1 convolution of channels-last bf16 activations as an implicit GEMM on the sm_100a
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA), with bias / leaky-ReLU fused in the
+// epilogue.  It replaces the cuDNN calls for the dense 3x3 convolutions of the consumer and feeder networks
+// (tools/models.py:334-379 forward_ocr conv5..conv10_s; :142-166 BasicBlockIn; :257-264 layer0_1), where the
+// path really is a dense contraction.
+//
+// GEMM view:  D[pixel, cout] = sum_{r,s,cin} X[n, h+r-pad_h, w+s-pad_w, cin] * Wt[cout, r, s, cin]
+//   M = N*Ho*Wo output pixels, tile = 128 pixels shaped TN x TH x TW (a box of the NHWC tensor)
+//   N = Cout, tile BN in {64,128,256};   K = R*S*Cin walked as (tap, 64-channel chunk) blocks.
+// No im2col buffer exists anywhere: for one k-block the A operand is the input box shifted by the tap, fetched by
+// ONE 4-D TMA load whose out-of-bounds rows/columns are zero-filled by the hardware (that is the padding), landing
+// in shared memory as a K-major 128x64 tile in the 128-byte swizzle the UMMA descriptor expects.
+//
+// CTA = 6 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers
+// -> bias/activation -> bf16 -> swizzled shared tile -> TMA store).  One output tile per CTA; two CTAs are resident
+// per SM for BN <= 128 so one CTA's epilogue overlaps the other's main loop.
+#include "../../../include/fots_b200_pipeline.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128;          // pixels per tile = UMMA M (accumulator row i lives in TMEM lane i)
+constexpr int BK = 64;           // channels per k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int UK = 16;           // K of one tcgen05.mma.kind::f16
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2;
+
+struct ConvParams {
+    int n_tiles_w, n_tiles_h, n_tiles_n;   // tile grid over (Wo, Ho, N)
+    int tw, th, tn;                        // tile box (tw*th*tn == 128)
+    int cin_chunks;                        // Cin / 64
+    int S;                                 // filter width (taps = R*S)
+    int taps;
+    int pad_h, pad_w;
+    int cout_tiles;                        // Cout / BN
+    float slope;                           // leaky slope; 1 = identity
+    const float* bias;                     // [Cout] or nullptr
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on the phase parity.  A barrier that never flips would hang the device until the driver's watchdog; trap
+// after ~2 s instead so a broken pipeline shows up as a launch failure.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spin & 0xfff) == 0xfff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  Advancing K by 16 bf16 inside the swizzle row is
+// +32 bytes on the start address (+2 in the 16-byte units of the field).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_y, const ConvParams P) {
+    constexpr uint32_t kBBytes = BN * BK * 2;
+    constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static_assert(BM * BN * 2 <= STAGES * kStageBytes, "output staging tile must fit in the operand stages");
+    // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
+    uint8_t* const base_ptr = smem_raw + (base - raw);
+    const uint32_t bars = base + STAGES * kStageBytes;            // full[STAGES], empty[STAGES], accum, tmem slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    volatile uint32_t* const tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * kStageBytes + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates: cout tile fastest so the CTAs sharing an input box run together
+    int t = blockIdx.x;
+    const int ct = t % P.cout_tiles;  t /= P.cout_tiles;
+    const int tw_i = t % P.n_tiles_w; t /= P.n_tiles_w;
+    const int th_i = t % P.n_tiles_h; t /= P.n_tiles_h;
+    const int w0 = tw_i * P.tw, h0 = th_i * P.th, n0 = t * P.tn, c_out0 = ct * BN;
+    const int num_kb = P.taps * P.cin_chunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(empty_bar(s), phase ^ 1u);
+                const int tap = kb / P.cin_chunks, cc = kb - tap * P.cin_chunks;
+                const int r = tap / P.S, sx = tap - r * P.S;
+                const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + kABytes;
+                mbar_expect_tx(full_bar(s), kStageBytes);
+                tma_load_4d(a_dst, &map_x, full_bar(s), cc * BK, w0 + sx - P.pad_w, h0 + r - P.pad_h, n0);
+                tma_load_2d(b_dst, &map_w, full_bar(s), kb * BK, c_out0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(full_bar(s), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = base + s * kStageBytes;
+                const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kABytes);
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * UK * 2 / 16), bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc,
+                              (uint32_t)((kb | k) != 0));
+                umma_commit(empty_bar(s));        // frees the stage when the MMAs that read it have retired
+            }
+            umma_commit(accum_bar);               // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ----
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(t_row + (uint32_t)(c32 * 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (P.bias != nullptr) {
+                const float4* b4 = reinterpret_cast<const float4*>(P.bias + c_out0 + c32 * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = __ldg(b4 + i);
+                    f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+                }
+            }
+            if (P.slope != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : f[i] * P.slope;
+            }
+            // staging tile: one [128 rows][128 B] block per 64 output channels, 16-byte chunk j of row r at
+            // r*128 + ((j ^ (r & 7)) * 16) -- the layout a SWIZZLE_128B tensor map reads back
+            uint8_t* blk = base_ptr + (c32 >> 1) * (BM * 128) + row * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = (c32 & 1) * 4 + i;
+                uint4 o;
+                o.x = pack_bf16(f[8 * i], f[8 * i + 1]);
+                o.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+                o.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+                o.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                *reinterpret_cast<uint4*>(blk + ((j ^ (row & 7)) << 4)) = o;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to TMA
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 64; ++cb)
+                tma_store_4d(&map_y, base + cb * (BM * 128), c_out0 + cb * 64, w0, h0, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+bool make_map_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bn, int bh, int bw) {
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_map_weights(CUtensorMap* m, const void* ptr, int cout, int k, int bn) {
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+    const cuuint32_t es[2] = {1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& P,
+                   long long ctas, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)STAGES * (kABytes + BN * BK * 2) + 8 * (2 * STAGES + 2) + 1024;
+    static bool attr_set = false;           // per instantiation; benign race (idempotent)
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    conv_tc_kernel<BN, STAGES><<<(unsigned)ctas, kThreads, smem, stream>>>(mx, mw, my, P);
+    return cudaGetLastError();
+}
+
+int g_force_bn = 0;        // 0 = automatic; set through fots_b200_conv_set_tile for sweeps
+
+}  // namespace
+
+extern "C" int fots_b200_conv_set_tile(int bn) {
+    if (bn != 0 && bn != 64 && bn != 128 && bn != 256) return RROI_B200_ERR_INVALID_ARG;
+    g_force_bn = bn;
+    return RROI_B200_OK;
+}
+
+extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                                          int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope,
+                                          cudaStream_t stream) {
+    if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || R <= 0 || S <= 0 || pad_h < 0 || pad_w < 0)
+        return RROI_B200_ERR_INVALID_ARG;
+    if (Cin % BK != 0 || Cout % 64 != 0 || R > 7 || S > 7) return RROI_B200_ERR_INVALID_ARG;
+    const int Ho = H + 2 * pad_h - R + 1, Wo = W + 2 * pad_w - S + 1;
+    if (Ho <= 0 || Wo <= 0) return RROI_B200_ERR_INVALID_ARG;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return RROI_B200_ERR_INVALID_ARG;
+    if (bias && ((uintptr_t)bias & 15)) return RROI_B200_ERR_INVALID_ARG;
+    if (!encode_fn()) return RROI_B200_ERR_CUDA;
+
+    // tile box: tw*th*tn = 128, fewest tiles wins, wider boxes on ties (longer contiguous runs per TMA row)
+    int best_tw = 0, best_th = 0, best_tn = 0;
+    long long best = -1;
+    for (int tw = 128; tw >= 8; tw >>= 1)
+        for (int th = 128 / tw; th >= 1; th >>= 1) {
+            const int tn = 128 / (tw * th);
+            const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+            if (best < 0 || tiles < best) { best = tiles; best_tw = tw; best_th = th; best_tn = tn; }
+        }
+    int bn = g_force_bn ? g_force_bn : (Cout % 128 == 0 ? 128 : 64);
+    if (Cout % bn != 0) bn = 64;
+
+    ConvParams P;
+    P.tw = best_tw; P.th = best_th; P.tn = best_tn;
+    P.n_tiles_w = (Wo + P.tw - 1) / P.tw; P.n_tiles_h = (Ho + P.th - 1) / P.th; P.n_tiles_n = (N + P.tn - 1) / P.tn;
+    P.cin_chunks = Cin / BK; P.S = S; P.taps = R * S; P.pad_h = pad_h; P.pad_w = pad_w;
+    P.cout_tiles = Cout / bn; P.slope = slope; P.bias = bias;
+    const long long ctas = best * P.cout_tiles;
+    if (ctas > 0x7fffffffLL) return RROI_B200_ERR_TOO_LARGE;
+
+    CUtensorMap mx, mw, my;
+    if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
+    if (!make_map_weights(&mw, w, Cout, R * S * Cin, bn)) return RROI_B200_ERR_INVALID_ARG;
+    if (!make_map_nhwc(&my, y, N, Ho, Wo, Cout, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
+
+    cudaError_t e;
+    if (bn == 64) e = launch<64, 4>(mx, mw, my, P, ctas, stream);
+    else if (bn == 128) e = launch<128, 3>(mx, mw, my, P, ctas, stream);
+    else e = launch<256, 4>(mx, mw, my, P, ctas, stream);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}

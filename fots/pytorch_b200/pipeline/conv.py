@@ -1,0 +1,67 @@
+"""Host side of the tcgen05 implicit-GEMM convolution (include/fots_b200_pipeline.h:
+fots_b200_conv2d_nhwc_bf16; csrc/conv_tc.cu).  Used by pipeline.nets on the CUDA bf16 channels-last inference path
+for the dense stride-1 convolutions (tools/models.py:336-366 forward_ocr, :142-166 BasicBlockIn); everything else
+(CPU, fp32, training, strided / grouped / tiny-channel convolutions) stays on torch's own ops, which are the
+definition this kernel is tested against."""
+import ctypes
+
+import torch
+
+from .. import _cabi
+
+ENABLED = True            # pipeline-level switch (bench sweeps compare against the library convolution)
+
+
+def _lib():
+    L = _cabi.lib()
+    if not getattr(L, "_conv_bound", False):
+        i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+        L.fots_b200_conv2d_nhwc_bf16.restype = i
+        L.fots_b200_conv2d_nhwc_bf16.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, f, vp]
+        L.fots_b200_conv_set_tile.restype = i
+        L.fots_b200_conv_set_tile.argtypes = [i]
+        L._conv_bound = True
+    return L
+
+
+def set_tile(bn):
+    _cabi.check(_lib().fots_b200_conv_set_tile(int(bn)), "fots_b200_conv_set_tile")
+
+
+def eligible(x, conv):
+    """True when `conv` (an nn.Conv2d) applied to `x` can run on the tensor-core kernel."""
+    w = conv.weight
+    return (ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last)
+            and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.padding_mode == "zeros" and not isinstance(conv.padding, str)
+            and w.size(1) % 64 == 0 and w.size(0) % 64 == 0 and w.size(2) <= 7 and w.size(3) <= 7
+            and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)))
+
+
+def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0):
+    """act(conv2d(x, weight, bias, stride 1, padding)) -> bf16 channels-last [N, Cout, Ho, Wo].
+    x: bf16 channels-last [N, Cin, H, W]; weight: bf16 [Cout, Cin, R, S]; bias: fp32/bf16 [Cout] or None."""
+    N, Cin, H, W = x.shape
+    Cout, Cin_w, R, S = weight.shape
+    if Cin_w != Cin:
+        raise ValueError("conv2d: weight expects %d input channels, x has %d" % (Cin_w, Cin))
+    ph, pw = (padding, padding) if isinstance(padding, int) else padding
+    Ho, Wo = H + 2 * ph - R + 1, W + 2 * pw - S + 1
+    wk = weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
+    b = None if bias is None else bias.float().contiguous()
+    y = torch.empty((N, Cout, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        st = _lib().fots_b200_conv2d_nhwc_bf16(
+            x.data_ptr(), wk.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
+            N, H, W, Cin, Cout, R, S, ph, pw, float(slope), torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(st, "fots_b200_conv2d_nhwc_bf16")
+    return y
+
+
+def apply(conv, x, slope=1.0):
+    """conv(x) followed by leaky-ReLU(slope) through the tensor-core kernel when eligible, else torch."""
+    if eligible(x, conv):
+        return conv2d(x, conv.weight, conv.bias, conv.padding, slope)
+    y = conv(x)
+    return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)

@@ -87,6 +87,24 @@ int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, con
 int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo, void* y,
                                   int B, int h, int w, int H, int W, int C, cudaStream_t stream);
 
+/*
+ * Stride-1 convolution of channels-last bf16 activations on the sm_100a tensor cores (tcgen05.mma with TMEM
+ * accumulators, TMA-staged operands; csrc/conv_tc.cu), bias and leaky-ReLU fused in the epilogue.  Replaces the
+ * cuDNN calls behind nn.Conv2d for the dense convolutions of forward_ocr (tools/models.py:336-366: conv5..conv10_s)
+ * and of the feeder's BasicBlockIn stages (tools/models.py:142-166).
+ *   x     bf16 [N, H, W, Cin]            (NHWC storage; Cin % 64 == 0)
+ *   w     bf16 [Cout, R, S, Cin]         (the storage of a channels-last [Cout, Cin, R, S] weight; Cout % 64 == 0)
+ *   bias  fp32 [Cout] or NULL
+ *   y     bf16 [N, Ho, Wo, Cout],  Ho = H + 2*pad_h - R + 1,  Wo = W + 2*pad_w - S + 1
+ *   slope leaky-ReLU negative slope applied to (conv + bias): 1 = none, 0 = ReLU
+ * fp32 accumulation; the result is rounded to bf16 once.  All pointers 16-byte aligned.
+ */
+int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                               int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope,
+                               cudaStream_t stream);
+/* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
+int fots_b200_conv_set_tile(int bn);
+
 #ifdef __cplusplus
 }
 #endif
