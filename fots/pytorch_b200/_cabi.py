@@ -28,7 +28,7 @@ ABI_VERSION = 1
 # every symbol include/*.h declares
 EXPORTS = (
     "RROIAlignForwardLaucher", "RROIAlignBackwardLaucher",
-    "rroi_b200_forward", "rroi_b200_backward", "rroi_b200_expand_idx",
+    "rroi_b200_forward", "rroi_b200_backward", "rroi_b200_expand_idx", "rroi_b200_forward_bf16",
     "rroi_b200_set_tuning", "rroi_b200_get_tuning", "rroi_b200_last_cuda_error",
     "rroi_b200_strerror", "rroi_b200_abi_version", "rroi_b200_build_info",
     # include/fots_b200_pipeline.h
@@ -62,6 +62,8 @@ def lib():
     L.RROIAlignBackwardLaucher.argtypes = [vp, f, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     L.rroi_b200_forward.restype = i
     L.rroi_b200_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, vp]
+    L.rroi_b200_forward_bf16.restype = i
+    L.rroi_b200_forward_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, vp]
     L.rroi_b200_backward.restype = i
     L.rroi_b200_backward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, i, vp]
     L.rroi_b200_expand_idx.restype = i

@@ -355,7 +355,7 @@ extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const fl
             const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
             if (best < 0 || tiles < best) { best = tiles; best_tw = tw; best_th = th; best_tn = tn; }
         }
-    int bn = g_force_bn ? g_force_bn : (Cout % 128 == 0 ? 128 : 64);
+    int bn = g_force_bn ? g_force_bn : (Cout % 256 == 0 ? 256 : Cout % 128 == 0 ? 128 : 64);
     if (Cout % bn != 0) bn = 64;
 
     ConvParams P;

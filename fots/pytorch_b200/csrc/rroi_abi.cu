@@ -85,6 +85,26 @@ int rroi_b200_forward(const float* features, const float* rois, float* pooled, f
     return cuda_status(e);
 }
 
+int rroi_b200_forward_bf16(const void* features, const float* rois, void* pooled, float* idx_x, float* idx_y,
+                           int num_rois, int batch, int channels, int height, int width,
+                           int pooled_height, int pooled_width, float spatial_scale, cudaStream_t stream) {
+    if (!features || !pooled || (num_rois > 0 && !rois) || ((idx_x == nullptr) != (idx_y == nullptr)))
+        return RROI_B200_ERR_INVALID_ARG;
+    if (!dims_ok(num_rois, batch, channels, height, width, pooled_height, pooled_width)) return RROI_B200_ERR_INVALID_ARG;
+    if (channels != 32 && channels != 64 && channels != 128 && channels != 256) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(features) | reinterpret_cast<uintptr_t>(pooled)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    if (num_rois == 0) return RROI_B200_OK;
+    rroi::FwdParams p = {};
+    p.feat = static_cast<const float*>(features); p.rois = rois; p.out = static_cast<float*>(pooled);
+    p.idx_x = idx_x; p.idx_y = idx_y;
+    p.N = num_rois; p.B = batch; p.C = channels; p.H = height; p.W = width;
+    p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale;
+    p.idx_mode = idx_x ? rroi::IDX_COMPACT : rroi::IDX_NONE;
+    const cudaError_t e = rroi::launch_fwd_nhwc_bf16(p, stream);
+    if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
+    return cuda_status(e);
+}
+
 int rroi_b200_backward(const float* top_diff, const float* rois, const float* idx_x, const float* idx_y,
                        float* bottom_diff, int num_rois, int batch, int channels, int height, int width,
                        int pooled_height, int pooled_width, float spatial_scale, int layout,

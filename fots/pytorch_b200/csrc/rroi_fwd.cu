@@ -554,4 +554,163 @@ cudaError_t launch_fwd_nhwc(const FwdParams& p0, cudaStream_t s) {
     return launch_fwd_nhwc_vec<0, 1>(p, s, pdl, variant);
 }
 
+// ------------------------------------------------------------------------------ NHWC, bf16 -> bf16
+// Inference variant for the end-to-end path: the feeder hands over bf16 channels-last
+// features and the recogniser's first convolution wants bf16 channels-last input, so sampling bf16 -> bf16
+// removes the fp32 copy of the map, the fp32 pooled tensor and the cast back to bf16 (half the bytes of the
+// fp32 kernel on both sides).  Arithmetic is unchanged: the four taps are widened to fp32 (exact), blended by
+// the reference's 4-FFMA chain (kernel.cu:136-141; weights in {0, 1/4, 1/2, 1}) and the fp32 result is rounded
+// to bf16 once (round-to-nearest-even), i.e. out = bf16(reference(float(features))).
+// Same shape as the packed fp32 kernel: every lane moves 16 bytes = 8 channels, LPP = C/8 lanes span a pixel.
+__device__ __forceinline__ uint4 ldg_pred_u4(const uint4* ptr, uint32_t pred) {
+    uint4 r;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+        "@q ld.global.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+        : "l"(ptr), "r"(pred));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t blend_bf16x2(uint32_t lt, uint32_t rt, uint32_t rb, uint32_t lb, float wlt, float wrt,
+                                                 float wrb, float wlb) {
+    float lo = __fmaf_rn(__uint_as_float(lt << 16), wlt, 0.0f);
+    lo = __fmaf_rn(__uint_as_float(rt << 16), wrt, lo);
+    lo = __fmaf_rn(wrb, __uint_as_float(rb << 16), lo);
+    lo = __fmaf_rn(__uint_as_float(lb << 16), wlb, lo);
+    float hi = __fmaf_rn(__uint_as_float(lt & 0xffff0000u), wlt, 0.0f);
+    hi = __fmaf_rn(__uint_as_float(rt & 0xffff0000u), wrt, hi);
+    hi = __fmaf_rn(wrb, __uint_as_float(rb & 0xffff0000u), hi);
+    hi = __fmaf_rn(__uint_as_float(lb & 0xffff0000u), wlb, hi);
+    uint32_t out;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out) : "f"(hi), "f"(lo));
+    return out;
+}
+
+template <int CT, int TILE, int UN>
+__global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_bf16_kernel(const FwdParams p) {
+    constexpr int LPP = CT / 8;                          // lanes per pixel (16 bytes = 8 bf16 per lane)
+    constexpr int PPI = 32 / LPP;                        // pixels per warp iteration
+    constexpr int PIXW = TILE / kNhwcWarps;              // pixels per warp
+    constexpr int ITERS = PIXW / PPI;
+    static_assert(LPP >= 1 && LPP <= 32 && PIXW * kNhwcWarps == TILE && ITERS > 0 && ITERS % UN == 0, "tile shape");
+    __shared__ RoiXform sX;
+    __shared__ BinRec rec[TILE];
+
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+    const int bin0 = tile * TILE;
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (warp == 0) {
+        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        if (lane == 0) sX = X;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TILE; t += kNhwcWarps * 32) {
+        BinRec r;
+        r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
+        const int bin = bin0 + t;
+        if (bin < bins) {
+            const RoiXform X = sX;
+            const int ph = bin / p.PW, pw = bin - ph * p.PW;
+            const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+            const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+            const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+            r.pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+            r.code = C_LIVE;
+            if (in) {
+                const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+                const bool l_lt = g.flags & TAP_LT;
+                const bool l_rt = (g.flags & TAP_RT) && two_c;
+                const bool l_lb = (g.flags & TAP_LB) && two_r;
+                const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+                r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+                r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+                r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+                r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+                r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+            }
+            if (p.idx_mode == IDX_COMPACT) {
+                p.idx_x[(size_t)n * bins + bin] = in ? g.cx : 0.0f;
+                p.idx_y[(size_t)n * bins + bin] = in ? g.cy : 0.0f;
+            }
+        }
+        rec[t] = r;
+    }
+    __syncthreads();
+
+    const int sub = lane / LPP, cvl = lane % LPP;
+    const long long rowU = (long long)p.W * LPP;         // one feature row in 16-byte units
+    const uint4* fbase = reinterpret_cast<const uint4*>(p.feat) + cvl;
+    const int pw0 = warp * PIXW;
+    uint4* obase = reinterpret_cast<uint4*>(p.out) + ((size_t)n * bins + bin0 + pw0 + sub) * LPP + cvl;
+    const BinRec* rbase = rec + pw0 + sub;
+
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += UN) {
+        uint4 lt[UN], rt[UN], lb[UN], rb[UN];
+        BinRec r[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) r[u] = rbase[(it0 + u) * PPI];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const uint4* s = fbase + (long long)r[u].pix * LPP;
+            const uint4* s2 = s + rowU;
+            lt[u] = ldg_pred_u4(s, r[u].code & C_LT);
+            rt[u] = ldg_pred_u4(s + LPP, r[u].code & C_RT);
+            lb[u] = ldg_pred_u4(s2, r[u].code & C_LB);
+            rb[u] = ldg_pred_u4(s2 + LPP, r[u].code & C_RB);
+        }
+        uint32_t any_live = 0;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) any_live |= r[u].code;
+        if (any_live & C_LIVE) {                         // own basic block: keeps the UN iterations' loads batched
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const float wlt = r[u].wlt, wrt = r[u].wrt, wrb = r[u].wrb, wlb = r[u].wlb;
+                uint4 o;
+                o.x = blend_bf16x2(lt[u].x, rt[u].x, rb[u].x, lb[u].x, wlt, wrt, wrb, wlb);
+                o.y = blend_bf16x2(lt[u].y, rt[u].y, rb[u].y, lb[u].y, wlt, wrt, wrb, wlb);
+                o.z = blend_bf16x2(lt[u].z, rt[u].z, rb[u].z, lb[u].z, wlt, wrt, wrb, wlb);
+                o.w = blend_bf16x2(lt[u].w, rt[u].w, rb[u].w, lb[u].w, wlt, wrt, wrb, wlb);
+                if (r[u].code & C_LIVE) obase[(size_t)(it0 + u) * PPI * LPP] = o;
+            }
+        }
+    }
+}
+
+template <int CT>
+static cudaError_t launch_fwd_nhwc_bf16_ct(FwdParams& p, cudaStream_t s, bool pdl) {
+    const int bins = p.PH * p.PW;
+    auto go = [&](auto kernel, int tile) {
+        p.tiles = (bins + tile - 1) / tile;
+        return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, pdl);
+    };
+    constexpr int PPI = 256 / CT;                        // pixels per warp iteration
+    constexpr int I64 = 8 / PPI, I256 = 32 / PPI;        // per-warp iterations of a 64- / 256-bin tile
+    const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
+    const int variant = g_tuning.nhwc_unroll;            // 0 = by grid size, like the fp32 kernel
+    if (variant == 1 || variant == 6 || (variant == 0 && ctas256 < 148 * 4))
+        return go(rroi_fwd_nhwc_bf16_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
+    return go(rroi_fwd_nhwc_bf16_kernel<CT, 256, (I256 >= 4 ? 4 : 2)>, 256);
+}
+
+cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p0, cudaStream_t s) {
+    FwdParams p = p0;
+    p.cgroups = 1;
+    const bool pdl = g_tuning.use_pdl != 0;
+    switch (p.C) {
+        case 32:  return launch_fwd_nhwc_bf16_ct<32>(p, s, pdl);
+        case 64:  return launch_fwd_nhwc_bf16_ct<64>(p, s, pdl);
+        case 128: return launch_fwd_nhwc_bf16_ct<128>(p, s, pdl);
+        case 256: return launch_fwd_nhwc_bf16_ct<256>(p, s, pdl);
+        default:  return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace rroi

@@ -49,6 +49,8 @@ extern Tuning g_tuning;
 
 cudaError_t launch_fwd_nchw(const FwdParams& p, cudaStream_t s);
 cudaError_t launch_fwd_nhwc(const FwdParams& p, cudaStream_t s);
+// bf16 features / bf16 pooled, channels-last, C in {32,64,128,256}; p.feat / p.out alias the bf16 buffers
+cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p, cudaStream_t s);
 cudaError_t launch_bwd_nchw(const BwdParams& p, cudaStream_t s);
 cudaError_t launch_bwd_nhwc(const BwdParams& p, cudaStream_t s);
 // the reference-layout backward that honours caller-supplied [N,C,PH,PW] centres element by element

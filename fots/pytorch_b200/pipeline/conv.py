@@ -4,12 +4,13 @@ for the dense stride-1 convolutions (tools/models.py:336-366 forward_ocr, :142-1
 (CPU, fp32, training, strided / grouped / tiny-channel convolutions) stays on torch's own ops, which are the
 definition this kernel is tested against."""
 import ctypes
+import os
 
 import torch
 
 from .. import _cabi
 
-ENABLED = True            # pipeline-level switch (bench sweeps compare against the library convolution)
+ENABLED = os.environ.get("FOTS_B200_TC_CONV", "1") != "0"   # A/B switch against the library convolution (sweeps)
 
 
 def _lib():

@@ -13,7 +13,7 @@ protocol -- while the backbone and the detection heads are still computed for re
 import numpy as np
 import torch
 
-from ..rroi_align.functions.rroi_align import rroi_align
+from ..rroi_align.functions.rroi_align import rroi_align, rroi_align_bf16
 from .decode import greedy_ctc_decode
 from .rois import boxes_to_rois
 from .shard import all_gather_records, pack_records, shard_range
@@ -58,10 +58,15 @@ class FOTSPipeline:
         x = images.contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             seg, rbox, angle, feats = self.net(x)
-        focr = feats[1].float().contiguous(memory_format=torch.channels_last)     # fp32 sampler input
         bidx = torch.arange(b, device=quads.device, dtype=torch.int32).repeat_interleave(R)
         rois = boxes_to_rois(quads.reshape(b * R, 9), bidx)
-        pooled = rroi_align(focr, rois, self.ph, self.pw, self.scale)             # [b*R, 64, PH, PW] channels-last
+        focr = feats[1]
+        if focr.dtype == torch.bfloat16 and focr.size(1) in (32, 64, 128, 256):
+            # bf16 map in, bf16 channels-last pooled out: what conv5 consumes, no fp32 copies either side
+            pooled = rroi_align_bf16(focr, rois, self.ph, self.pw, self.scale)
+        else:
+            focr = focr.float().contiguous(memory_format=torch.channels_last)    # fp32 sampler input
+            pooled = rroi_align(focr, rois, self.ph, self.pw, self.scale)         # [b*R, 64, PH, PW] channels-last
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             logp = self.net.forward_ocr(pooled)                                   # [b*R, nclass, T]
         ids, lens = greedy_ctc_decode(logp)

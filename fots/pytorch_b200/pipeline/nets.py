@@ -14,6 +14,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import conv as tc
 from . import fused
 
 
@@ -186,13 +187,13 @@ class FOTSNet(nn.Module):
 
     # ---- consumer A ---------------------------------------------------------------------------
     def forward_ocr(self, x):
-        a = self.leaky
-        x = _in_act(self.batch5, self.conv5(x), 0.01)
-        x = a(self.conv6(a(self.conv6(x))))
-        x = _in_act(self.batch7, self.conv7(self.max2(x)), 0.01)
-        x = a(self.conv8(a(self.conv8(x))))
-        x = a(self.conv9(a(self.conv9(x))))
-        x = _in_act(self.batch10_s, self.conv10_s(self.max2(x)), 0.01)
+        # tc.apply = conv + leaky-ReLU in one tcgen05 kernel on the bf16 channels-last inference path, torch otherwise
+        x = _in_act(self.batch5, tc.apply(self.conv5, x), 0.01)
+        x = tc.apply(self.conv6, tc.apply(self.conv6, x, 0.01), 0.01)
+        x = _in_act(self.batch7, tc.apply(self.conv7, self.max2(x)), 0.01)
+        x = tc.apply(self.conv8, tc.apply(self.conv8, x, 0.01), 0.01)
+        x = tc.apply(self.conv9, tc.apply(self.conv9, x, 0.01), 0.01)
+        x = _in_act(self.batch10_s, tc.apply(self.conv10_s, self.max2(x)), 0.01)
         x = self.conv11(self.drop1(x)).squeeze(2)            # [N, nclass, T]
         return F.log_softmax(x.float(), dim=1)
 

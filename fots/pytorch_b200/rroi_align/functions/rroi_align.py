@@ -114,6 +114,29 @@ def rroi_align(features, rois, pooled_height, pooled_width, spatial_scale):
     return _RRoiAlignOp.apply(features, rois, int(pooled_height), int(pooled_width), float(spatial_scale), None)
 
 
+def rroi_align_bf16(features, rois, pooled_height, pooled_width, spatial_scale):
+    """Inference-only bf16 RoIRotate (rroi_b200_forward_bf16): bf16 channels-last features [B, C, H, W] ->
+    bf16 channels-last pooled [N, C, PH, PW], C in {32, 64, 128, 256}.  Equal to
+    rroi_align(features.float(), ...) rounded to bf16; not differentiable (training uses the fp32 op)."""
+    if not (features.is_cuda and rois.is_cuda and features.dtype == torch.bfloat16 and rois.dtype == torch.float32):
+        raise TypeError("rroi_align_bf16: CUDA bf16 features and fp32 rois required")
+    if features.dim() != 4 or rois.dim() != 2 or rois.size(1) != 6:
+        raise ValueError("rroi_align_bf16: features [B, C, H, W], rois [N, 6]")
+    ph, pw = int(pooled_height), int(pooled_width)
+    features = features.contiguous(memory_format=torch.channels_last)
+    rois = rois.contiguous()
+    B, C, H, W = features.shape
+    N = rois.size(0)
+    with torch.cuda.device(features.device):
+        pooled = torch.empty((N, C, ph, pw), dtype=torch.bfloat16, device=features.device,
+                             memory_format=torch.channels_last)
+        if N > 0:
+            st = _cabi.lib().rroi_b200_forward_bf16(features.data_ptr(), rois.data_ptr(), pooled.data_ptr(), None, None,
+                                                    N, B, C, H, W, ph, pw, float(spatial_scale), _stream(features.device))
+            _cabi.check(st, "rroi_b200_forward_bf16")
+    return pooled
+
+
 class RRoiAlignFunction(object):
     """Call-compatible stand-in for the reference's legacy Function instance.
 

@@ -82,6 +82,18 @@ int rroi_b200_forward(const float* features, const float* rois, float* pooled, f
                       cudaStream_t stream);
 
 /*
+ * bf16 forward for the inference pipeline (hand the recogniser's first convolution the
+ * dtype and layout it wants).  Channels-last only:
+ *   features  bf16 [batch,height,width,channels]     pooled  bf16 [num_rois,PH,PW,channels]
+ *   channels in {32, 64, 128, 256}; both pointers 16-byte aligned; rois / idx_x / idx_y fp32 as above.
+ * Same geometry and the same fp32 4-product sum as rroi_b200_forward (rroi_align_kernel.cu:86-141) on the
+ * widened taps; the fp32 result is rounded to bf16 once (RNE): pooled == bf16(rroi_b200_forward(float(features))).
+ */
+int rroi_b200_forward_bf16(const void* features, const float* rois, void* pooled, float* idx_x, float* idx_y,
+                           int num_rois, int batch, int channels, int height, int width,
+                           int pooled_height, int pooled_width, float spatial_scale, cudaStream_t stream);
+
+/*
  * v2 backward (replaces rroi_align_backward_cuda, rroi_align_cuda.h:6-8).
  *   top_diff     pooled-shaped gradient, in `layout`
  *   idx_x/y      the compact centres saved by rroi_b200_forward, or NULL/NULL to recompute them

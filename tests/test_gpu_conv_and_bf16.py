@@ -1,0 +1,142 @@
+"""GPU parity of the two kernels that join RoIRotate to the recogniser on the bf16 inference path:
+
+* rroi_b200_forward_bf16 against the CPU oracle: bit-exact after one bf16 rounding;
+* fots_b200_conv2d_nhwc_bf16 (tcgen05 implicit GEMM, csrc/conv_tc.cu) against torch's fp32 convolution of the same
+  bf16-rounded operands: tolerance = one bf16 rounding of the result (2^-8 relative) plus fp32 sum-order noise.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers as Hh
+import workloads as WL
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_bits(t):
+    return t.contiguous().view(torch.int16).cpu().numpy()
+
+
+@pytest.mark.parametrize("C,B,n_per,ph,pw,scale", [(64, 1, 64, 8, 64, 0.25), (256, 1, 64, 8, 64, 0.25), (32, 2, 9, 8, 48, 0.25),
+                                                    (128, 3, 17, 4, 33, 0.5), (64, 4, 64, 8, 64, 0.25)])
+def test_bf16_forward_is_the_rounded_fp32_forward(oracle, cuda, C, B, n_per, ph, pw, scale):
+    """pooled_bf16 == bf16(oracle(float(features_bf16))) bit for bit, including the zero tail (pw > roi width) and
+    RoIs overhanging the border; small grids take the 64-bin-tile kernel, the 4-image case the 256-bin one."""
+    from fots.pytorch_b200 import _cabi
+    from fots.pytorch_b200.rroi_align.functions.rroi_align import rroi_align_bf16
+    H, W = 180, 320
+    feats = torch.from_numpy(WL.features(C + B, B, C, H, W)).to(cuda).to(torch.bfloat16)
+    rois = np.concatenate([WL.random_rois(7 + i, n_per, i) for i in range(B)], 0)
+    rois[0, 1:3] = (3.0, 5.0)                                   # hangs over the top-left corner
+    x = feats.contiguous(memory_format=torch.channels_last)
+    want, _, _ = oracle.forward(feats.float().cpu().numpy(), rois, ph, pw, scale, threads=0)
+    rois[-1, 0] = B + 3                                          # batch index out of range -> zeros (the oracle,
+    want[-1] = 0.0                                               # like the reference, would read out of bounds)
+    want_bits = _bf16_bits(torch.from_numpy(want).to(torch.bfloat16))
+    for variant in (0, 1, 5):
+        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, variant)
+        try:
+            got = rroi_align_bf16(x, torch.from_numpy(rois).to(cuda), ph, pw, scale)
+        finally:
+            _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, 0)
+        assert got.dtype == torch.bfloat16 and got.shape == (rois.shape[0], C, ph, pw)
+        assert got.is_contiguous(memory_format=torch.channels_last)
+        got_bits = _bf16_bits(got.contiguous())                  # logical NCHW order, like the oracle
+        neq = got_bits != want_bits
+        assert not neq.any(), "variant %d: %d / %d bf16 values differ" % (variant, int(neq.sum()), neq.size)
+
+
+def test_bf16_forward_rejects_what_it_cannot_do(cuda):
+    from fots.pytorch_b200 import _cabi
+    from fots.pytorch_b200.rroi_align.functions.rroi_align import rroi_align_bf16
+    rois = torch.tensor([[0, 10, 10, 8, 16, 0]], dtype=torch.float32, device=cuda)
+    with pytest.raises(TypeError):
+        rroi_align_bf16(torch.zeros(1, 64, 8, 8, device=cuda), rois, 8, 16, 1.0)           # fp32 features
+    with pytest.raises(_cabi.RRoiAlignError):
+        rroi_align_bf16(torch.zeros(1, 48, 8, 8, device=cuda, dtype=torch.bfloat16), rois, 8, 16, 1.0)   # C = 48
+    out = rroi_align_bf16(torch.zeros(1, 64, 8, 8, device=cuda, dtype=torch.bfloat16), rois[:0], 8, 16, 1.0)
+    assert out.shape == (0, 64, 8, 16)
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, R, S, pad_h, pad_w, bias, slope
+    (1, 2, 64, 64, 64, 1, 1, 0, 0, False, 1.0),          # plain GEMM, one tile
+    (2, 4, 64, 128, 128, 1, 1, 0, 0, True, 1.0),
+    (2, 4, 64, 64, 64, 3, 3, 1, 1, False, 1.0),          # zero padding comes from the TMA out-of-bounds fill
+    (3, 8, 64, 64, 128, 3, 3, 1, 1, False, 1.0),         # conv5
+    (3, 8, 64, 128, 128, 3, 3, 1, 1, True, 0.01),        # conv6 + leaky
+    (3, 4, 64, 128, 256, 3, 3, 1, 1, False, 1.0),        # conv7
+    (3, 4, 64, 256, 256, 3, 3, 1, 1, False, 0.01),       # conv8 / conv9 + leaky
+    (5, 2, 64, 256, 256, 2, 3, 0, 1, True, 1.0),         # conv10_s: 2x3, pad (0,1); tiles span two RoIs
+    (1, 45, 80, 64, 64, 3, 3, 1, 1, False, 0.0),         # ragged tiles in h and w, ReLU
+    (2, 23, 37, 128, 192, 3, 3, 1, 1, True, 0.0),        # odd sizes, Cout = 3 x 64
+    (1, 90, 160, 128, 128, 3, 3, 1, 1, False, 1.0),      # layer2 block at 720p
+    (2, 5, 9, 64, 64, 5, 5, 2, 2, True, 1.0),            # 25 taps, image smaller than a tile
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_tcgen05_conv_matches_torch_fp32(cuda, case, bn):
+    from fots.pytorch_b200.pipeline import conv as TC
+    N, H, W, Cin, Cout, R, S, ph, pw, bias, slope = case
+    if bn and Cout % bn:
+        pytest.skip("Cout is not a multiple of the forced tile")
+    g = torch.Generator().manual_seed(N * 131 + Cin + Cout + R)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, R, S, generator=g) / (Cin * R * S) ** 0.5).to(cuda).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g).to(cuda) if bias else None
+    TC.set_tile(bn)
+    try:
+        y = TC.conv2d(x, w, b, (ph, pw), slope)
+    finally:
+        TC.set_tile(0)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float(), w.float(), b, 1, (ph, pw))
+    if slope != 1.0:
+        ref = F.leaky_relu(ref, slope)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    err = (y.float() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3 * float(ref.abs().max())      # one bf16 rounding + fp32 sum-order noise
+    assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
+
+
+def test_tcgen05_conv_argument_checks(cuda):
+    from fots.pytorch_b200 import _cabi
+    from fots.pytorch_b200.pipeline import conv as TC
+    x = torch.zeros(1, 48, 8, 8, device=cuda, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.zeros(64, 48, 3, 3, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(_cabi.RRoiAlignError):
+        TC.conv2d(x, w, None, (1, 1))                                # Cin % 64 != 0
+    conv = torch.nn.Conv2d(48, 64, 3, 1, 1).to(cuda).to(torch.bfloat16)
+    assert not TC.eligible(x, conv)
+    conv = torch.nn.Conv2d(64, 64, 3, 2, 1).to(cuda).to(torch.bfloat16)
+    x = torch.zeros(1, 64, 8, 8, device=cuda, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert not TC.eligible(x, conv)                                  # stride 2 stays on the library path
+    conv = torch.nn.Conv2d(64, 64, 3, 1, 1).to(cuda).to(torch.bfloat16)
+    with torch.no_grad():
+        assert TC.eligible(x, conv)
+        assert TC.apply(conv, x, 0.01).shape == (1, 64, 8, 8)
+
+
+def test_recogniser_on_tensor_cores_matches_library_path(cuda):
+    """forward_ocr (tools/models.py:334-379) on bf16 channels-last input: the tcgen05 convolutions (+ fused leaky-ReLU)
+    against the same network on torch's library convolutions; both round every layer to bf16 once."""
+    from fots.pytorch_b200.pipeline import FOTSNet
+    from fots.pytorch_b200.pipeline import conv as TC
+    torch.manual_seed(0)
+    net = FOTSNet(attention=True, nclass=89).to_b200(cuda, inference=True)
+    pooled = torch.randn(6, 64, 8, 64, device=cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert TC.eligible(pooled, net.conv5)
+        a = net.forward_ocr(pooled)
+        TC.ENABLED = False
+        try:
+            b = net.forward_ocr(pooled)
+        finally:
+            TC.ENABLED = True
+    assert a.shape == b.shape == (6, 89, 64)
+    assert float((a - b).abs().max()) < 0.15 and float((a - b).abs().mean()) < 0.02      # log-probabilities
+    assert float((a.argmax(1) == b.argmax(1)).float().mean()) > 0.9
