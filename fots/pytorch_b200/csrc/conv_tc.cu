@@ -12,8 +12,9 @@
 // in shared memory as a K-major 128x64 tile in the 128-byte swizzle the UMMA descriptor expects.
 //
 // CTA = 6 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers
-// -> bias/activation -> bf16 -> swizzled shared tile -> TMA store).  One output tile per CTA; two CTAs are resident
-// per SM for BN <= 128 so one CTA's epilogue overlaps the other's main loop.
+// -> bias/activation -> bf16 -> swizzled shared block -> TMA store).  Persistent: one CTA per SM walks the tile
+// list; the accumulator is double-buffered in TMEM (2 x BN columns) and the producer runs ahead across tile
+// boundaries, so the epilogue of tile i and the pipeline fill of tile i+1 hide behind the MMAs.
 #include "../../../include/fots_b200_pipeline.h"
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -31,7 +32,9 @@ constexpr uint32_t kABytes = BM * BK * 2;
 
 struct ConvParams {
     int n_tiles_w, n_tiles_h, n_tiles_n;   // tile grid over (Wo, Ho, N)
-    int tw, th, tn;                        // tile box (tw*th*tn == 128)
+    int tw, th, tn;                        // 128-pixel sub-tile box (tw*th*tn == 128)
+    int cta_h, cta_n;                      // CTA tile extent in h and n: MT sub-tiles stacked along h (tn == 1) or n
+    int sub_h, sub_n;                      // offset of sub-tile j from sub-tile j-1
     int cin_chunks;                        // Cin / 64
     int S;                                 // filter width (taps = R*S)
     int taps;
@@ -133,13 +136,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&p);
 }
 
-template <int BN, int STAGES>
+template <int MT, int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const ConvParams P) {
     constexpr uint32_t kBBytes = BN * BK * 2;
-    constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    static_assert(BM * BN * 2 <= STAGES * kStageBytes, "output staging tile must fit in the operand stages");
+    constexpr uint32_t kStageBytes = MT * kABytes + kBBytes;     // MT pixel sub-tiles share one weight tile
+    constexpr uint32_t kOutBlk = BM * 128;                       // staging block: 128 pixels x 64 channels of bf16
+    constexpr uint32_t kAccCols = MT * BN;                       // one accumulator set: MT sub-tiles x BN columns
+    constexpr uint32_t kTmemCols = 2 * kAccCols;                 // two sets: epilogue of tile i overlaps MMA of i+1
+    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -147,33 +153,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
     uint8_t* const base_ptr = smem_raw + (base - raw);
-    const uint32_t bars = base + STAGES * kStageBytes;            // full[STAGES], empty[STAGES], accum, tmem slot
+    const uint32_t out_stage = base + STAGES * kStageBytes;       // 2 staging blocks for the TMA stores
+    uint8_t* const out_ptr = base_ptr + STAGES * kStageBytes;
+    const uint32_t bars = out_stage + 2 * kOutBlk;                // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
-    volatile uint32_t* const tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * kStageBytes + 8 * (2 * STAGES + 1));
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    volatile uint32_t* const tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * kStageBytes + 2 * kOutBlk + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates: cout tile fastest so the CTAs sharing an input box run together
-    int t = blockIdx.x;
-    const int ct = t % P.cout_tiles;  t /= P.cout_tiles;
-    const int tw_i = t % P.n_tiles_w; t /= P.n_tiles_w;
-    const int th_i = t % P.n_tiles_h; t /= P.n_tiles_h;
-    const int w0 = tw_i * P.tw, h0 = th_i * P.th, n0 = t * P.tn, c_out0 = ct * BN;
     const int num_kb = P.taps * P.cin_chunks;
+    const int num_tiles = P.cout_tiles * P.n_tiles_w * P.n_tiles_h * P.n_tiles_n;
+
+    struct Tile { int w0, h0, n0, c_out0; };
+    // cout tile fastest: the CTAs that share an input box run at the same time (L2 reuse)
+    auto decode = [&](int t) {
+        Tile T;
+        const int ct = t % P.cout_tiles;  t /= P.cout_tiles;
+        const int tw_i = t % P.n_tiles_w; t /= P.n_tiles_w;
+        const int th_i = t % P.n_tiles_h; t /= P.n_tiles_h;
+        T.w0 = tw_i * P.tw; T.h0 = th_i * P.cta_h; T.n0 = t * P.cta_n; T.c_out0 = ct * BN;
+        return T;
+    };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)BN) : "memory");
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -183,92 +198,126 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---- TMA producer ----
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(empty_bar(s), phase ^ 1u);
-                const int tap = kb / P.cin_chunks, cc = kb - tap * P.cin_chunks;
-                const int r = tap / P.S, sx = tap - r * P.S;
-                const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + kABytes;
-                mbar_expect_tx(full_bar(s), kStageBytes);
-                tma_load_4d(a_dst, &map_x, full_bar(s), cc * BK, w0 + sx - P.pad_w, h0 + r - P.pad_h, n0);
-                tma_load_2d(b_dst, &map_w, full_bar(s), kb * BK, c_out0);
+            // ---- TMA producer: runs ahead of the MMA by up to STAGES k-blocks, across tile boundaries ----
+            uint32_t it = 0;                                     // global k-block counter -> stage / phase
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const Tile T = decode(tile);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t phase = (it / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), phase ^ 1u);
+                    const int tap = kb / P.cin_chunks, cc = kb - tap * P.cin_chunks;
+                    const int r = tap / P.S, sx = tap - r * P.S;
+                    const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + MT * kABytes;
+                    mbar_expect_tx(full_bar(s), kStageBytes);
+#pragma unroll
+                    for (int j = 0; j < MT; ++j)
+                        tma_load_4d(a_dst + j * kABytes, &map_x, full_bar(s), cc * BK, T.w0 + sx - P.pad_w,
+                                    T.h0 + j * P.sub_h + r - P.pad_h, T.n0 + j * P.sub_n);
+                    tma_load_2d(b_dst, &map_w, full_bar(s), kb * BK, T.c_out0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---- MMA issuer ----
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(full_bar(s), phase);
+            uint32_t it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                mbar_wait(tempty_bar(as), ((local >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = base + s * kStageBytes;
-                const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kABytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccCols;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t phase = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = base + s * kStageBytes;
+                    const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + MT * kABytes);
 #pragma unroll
-                for (int k = 0; k < BK / UK; ++k)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * UK * 2 / 16), bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc,
-                              (uint32_t)((kb | k) != 0));
-                umma_commit(empty_bar(s));        // frees the stage when the MMAs that read it have retired
+                    for (int k = 0; k < BK / UK; ++k)
+#pragma unroll
+                        for (int j = 0; j < MT; ++j)
+                            umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(j * (kABytes / 16) + k * UK * 2 / 16),
+                                      bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(empty_bar(s));        // frees the stage when the MMAs that read it have retired
+                }
+                umma_commit(tfull_bar(as));           // accumulator complete
             }
-            umma_commit(accum_bar);               // accumulator complete
         }
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ----
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool issuer = (warp == 2 && lane == 0);
+        uint32_t blk = 0;                                        // staging blocks issued so far (buffer = blk & 1)
+        uint32_t local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const Tile T = decode(tile);
+            const int as = local & 1;
+            mbar_wait(tfull_bar(as), (local >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccCols;
 #pragma unroll 1
-        for (int c32 = 0; c32 < BN / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(t_row + (uint32_t)(c32 * 32), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float f[32];
+            for (int cb = 0; cb < MT * BN / 64; ++cb, ++blk) {         // cb walks sub-tile j = cb / (BN/64), then channels
+                const int j = cb / (BN / 64), cblk = cb - j * (BN / 64);
+                // the TMA store issued two blocks ago has finished reading this staging buffer
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                uint8_t* const srow = out_ptr + (blk & 1) * kOutBlk + row * 128;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            if (P.bias != nullptr) {
-                const float4* b4 = reinterpret_cast<const float4*>(P.bias + c_out0 + c32 * 32);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(cb * 64 + half * 32), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cb == MT * BN / 64 - 1 && half == 1) {
+                        // last read of this accumulator: hand it back to the MMA warp before the stores
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+                    }
+                    float f[32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 b = __ldg(b4 + i);
-                    f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (P.bias != nullptr) {
+                        const float4* b4 = reinterpret_cast<const float4*>(P.bias + T.c_out0 + cblk * 64 + half * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = __ldg(b4 + i);
+                            f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+                        }
+                    }
+                    if (P.slope != 1.0f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : f[i] * P.slope;
+                    }
+                    // staging block [128 rows][128 B]: 16-byte chunk j of row r sits at r*128 + ((j ^ (r & 7)) * 16),
+                    // the layout a SWIZZLE_128B tensor map reads back
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ch = half * 4 + i;
+                        uint4 o;
+                        o.x = pack_bf16(f[8 * i], f[8 * i + 1]);
+                        o.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+                        o.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+                        o.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+                        *reinterpret_cast<uint4*>(srow + ((ch ^ (row & 7)) << 4)) = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to TMA
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (issuer) {
+                    tma_store_4d(&map_y, out_stage + (blk & 1) * kOutBlk, T.c_out0 + cblk * 64, T.w0, T.h0 + j * P.sub_h,
+                                 T.n0 + j * P.sub_n);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
-            if (P.slope != 1.0f) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : f[i] * P.slope;
-            }
-            // staging tile: one [128 rows][128 B] block per 64 output channels, 16-byte chunk j of row r at
-            // r*128 + ((j ^ (r & 7)) * 16) -- the layout a SWIZZLE_128B tensor map reads back
-            uint8_t* blk = base_ptr + (c32 >> 1) * (BM * 128) + row * 128;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = (c32 & 1) * 4 + i;
-                uint4 o;
-                o.x = pack_bf16(f[8 * i], f[8 * i + 1]);
-                o.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-                o.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-                o.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-                *reinterpret_cast<uint4*>(blk + ((j ^ (row & 7)) << 4)) = o;
-            }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to TMA
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-#pragma unroll 1
-            for (int cb = 0; cb < BN / 64; ++cb)
-                tma_store_4d(&map_y, base + cb * (BM * 128), c_out0 + cb * 64, w0, h0, n0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -310,17 +359,26 @@ bool make_map_weights(CUtensorMap* m, const void* ptr, int cout, int k, int bn) 
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
+template <int MT, int BN, int STAGES>
 cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& P,
                    long long ctas, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)STAGES * (kABytes + BN * BK * 2) + 8 * (2 * STAGES + 2) + 1024;
+    constexpr size_t smem = (size_t)STAGES * (MT * kABytes + BN * BK * 2) + 2 * BM * 128 + 8 * (2 * STAGES + 5) + 1024;
+    static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
     static bool attr_set = false;           // per instantiation; benign race (idempotent)
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MT, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<BN, STAGES><<<(unsigned)ctas, kThreads, smem, stream>>>(mx, mw, my, P);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms = n;
+    }
+    // persistent: one CTA per SM walks the tile list with stride gridDim.x
+    const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
+    conv_tc_kernel<MT, BN, STAGES><<<grid, kThreads, smem, stream>>>(mx, mw, my, P);
     return cudaGetLastError();
 }
 
@@ -346,24 +404,33 @@ extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const fl
     if (bias && ((uintptr_t)bias & 15)) return RROI_B200_ERR_INVALID_ARG;
     if (!encode_fn()) return RROI_B200_ERR_CUDA;
 
-    // tile box: tw*th*tn = 128, fewest tiles wins, wider boxes on ties (longer contiguous runs per TMA row)
+    int bn = g_force_bn ? g_force_bn : (Cout % 256 == 0 ? 256 : Cout % 128 == 0 ? 128 : 64);
+    if (Cout % bn != 0) bn = 64;
+    // BN < 256: two pixel sub-tiles per CTA share the weight tile (same bytes per MMA cycle as 128 x 256, and enough
+    // MMAs per k-block to hide the single-thread issue path)
+    const int mt = bn == 256 ? 1 : 2;
+
+    // sub-tile box: tw*th*tn = 128 pixels; the CTA stacks mt of them along h (tn == 1) or n.  Fewest CTA tiles wins,
+    // wider boxes on ties (longer contiguous runs per TMA row).
     int best_tw = 0, best_th = 0, best_tn = 0;
     long long best = -1;
     for (int tw = 128; tw >= 8; tw >>= 1)
         for (int th = 128 / tw; th >= 1; th >>= 1) {
             const int tn = 128 / (tw * th);
-            const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+            const int ch = tn > 1 ? th : th * mt, cn = tn > 1 ? tn * mt : tn;
+            const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + ch - 1) / ch) * ((N + cn - 1) / cn);
             if (best < 0 || tiles < best) { best = tiles; best_tw = tw; best_th = th; best_tn = tn; }
         }
-    int bn = g_force_bn ? g_force_bn : (Cout % 256 == 0 ? 256 : Cout % 128 == 0 ? 128 : 64);
-    if (Cout % bn != 0) bn = 64;
 
     ConvParams P;
     P.tw = best_tw; P.th = best_th; P.tn = best_tn;
-    P.n_tiles_w = (Wo + P.tw - 1) / P.tw; P.n_tiles_h = (Ho + P.th - 1) / P.th; P.n_tiles_n = (N + P.tn - 1) / P.tn;
+    const bool stack_n = best_tn > 1;
+    P.cta_h = stack_n ? P.th : P.th * mt;  P.cta_n = stack_n ? P.tn * mt : P.tn;
+    P.sub_h = stack_n ? 0 : P.th;          P.sub_n = stack_n ? P.tn : 0;
+    P.n_tiles_w = (Wo + P.tw - 1) / P.tw; P.n_tiles_h = (Ho + P.cta_h - 1) / P.cta_h; P.n_tiles_n = (N + P.cta_n - 1) / P.cta_n;
     P.cin_chunks = Cin / BK; P.S = S; P.taps = R * S; P.pad_h = pad_h; P.pad_w = pad_w;
     P.cout_tiles = Cout / bn; P.slope = slope; P.bias = bias;
-    const long long ctas = best * P.cout_tiles;
+    const long long ctas = (long long)P.n_tiles_w * P.n_tiles_h * P.n_tiles_n * P.cout_tiles;
     if (ctas > 0x7fffffffLL) return RROI_B200_ERR_TOO_LARGE;
 
     CUtensorMap mx, mw, my;
@@ -372,9 +439,9 @@ extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const fl
     if (!make_map_nhwc(&my, y, N, Ho, Wo, Cout, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
 
     cudaError_t e;
-    if (bn == 64) e = launch<64, 4>(mx, mw, my, P, ctas, stream);
-    else if (bn == 128) e = launch<128, 3>(mx, mw, my, P, ctas, stream);
-    else e = launch<256, 4>(mx, mw, my, P, ctas, stream);
+    if (bn == 64) e = launch<2, 64, 4>(mx, mw, my, P, ctas, stream);
+    else if (bn == 128) e = launch<2, 128, 4>(mx, mw, my, P, ctas, stream);
+    else e = launch<1, 256, 4>(mx, mw, my, P, ctas, stream);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
 }

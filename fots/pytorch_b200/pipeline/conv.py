@@ -65,4 +65,6 @@ def apply(conv, x, slope=1.0):
     if eligible(x, conv):
         return conv2d(x, conv.weight, conv.bias, conv.padding, slope)
     y = conv(x)
-    return y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
+    if slope == 1.0:
+        return y
+    return torch.relu(y) if slope == 0.0 else torch.nn.functional.leaky_relu(y, slope)

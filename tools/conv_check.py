@@ -79,9 +79,15 @@ if __name__ == "__main__":
     print("ALL OK" if ok else "SOME FAILED", flush=True)
     if ok and len(sys.argv) > 1 and sys.argv[1] == "bench":
         for bn in (128, 256, 64):
-            bench(512, 4, 64, 256, 256, 3, 3, 1, 1, bn)
-        bench(512, 8, 64, 128, 128, 3, 3, 1, 1, 128)
+            bench(512, 4, 64, 256, 256, 3, 3, 1, 1, bn)          # conv8 / conv9
+        bench(512, 8, 64, 64, 128, 3, 3, 1, 1, 128)              # conv5
+        bench(512, 8, 64, 128, 128, 3, 3, 1, 1, 128)             # conv6
         bench(512, 8, 64, 128, 128, 3, 3, 1, 1, 64)
-        bench(8, 180, 320, 64, 64, 3, 3, 1, 1, 64)
-        bench(8, 90, 160, 128, 128, 3, 3, 1, 1, 128)
+        bench(512, 4, 64, 128, 256, 3, 3, 1, 1, 256)             # conv7
+        bench(512, 4, 64, 128, 256, 3, 3, 1, 1, 128)
+        bench(512, 2, 64, 256, 256, 2, 3, 0, 1, 256)             # conv10_s
+        bench(8, 360, 640, 64, 64, 3, 3, 1, 1, 64)               # layer0_1[0]
+        bench(8, 180, 320, 64, 64, 3, 3, 1, 1, 64)               # layer1 blocks
+        bench(8, 90, 160, 128, 128, 3, 3, 1, 1, 128)             # layer2 blocks
+        bench(8, 90, 160, 128, 128, 3, 3, 1, 1, 64)
     sys.exit(0 if ok else 1)
