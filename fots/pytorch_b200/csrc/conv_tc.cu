@@ -40,8 +40,11 @@ struct ConvParams {
     int taps;
     int pad_h, pad_w;
     int cout_tiles;                        // Cout / BN
+    int chunk;                             // consecutive tiles per CTA visit
     float slope;                           // leaky slope; 1 = identity
     const float* bias;                     // [Cout] or nullptr
+    double* stats;                         // [N, Cout, 2] (sum, sum of squares) of the bf16 output per image, or nullptr
+    int N, Ho, Wo, Cout;                   // output extent (to mask the rows of ragged tiles out of the statistics)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,7 +169,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = P.taps * P.cin_chunks;
     const int num_tiles = P.cout_tiles * P.n_tiles_w * P.n_tiles_h * P.n_tiles_n;
-
+    // This CTA's tiles: runs of P.chunk consecutive tiles, the runs dealt round-robin to the CTAs.  chunk = 1 keeps all
+    // CTAs on one front through the tensor (best L2/DRAM locality); with fused statistics longer runs keep a CTA
+    // inside one image so that its running sums are flushed rarely.
+    const int run_stride = (int)gridDim.x * P.chunk;
+    auto tile_at = [&](int i) { return (i / P.chunk) * run_stride + (int)blockIdx.x * P.chunk + i % P.chunk; };
     struct Tile { int w0, h0, n0, c_out0; };
     // cout tile fastest: the CTAs that share an input box run at the same time (L2 reuse)
     auto decode = [&](int t) {
@@ -200,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0) {
             // ---- TMA producer: runs ahead of the MMA by up to STAGES k-blocks, across tile boundaries ----
             uint32_t it = 0;                                     // global k-block counter -> stage / phase
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int ti = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++ti)) {
                 const Tile T = decode(tile);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -222,7 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0) {
             // ---- MMA issuer ----
             uint32_t it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            for (int ti = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++ti), ++local) {
                 const int as = local & 1;
                 mbar_wait(tempty_bar(as), ((local >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -252,7 +259,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const bool issuer = (warp == 2 && lane == 0);
         uint32_t blk = 0;                                        // staging blocks issued so far (buffer = blk & 1)
         uint32_t local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        // running InstanceNorm sums of this thread: [64-channel block][sum, sumsq of channel 2*lane, of 2*lane + 1]
+        float st_acc[BN / 64][4];
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i) st_acc[i][0] = st_acc[i][1] = st_acc[i][2] = st_acc[i][3] = 0.f;
+        int st_key = -1;                                         // image * cout_tiles + cout tile the sums belong to
+        auto stats_flush = [&]() {
+            if (st_key >= 0) {
+                const int n = st_key / P.cout_tiles, ct = st_key - n * P.cout_tiles;
+#pragma unroll
+                for (int i = 0; i < BN / 64; ++i) {
+                    double* dst = P.stats + ((size_t)n * P.Cout + ct * BN + i * 64 + 2 * lane) * 2;
+                    atomicAdd(dst, (double)st_acc[i][0]); atomicAdd(dst + 1, (double)st_acc[i][1]);
+                    atomicAdd(dst + 2, (double)st_acc[i][2]); atomicAdd(dst + 3, (double)st_acc[i][3]);
+                    st_acc[i][0] = st_acc[i][1] = st_acc[i][2] = st_acc[i][3] = 0.f;
+                }
+            }
+        };
+        for (int ti = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++ti), ++local) {
             const Tile T = decode(tile);
             const int as = local & 1;
             mbar_wait(tfull_bar(as), (local >> 1) & 1u);
@@ -310,8 +334,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                  T.n0 + j * P.sub_n);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                if (P.stats != nullptr) {
+                    // InstanceNorm statistics of what was just stored (the bf16-rounded values, as a separate
+                    // statistics pass over y would see them): thread = channel pair x one 32-row group of the block.
+                    // One row of the staging block is 128 contiguous bytes -> a warp's 32 words never conflict.
+                    // Sums stay in registers across blocks and tiles and go to memory only when the image or the
+                    // channel tile changes (the CTA's tiles are consecutive, so that is rare).
+                    const int r_mine = q * 32 + lane;                                  // lane rr describes row q*32 + rr
+                    const int rows_per_img = P.tw * P.th;
+                    const int in_img = r_mine % rows_per_img;
+                    const int n_mine = T.n0 + j * P.sub_n + r_mine / rows_per_img;
+                    const bool ok_mine = n_mine < P.N && (T.h0 + j * P.sub_h + in_img / P.tw) < P.Ho && (T.w0 + in_img % P.tw) < P.Wo;
+                    const uint32_t valid = __ballot_sync(0xffffffffu, ok_mine);
+                    const uint8_t* const grp = out_ptr + (blk & 1) * kOutBlk + (q * 32) * 128 + (lane & 3) * 4;
+                    const int chunk = lane >> 2;
+                    if (valid == 0xffffffffu && P.tn == 1) {
+                        // common case: the whole 32-row group lies inside one image -> 32 independent loads, then sums
+                        const int key = (T.n0 + j * P.sub_n) * P.cout_tiles + (T.c_out0 / BN);
+                        if (key != st_key) { stats_flush(); st_key = key; }
+                        uint32_t wv[32];
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr)
+                            wv[rr] = *reinterpret_cast<const uint32_t*>(grp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                        float p[4][4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) p[u][0] = p[u][1] = p[u][2] = p[u][3] = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float a = __uint_as_float(wv[rr] << 16), b = __uint_as_float(wv[rr] & 0xffff0000u);
+                            float* pp = p[rr & 3];
+                            pp[0] += a; pp[1] = fmaf(a, a, pp[1]); pp[2] += b; pp[3] = fmaf(b, b, pp[3]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)                              // static index: stays in registers
+                            if (i == cblk) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) st_acc[i][e] += (p[0][e] + p[1][e]) + (p[2][e] + p[3][e]);
+                            }
+                    } else {
+                        // ragged tile or a tile spanning several (tiny) images: row by row
+#pragma unroll 1
+                        for (int rr = 0; rr < 32; ++rr) {
+                            if (!((valid >> rr) & 1u)) continue;                       // warp-uniform
+                            const int n = __shfl_sync(0xffffffffu, n_mine, rr);
+                            const int key = n * P.cout_tiles + (T.c_out0 / BN);
+                            if (key != st_key) { stats_flush(); st_key = key; }
+                            const uint32_t word = *reinterpret_cast<const uint32_t*>(grp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                            const float a = __uint_as_float(word << 16), b = __uint_as_float(word & 0xffff0000u);
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                if (i == cblk) {
+                                    st_acc[i][0] += a; st_acc[i][1] = fmaf(a, a, st_acc[i][1]);
+                                    st_acc[i][2] += b; st_acc[i][3] = fmaf(b, b, st_acc[i][3]);
+                                }
+                        }
+                    }
+                }
             }
         }
+        if (P.stats != nullptr) stats_flush();
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -392,9 +473,8 @@ extern "C" int fots_b200_conv_set_tile(int bn) {
     return RROI_B200_OK;
 }
 
-extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
-                                          int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope,
-                                          cudaStream_t stream) {
+static int conv2d_impl(const void* x, const void* w, const float* bias, void* y, double* stats, int N, int H, int W,
+                       int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope, cudaStream_t stream) {
     if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || R <= 0 || S <= 0 || pad_h < 0 || pad_w < 0)
         return RROI_B200_ERR_INVALID_ARG;
     if (Cin % BK != 0 || Cout % 64 != 0 || R > 7 || S > 7) return RROI_B200_ERR_INVALID_ARG;
@@ -430,8 +510,18 @@ extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const fl
     P.n_tiles_w = (Wo + P.tw - 1) / P.tw; P.n_tiles_h = (Ho + P.cta_h - 1) / P.cta_h; P.n_tiles_n = (N + P.cta_n - 1) / P.cta_n;
     P.cin_chunks = Cin / BK; P.S = S; P.taps = R * S; P.pad_h = pad_h; P.pad_w = pad_w;
     P.cout_tiles = Cout / bn; P.slope = slope; P.bias = bias;
+    P.stats = stats; P.N = N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout;
+    P.chunk = 1;
+    if (stats) {
+        const cudaError_t em = cudaMemsetAsync(stats, 0, (size_t)N * Cout * 2 * sizeof(double), stream);
+        if (em != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    }
     const long long ctas = (long long)P.n_tiles_w * P.n_tiles_h * P.n_tiles_n * P.cout_tiles;
     if (ctas > 0x7fffffffLL) return RROI_B200_ERR_TOO_LARGE;
+    if (stats) {                           // runs of up to 8 tiles, but keep at least two runs per CTA for balance
+        const long long c = ctas / (2 * 148);
+        P.chunk = (int)(c < 1 ? 1 : c > 8 ? 8 : c);
+    }
 
     CUtensorMap mx, mw, my;
     if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
@@ -444,4 +534,17 @@ extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const fl
     else e = launch<1, 256, 4>(mx, mw, my, P, ctas, stream);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
+}
+
+extern "C" int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                                          int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope,
+                                          cudaStream_t stream) {
+    return conv2d_impl(x, w, bias, y, nullptr, N, H, W, Cin, Cout, R, S, pad_h, pad_w, slope, stream);
+}
+
+extern "C" int fots_b200_conv2d_stats_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, double* stats,
+                                                int N, int H, int W, int Cin, int Cout, int R, int S, int pad_h, int pad_w,
+                                                cudaStream_t stream) {
+    if (!stats) return RROI_B200_ERR_INVALID_ARG;
+    return conv2d_impl(x, w, bias, y, stats, N, H, W, Cin, Cout, R, S, pad_h, pad_w, 1.0f, stream);
 }

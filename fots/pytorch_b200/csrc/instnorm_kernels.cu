@@ -199,9 +199,9 @@ extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi,
     return RROI_B200_OK;
 }
 
-extern "C" int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
-                                            const void* residual, double* workspace, int B, int HW, int C,
-                                            float eps, float slope, int crelu, cudaStream_t stream) {
+static int instnorm_impl(const void* x, void* y, const float* gamma, const float* beta, const void* residual,
+                         double* workspace, int B, int HW, int C, float eps, float slope, int crelu, bool have_stats,
+                         cudaStream_t stream) {
     if (!x || !y || !workspace || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || C > 1024 || (C / 8) > kThreads ||
         ((gamma == nullptr) != (beta == nullptr)) || (crelu && residual))
         return RROI_B200_ERR_INVALID_ARG;
@@ -213,10 +213,13 @@ extern "C" int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float*
     rows = ((rows + nphase - 1) / nphase) * nphase;
     if (rows < nphase * 4) rows = nphase * 4;
     const int chunks = (HW + rows - 1) / rows;
-    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    cudaError_t e = cudaSuccess;
     const dim3 grid(chunks, B);
-    in_stats_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
+    if (!have_stats) {
+        e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+        in_stats_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
+    }
     const size_t smem = (size_t)(crelu ? 4 : 2) * C * sizeof(float);
     const Bf16x8* xr = static_cast<const Bf16x8*>(x);
     Bf16x8* yr = static_cast<Bf16x8*>(y);
@@ -230,4 +233,16 @@ extern "C" int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float*
     e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
+}
+
+extern "C" int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
+                                            const void* residual, double* workspace, int B, int HW, int C,
+                                            float eps, float slope, int crelu, cudaStream_t stream) {
+    return instnorm_impl(x, y, gamma, beta, residual, workspace, B, HW, C, eps, slope, crelu, false, stream);
+}
+
+extern "C" int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
+                                                  const void* residual, const double* stats, int B, int HW, int C,
+                                                  float eps, float slope, int crelu, cudaStream_t stream) {
+    return instnorm_impl(x, y, gamma, beta, residual, const_cast<double*>(stats), B, HW, C, eps, slope, crelu, true, stream);
 }

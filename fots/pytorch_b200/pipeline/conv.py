@@ -11,6 +11,10 @@ import torch
 from .. import _cabi
 
 ENABLED = os.environ.get("FOTS_B200_TC_CONV", "1") != "0"   # A/B switch against the library convolution (sweeps)
+# Convolutions followed by an InstanceNorm: run them here with the statistics accumulated in the epilogue?  Measured
+# on B200 (profiles/r01_conv_tc_bench.txt) the bare library convolution + a separate statistics pass is still a
+# little faster for these shapes (the statistics make the 4-warp epilogue the bottleneck), so the default is off.
+FUSE_STATS = os.environ.get("FOTS_B200_TC_STATS", "0") != "0"
 
 
 def _lib():
@@ -19,6 +23,8 @@ def _lib():
         i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
         L.fots_b200_conv2d_nhwc_bf16.restype = i
         L.fots_b200_conv2d_nhwc_bf16.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, f, vp]
+        L.fots_b200_conv2d_stats_nhwc_bf16.restype = i
+        L.fots_b200_conv2d_stats_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
         L.fots_b200_conv_set_tile.restype = i
         L.fots_b200_conv_set_tile.argtypes = [i]
         L._conv_bound = True
@@ -40,9 +46,11 @@ def eligible(x, conv):
             and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)))
 
 
-def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0):
+def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0, stats=False):
     """act(conv2d(x, weight, bias, stride 1, padding)) -> bf16 channels-last [N, Cout, Ho, Wo].
-    x: bf16 channels-last [N, Cin, H, W]; weight: bf16 [Cout, Cin, R, S]; bias: fp32/bf16 [Cout] or None."""
+    x: bf16 channels-last [N, Cin, H, W]; weight: bf16 [Cout, Cin, R, S]; bias: fp32/bf16 [Cout] or None.
+    stats=True (slope must be 1): returns (y, ws) where ws is the fp64 [N, Cout, 2] per-image sum / sum of squares
+    of y accumulated by the epilogue, for fused.instnorm_act(y, ..., stats=ws)."""
     N, Cin, H, W = x.shape
     Cout, Cin_w, R, S = weight.shape
     if Cin_w != Cin:
@@ -52,12 +60,22 @@ def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0):
     wk = weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
     b = None if bias is None else bias.float().contiguous()
     y = torch.empty((N, Cout, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
     with torch.cuda.device(x.device):
-        st = _lib().fots_b200_conv2d_nhwc_bf16(
-            x.data_ptr(), wk.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
-            N, H, W, Cin, Cout, R, S, ph, pw, float(slope), torch.cuda.current_stream(x.device).cuda_stream)
+        if stats:
+            if slope != 1.0:
+                raise ValueError("conv2d: stats=True computes the statistics of the raw convolution (slope must be 1)")
+            from . import fused
+            ws = fused.workspace(x.device, N * Cout * 2)
+            st = _lib().fots_b200_conv2d_stats_nhwc_bf16(
+                x.data_ptr(), wk.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(), ws.data_ptr(),
+                N, H, W, Cin, Cout, R, S, ph, pw, stream)
+        else:
+            st = _lib().fots_b200_conv2d_nhwc_bf16(
+                x.data_ptr(), wk.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
+                N, H, W, Cin, Cout, R, S, ph, pw, float(slope), stream)
     _cabi.check(st, "fots_b200_conv2d_nhwc_bf16")
-    return y
+    return (y, ws) if stats else y
 
 
 def apply(conv, x, slope=1.0):

@@ -17,6 +17,8 @@ def _lib():
         i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
         L.fots_b200_instnorm_nhwc_bf16.restype = i
         L.fots_b200_instnorm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
+        L.fots_b200_instnorm_apply_nhwc_bf16.restype = i
+        L.fots_b200_instnorm_apply_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
         L.fots_b200_fpn_merge_nhwc_bf16.restype = i
         L.fots_b200_fpn_merge_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
         L._instnorm_bound = True
@@ -32,23 +34,33 @@ def eligible(x, residual=None):
     return ok
 
 
-def instnorm_act(x, weight, bias, eps, slope, residual=None, crelu=False):
-    """act(IN(x) * weight + bias [+ residual]); crelu=True: act(IN(concat(x, -x))) with [2C] weight/bias."""
+def workspace(device, numel):
+    """fp64 statistics workspace [B, C, 2] of the current stream (one per stream: producer and consumer of the
+    statistics are consecutive launches on it)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws.get(key)
+    if ws is None or ws.numel() < numel:
+        ws = torch.empty(max(numel, 1 << 16), dtype=torch.float64, device=device)
+        _ws[key] = ws
+    return ws
+
+
+def instnorm_act(x, weight, bias, eps, slope, residual=None, crelu=False, stats=None):
+    """act(IN(x) * weight + bias [+ residual]); crelu=True: act(IN(concat(x, -x))) with [2C] weight/bias.
+    stats: the [B, C, 2] fp64 sums a producer already accumulated (conv.conv2d(..., stats=True)) -- the statistics
+    pass over x is then skipped."""
     B, C, H, W = x.shape
     cout = 2 * C if crelu else C
     y = torch.empty((B, cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-    key = (x.device, torch.cuda.current_stream(x.device).cuda_stream)
-    ws = _ws.get(key)
-    if ws is None or ws.numel() < B * C * 2:
-        ws = torch.empty(max(B * C * 2, 1 << 16), dtype=torch.float64, device=x.device)
-        _ws[key] = ws
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    ws = stats if stats is not None else workspace(x.device, B * C * 2)
     w = weight.float().contiguous() if weight is not None else None
     b = bias.float().contiguous() if bias is not None else None
+    fn = _lib().fots_b200_instnorm_apply_nhwc_bf16 if stats is not None else _lib().fots_b200_instnorm_nhwc_bf16
     with torch.cuda.device(x.device):
-        st = _lib().fots_b200_instnorm_nhwc_bf16(
-            x.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else None,
-            b.data_ptr() if b is not None else None, residual.data_ptr() if residual is not None else None,
-            ws.data_ptr(), B, H * W, C, float(eps), float(slope), 1 if crelu else 0, key[1])
+        st = fn(x.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else None,
+                b.data_ptr() if b is not None else None, residual.data_ptr() if residual is not None else None,
+                ws.data_ptr(), B, H * W, C, float(eps), float(slope), 1 if crelu else 0, stream)
     _cabi.check(st, "fots_b200_instnorm_nhwc_bf16")
     return y
 

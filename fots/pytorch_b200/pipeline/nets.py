@@ -33,6 +33,19 @@ def _in_act(norm, x, slope, residual=None):
     return y if slope == 1.0 else F.leaky_relu(y, slope)
 
 
+def _conv_in_act(conv, norm, x, slope, residual=None):
+    """act(norm(conv(x)) [+ residual]).  On the bf16 channels-last inference path the convolution runs on the
+    tcgen05 kernel, whose epilogue also accumulates the InstanceNorm statistics, so the normalisation is a single
+    pass over the convolution's output (opt-in, conv.FUSE_STATS); otherwise conv + _in_act."""
+    # Cout = 64 (stage 1) stays on the library: one 64-wide weight tile cannot feed the tensor pipe from L2 fast enough
+    if tc.FUSE_STATS and tc.eligible(x, conv) and 128 <= conv.out_channels <= 1024:
+        y, ws = tc.conv2d(x, conv.weight, conv.bias, conv.padding, 1.0, stats=True)
+        if fused.eligible(y, residual):
+            return fused.instnorm_act(y, norm.weight, norm.bias, norm.eps, slope, residual, stats=ws)
+        return _in_act(norm, y, slope, residual)
+    return _in_act(norm, conv(x), slope, residual)
+
+
 class _CReLUNorm(nn.Module):
     """concat(x, -x) -> affine InstanceNorm -> leaky ReLU (the stem's channel-doubling activation)."""
 
@@ -64,8 +77,8 @@ class _ResIN(nn.Module):
 
     def forward(self, x):
         res = x if self.downsample is None else self.downsample(x)
-        y = _in_act(self.bn1, self.conv1(x), 0.0)
-        return _in_act(self.bn2, self.conv2(y), 0.0, res)
+        y = _conv_in_act(self.conv1, self.bn1, x, 0.0)
+        return _conv_in_act(self.conv2, self.bn2, y, 0.0, res)
 
 
 class _ResSepIN(nn.Module):
@@ -141,7 +154,9 @@ class FOTSNet(nn.Module):
 
     # ---- feeder -------------------------------------------------------------------------------
     def forward_features(self, x):
-        return self.layer0_1(self.layer0(x))
+        c1, _, c2, _ = self.layer0_1
+        y = tc.apply(c1, self.layer0(x), 0.0)           # conv + ReLU in one kernel on the inference path
+        return F.relu(c2(y))
 
     def _gate(self, x, like):
         return _up(torch.sigmoid(self.conv_attenton(x)), like)
@@ -188,12 +203,12 @@ class FOTSNet(nn.Module):
     # ---- consumer A ---------------------------------------------------------------------------
     def forward_ocr(self, x):
         # tc.apply = conv + leaky-ReLU in one tcgen05 kernel on the bf16 channels-last inference path, torch otherwise
-        x = _in_act(self.batch5, tc.apply(self.conv5, x), 0.01)
+        x = _conv_in_act(self.conv5, self.batch5, x, 0.01)
         x = tc.apply(self.conv6, tc.apply(self.conv6, x, 0.01), 0.01)
-        x = _in_act(self.batch7, tc.apply(self.conv7, self.max2(x)), 0.01)
+        x = _conv_in_act(self.conv7, self.batch7, self.max2(x), 0.01)
         x = tc.apply(self.conv8, tc.apply(self.conv8, x, 0.01), 0.01)
         x = tc.apply(self.conv9, tc.apply(self.conv9, x, 0.01), 0.01)
-        x = _in_act(self.batch10_s, tc.apply(self.conv10_s, self.max2(x)), 0.01)
+        x = _conv_in_act(self.conv10_s, self.batch10_s, self.max2(x), 0.01)
         x = self.conv11(self.drop1(x)).squeeze(2)            # [N, nclass, T]
         return F.log_softmax(x.float(), dim=1)
 

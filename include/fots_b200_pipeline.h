@@ -102,6 +102,20 @@ int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void
 int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
                                int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope,
                                cudaStream_t stream);
+/*
+ * The same convolution (no activation) that also accumulates, in its epilogue, the per-image per-channel sum and sum
+ * of squares of the bf16 values it stores -- the statistics pass of the InstanceNorm that follows every such
+ * convolution in tools/models.py (:336-338 conv5+batch5, :346-347, :362-364, :148-160 BasicBlockIn) -- so that
+ * fots_b200_instnorm_apply_nhwc_bf16 can normalise without reading y a first time.
+ *   stats  fp64 [N, Cout, 2], cleared and filled by the call (same format as the instnorm workspace)
+ */
+int fots_b200_conv2d_stats_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, double* stats,
+                                     int N, int H, int W, int Cin, int Cout, int R, int S, int pad_h, int pad_w,
+                                     cudaStream_t stream);
+/* fots_b200_instnorm_nhwc_bf16 without its statistics pass: `stats` [B, C, 2] comes from the call above. */
+int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
+                                       const void* residual, const double* stats, int B, int HW, int C,
+                                       float eps, float slope, int crelu, cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 

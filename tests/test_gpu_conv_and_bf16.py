@@ -103,6 +103,32 @@ def test_tcgen05_conv_matches_torch_fp32(cuda, case, bn):
     assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,S,ph,pw", [(3, 8, 64, 64, 128, 3, 3, 1, 1), (5, 2, 64, 256, 256, 2, 3, 0, 1),
+                                                       (2, 45, 80, 64, 64, 3, 3, 1, 1), (2, 23, 37, 128, 192, 3, 3, 1, 1),
+                                                       (7, 3, 5, 64, 64, 3, 3, 1, 1)])
+def test_conv_epilogue_statistics_feed_instancenorm(cuda, N, H, W, Cin, Cout, R, S, ph, pw):
+    """fots_b200_conv2d_stats_nhwc_bf16: the [N, Cout, 2] sums equal the sums of the bf16 tensor it stored (ragged
+    tiles and tiles spanning several images included), and conv -> fused InstanceNorm through them equals the
+    two-pass kernel on the same convolution output."""
+    from fots.pytorch_b200.pipeline import conv as TC, fused
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, R, S, generator=g) / (Cin * R * S) ** 0.5).to(cuda).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    y, ws = TC.conv2d(x, w, b, (ph, pw), 1.0, stats=True)
+    y_plain = TC.conv2d(x, w, b, (ph, pw), 1.0)
+    assert torch.equal(y, y_plain)
+    got = ws[:N * Cout * 2].view(N, Cout, 2).clone()
+    yd = y.double()
+    want = torch.stack([yd.sum((2, 3)), (yd * yd).sum((2, 3))], 2)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-3), float((got - want).abs().max())
+    gamma, beta = torch.randn(Cout, device=cuda), torch.randn(Cout, device=cuda)
+    two_pass = fused.instnorm_act(y, gamma, beta, 1e-5, 0.01)
+    y2, ws2 = TC.conv2d(x, w, b, (ph, pw), 1.0, stats=True)
+    one_pass = fused.instnorm_act(y2, gamma, beta, 1e-5, 0.01, stats=ws2)
+    assert float((one_pass.float() - two_pass.float()).abs().max()) <= 2.0 ** -6 * float(two_pass.float().abs().max())
+
+
 def test_tcgen05_conv_argument_checks(cuda):
     from fots.pytorch_b200 import _cabi
     from fots.pytorch_b200.pipeline import conv as TC
@@ -137,6 +163,17 @@ def test_recogniser_on_tensor_cores_matches_library_path(cuda):
             b = net.forward_ocr(pooled)
         finally:
             TC.ENABLED = True
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        img = torch.randn(2, 3, 64, 128, device=cuda).contiguous(memory_format=torch.channels_last)
+        fa = net(img)                                       # backbone: tcgen05 convs + epilogue statistics in layer1/2
+        TC.ENABLED = False
+        try:
+            fb = net(img)
+        finally:
+            TC.ENABLED = True
+    for ta, tb in zip(fa[0] + fa[3], fb[0] + fb[3]):
+        assert ta.shape == tb.shape
+        assert float((ta.float() - tb.float()).abs().mean()) < 0.03 * float(tb.float().abs().mean()) + 1e-3
     assert a.shape == b.shape == (6, 89, 64)
     assert float((a - b).abs().max()) < 0.15 and float((a - b).abs().mean()) < 0.02      # log-probabilities
     assert float((a.argmax(1) == b.argmax(1)).float().mean()) > 0.9

@@ -45,6 +45,7 @@ def bench(N, H, W, Cin, Cout, R, S, ph, pw, bn=0, iters=20):
     flops = 2.0 * N * (H + 2 * ph - R + 1) * (W + 2 * pw - S + 1) * Cout * Cin * R * S
     res = []
     for name, fn in (("tcgen05", lambda: TC.conv2d(x, conv.weight, None, (ph, pw), 0.01)),
+                     ("tcgen05+stats", lambda: TC.conv2d(x, conv.weight, None, (ph, pw), 1.0, stats=True)),
                      ("cudnn+leaky", lambda: F.leaky_relu(conv(x), 0.01)), ("cudnn", lambda: conv(x))):
         with torch.no_grad():
             for _ in range(3):
