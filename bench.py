@@ -167,7 +167,9 @@ class Workload:
         self.B = args.images
         self.N = args.images * args.rois_per_image
         self.layout = args.layout
-        per_set = 4 * (self.B * self.C * self.H * self.W + self.N * self.C * self.PH * self.PW)
+        self.bf16 = getattr(args, "dtype", "fp32") == "bf16"         # rroi_b200_forward_bf16 (channels-last only)
+        esz = 2 if self.bf16 else 4
+        per_set = esz * (self.B * self.C * self.H * self.W + self.N * self.C * self.PH * self.PW)
         # rotate over ~12x the L2 capacity: with a non-LRU replacement policy a cyclic working set of k x L2 can
         # still hit ~1/k of the time, so 3x (the first choice) flattered the kernel by up to 30 %
         self.sets = args.sets if args.sets > 0 else max(4, int(np.ceil(12 * 126e6 / per_set)) + 1)
@@ -177,14 +179,18 @@ class Workload:
         self.feats, self.rois, self.rois_np, self.alg_bytes = [], [], [], []
         for s in range(self.sets):
             f = torch.randn(self.B, self.C, self.H, self.W, device=device, generator=gen)
+            if self.bf16:
+                f = f.to(torch.bfloat16)
             self.feats.append(f.contiguous(memory_format=fmt))
             r = WL.batch_rois(self.B, args.rois_per_image, seed0=s * self.B)
             self.rois_np.append(r)
             self.rois.append(torch.from_numpy(r).to(device))
-            self.alg_bytes.append(WL.algorithmic_bytes_fwd(r, self.C, self.PH, self.PW))
+            alg = WL.algorithmic_bytes_fwd(r, self.C, self.PH, self.PW)
+            # bf16: the same element counts at 2 bytes (the 24-byte RoI rows stay fp32)
+            self.alg_bytes.append((alg - 24 * self.N) / 2 + 24 * self.N if self.bf16 else alg)
         self.feat_px_per_step = self.N * self.C * self.PH * self.PW
-        self.out = [torch.empty((self.N, self.C, self.PH, self.PW), device=device, memory_format=fmt)
-                    for _ in range(self.sets)]
+        self.out = [torch.empty((self.N, self.C, self.PH, self.PW), device=device, memory_format=fmt,
+                                dtype=torch.bfloat16 if self.bf16 else torch.float32) for _ in range(self.sets)]
 
     def enable_backward(self, torch):
         """Allocate top_diff / bottom_diff per buffer set (tools/sweep.py --backward, not the headline)."""
@@ -204,6 +210,13 @@ class Workload:
         """One step on buffer set s: exactly one kernel launch through the C ABI (rroi_b200_forward)."""
         if getattr(self, "backward", False):
             return self.launch_bwd(s, lib, cabi, stream)
+        if self.bf16:
+            st = lib.rroi_b200_forward_bf16(self.feats[s].data_ptr(), self.rois[s].data_ptr(), self.out[s].data_ptr(),
+                                            None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
+                                            self.scale, stream)
+            if st != 0:
+                raise RuntimeError("rroi_b200_forward_bf16 -> %d" % st)
+            return
         st = lib.rroi_b200_forward(self.feats[s].data_ptr(), self.rois[s].data_ptr(), self.out[s].data_ptr(),
                                    None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
                                    self.scale, cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW,
@@ -337,11 +350,14 @@ def variants_leg(args, torch, device, lib, cabi, peak):
             ("nchw_reference_layout", dict(channels=args.channels, layout="nchw", images=1, streams=args.streams)),
             ("fpn_c256", dict(channels=256, layout=args.layout, images=1, streams=args.streams)),
             ("cfg4_per_gpu_32img_2048rois", dict(channels=args.channels, layout=args.layout, images=32, streams=1)),
-            ("cfg4_per_gpu_nchw", dict(channels=args.channels, layout="nchw", images=32, streams=1))]
+            ("cfg4_per_gpu_nchw", dict(channels=args.channels, layout="nchw", images=32, streams=1)),
+            # the inference pipeline's variant: bf16 map in, bf16 pooled out (half the bytes, same arithmetic)
+            ("bf16_io", dict(channels=args.channels, layout="nhwc", images=1, streams=args.streams, dtype="bf16")),
+            ("bf16_io_cfg4_per_gpu", dict(channels=args.channels, layout="nhwc", images=32, streams=1, dtype="bf16"))]
     for name, kw in grid:
         cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, 0 if kw["streams"] == 1 else max(args.variant, 0))
         a = types.SimpleNamespace(channels=kw["channels"], layout=kw["layout"], images=kw["images"],
-                                  rois_per_image=args.rois_per_image, sets=0)
+                                  rois_per_image=args.rois_per_image, sets=0, dtype=kw.get("dtype", "fp32"))
         w = Workload(a, device, torch)
         steps = max(200, 20000 // kw["images"])
         ms = timed_steps(w, steps, 20, args.graph_chunk, torch, lib, cabi, lambda: None, kw["streams"])
@@ -349,7 +365,7 @@ def variants_leg(args, torch, device, lib, cabi, peak):
         alg = float(np.mean(w.alg_bytes))
         out[name] = {"us_per_launch": us, "mfeat_px_per_s": w.feat_px_per_step / us, "alg_mb": alg / 1e6,
                      "achieved_gbs": alg / us / 1e3, "frac": alg / us / 1e3 / peak, "streams": kw["streams"],
-                     "layout": kw["layout"], "channels": kw["channels"], "rois": w.N}
+                     "layout": kw["layout"], "channels": kw["channels"], "rois": w.N, "dtype": kw.get("dtype", "fp32")}
         del w
         torch.cuda.empty_cache()
     return out
@@ -357,7 +373,7 @@ def variants_leg(args, torch, device, lib, cabi, peak):
 
 def pipeline_leg(args, torch, device, dist, world, rank):
     """End-to-end images/s (BASELINE.json configs[2]/[4]): random-init FOTSNet in bf16 channels-last, 1280x720
-    synthetic images, 64 planted boxes per image, backbone + heads -> RoI rows -> RoIRotate (fp32) -> forward_ocr ->
+    synthetic images, 64 planted boxes per image, backbone + heads -> RoI rows -> RoIRotate (bf16 in/out) -> forward_ocr ->
     greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 8, the rank-local part replayed
     from one CUDA graph) with ONE all_gather of the per-image records per step.  Images start on the device; timed with CUDA events, max over ranks."""
     from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
@@ -439,7 +455,8 @@ def pipeline_leg(args, torch, device, dist, world, rank):
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
             "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
-            "dtype": "bf16 convolutions (cuDNN via torch), fused bf16 InstanceNorm/FPN-merge kernels, fp32 RoIRotate",
+            "dtype": "bf16: tcgen05 convolutions (conv6/8/9, layer0_1) + cuDNN for the rest, fused InstanceNorm/FPN-merge "
+                     "kernels, bf16-in/bf16-out RoIRotate (fp32 arithmetic)",
             "collective": "one all_gather of int32 [images, 64, 74] records per step" if world > 1 else "none (1 rank)",
             "boxes": "planted (seeded) -- reference NMS is pathological on random-init maps, SURVEY 8d",
             "flop_per_image": 221.7e9}

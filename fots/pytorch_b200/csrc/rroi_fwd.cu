@@ -588,8 +588,8 @@ __device__ __forceinline__ uint32_t blend_bf16x2(uint32_t lt, uint32_t rt, uint3
     return out;
 }
 
-template <int CT, int TILE, int UN>
-__global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_bf16_kernel(const FwdParams p) {
+template <int CT, int TILE, int UN, int MINB>
+__global__ void __launch_bounds__(kNhwcWarps * 32, MINB) rroi_fwd_nhwc_bf16_kernel(const FwdParams p) {
     constexpr int LPP = CT / 8;                          // lanes per pixel (16 bytes = 8 bf16 per lane)
     constexpr int PPI = 32 / LPP;                        // pixels per warp iteration
     constexpr int PIXW = TILE / kNhwcWarps;              // pixels per warp
@@ -692,12 +692,21 @@ static cudaError_t launch_fwd_nhwc_bf16_ct(FwdParams& p, cudaStream_t s, bool pd
         return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, pdl);
     };
     constexpr int PPI = 256 / CT;                        // pixels per warp iteration
-    constexpr int I64 = 8 / PPI, I256 = 32 / PPI;        // per-warp iterations of a 64- / 256-bin tile
+    constexpr int I64 = 8 / PPI, I128 = 16 / PPI, I256 = 32 / PPI;   // per-warp iterations of a 64/128/256-bin tile
+    constexpr int U64 = I64 >= 2 ? 2 : 1, U128 = I128 >= 2 ? 2 : 1, U256 = I256 >= 4 ? 4 : 2;
     const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
-    const int variant = g_tuning.nhwc_unroll;            // 0 = by grid size, like the fp32 kernel
-    if (variant == 1 || variant == 6 || (variant == 0 && ctas256 < 148 * 4))
-        return go(rroi_fwd_nhwc_bf16_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
-    return go(rroi_fwd_nhwc_bf16_kernel<CT, 256, (I256 >= 4 ? 4 : 2)>, 256);
+    int variant = g_tuning.nhwc_unroll;                  // 0 = by grid size, like the fp32 kernel
+    if (variant == 0) variant = ctas256 < 148 * 4 ? 1 : 5;
+    // Measured on B200 (profiles/r01_sweep_bf16.txt): occupancy is what matters once the bytes per bin are halved --
+    // 256-bin tiles, 2 iterations in flight, 64 registers (4 CTAs/SM) beat every wider-unrolled shape.
+    switch (variant) {
+        case 1:  return go(rroi_fwd_nhwc_bf16_kernel<CT, 64, U64, 1>, 64);
+        case 2:  return go(rroi_fwd_nhwc_bf16_kernel<CT, 128, U128, 3>, 128);
+        case 3:  return go(rroi_fwd_nhwc_bf16_kernel<CT, 128, (I128 >= 4 ? 4 : U128), 2>, 128);
+        case 4:  return go(rroi_fwd_nhwc_bf16_kernel<CT, 256, U256, 2>, 256);
+        case 6:  return go(rroi_fwd_nhwc_bf16_kernel<CT, 256, 2, 3>, 256);
+        default: return go(rroi_fwd_nhwc_bf16_kernel<CT, 256, 2, 4>, 256);
+    }
 }
 
 cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p0, cudaStream_t s) {

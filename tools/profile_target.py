@@ -27,9 +27,10 @@ if __name__ == "__main__":
     ap.add_argument("--pdl", type=int, default=0)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--backward", type=int, default=0)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     a = ap.parse_args()
     args = types.SimpleNamespace(channels=a.channels, layout=a.layout, images=a.images, rois_per_image=64,
-                                 sets=0, graph_chunk=1, pdl=a.pdl)
+                                 sets=0, graph_chunk=1, pdl=a.pdl, dtype=a.dtype)
     dev = torch.device("cuda:0")
     wl = bench.Workload(args, dev, torch)
     if a.backward:
