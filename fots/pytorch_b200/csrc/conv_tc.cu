@@ -11,7 +11,7 @@
 // ONE 4-D TMA load whose out-of-bounds rows/columns are zero-filled by the hardware (that is the padding), landing
 // in shared memory as a K-major 128x64 tile in the 128-byte swizzle the UMMA descriptor expects.
 //
-// CTA = 6 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers
+// CTA = 10 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2-9 = epilogue (TMEM -> registers
 // -> bias/activation -> bf16 -> swizzled shared block -> TMA store).  Persistent: one CTA per SM walks the tile
 // list; the accumulator is double-buffered in TMEM (2 x BN columns) and the producer runs ahead across tile
 // boundaries, so the epilogue of tile i and the pipeline fill of tile i+1 hide behind the MMAs.
@@ -27,7 +27,8 @@ namespace {
 constexpr int BM = 128;          // pixels per tile = UMMA M (accumulator row i lives in TMEM lane i)
 constexpr int BK = 64;           // channels per k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;           // K of one tcgen05.mma.kind::f16
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;       // producer warp, MMA warp, 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr uint32_t kABytes = BM * BK * 2;
 
 struct ConvParams {
@@ -190,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -254,7 +255,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ----
+        // Two warps per lane quarter: warp 2+q takes the first 32 columns of every 64-channel block, warp 6+q the second.
         const int q = warp & 3;
+        const int eh = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const bool issuer = (warp == 2 && lane == 0);
         uint32_t blk = 0;                                        // staging blocks issued so far (buffer = blk & 1)
@@ -287,14 +290,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int j = cb / (BN / 64), cblk = cb - j * (BN / 64);
                 // the TMA store issued two blocks ago has finished reading this staging buffer
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 uint8_t* const srow = out_ptr + (blk & 1) * kOutBlk + row * 128;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                {
+                    const int half = eh;
                     uint32_t v[32];
                     tmem_ld32(t_row + (uint32_t)(cb * 64 + half * 32), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cb == MT * BN / 64 - 1 && half == 1) {
+                    if (cb == MT * BN / 64 - 1) {
                         // last read of this accumulator: hand it back to the MMA warp before the stores
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
@@ -328,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to TMA
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (issuer) {
                     tma_store_4d(&map_y, out_stage + (blk & 1) * kOutBlk, T.c_out0 + cblk * 64, T.w0, T.h0 + j * P.sub_h,
                                  T.n0 + j * P.sub_n);
@@ -345,22 +348,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int in_img = r_mine % rows_per_img;
                     const int n_mine = T.n0 + j * P.sub_n + r_mine / rows_per_img;
                     const bool ok_mine = n_mine < P.N && (T.h0 + j * P.sub_h + in_img / P.tw) < P.Ho && (T.w0 + in_img % P.tw) < P.Wo;
-                    const uint32_t valid = __ballot_sync(0xffffffffu, ok_mine);
-                    const uint8_t* const grp = out_ptr + (blk & 1) * kOutBlk + (q * 32) * 128 + (lane & 3) * 4;
+                    const uint32_t valid = (__ballot_sync(0xffffffffu, ok_mine) >> (eh * 16)) & 0xffffu;   // this warp's 16 rows
+                    const uint8_t* const grp = out_ptr + (blk & 1) * kOutBlk + (q * 32 + eh * 16) * 128 + (lane & 3) * 4;
                     const int chunk = lane >> 2;
-                    if (valid == 0xffffffffu && P.tn == 1) {
+                    if (valid == 0xffffu && P.tn == 1) {
                         // common case: the whole 32-row group lies inside one image -> 32 independent loads, then sums
                         const int key = (T.n0 + j * P.sub_n) * P.cout_tiles + (T.c_out0 / BN);
                         if (key != st_key) { stats_flush(); st_key = key; }
-                        uint32_t wv[32];
+                        uint32_t wv[16];
 #pragma unroll
-                        for (int rr = 0; rr < 32; ++rr)
+                        for (int rr = 0; rr < 16; ++rr)
                             wv[rr] = *reinterpret_cast<const uint32_t*>(grp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
                         float p[4][4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) p[u][0] = p[u][1] = p[u][2] = p[u][3] = 0.f;
 #pragma unroll
-                        for (int rr = 0; rr < 32; ++rr) {
+                        for (int rr = 0; rr < 16; ++rr) {
                             const float a = __uint_as_float(wv[rr] << 16), b = __uint_as_float(wv[rr] & 0xffff0000u);
                             float* pp = p[rr & 3];
                             pp[0] += a; pp[1] = fmaf(a, a, pp[1]); pp[2] += b; pp[3] = fmaf(b, b, pp[3]);
@@ -374,9 +377,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     } else {
                         // ragged tile or a tile spanning several (tiny) images: row by row
 #pragma unroll 1
-                        for (int rr = 0; rr < 32; ++rr) {
+                        for (int rr = 0; rr < 16; ++rr) {
                             if (!((valid >> rr) & 1u)) continue;                       // warp-uniform
-                            const int n = __shfl_sync(0xffffffffu, n_mine, rr);
+                            const int n = __shfl_sync(0xffffffffu, n_mine, eh * 16 + rr);
                             const int key = n * P.cout_tiles + (T.c_out0 / BN);
                             if (key != st_key) { stats_flush(); st_key = key; }
                             const uint32_t word = *reinterpret_cast<const uint32_t*>(grp + rr * 128 + ((chunk ^ (rr & 7)) << 4));

@@ -1,7 +1,11 @@
 """Detection decode on the GPU: threshold + per-pixel quadrangle + raster-order
 compaction in two launches, replacing the first half of nms/adaptor.cpp (:76-117) and the three full-map D2H
-copies of test.py:86-96.  The merge itself (nms/nms.h + Clipper) is CPU code and out of scope; it can be fed the
-compact candidate rows this returns."""
+copies of test.py:86-96; then the reference's sequential merge (nms/nms.h) on the host over the compact candidate
+rows, after one device-to-host copy (`merge_candidates`) -- together the replacement of nms.get_boxes
+(nms/__init__.py:19-30, called at test.py:96)."""
+import ctypes
+
+import numpy as np
 import torch
 
 from .. import _cabi
@@ -47,3 +51,34 @@ def candidates_to_quads(cand_rows):
     """int32 rows [M,16] -> float32 [M,9] (x0..y3 in pixels, score), the row format nms/__init__.py:10-15 returns."""
     q = cand_rows[:, :8].to(torch.float32) / 10000.0
     return torch.cat((q, cand_rows[:, 8:9].contiguous().view(torch.float32)), 1)
+
+
+def merge_candidates(counts, cand, w, h, iou_threshold1=0.4, iou_threshold2=0.2, max_boxes=1024):
+    """Host stage of the detector post-processing (fots_b200_merge_candidates_host): counts int32 [B], cand int32
+    [B, cap, 16] as returned by decode_candidates (CUDA or CPU tensors) -> list of B float32 arrays [k_b, 9]
+    (x0,y0..x3,y3 in input-image pixels + accumulated score), what nms.get_boxes returns per image.  One D2H copy of
+    the candidate rows that exist; thresholds default to the reference's (nms/__init__.py:29)."""
+    L = _bind()
+    if not getattr(L, "_merge_bound", False):
+        i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+        L.fots_b200_merge_candidates_host.restype = i
+        L.fots_b200_merge_candidates_host.argtypes = [vp, i, i, i, f, f, vp, i, vp]
+        L._merge_bound = True
+    counts_h = counts.detach().cpu().numpy()
+    cap = cand.size(1)
+    top = int(min(int(counts_h.max()) if counts_h.size else 0, cap))
+    rows = np.ascontiguousarray(cand[:, :top].detach().cpu().numpy()) if top > 0 else np.zeros((cand.size(0), 0, 16), np.int32)
+    out = []
+    buf = np.empty((max_boxes, 9), np.float32)
+    nb = ctypes.c_int(0)
+    for b in range(rows.shape[0]):
+        n = int(min(counts_h[b], cap))
+        img = np.ascontiguousarray(rows[b, :n])
+        st = L.fots_b200_merge_candidates_host(img.ctypes.data if n else None, n, int(w), int(h), float(iou_threshold1),
+                                               float(iou_threshold2), buf.ctypes.data, int(max_boxes), ctypes.byref(nb))
+        _cabi.check(st, "fots_b200_merge_candidates_host")
+        k = min(nb.value, max_boxes)
+        boxes = buf[:k].copy()
+        boxes[:, :8] /= 10000.0                     # nms/__init__.py:13-15
+        out.append(boxes)
+    return out

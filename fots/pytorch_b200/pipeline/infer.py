@@ -75,6 +75,17 @@ class FOTSPipeline:
         return rec, (seg[0], rbox[0], angle[0])
 
     @torch.no_grad()
+    def detect_boxes(self, seg, rbox, angle, segm_threshold=0.5, max_per_image=16384):
+        """The reference's box extraction (test.py:86-96 -> nms.get_boxes) on the first-scale head outputs: threshold +
+        quadrangle decode + raster-order compaction on the GPU, ONE device-to-host copy of the compact candidates, the
+        sequential merge on the host.  Returns a list of float32 arrays [k_b, 9] (x0,y0..x3,y3 in image pixels, score).
+        Not part of the graph-captured step: with random-init weights half the map is positive, so the
+        benchmark plants its boxes; with trained weights this is the path that produces `quads`."""
+        from .detect import decode_candidates, merge_candidates
+        counts, cand = decode_candidates(seg, rbox, angle, segm_threshold, max_per_image)
+        return merge_candidates(counts, cand, seg.size(3), seg.size(2))
+
+    @torch.no_grad()
     def capture(self, images, quads, micro=8):
         """Capture this rank's whole local step (micro-batches of `micro` images, no host sync inside) into one
         CUDA graph bound to the given `images` / `quads` buffers.  Returns a callable `replay()` -> records

@@ -59,6 +59,23 @@ int fots_b200_decode_candidates(const float* segm, const float* rbox, const floa
                                 cudaStream_t stream);
 
 /*
+ * HOST function (CPU, no stream): the locality-aware merge + standard NMS of the reference's detector
+ * post-processing (nms/nms.h:149-213 merge_iou, :112-146 standard_nms, :49-109 PolyMerger; nms/adaptor.cpp:118),
+ * over the compact raster-ordered candidate rows fots_b200_decode_candidates produced, after ONE device-to-host copy
+ * of `cand[0 .. num_cand)`.  Sequential by construction, hence CPU like the reference's.
+ *   cand        host int32 [num_cand, 16], rows as documented above (one image)
+ *   w, h        size of the score map the candidates came from
+ *   iou_threshold1 / 2   merge thresholds of the two stages (nms/__init__.py:29 passes 0.4 and 0.2)
+ *   boxes       host fp32 [max_boxes, 9] out: x0,y0..x3,y3 in the x10000 fixed-point units (divide by 10000 for pixels,
+ *               nms/__init__.py:14) + accumulated score, in the order the reference returns them
+ *   num_boxes   out: number of polygons kept (may exceed max_boxes; only the first max_boxes are written)
+ * Polygon IoU is an exact-input convex clip in double precision (the reference calls Clipper; same value for the convex
+ * quadrangles the decode emits, up to Clipper's integer rounding of intersection vertices).
+ */
+int fots_b200_merge_candidates_host(const int* cand, int num_cand, int w, int h, float iou_threshold1,
+                                    float iou_threshold2, float* boxes, int max_boxes, int* num_boxes);
+
+/*
  * Fused channels-last InstanceNorm (+ affine) (+ residual add) + leaky-ReLU for the feeder/consumer networks
  * (tools/models.py:41-48 CReLU_IN, :142-166 BasicBlockIn, :87-103 conv_dw_*_in, :336-364 forward_ocr).  torch's
  * instance_norm converts a channels-last tensor to NCHW and back around a batch-norm kernel; this is one

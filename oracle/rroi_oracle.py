@@ -182,3 +182,34 @@ def ref_gpu_backward(top_diff, rois, idx_x, idx_y, feature_size, spatial_scale):
                                                 idx_y.contiguous().data_ptr(), st)
     assert rc == 1
     return grad
+
+
+# --------------------------------------------------------------------------------------
+# The reference's own merge (nms/nms.h + vendored Clipper) behind oracle/nms_ref_shim.cpp:
+# oracle/_ref/libref_nms.so, built by oracle/Makefile where /root/reference is present; CPU code, so it
+# runs in the build container and on the GPU box alike.
+_REF_NMS_SO = os.path.join(_HERE, "_ref", "libref_nms.so")
+_ref_nms = None
+
+
+def ref_nms_available():
+    return os.path.exists(_REF_NMS_SO)
+
+
+def ref_merge_candidates(cand, w, h, thr1=0.4, thr2=0.2, max_boxes=4096):
+    """cand int32 [n,16] (one image, raster order) -> float32 [k,9] exactly as nms/adaptor.cpp:13-29 flattens the
+    result of nms::merge_iou (coordinates in x10000 units)."""
+    global _ref_nms
+    if _ref_nms is None:
+        if not os.path.exists(_REF_NMS_SO):
+            raise RuntimeError("oracle/_ref/libref_nms.so missing: run `make -C oracle ref` in the build container")
+        lib = ctypes.CDLL(_REF_NMS_SO)
+        lib.ref_merge_candidates.restype = ctypes.c_int
+        lib.ref_merge_candidates.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                             ctypes.c_float, ctypes.c_void_p, ctypes.c_int]
+        _ref_nms = lib
+    cand = np.ascontiguousarray(cand, dtype=np.int32).reshape(-1, 16)
+    out = np.zeros((max_boxes, 9), np.float32)
+    n = _ref_nms.ref_merge_candidates(cand.ctypes.data, cand.shape[0], int(w), int(h), float(thr1), float(thr2),
+                                      out.ctypes.data, int(max_boxes))
+    return out[:min(n, max_boxes)].copy()

@@ -261,3 +261,36 @@ def test_decode_candidates_matches_adaptor_restatement(oracle, cuda, B, h, w, th
         assert (cand[b, m:] == 0).all()
     q = candidates_to_quads(torch.from_numpy(cand[0, :min(counts[0], cap)]).to(cuda))
     assert q.shape[1] == 9 and torch.isfinite(q).all()
+
+
+def test_detector_postprocessing_gpu_decode_plus_host_merge(oracle, cuda):
+    """SURVEY 8f-2 end to end: planted detection maps -> fots_b200_decode_candidates (GPU) -> one D2H ->
+    fots_b200_merge_candidates_host, against the reference's own merge (oracle/_ref/libref_nms.so: nms/nms.h + Clipper,
+    unmodified) fed by the CPU restatement of the decode.  Boxes, order and scores must agree; the planted boxes come
+    back at the right place."""
+    import workloads as WL
+    from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
+    if not oracle.ref_nms_available():
+        pytest.skip("oracle/_ref/libref_nms.so not built")
+    h, w = 180, 320
+    scenes = [[(60, 40, 80, 14, 0.3), (200, 100, 100, 16, -0.6), (120, 150, 50, 10, 1.1), (62, 44, 80, 14, 0.3)],
+              [(250, 30, 60, 12, 0.0), (80, 120, 120, 12, 0.15)]]
+    maps = [WL.planted_detection_maps(h, w, sc, seed=i) for i, sc in enumerate(scenes)]
+    seg = torch.from_numpy(np.stack([m[0] for m in maps])[:, None]).to(cuda)
+    rbox = torch.from_numpy(np.stack([m[1] for m in maps])).to(cuda)
+    ang = torch.from_numpy(np.stack([m[2] for m in maps])).to(cuda)
+    pipe = FOTSPipeline(FOTSNet(attention=True, nclass=89), 8, 64, 0.25)
+    got = pipe.detect_boxes(seg, rbox, ang)
+    assert len(got) == 2
+    for b, (m, sc) in enumerate(zip(maps, scenes)):
+        n, cand = oracle.decode_candidates(m[0], m[1], m[2], 0.5, 1 << 16)
+        want = oracle.ref_merge_candidates(cand[:n], w, h, 0.4, 0.2)
+        want[:, :8] /= 10000.0
+        assert got[b].shape == want.shape
+        # GPU expf vs libm expf differ by <= 2 ulp in the merge weights: coordinates agree to a fraction of a pixel
+        assert np.abs(got[b][:, :8] - want[:, :8]).max() < 0.05 and np.allclose(got[b][:, 8], want[:, 8], rtol=1e-5)
+    # the two overlapping copies of scene 0 collapse: 3 boxes; each planted centre is recovered (map px * 4 = image px)
+    assert got[0].shape[0] == 3 and got[1].shape[0] == 2
+    centres = got[0][:, :8].reshape(-1, 4, 2).mean(1) / 4.0
+    for cx, cy in ((200, 100), (120, 150)):
+        assert np.min(np.hypot(centres[:, 0] - cx, centres[:, 1] - cy)) < 2.0

@@ -115,3 +115,31 @@ def stress_rois(seed, n, batch, img_w, img_h):
     ang = np.where(snap, rng.choice([0.0, 90.0, 180.0, -90.0], n), ang)
     b = rng.integers(0, batch, n).astype(np.float64)
     return np.stack([b, cx, cy, h, h * ratio, ang], axis=1).astype(np.float32)
+
+
+def planted_detection_maps(h, w, boxes, seed=0, noise=0.15):
+    """Synthetic first-scale detector outputs (SURVEY 8d protocol) with `boxes` = [(cx, cy, bw, bh, angle_rad), ...] in
+    MAP pixels planted in them: seg [h,w] is 0.9 inside each box shrunk by 30 % and 0.1 elsewhere; rbox [4,h,w] holds
+    each inside pixel's distances (top, bottom, left, right) to the box edges and angle [2,h,w] its (sin, cos), with a
+    little seeded noise, so every inside pixel decodes (nms/adaptor.cpp:85-113) to nearly the same quadrangle."""
+    rng = np.random.default_rng(seed)
+    seg = np.full((h, w), 0.1, np.float32)
+    rbox = np.zeros((4, h, w), np.float32)
+    angle = np.zeros((2, h, w), np.float32)
+    angle[1] = 1.0
+    ys, xs = np.mgrid[0:h, 0:w]
+    px, py = xs + 0.25, ys + 0.25                     # the decode's pixel position
+    for (cx, cy, bw, bh, a) in boxes:
+        ca, sa = np.cos(a), np.sin(a)
+        u = (px - cx) * ca + (py - cy) * sa           # along the width direction
+        v = -(px - cx) * sa + (py - cy) * ca          # along the height direction
+        inside = (np.abs(u) < 0.35 * bw) & (np.abs(v) < 0.35 * bh)
+        seg[inside] = 0.9
+        jitter = lambda: 1.0 + noise * (rng.random(int(inside.sum()), dtype=np.float32) - 0.5) * 0.1
+        rbox[0][inside] = (bh / 2 + v[inside]) * jitter()        # top
+        rbox[1][inside] = (bh / 2 - v[inside]) * jitter()        # bottom
+        rbox[2][inside] = (bw / 2 + u[inside]) * jitter()        # left
+        rbox[3][inside] = (bw / 2 - u[inside]) * jitter()        # right
+        angle[0][inside] = sa
+        angle[1][inside] = ca
+    return seg, rbox.astype(np.float32), angle.astype(np.float32)
