@@ -25,6 +25,8 @@ def _lib():
         L.fots_b200_conv2d_nhwc_bf16.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, f, vp]
         L.fots_b200_conv2d_stats_nhwc_bf16.restype = i
         L.fots_b200_conv2d_stats_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+        L.fots_b200_stem_conv3x3_c3_c16.restype = i
+        L.fots_b200_stem_conv3x3_c3_c16.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.fots_b200_conv_set_tile.restype = i
         L.fots_b200_conv_set_tile.argtypes = [i]
         L._conv_bound = True
@@ -86,3 +88,28 @@ def apply(conv, x, slope=1.0):
     if slope == 1.0:
         return y
     return torch.relu(y) if slope == 0.0 else torch.nn.functional.leaky_relu(y, slope)
+
+
+def stem_eligible(x, conv):
+    """The first layer: fp32 channels-last image, Conv2d(3, 16, 3, 1, 1, bias=False) with bf16 weights."""
+    w = conv.weight
+    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.size(1) == 3
+            and x.is_contiguous(memory_format=torch.channels_last) and w.dtype == torch.bfloat16
+            and tuple(w.shape) == (16, 3, 3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+            and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)))
+
+
+def stem_conv_stats(x, weight):
+    """conv2d(bf16(x), weight, pad 1) -> (y bf16 channels-last [B, 16, H, W], ws fp64 [B, 16, 2] statistics of y)
+    in one pass (fots_b200_stem_conv3x3_c3_c16)."""
+    from . import fused
+    B, _, H, W = x.shape
+    wk = weight.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, 16, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    ws = fused.workspace(x.device, B * 32)
+    with torch.cuda.device(x.device):
+        st = _lib().fots_b200_stem_conv3x3_c3_c16(x.data_ptr(), wk.data_ptr(), y.data_ptr(), ws.data_ptr(), B, H, W,
+                                                  torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(st, "fots_b200_stem_conv3x3_c3_c16")
+    return y, ws

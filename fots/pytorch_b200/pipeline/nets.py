@@ -154,8 +154,17 @@ class FOTSNet(nn.Module):
 
     # ---- feeder -------------------------------------------------------------------------------
     def forward_features(self, x):
+        conv0, crelu0, conv1, crelu1 = self.layer0
+        if tc.stem_eligible(x, conv0) and x.size(0) * 32 <= (1 << 16):
+            # first layer + the statistics of its CReLU_IN in one HBM pass (csrc/stem_conv.cu), then the apply pass
+            y, ws = tc.stem_conv_stats(x, conv0.weight)
+            bn = crelu0.bn
+            y = fused.instnorm_act(y, bn.weight, bn.bias, bn.eps, 0.01, crelu=True, stats=ws)
+            y = crelu1(conv1(y))
+        else:
+            y = self.layer0(x)
         c1, _, c2, _ = self.layer0_1
-        y = tc.apply(c1, self.layer0(x), 0.0)           # conv + ReLU in one kernel on the inference path
+        y = tc.apply(c1, y, 0.0)                        # conv + ReLU in one kernel on the inference path
         return F.relu(c2(y))
 
     def _gate(self, x, like):

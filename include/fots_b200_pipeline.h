@@ -133,6 +133,17 @@ int fots_b200_conv2d_stats_nhwc_bf16(const void* x, const void* w, const float* 
 int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
                                        const void* residual, const double* stats, int B, int HW, int C,
                                        float eps, float slope, int crelu, cudaStream_t stream);
+/*
+ * The feature extractor's first layer (tools/models.py:250-251: Conv2d(3, 16, 3, stride 1, pad 1, bias=False)) fused
+ * with the statistics pass of the CReLU_IN that follows it (tools/models.py:41-48); csrc/stem_conv.cu.
+ *   x      fp32 [B, H, W, 3]   (channels-last image; rounded to bf16 on load, as autocast does for the library call)
+ *   w      bf16 [16, 3, 3, 3]  = [cout][r][s][cin] (the storage of the channels-last weight)
+ *   y      bf16 [B, H, W, 16]
+ *   stats  fp64 [B, 16, 2] sum / sum of squares of the bf16 values stored (cleared by the call), or NULL
+ * HBM-bound (27 MACs per output value); the arithmetic runs on mma.sync fragments built from a shared-memory tile.
+ */
+int fots_b200_stem_conv3x3_c3_c16(const float* x, const void* w, void* y, double* stats, int B, int H, int W,
+                                  cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 

@@ -129,6 +129,27 @@ def test_conv_epilogue_statistics_feed_instancenorm(cuda, N, H, W, Cin, Cout, R,
     assert float((one_pass.float() - two_pass.float()).abs().max()) <= 2.0 ** -6 * float(two_pass.float().abs().max())
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 256), (1, 37, 150), (3, 8, 128), (1, 720, 1280), (9, 17, 33)])
+def test_stem_convolution_and_statistics(cuda, B, H, W):
+    """fots_b200_stem_conv3x3_c3_c16 vs torch: the 3 -> 16 convolution on the bf16-rounded image (one bf16 rounding of
+    the result) and the [B, 16, 2] sums of exactly the tensor it stored; ragged tiles, several images per CTA range."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(B * 7 + H)
+    x = torch.randn(B, 3, H, W, generator=g).to(cuda).contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(3, 16, 3, 1, 1, bias=False).to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    with torch.no_grad():
+        assert TC.stem_eligible(x, conv)
+        y, ws = TC.stem_conv_stats(x, conv.weight)
+        ref = F.conv2d(x.to(torch.bfloat16).float(), conv.weight.float(), None, 1, 1)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    err = (y.float() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-3 * float(ref.abs().max())).all()), float(err.max())
+    yd = y.double()
+    want = torch.stack([yd.sum((2, 3)), (yd * yd).sum((2, 3))], 2)
+    got = ws[:B * 32].view(B, 16, 2)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-3), float((got - want).abs().max())
+
+
 def test_tcgen05_conv_argument_checks(cuda):
     from fots.pytorch_b200 import _cabi
     from fots.pytorch_b200.pipeline import conv as TC

@@ -23,3 +23,9 @@ with torch.no_grad():
         x = torch.randn(8, cin, h, h * 16 // 9, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         conv = torch.nn.Conv2d(cin, cout, 3, s, 1, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
         print("conv %d->%d s%d at %d: %.1f us" % (cin, cout, s, h, t(lambda: conv(x))), flush=True)
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from fots.pytorch_b200.pipeline import conv as TC
+    xf = torch.randn(8, 3, 720, 1280, device=dev).contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(3, 16, 3, 1, 1, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    print("stem conv+stats (fp32 image in): %.1f us" % t(lambda: TC.stem_conv_stats(xf, conv.weight)))
