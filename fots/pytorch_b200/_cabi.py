@@ -36,7 +36,7 @@ EXPORTS = (
     "fots_b200_fpn_merge_nhwc_bf16", "fots_b200_decode_candidates",
     "fots_b200_conv2d_nhwc_bf16", "fots_b200_conv_set_tile", "fots_b200_conv2d_stats_nhwc_bf16",
     "fots_b200_instnorm_apply_nhwc_bf16", "fots_b200_merge_candidates_host",
-    "fots_b200_stem_conv3x3_c3_c16",
+    "fots_b200_stem_conv3x3_c3_c16", "fots_b200_maxpool_h2_nhwc_bf16",
 )
 
 _lib = None

@@ -181,7 +181,40 @@ __global__ void __launch_bounds__(kThreads) fpn_merge_kernel(const Bf16x8* __res
     }
 }
 
+// ---- max-pool (2,1)/(2,1) over H of a channels-last tensor (tools/models.py:344, :360 `max2`) --------------------
+// thread = 8 channels of one output pixel; the two input rows are W*C elements apart.  NaNs propagate like torch's.
+__global__ void __launch_bounds__(kThreads) maxpool_h2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                               long long total, int Ho, long long rowv, int H) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const long long r = i / rowv, e = i - r * rowv;        // r = n * Ho + ho
+        const long long n = r / Ho, ho = r - n * Ho;
+        const uint4* src = x + ((n * H + 2 * ho) * rowv + e);
+        const uint4 a = __ldg(src), b = __ldg(src + rowv);
+        uint4 o;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) po[k] = __hmax2_nan(pa[k], pb[k]);
+        y[i] = o;
+    }
+}
+
 }  // namespace
+
+extern "C" int fots_b200_maxpool_h2_nhwc_bf16(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream) {
+    if (!x || !y || N <= 0 || H < 2 || W <= 0 || C <= 0 || C % 8 != 0) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    const int Ho = H / 2;
+    const long long rowv = (long long)W * (C / 8);
+    const long long total = (long long)N * Ho * rowv;
+    long long grid = (total + kThreads - 1) / kThreads;
+    if (grid > 148LL * 16) grid = 148LL * 16;
+    maxpool_h2_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), total, Ho, rowv, H);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
 
 extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo,
                                              void* y, int B, int h, int w, int H, int W, int C, cudaStream_t stream) {

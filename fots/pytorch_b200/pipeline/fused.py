@@ -19,6 +19,8 @@ def _lib():
         L.fots_b200_instnorm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
         L.fots_b200_instnorm_apply_nhwc_bf16.restype = i
         L.fots_b200_instnorm_apply_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
+        L.fots_b200_maxpool_h2_nhwc_bf16.restype = i
+        L.fots_b200_maxpool_h2_nhwc_bf16.argtypes = [vp, vp, i, i, i, i, vp]
         L.fots_b200_fpn_merge_nhwc_bf16.restype = i
         L.fots_b200_fpn_merge_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
         L._instnorm_bound = True
@@ -91,4 +93,16 @@ def fpn_merge(a_lo=None, c_hi=None, b_hi=None, gate_logits_lo=None, size=None):
         st = _lib().fots_b200_fpn_merge_nhwc_bf16(ptr(a_lo), ptr(c_hi), ptr(b_hi), ptr(gate_logits_lo), y.data_ptr(),
                                                   B, h, w, H, W, C, torch.cuda.current_stream(ref.device).cuda_stream)
     _cabi.check(st, "fots_b200_fpn_merge_nhwc_bf16")
+    return y
+
+
+def maxpool_h2(x):
+    """MaxPool2d((2, 1), stride (2, 1)) of a bf16 channels-last tensor in one HBM pass (fots_b200_maxpool_h2_nhwc_bf16);
+    the caller checks `eligible(x)` and H >= 2."""
+    N, C, H, W = x.shape
+    y = torch.empty((N, C, H // 2, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        st = _lib().fots_b200_maxpool_h2_nhwc_bf16(x.data_ptr(), y.data_ptr(), N, H, W, C,
+                                                   torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(st, "fots_b200_maxpool_h2_nhwc_bf16")
     return y

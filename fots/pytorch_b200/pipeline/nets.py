@@ -210,14 +210,19 @@ class FOTSNet(nn.Module):
         return [seg, seg2], [rbox, rbox2], [ang, ang2], [x, focr]
 
     # ---- consumer A ---------------------------------------------------------------------------
+    def _max2(self, x):
+        if fused.eligible(x) and x.size(2) >= 2:
+            return fused.maxpool_h2(x)
+        return self.max2(x)
+
     def forward_ocr(self, x):
         # tc.apply = conv + leaky-ReLU in one tcgen05 kernel on the bf16 channels-last inference path, torch otherwise
         x = _conv_in_act(self.conv5, self.batch5, x, 0.01)
         x = tc.apply(self.conv6, tc.apply(self.conv6, x, 0.01), 0.01)
-        x = _conv_in_act(self.conv7, self.batch7, self.max2(x), 0.01)
+        x = _conv_in_act(self.conv7, self.batch7, self._max2(x), 0.01)
         x = tc.apply(self.conv8, tc.apply(self.conv8, x, 0.01), 0.01)
         x = tc.apply(self.conv9, tc.apply(self.conv9, x, 0.01), 0.01)
-        x = _conv_in_act(self.conv10_s, self.batch10_s, self.max2(x), 0.01)
+        x = _conv_in_act(self.conv10_s, self.batch10_s, self._max2(x), 0.01)
         x = self.conv11(self.drop1(x)).squeeze(2)            # [N, nclass, T]
         return F.log_softmax(x.float(), dim=1)
 

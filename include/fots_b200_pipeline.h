@@ -93,6 +93,12 @@ int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, con
                                  float eps, float slope, int crelu, cudaStream_t stream);
 
 /*
+ * MaxPool2d((2,1), stride (2,1)) of a channels-last bf16 tensor (`max2`, tools/models.py:344, :360):
+ *   x bf16 [N, H, W, C] -> y bf16 [N, H/2, W, C];  C % 8 == 0, 16-byte aligned.  HBM-bound, 16-byte accesses.
+ */
+int fots_b200_maxpool_h2_nhwc_bf16(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream);
+
+/*
  * One step of the top-down feature merge of tools/models.py:411-438, fused (channels-last bf16, fp32 arithmetic):
  *     y = (a_lo ? upsample(a_lo) : c_hi)  +  (b_hi ? b_hi * (g_lo ? upsample(sigmoid(g_lo)) : 1) : 0)
  * upsample = bilinear, align_corners=True (torch's source-index arithmetic), from [h, w] to [H, W].

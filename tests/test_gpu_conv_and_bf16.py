@@ -150,6 +150,17 @@ def test_stem_convolution_and_statistics(cuda, B, H, W):
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-3), float((got - want).abs().max())
 
 
+@pytest.mark.parametrize("N,C,H,W", [(5, 128, 8, 64), (3, 256, 4, 64), (2, 64, 7, 33), (1, 8, 2, 1)])
+def test_maxpool_h2_matches_torch(cuda, N, C, H, W):
+    from fots.pytorch_b200.pipeline import fused
+    x = torch.randn(N, C, H, W, device=cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x[0, 0, 0, 0] = float("nan")
+    got = fused.maxpool_h2(x)
+    want = F.max_pool2d(x.float(), (2, 1), (2, 1)).to(torch.bfloat16)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.nan_to_num(got.float(), nan=-7.0), torch.nan_to_num(want.float(), nan=-7.0))
+
+
 def test_tcgen05_conv_argument_checks(cuda):
     from fots.pytorch_b200 import _cabi
     from fots.pytorch_b200.pipeline import conv as TC
