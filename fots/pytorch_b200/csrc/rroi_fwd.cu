@@ -573,16 +573,31 @@ __device__ __forceinline__ uint4 ldg_pred_u4(const uint4* ptr, uint32_t pred) {
     return r;
 }
 
-__device__ __forceinline__ uint32_t blend_bf16x2(uint32_t lt, uint32_t rt, uint32_t rb, uint32_t lb, float wlt, float wrt,
-                                                 float wrb, float wlb) {
-    float lo = __fmaf_rn(__uint_as_float(lt << 16), wlt, 0.0f);
-    lo = __fmaf_rn(__uint_as_float(rt << 16), wrt, lo);
-    lo = __fmaf_rn(wrb, __uint_as_float(rb << 16), lo);
-    lo = __fmaf_rn(__uint_as_float(lb << 16), wlb, lo);
-    float hi = __fmaf_rn(__uint_as_float(lt & 0xffff0000u), wlt, 0.0f);
-    hi = __fmaf_rn(__uint_as_float(rt & 0xffff0000u), wrt, hi);
-    hi = __fmaf_rn(wrb, __uint_as_float(rb & 0xffff0000u), hi);
-    hi = __fmaf_rn(__uint_as_float(lb & 0xffff0000u), wlb, hi);
+// Two fp32 lanes per instruction (sm_100 FFMA2, PTX fma.rn.f32x2): each half is an ordinary IEEE fp32 FMA, so the
+// result is bit-identical to the scalar chain; it halves the FFMA issue slots of this (issue-limited) kernel.
+__device__ __forceinline__ uint64_t pair_f32(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t widen_bf16x2(uint32_t w) {          // {bf16 lo, bf16 hi} -> {f32, f32}, exact
+    return pair_f32(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// wXX2 = the tap weight duplicated into both halves
+__device__ __forceinline__ uint32_t blend_bf16x2(uint32_t lt, uint32_t rt, uint32_t rb, uint32_t lb, uint64_t wlt2,
+                                                 uint64_t wrt2, uint64_t wrb2, uint64_t wlb2) {
+    uint64_t v = fma2(widen_bf16x2(lt), wlt2, 0ull);                    // {+0.0f, +0.0f}: the reference's sum starts at 0
+    v = fma2(widen_bf16x2(rt), wrt2, v);
+    v = fma2(wrb2, widen_bf16x2(rb), v);
+    v = fma2(widen_bf16x2(lb), wlb2, v);
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     uint32_t out;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out) : "f"(hi), "f"(lo));
     return out;
@@ -672,7 +687,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, MINB) rroi_fwd_nhwc_bf16_kern
         if (any_live & C_LIVE) {                         // own basic block: keeps the UN iterations' loads batched
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                const float wlt = r[u].wlt, wrt = r[u].wrt, wrb = r[u].wrb, wlb = r[u].wlb;
+                const uint64_t wlt = pair_f32(r[u].wlt, r[u].wlt), wrt = pair_f32(r[u].wrt, r[u].wrt);
+                const uint64_t wrb = pair_f32(r[u].wrb, r[u].wrb), wlb = pair_f32(r[u].wlb, r[u].wlb);
                 uint4 o;
                 o.x = blend_bf16x2(lt[u].x, rt[u].x, rb[u].x, lb[u].x, wlt, wrt, wrb, wlb);
                 o.y = blend_bf16x2(lt[u].y, rt[u].y, rb[u].y, lb[u].y, wlt, wrt, wrb, wlb);
