@@ -22,6 +22,7 @@ TUNE_NCHW_CG = 0
 TUNE_NHWC_UNROLL = 1
 TUNE_USE_PDL = 2
 TUNE_BWD_DEDUPE = 3
+TUNE_NCHW_TMA = 4
 
 ABI_VERSION = 1
 

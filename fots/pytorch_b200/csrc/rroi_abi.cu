@@ -154,6 +154,9 @@ int rroi_b200_set_tuning(int key, int value) {
         case RROI_B200_TUNE_BWD_DEDUPE:
             if (value < 0 || value > 2) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.bwd_dedupe = value; return RROI_B200_OK;
+        case RROI_B200_TUNE_NCHW_TMA:
+            if (value < 0 || value > 5) return RROI_B200_ERR_INVALID_ARG;
+            rroi::g_tuning.nchw_tma = value; return RROI_B200_OK;
         default: return RROI_B200_ERR_INVALID_ARG;
     }
 }
@@ -164,6 +167,7 @@ int rroi_b200_get_tuning(int key) {
         case RROI_B200_TUNE_NHWC_UNROLL: return rroi::g_tuning.nhwc_unroll;
         case RROI_B200_TUNE_USE_PDL:     return rroi::g_tuning.use_pdl;
         case RROI_B200_TUNE_BWD_DEDUPE:  return rroi::g_tuning.bwd_dedupe;
+        case RROI_B200_TUNE_NCHW_TMA:    return rroi::g_tuning.nchw_tma;
         default: return -1;
     }
 }

@@ -16,10 +16,13 @@
 // read once per CTA; reuse between neighbouring bins is served by L1/L2).
 #include "rroi_geom.cuh"
 #include "rroi_kernels.cuh"
+#include <cuda.h>
+#include <climits>
+#include <mutex>
 
 namespace rroi {
 
-Tuning g_tuning = {0, 0, 0, 1};
+Tuning g_tuning = {0, 0, 0, 1, 0};
 
 // code word of a bin
 enum : uint32_t {
@@ -158,12 +161,288 @@ __global__ void __launch_bounds__(kNchwBlock) rroi_fwd_nchw_kernel(const FwdPara
     }
 }
 
+// ------------------------------------------------------------------------------ NCHW, TMA-staged
+// The gather kernel above is bound by L1 wavefronts: a warp-wide tap load of 32 bins of one plane touches ~8 different
+// 128-byte lines (ncu: 7.8 sectors per request, L1 throughput 76 %).  Here the feature data does not go through the
+// load/store unit at all: for every group of CG channels the CTA's footprint in the planes -- the bounding box of
+// the taps of its 8x8 bin patch, at most 32x32 pixels -- is fetched by ONE 3-D TMA box load {BX, BY, CG planes}
+// (cp.async.bulk.tensor.3d, out-of-image parts zero-filled) into shared memory, double-buffered over the channel
+// groups, and the four taps of every bin are read from there.  Four tensor maps with boxes 12x8x32, 20x16x16, 28x24x8
+// and 36x32x4 (12-21 KB per stage; four pixels wider than tall because the box must start on a 16-byte boundary of the
+// row) are encoded per call; each CTA picks the smallest that holds its footprint.  CTAs
+// whose footprint is larger (huge RoIs) or empty fall back to the gather loop.  Same records, same FFMA chain, same
+// stores as the gather kernel: bit-identical results.
+struct NchwTmaMaps { CUtensorMap m[4]; };
+constexpr int kTmaStageBytes = 28 * 24 * 8 * 4;          // the largest of the four boxes (21 504 B)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kNchwBlock)
+rroi_fwd_nchw_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                         const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3) {
+    extern __shared__ __align__(128) uint8_t stage_mem[];    // 2 x kTmaStageBytes
+    __shared__ RoiXform sX;
+    __shared__ BinRecP rec[kPatch * kPatch];
+    __shared__ int sL[kPatch * kPatch], sT[kPatch * kPatch];
+    __shared__ int bb[4];                                   // x_min, y_min, x_max, y_max of the patch's taps
+    __shared__ __align__(8) uint64_t full_bar[2];
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int tiles_w = (p.PW + kPatch - 1) / kPatch;
+    const int ph0 = (tile / tiles_w) * kPatch, pw0 = (tile % tiles_w) * kPatch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (warp == 0) {
+        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        if (lane == 0) {
+            sX = X;
+            bb[0] = INT_MAX; bb[1] = INT_MAX; bb[2] = INT_MIN; bb[3] = INT_MIN;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full_bar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full_bar[1])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    const RoiXform X = sX;
+    const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+    if (threadIdx.x < kPatch * kPatch) {
+        BinRecP r;
+        r.off = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.cx = r.cy = 0.0f;
+        int xl = INT_MAX, yt = INT_MAX, xr = INT_MIN, yb = INT_MIN, gl = 0, gt = 0;
+        const int ph = ph0 + (int)threadIdx.x / kPatch, pw = pw0 + (int)threadIdx.x % kPatch;
+        if (ph < p.PH && pw < p.PW) {
+            const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+            const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+            r.off = (int)((unsigned)g.t * (unsigned)p.W + (unsigned)g.l);
+            r.code = C_LIVE;
+            if (in) {
+                const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+                const bool l_lt = g.flags & TAP_LT;
+                const bool l_rt = (g.flags & TAP_RT) && two_c;
+                const bool l_lb = (g.flags & TAP_LB) && two_r;
+                const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+                r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+                r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+                r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+                r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+                r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+                r.cx = g.cx; r.cy = g.cy;
+                if (r.code & (C_LT | C_RT | C_LB | C_RB)) {       // loaded taps are inside the image: 0 <= l,t and l+1 < W, t+1 < H when used
+                    gl = g.l; gt = g.t;
+                    xl = g.l; yt = g.t; xr = g.l + (two_c ? 1 : 0); yb = g.t + (two_r ? 1 : 0);
+                }
+            }
+            if (p.idx_mode == IDX_COMPACT) {
+                p.idx_x[(size_t)n * bins + ph * p.PW + pw] = r.cx;
+                p.idx_y[(size_t)n * bins + ph * p.PW + pw] = r.cy;
+            }
+        }
+        rec[threadIdx.x] = r;
+        sL[threadIdx.x] = gl; sT[threadIdx.x] = gt;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            xl = min(xl, __shfl_xor_sync(0xffffffffu, xl, m)); yt = min(yt, __shfl_xor_sync(0xffffffffu, yt, m));
+            xr = max(xr, __shfl_xor_sync(0xffffffffu, xr, m)); yb = max(yb, __shfl_xor_sync(0xffffffffu, yb, m));
+        }
+        if (lane == 0) { atomicMin(&bb[0], xl); atomicMin(&bb[1], yt); atomicMax(&bb[2], xr); atomicMax(&bb[3], yb); }
+    }
+    __syncthreads();
+    const bool any_tap = bb[2] >= bb[0];                    // false when the patch loads nothing
+    // TMA wants the box to start on a 16-byte boundary of the innermost dimension: x0 is rounded down to a multiple of
+    // four pixels and every box is four pixels wider than it is tall.
+    const int x0 = any_tap ? (bb[0] & ~3) : 0, y0 = any_tap ? bb[1] : 0;
+    const int need_w = any_tap ? bb[2] - x0 + 1 : 0, need_h = any_tap ? bb[3] - y0 + 1 : 0;
+    const int side = max(need_w - 4, need_h);
+    // box index: 0: 12x8x32, 1: 20x16x16, 2: 28x24x8, 3: 36x32x4  (width x height x channels)
+    int k = side <= 8 ? 0 : side <= 16 ? 1 : side <= 24 ? 2 : 3;
+    if (p.cgroups >= 2 && p.cgroups - 2 >= k) k = p.cgroups - 2;       // tuning/debug: force a (larger) box
+    const bool use_tma = any_tap && side <= 32;
+    const int BY = 8 * (k + 1), BX = BY + 4;
+    const int CG = k == 0 ? 32 : k == 1 ? 16 : k == 2 ? 8 : 4;
+
+    // lane -> bin of this warp's half patch; warp -> channel phase (as in the gather kernel)
+    const int half = warp & 1, cq = warp >> 1;
+    const int slot = half * 32 + lane;
+    const BinRecP r = rec[slot];
+    const bool live = r.code & C_LIVE;
+    const int ph = ph0 + slot / kPatch, pw = pw0 + slot % kPatch;
+    const size_t HW = (size_t)p.H * p.W;
+    const size_t obin = (size_t)ph * p.PW + pw;
+    float* dst = p.out + (size_t)n * p.C * bins + obin;
+    const bool full_idx = p.idx_mode == IDX_FULL;
+
+    if (use_tma) {
+        const int soff = (sT[slot] - y0) * BX + (sL[slot] - x0);         // top-left tap inside one staged plane
+        const int plane_elems = BX * BY;
+        const uint32_t stage_bytes = (uint32_t)(plane_elems * CG * 4);
+        const int nst = (p.C + CG - 1) / CG;
+        const int plane0 = (batch_ok ? X.batch : 0) * p.C;
+        auto tma3d = [&](const CUtensorMap* map, uint32_t dsts, uint32_t bar, int cz) {
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(dsts), "l"(map), "r"(bar), "r"(x0), "r"(y0), "r"(cz) : "memory");
+        };
+        auto issue = [&](int st) {
+            const uint32_t bar = smem_addr(&full_bar[st & 1]);
+            const uint32_t dsts = smem_addr(stage_mem + (st & 1) * kTmaStageBytes);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
+            const int cz = plane0 + st * CG;
+            // each tensor map is addressed as the kernel parameter it is (no run-time indexing of parameter space)
+            if (k == 0) tma3d(&map0, dsts, bar, cz);
+            else if (k == 1) tma3d(&map1, dsts, bar, cz);
+            else if (k == 2) tma3d(&map2, dsts, bar, cz);
+            else tma3d(&map3, dsts, bar, cz);
+        };
+        if (threadIdx.x == 0) {
+            issue(0);
+            if (nst > 1) issue(1);
+        }
+        for (int st = 0; st < nst; ++st) {
+            const uint32_t bar = smem_addr(&full_bar[st & 1]);
+            const uint32_t parity = (uint32_t)(st >> 1) & 1u;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            }
+            const float* tl = reinterpret_cast<const float*>(stage_mem + (st & 1) * kTmaStageBytes) + soff;
+            if (live) {
+#pragma unroll 4
+                for (int cl = cq; cl < CG; cl += 4) {
+                    const int c = st * CG + cl;
+                    if (c >= p.C) break;
+                    const float* s0 = tl + cl * plane_elems;
+                    const float lt = (r.code & C_LT) ? s0[0] : 0.0f;
+                    const float rt = (r.code & C_RT) ? s0[1] : 0.0f;
+                    const float lb = (r.code & C_LB) ? s0[BX] : 0.0f;
+                    const float rb = (r.code & C_RB) ? s0[BX + 1] : 0.0f;
+                    float v = __fmaf_rn(lt, r.wlt, 0.0f);
+                    v = __fmaf_rn(rt, r.wrt, v);
+                    v = __fmaf_rn(r.wrb, rb, v);
+                    v = __fmaf_rn(lb, r.wlb, v);
+                    dst[(size_t)c * bins] = v;
+                    if (full_idx) {
+                        p.idx_x[((size_t)n * p.C + c) * bins + obin] = r.cx;
+                        p.idx_y[((size_t)n * p.C + c) * bins + obin] = r.cy;
+                    }
+                }
+            }
+            __syncthreads();                                  // everybody is done with this stage's buffer
+            if (threadIdx.x == 0 && st + 2 < nst) issue(st + 2);
+        }
+        return;
+    }
+
+    // ---- fallback: footprint larger than 32x32 pixels, or nothing to load -- the gather loop ----
+    if (!live) return;
+    const float* top = p.feat + ((size_t)(batch_ok ? X.batch : 0) * p.C) * HW + r.off;
+    const float* bot = top + p.W;
+    constexpr int UN = 4;
+#pragma unroll 1
+    for (int c0 = cq; c0 < p.C; c0 += 4 * UN) {
+        float lt[UN], rt[UN], lb[UN], rb[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int c = c0 + 4 * u;
+            const uint32_t okc = c < p.C;
+            const size_t po = (size_t)c * HW;
+            lt[u] = ldg_pred_f32<0>(top + po, okc ? (r.code & C_LT) : 0u);
+            rt[u] = ldg_pred_f32<4>(top + po, okc ? (r.code & C_RT) : 0u);
+            lb[u] = ldg_pred_f32<0>(bot + po, okc ? (r.code & C_LB) : 0u);
+            rb[u] = ldg_pred_f32<4>(bot + po, okc ? (r.code & C_RB) : 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int c = c0 + 4 * u;
+            if (c < p.C) {
+                float v = __fmaf_rn(lt[u], r.wlt, 0.0f);
+                v = __fmaf_rn(rt[u], r.wrt, v);
+                v = __fmaf_rn(r.wrb, rb[u], v);
+                v = __fmaf_rn(lb[u], r.wlb, v);
+                dst[(size_t)c * bins] = v;
+                if (full_idx) {
+                    p.idx_x[((size_t)n * p.C + c) * bins + obin] = r.cx;
+                    p.idx_y[((size_t)n * p.C + c) * bins + obin] = r.cy;
+                }
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tma_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &res) == cudaSuccess &&
+            res == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(q);
+    });
+    return fn;
+}
+
+// true when the four maps could be built: planes [B*C][H][W] fp32, rows a multiple of 16 bytes, 16-byte aligned base
+static bool make_nchw_maps(const FwdParams& p, NchwTmaMaps* out) {
+    if (p.B <= 0 || p.B > (1 << 20) || (p.W % 4) != 0 || (reinterpret_cast<uintptr_t>(p.feat) & 15)) return false;
+    if (!tma_encode_fn()) return false;
+    const cuuint64_t planes = (cuuint64_t)p.B * (cuuint64_t)p.C;
+    if (planes > 0xffffffffull) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H * p.W * 4};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const int side[4] = {8, 16, 24, 32}, cg[4] = {32, 16, 8, 4};
+    for (int k = 0; k < 4; ++k) {
+        const cuuint32_t box[3] = {(cuuint32_t)side[k] + 4, (cuuint32_t)side[k], (cuuint32_t)cg[k]};
+        if (tma_encode_fn()(&out->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.feat), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 cudaError_t launch_fwd_nchw(const FwdParams& p0, cudaStream_t s) {
     FwdParams p = p0;
     p.tiles = ((p.PH + kPatch - 1) / kPatch) * ((p.PW + kPatch - 1) / kPatch);
     p.cgroups = 1;
     const long long grid = (long long)p.N * p.tiles;
     const bool pdl = g_tuning.use_pdl != 0;
+    // Measured on B200: the TMA-staged kernel is bit-identical but not faster than the gather kernel
+    // (5.46 vs 5.54 us on cfg1, 179.8 vs 183.2 us on cfg4's per-GPU batch) -- the boxes over-fetch 3-4x from L2, which
+    // trades the L1-wavefront bound for an L2-bandwidth bound -- and it costs four tensor-map encodes per call on the
+    // host, so it is opt-in (RROI_B200_TUNE_NCHW_TMA >= 1).
+    if (g_tuning.nchw_tma >= 1 && p.B != 0x7fffffff) {      // the legacy launcher does not know the batch size
+        p.cgroups = g_tuning.nchw_tma >= 2 ? g_tuning.nchw_tma : 1;
+        NchwTmaMaps maps;
+        if (make_nchw_maps(p, &maps)) {
+            if (grid <= 0) return cudaSuccess;
+            if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+            static bool attr = false;
+            if (!attr) {
+                const cudaError_t e = cudaFuncSetAttribute(rroi_fwd_nchw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTmaStageBytes);
+                if (e != cudaSuccess) return e;
+                attr = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(kNchwBlock);
+            cfg.dynamicSmemBytes = 2 * kTmaStageBytes;
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = pdl ? 1 : 0;
+            return cudaLaunchKernelEx(&cfg, rroi_fwd_nchw_tma_kernel, p, maps.m[0], maps.m[1], maps.m[2], maps.m[3]);
+        }
+    }
     switch (g_tuning.nchw_cg) {     // channels in flight per lane
         case 1:  return launch_1d(rroi_fwd_nchw_kernel<1>, grid, kNchwBlock, p, s, pdl);
         case 2:  return launch_1d(rroi_fwd_nchw_kernel<2>, grid, kNchwBlock, p, s, pdl);

@@ -44,6 +44,7 @@ struct Tuning {
     int nhwc_unroll;   // NHWC forward variant 0..5 (bins per warp x bins in flight), see launch_fwd_nhwc_vec
     int use_pdl;       // launch with programmatic stream serialization
     int bwd_dedupe;    // warp-level merge of equal sample points before the atomics (NCHW backward)
+    int nchw_tma;      // 0 = NCHW forward gathers through L1 (default); 1 = stages its footprint with TMA box loads; 2..5 = same, box index >= value - 2
 };
 extern Tuning g_tuning;
 

@@ -309,3 +309,36 @@ def test_error_behaviour(cuda):
     assert (y == 0).all()
     assert _cabi.lib().rroi_b200_forward(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1.0, 0, None) == _cabi.ERR_INVALID_ARG
     assert _cabi.lib().rroi_b200_forward(f.data_ptr(), r.data_ptr(), y.data_ptr(), None, None, 2, 1, 3, 16, 16, 8, 32, 1.0, 7, None) == _cabi.ERR_INVALID_ARG
+
+
+@pytest.mark.parametrize("C,H,W,scale,rois", [
+    (64, 180, 320, 0.25, None),                                            # cfg1: boxes of 8..32 pixels
+    (7, 90, 160, 0.25, None),                                              # C smaller than every box's channel group
+    (16, 64, 64, 1.0, [[0, 32, 32, 60, 200, 33], [0, 10, 50, 40, 64, -70]]),   # footprints > 32 px: gather fallback per CTA
+    (5, 33, 50, 0.5, None),                                                # W % 4 != 0: no tensor map, gather kernel
+])
+def test_nchw_tma_staged_forward_equals_gather_kernel_and_oracle(oracle, cuda, C, H, W, scale, rois):
+    """The opt-in NCHW forward that stages each patch's footprint with TMA box loads (rroi_fwd_nchw_tma_kernel,
+    RROI_B200_TUNE_NCHW_TMA = 1, and 5 = largest box forced) must agree bit for bit with the gather kernel and with
+    the oracle, centres included."""
+    from fots.pytorch_b200 import _cabi
+    B = 2
+    feats = WL.features(C, B, C, H, W)
+    if rois is None:
+        r = np.concatenate([WL.random_rois(3 + i, 24, i, img_w=int(W / scale), img_h=int(H / scale)) for i in range(B)], 0)
+        r[0, 1:3] = (2.0, 3.0)
+    else:
+        r = np.array(rois, np.float32)
+    ph, pw = 8, 64
+    want, wx, wy = oracle.forward(feats, r, ph, pw, scale, threads=0)
+    outs = []
+    for mode in (0, 1, 5):
+        _cabi.set_tuning(_cabi.TUNE_NCHW_TMA, mode)
+        try:
+            outs.append(Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False))
+        finally:
+            _cabi.set_tuning(_cabi.TUNE_NCHW_TMA, 0)
+    for got, ix, iy in outs:
+        Hh.assert_bit_equal(got, want, "NCHW forward")
+        Hh.assert_bit_equal(ix, wx[:, 0], "idx_x")
+        Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")

@@ -28,6 +28,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--backward", type=int, default=0)
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--nchw-tma", type=int, default=0)
     a = ap.parse_args()
     args = types.SimpleNamespace(channels=a.channels, layout=a.layout, images=a.images, rois_per_image=64,
                                  sets=0, graph_chunk=1, pdl=a.pdl, dtype=a.dtype)
@@ -38,6 +39,7 @@ if __name__ == "__main__":
     _cabi.set_tuning(_cabi.TUNE_NCHW_CG, a.cg)
     _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, a.variant)
     _cabi.set_tuning(_cabi.TUNE_USE_PDL, a.pdl)
+    _cabi.set_tuning(_cabi.TUNE_NCHW_TMA, a.nchw_tma)
     st = torch.cuda.current_stream().cuda_stream
     for i in range(a.steps):
         wl.launch(i % wl.sets, _cabi.lib(), _cabi, st)
