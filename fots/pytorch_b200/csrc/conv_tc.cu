@@ -122,6 +122,45 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster act as one 256-row MMA; only the even CTA issues ----
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address -> the even CTA of the pair
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_even_cta(uint32_t bar) {      // plain arrival on the even CTA's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {          // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -140,18 +179,24 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&p);
 }
 
-template <int MT, int BN, int STAGES>
+// PAIR: the kernel is launched in clusters of two CTAs that act as one 256-pixel x BN tile (tcgen05 cta_group::2):
+// each CTA stages its own 128 pixels of A and HALF of the weight tile (BN/2 rows), the even CTA issues M = 256 MMAs that
+// read both shared memories and write both TMEMs, and both CTAs run their own epilogue.  A third fewer operand bytes
+// per MMA cycle and per stage -> six stages instead of four in the same shared memory.
+template <int MT, int BN, int STAGES, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const ConvParams P) {
-    constexpr uint32_t kBBytes = BN * BK * 2;
+    static_assert(!PAIR || MT == 1, "pair mode: one 128-pixel sub-tile per CTA");
+    constexpr uint32_t kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
     constexpr uint32_t kStageBytes = MT * kABytes + kBBytes;     // MT pixel sub-tiles share one weight tile
     constexpr uint32_t kOutBlk = BM * 128;                       // staging block: 128 pixels x 64 channels of bf16
     constexpr uint32_t kAccCols = MT * BN;                       // one accumulator set: MT sub-tiles x BN columns
     constexpr uint32_t kTmemCols = 2 * kAccCols;                 // two sets: epilogue of tile i overlaps MMA of i+1
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two <= 512");
     // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -169,17 +214,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = P.taps * P.cin_chunks;
-    const int num_tiles = P.cout_tiles * P.n_tiles_w * P.n_tiles_h * P.n_tiles_n;
+    const int num_mtiles = P.n_tiles_w * P.n_tiles_h * P.n_tiles_n;
+    const int num_tiles = P.cout_tiles * (PAIR ? (num_mtiles + 1) / 2 : num_mtiles);
     // This CTA's tiles: runs of P.chunk consecutive tiles, the runs dealt round-robin to the CTAs.  chunk = 1 keeps all
     // CTAs on one front through the tensor (best L2/DRAM locality); with fused statistics longer runs keep a CTA
     // inside one image so that its running sums are flushed rarely.
-    const int run_stride = (int)gridDim.x * P.chunk;
-    auto tile_at = [&](int i) { return (i / P.chunk) * run_stride + (int)blockIdx.x * P.chunk + i % P.chunk; };
+    // PAIR: the work items are (cout tile, PAIR of pixel tiles); a cluster walks them, CTA rank r takes pixel tile 2*pair + r.
+    const uint32_t rank = PAIR ? cluster_cta_rank() : 0u;
+    const int walkers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+    const int walker = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    const int run_stride = walkers * P.chunk;
+    auto tile_at = [&](int i) { return (i / P.chunk) * run_stride + walker * P.chunk + i % P.chunk; };
     struct Tile { int w0, h0, n0, c_out0; };
     // cout tile fastest: the CTAs that share an input box run at the same time (L2 reuse)
     auto decode = [&](int t) {
         Tile T;
         const int ct = t % P.cout_tiles;  t /= P.cout_tiles;
+        if (PAIR) t = 2 * t + (int)rank;                       // may be one past the last pixel tile: every access is then out of bounds
         const int tw_i = t % P.n_tiles_w; t /= P.n_tiles_w;
         const int th_i = t % P.n_tiles_h; t /= P.n_tiles_h;
         T.w0 = tw_i * P.tw; T.h0 = th_i * P.cta_h; T.n0 = t * P.cta_n; T.c_out0 = ct * BN;
@@ -190,17 +241,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
+        // PAIR: the even CTA's full barrier collects its own expect_tx arrival, the odd CTA's plain arrival and the bytes of
+        // both CTAs' loads; its tempty barrier collects the epilogue threads of both CTAs
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), PAIR ? 2 : 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 2 * kEpiThreads : kEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32((const void*)tmem_slot)), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32((const void*)tmem_slot)), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();        // barriers of both CTAs exist before anybody signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -217,6 +276,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int tap = kb / P.cin_chunks, cc = kb - tap * P.cin_chunks;
                     const int r = tap / P.S, sx = tap - r * P.S;
                     const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + MT * kABytes;
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(full_bar(s), 2 * kStageBytes);
+                        tma_load_4d_pair(a_dst, &map_x, full_bar(s), cc * BK, T.w0 + sx - P.pad_w, T.h0 + r - P.pad_h, T.n0);
+                        tma_load_2d_pair(b_dst, &map_w, full_bar(s), kb * BK, T.c_out0 + (int)rank * (BN / 2));
+                        if (rank != 0) mbar_arrive_even_cta(full_bar(s));
+                        continue;
+                    }
                     mbar_expect_tx(full_bar(s), kStageBytes);
 #pragma unroll
                     for (int j = 0; j < MT; ++j)
@@ -227,8 +293,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer ----
+        if (lane == 0 && rank == 0) {
+            // ---- MMA issuer (PAIR: the even CTA only) ----
             uint32_t it = 0, local = 0;
             for (int ti = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++ti), ++local) {
                 const int as = local & 1;
@@ -245,12 +311,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k)
 #pragma unroll
-                        for (int j = 0; j < MT; ++j)
-                            umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(j * (kABytes / 16) + k * UK * 2 / 16),
-                                      bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc, (uint32_t)((kb | k) != 0));
-                    umma_commit(empty_bar(s));        // frees the stage when the MMAs that read it have retired
+                        for (int j = 0; j < MT; ++j) {
+                            if (PAIR)
+                                umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UK * 2 / 16), bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc,
+                                               (uint32_t)((kb | k) != 0));
+                            else
+                                umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(j * (kABytes / 16) + k * UK * 2 / 16),
+                                          bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc, (uint32_t)((kb | k) != 0));
+                        }
+                    if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));   // frees the stage (in both CTAs)
                 }
-                umma_commit(tfull_bar(as));           // accumulator complete
+                if (PAIR) umma_commit_pair(tfull_bar(as)); else umma_commit(tfull_bar(as));     // accumulator complete
             }
         }
     } else {
@@ -300,7 +371,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     if (cb == MT * BN / 64 - 1) {
                         // last read of this accumulator: hand it back to the MMA warp before the stores
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+                        if (PAIR) mbar_arrive_even_cta(tempty_bar(as));
+                        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
                     }
                     float f[32];
 #pragma unroll
@@ -399,9 +471,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();        // the peer may still be signalling this CTA's barriers / reading its smem
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -443,14 +516,14 @@ bool make_map_weights(CUtensorMap* m, const void* ptr, int cout, int k, int bn) 
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MT, int BN, int STAGES>
+template <int MT, int BN, int STAGES, bool PAIR = false>
 cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& P,
                    long long ctas, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)STAGES * (MT * kABytes + BN * BK * 2) + 2 * BM * 128 + 8 * (2 * STAGES + 5) + 1024;
+    constexpr size_t smem = (size_t)STAGES * (MT * kABytes + (PAIR ? BN / 2 : BN) * BK * 2) + 2 * BM * 128 + 8 * (2 * STAGES + 5) + 1024;
     static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
     static bool attr_set = false;           // per instantiation; benign race (idempotent)
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MT, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MT, BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -461,8 +534,24 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
         sms = n;
     }
     // persistent: one CTA per SM walks the tile list with stride gridDim.x
+    if (PAIR) {
+        // clusters of two CTAs (one per SM of a TPC); `ctas` counts pixel tiles x cout tiles, a cluster takes two pixel tiles
+        const long long items = (long long)P.cout_tiles * (((long long)P.n_tiles_w * P.n_tiles_h * P.n_tiles_n + 1) / 2);
+        const long long clusters = items < sms / 2 ? items : sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MT, BN, STAGES, PAIR>, mx, mw, my, P);
+    }
     const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
-    conv_tc_kernel<MT, BN, STAGES><<<grid, kThreads, smem, stream>>>(mx, mw, my, P);
+    conv_tc_kernel<MT, BN, STAGES, PAIR><<<grid, kThreads, smem, stream>>>(mx, mw, my, P);
     return cudaGetLastError();
 }
 
@@ -471,7 +560,7 @@ int g_force_bn = 0;        // 0 = automatic; set through fots_b200_conv_set_tile
 }  // namespace
 
 extern "C" int fots_b200_conv_set_tile(int bn) {
-    if (bn != 0 && bn != 64 && bn != 128 && bn != 256) return RROI_B200_ERR_INVALID_ARG;
+    if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return RROI_B200_ERR_INVALID_ARG;   // 512 = 256 on a CTA pair
     g_force_bn = bn;
     return RROI_B200_OK;
 }
@@ -487,7 +576,12 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     if (bias && ((uintptr_t)bias & 15)) return RROI_B200_ERR_INVALID_ARG;
     if (!encode_fn()) return RROI_B200_ERR_CUDA;
 
-    int bn = g_force_bn ? g_force_bn : (Cout % 256 == 0 ? 256 : Cout % 128 == 0 ? 128 : 64);
+    // CTA pairs (cta_group::2) for 256-wide cout tiles: forced with tile = 512, automatic when there are enough pixel tiles
+    // to keep all 74 clusters busy for several rounds (measured: conv8/9 1351 -> 1425 TF/s, conv7 1228 -> 1326; the
+    // 256-tile conv10_s is better off with single CTAs)
+    const long long px_tiles = ((long long)N * Ho * Wo + BM - 1) / BM;
+    bool pair = Cout % 256 == 0 && stats == nullptr && (g_force_bn == 512 || (g_force_bn == 0 && px_tiles >= 4 * 148));
+    int bn = pair ? 256 : (g_force_bn && g_force_bn != 512) ? g_force_bn : (Cout % 256 == 0 ? 256 : Cout % 128 == 0 ? 128 : 64);
     if (Cout % bn != 0) bn = 64;
     // BN < 256: two pixel sub-tiles per CTA share the weight tile (same bytes per MMA cycle as 128 x 256, and enough
     // MMAs per k-block to hide the single-thread issue path)
@@ -528,12 +622,13 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
 
     CUtensorMap mx, mw, my;
     if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
-    if (!make_map_weights(&mw, w, Cout, R * S * Cin, bn)) return RROI_B200_ERR_INVALID_ARG;
+    if (!make_map_weights(&mw, w, Cout, R * S * Cin, pair ? bn / 2 : bn)) return RROI_B200_ERR_INVALID_ARG;
     if (!make_map_nhwc(&my, y, N, Ho, Wo, Cout, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
 
     cudaError_t e;
     if (bn == 64) e = launch<2, 64, 4>(mx, mw, my, P, ctas, stream);
     else if (bn == 128) e = launch<2, 128, 4>(mx, mw, my, P, ctas, stream);
+    else if (pair) e = launch<1, 256, 6, true>(mx, mw, my, P, ctas, stream);
     else e = launch<1, 256, 4>(mx, mw, my, P, ctas, stream);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;

@@ -74,15 +74,18 @@ CONV_CASES = [
     (2, 23, 37, 128, 192, 3, 3, 1, 1, True, 0.0),        # odd sizes, Cout = 3 x 64
     (1, 90, 160, 128, 128, 3, 3, 1, 1, False, 1.0),      # layer2 block at 720p
     (2, 5, 9, 64, 64, 5, 5, 2, 2, True, 1.0),            # 25 taps, image smaller than a tile
+    (80, 4, 64, 128, 256, 3, 3, 1, 1, False, 0.01),      # 160 pixel tiles: every CTA (pair) walks several tiles
+    (2, 23, 37, 64, 512, 3, 3, 1, 1, True, 0.0),         # two 256-wide cout tiles, ragged pixel tiles
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 512])
 def test_tcgen05_conv_matches_torch_fp32(cuda, case, bn):
+    """bn: forced output-channel tile; 512 = a 256-wide tile on a CTA pair (tcgen05 cta_group::2, cluster of two)."""
     from fots.pytorch_b200.pipeline import conv as TC
     N, H, W, Cin, Cout, R, S, ph, pw, bias, slope = case
-    if bn and Cout % bn:
+    if bn and Cout % min(bn, 256):
         pytest.skip("Cout is not a multiple of the forced tile")
     g = torch.Generator().manual_seed(N * 131 + Cin + Cout + R)
     x = torch.randn(N, Cin, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)

@@ -77,9 +77,18 @@ if __name__ == "__main__":
     ok &= case(1, 45, 80, 64, 64, 3, 3, 1, 1, False, 1.0)          # ragged tiles in h and w
     ok &= case(2, 23, 37, 128, 192, 3, 3, 1, 1, True, 0.0)         # odd sizes, Cout = 3 x 64
     ok &= case(1, 180, 320, 64, 64, 3, 3, 1, 1, False, 1.0)
+    # CTA-pair variant (cta_group::2): bn = 512 selects it for Cout % 256 == 0
+    ok &= case(3, 4, 64, 256, 256, 3, 3, 1, 1, False, 0.01, bn=512)      # 6 pixel tiles -> 3 pairs
+    ok &= case(5, 2, 64, 256, 256, 2, 3, 0, 1, True, 1.0, bn=512)        # 3 pixel tiles -> the last pair is half empty
+    ok &= case(2, 23, 37, 128, 512, 3, 3, 1, 1, True, 0.0, bn=512)       # ragged, two cout tiles
+    ok &= case(64, 4, 64, 256, 256, 3, 3, 1, 1, False, 0.01, bn=512)     # more pairs than clusters: several tiles per CTA
     print("ALL OK" if ok else "SOME FAILED", flush=True)
     if ok and len(sys.argv) > 1 and sys.argv[1] == "bench":
-        for bn in (128, 256, 64):
+        for bn in (512, 256):
+            bench(512, 4, 64, 256, 256, 3, 3, 1, 1, bn)          # conv8 / conv9
+            bench(512, 4, 64, 128, 256, 3, 3, 1, 1, bn)          # conv7
+            bench(512, 2, 64, 256, 256, 2, 3, 0, 1, bn)          # conv10_s
+        for bn in (128, 64):
             bench(512, 4, 64, 256, 256, 3, 3, 1, 1, bn)          # conv8 / conv9
         bench(512, 8, 64, 64, 128, 3, 3, 1, 1, 128)              # conv5
         bench(512, 8, 64, 128, 128, 3, 3, 1, 1, 128)             # conv6
