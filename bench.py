@@ -351,11 +351,14 @@ def variants_leg(args, torch, device, lib, cabi, peak):
             ("fpn_c256", dict(channels=256, layout=args.layout, images=1, streams=args.streams)),
             ("cfg4_per_gpu_32img_2048rois", dict(channels=args.channels, layout=args.layout, images=32, streams=1)),
             ("cfg4_per_gpu_nchw", dict(channels=args.channels, layout="nchw", images=32, streams=1)),
+            # the opt-in NCHW kernel that stages each patch's footprint with TMA box loads (not faster)
+            ("cfg4_per_gpu_nchw_tma_staged", dict(channels=args.channels, layout="nchw", images=32, streams=1, nchw_tma=1)),
             # the inference pipeline's variant: bf16 map in, bf16 pooled out (half the bytes, same arithmetic)
             ("bf16_io", dict(channels=args.channels, layout="nhwc", images=1, streams=args.streams, dtype="bf16")),
             ("bf16_io_cfg4_per_gpu", dict(channels=args.channels, layout="nhwc", images=32, streams=1, dtype="bf16"))]
     for name, kw in grid:
         cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, 0 if kw["streams"] == 1 else max(args.variant, 0))
+        cabi.set_tuning(cabi.TUNE_NCHW_TMA, kw.get("nchw_tma", 0))
         a = types.SimpleNamespace(channels=kw["channels"], layout=kw["layout"], images=kw["images"],
                                   rois_per_image=args.rois_per_image, sets=0, dtype=kw.get("dtype", "fp32"))
         w = Workload(a, device, torch)
@@ -368,6 +371,7 @@ def variants_leg(args, torch, device, lib, cabi, peak):
                      "layout": kw["layout"], "channels": kw["channels"], "rois": w.N, "dtype": kw.get("dtype", "fp32")}
         del w
         torch.cuda.empty_cache()
+    cabi.set_tuning(cabi.TUNE_NCHW_TMA, 0)
     return out
 
 
@@ -455,8 +459,9 @@ def pipeline_leg(args, torch, device, dist, world, rank):
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
             "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
-            "dtype": "bf16: tcgen05 convolutions (conv6/8/9, layer0_1) + cuDNN for the rest, fused InstanceNorm/FPN-merge "
-                     "kernels, bf16-in/bf16-out RoIRotate (fp32 arithmetic)",
+            "dtype": "bf16: hand-written tcgen05 convolutions (conv6/8/9 incl. CTA pairs, layer0_1[0]) and mma.sync stem conv, "
+                     "cuDNN for the remaining convolutions, fused InstanceNorm / FPN-merge / max-pool kernels, "
+                     "bf16-in/bf16-out RoIRotate (fp32 arithmetic)",
             "collective": "one all_gather of int32 [images, 64, 74] records per step" if world > 1 else "none (1 rank)",
             "boxes": "planted (seeded) -- reference NMS is pathological on random-init maps, SURVEY 8d",
             "flop_per_image": 221.7e9}
