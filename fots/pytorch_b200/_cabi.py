@@ -23,6 +23,7 @@ TUNE_NHWC_UNROLL = 1
 TUNE_USE_PDL = 2
 TUNE_BWD_DEDUPE = 3
 TUNE_NCHW_TMA = 4
+TUNE_BWD_ZERO_FUSED = 5
 
 ABI_VERSION = 1
 

@@ -113,17 +113,26 @@ int rroi_b200_backward(const float* top_diff, const float* rois, const float* id
         return RROI_B200_ERR_INVALID_ARG;
     if (!dims_ok(num_rois, batch, channels, height, width, pooled_height, pooled_width)) return RROI_B200_ERR_INVALID_ARG;
     if (layout != RROI_B200_LAYOUT_NCHW && layout != RROI_B200_LAYOUT_NHWC) return RROI_B200_ERR_INVALID_ARG;
+    rroi::BwdParams p = {};
+    p.top_diff = top_diff; p.rois = rois; p.bottom_diff = bottom_diff; p.idx_x = idx_x; p.idx_y = idx_y;
+    p.N = num_rois; p.B = batch; p.C = channels; p.H = height; p.W = width;
+    p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale;
+    p.idx_mode = idx_x ? rroi::IDX_COMPACT : rroi::IDX_NONE;
+    if (zero_fill && num_rois > 0 && layout == RROI_B200_LAYOUT_NHWC) {
+        // large maps: zero-fill and scatter in ONE pass over the map (rroi_bwd.cu); not eligible -> memset + scatter below
+        const cudaError_t e = rroi::launch_bwd_nhwc_zero_fused(p, stream);
+        if (e == cudaSuccess) return RROI_B200_OK;
+        if (e != cudaErrorNotSupported) {
+            if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
+            return cuda_status(e);
+        }
+    }
     if (zero_fill) {
         const size_t bytes = (size_t)batch * channels * height * width * sizeof(float);
         const cudaError_t e = cudaMemsetAsync(bottom_diff, 0, bytes, stream);
         if (e != cudaSuccess) return cuda_status(e);
     }
     if (num_rois == 0) return RROI_B200_OK;
-    rroi::BwdParams p = {};
-    p.top_diff = top_diff; p.rois = rois; p.bottom_diff = bottom_diff; p.idx_x = idx_x; p.idx_y = idx_y;
-    p.N = num_rois; p.B = batch; p.C = channels; p.H = height; p.W = width;
-    p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale;
-    p.idx_mode = idx_x ? rroi::IDX_COMPACT : rroi::IDX_NONE;
     const cudaError_t e = layout == RROI_B200_LAYOUT_NCHW ? rroi::launch_bwd_nchw(p, stream) : rroi::launch_bwd_nhwc(p, stream);
     if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
     return cuda_status(e);
@@ -154,6 +163,7 @@ int rroi_b200_set_tuning(int key, int value) {
         case RROI_B200_TUNE_BWD_DEDUPE:
             if (value < 0 || value > 2) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.bwd_dedupe = value; return RROI_B200_OK;
+        case RROI_B200_TUNE_BWD_ZERO_FUSED: rroi::g_tuning.bwd_zero_fused = value != 0; return RROI_B200_OK;
         case RROI_B200_TUNE_NCHW_TMA:
             if (value < 0 || value > 5) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.nchw_tma = value; return RROI_B200_OK;
@@ -168,6 +178,7 @@ int rroi_b200_get_tuning(int key) {
         case RROI_B200_TUNE_USE_PDL:     return rroi::g_tuning.use_pdl;
         case RROI_B200_TUNE_BWD_DEDUPE:  return rroi::g_tuning.bwd_dedupe;
         case RROI_B200_TUNE_NCHW_TMA:    return rroi::g_tuning.nchw_tma;
+        case RROI_B200_TUNE_BWD_ZERO_FUSED: return rroi::g_tuning.bwd_zero_fused;
         default: return -1;
     }
 }

@@ -326,7 +326,52 @@ __device__ __forceinline__ float4 ld_v4(const float* ptr, uint32_t pred) {
 
 constexpr int kPackWarps = 8;
 
-template <int CT, int TILE, int UN>
+// L2 eviction-priority variants for the one-pass (ZF) kernel: the gradient map of the images in flight should stay in
+// L2 (evict_last) while top_diff streams through once (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_v4_hint(const float* ptr, uint32_t pred, uint64_t pol) {
+    float4 r;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+        "@q ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(ptr), "r"(pred), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void red_add_v4_hint(float* addr, float w, const float4& g, uint64_t pol) {
+    const float a = __fmul_rn(w, g.x), b = __fmul_rn(w, g.y), c = __fmul_rn(w, g.z), d = __fmul_rn(w, g.w);
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_zero_v4_hint(float4* addr, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(addr), "f"(0.0f), "l"(pol) : "memory");
+}
+
+// ZF (zero + scatter in one pass, opt-in: RROI_B200_TUNE_BWD_ZERO_FUSED = 1).  The gradient map has to be defined
+// everywhere, and with a separate memset every touched line of a map larger than L2 crosses DRAM three times (zero
+// written, read back by the first RED, final value written).  Here the map is zeroed by the scatter kernel itself,
+// image by image and `lookahead` images ahead of the scatter front: the CTAs of the j-th image that has RoIs zero the
+// map of image j + LA (the first team also images 0..LA), then wait on a per-image counter until THEIR image has been
+// zeroed -- by the team of image j - LA, whose CTAs have smaller block indices and are long done -- and scatter.  RoIs
+// must be grouped by image (checked by a one-CTA pre-pass, which also ranks the RoIs inside their image); if they are
+// not, a memset kernel runs instead and the scatter proceeds as usual.  Zero stores and REDs carry an L2 evict_last
+// policy, the top_diff stream evict_first.
+// MEASURED (tools/sweep_bwd.py, B200): correct (tests/test_gpu_parity.py::test_backward_zero_fill_fused_with_scatter)
+// but SLOWER than cudaMemsetAsync + scatter: 181 vs 159 us (C=64, 32 images, 472 MB map), 785 vs 624 us (C=256);
+// without the eviction hints 197 us, with a same-image rendezvous instead of the look-ahead 181 us.  The DRAM bytes it
+// saves (~400 MB) do not pay for pushing 472 MB of zero stores through the SMs' store path next to the RED traffic:
+// the copy-engine memset runs at the full 6.3 TB/s and the scatter alone is latency- rather than DRAM-bound (ncu:
+// 4.2 TB/s).  Kept opt-in for the record.
+template <int CT, int TILE, int UN, bool ZF = false>
 __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(const BwdParams p) {
     constexpr int LPP = CT / 4;
     constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;
@@ -344,6 +389,45 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
 
     pdl_wait();
     pdl_launch_dependents();
+    const bool zf = ZF && __ldg(p.zf_meta) != 0;          // 0: the pre-pass refused (RoIs not grouped, ...): a memset kernel ran
+    const uint64_t pol_keep = ZF ? l2_policy_evict_last() : 0ull, pol_stream = ZF ? l2_policy_evict_first() : 0ull;
+    if (zf) {
+        // Pipelined over the images that have RoIs (position j in p.zf_order): the CTAs of image j zero the map of image
+        // j + LA (the first team also zeroes images 0..LA), then wait until THEIR image has been zeroed -- by the team of
+        // image j - LA, whose CTAs have smaller block indices and finished long ago -- and scatter.
+        const int LA = __ldg(p.zf_meta + 2), n_img = __ldg(p.zf_meta + 3);
+        const int b = __float2int_rz(__ldg(p.rois + (size_t)n * 6));
+        const int j = __ldg(p.zf_pos + b);
+        const int mine = __ldg(p.zf_rank + n) * p.tiles + tile;               // this CTA's rank among its image's CTAs
+        const int team = __ldg(p.zf_count + b) * p.tiles;
+        const size_t map4 = (size_t)p.H * p.W * CT / 4;                        // float4 per image
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int t_first = j == 0 ? 0 : j + LA, t_last = j + LA;              // positions this team zeroes
+        for (int t = t_first; t <= t_last && t < n_img; ++t) {
+            const int tb = __ldg(p.zf_order + t);
+            float4* img = reinterpret_cast<float4*>(p.bottom_diff) + (size_t)tb * map4;
+            for (size_t i = (size_t)mine * (kPackWarps * 32) + threadIdx.x; i < map4; i += (size_t)team * (kPackWarps * 32)) st_zero_v4_hint(img + i, pol_keep);
+        }
+        // images nobody scatters into: shared by the whole grid
+        const int n_empty = __ldg(p.zf_meta + 1);
+        for (int e = 0; e < n_empty; ++e) {
+            float4* eimg = reinterpret_cast<float4*>(p.bottom_diff) + (size_t)__ldg(p.zf_empty + e) * map4;
+            for (size_t i = (size_t)blockIdx.x * (kPackWarps * 32) + threadIdx.x; i < map4; i += (size_t)gridDim.x * (kPackWarps * 32)) eimg[i] = z;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int t = t_first; t <= t_last && t < n_img; ++t) atomicAdd(p.zf_arrived + __ldg(p.zf_order + t), 1);
+            const int zeroer = j <= LA ? 0 : j - LA;                           // position of the team that zeroes image j
+            const int need = __ldg(p.zf_count + __ldg(p.zf_order + zeroer)) * p.tiles;
+            int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.zf_arrived + b) : "memory");
+                if (seen < need) __nanosleep(64);
+            } while (seen < need);
+        }
+        __syncthreads();
+    }
     if (warp == 0) {
         RoiXform X;
         if (p.idx_mode == IDX_NONE) {
@@ -398,7 +482,8 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
             const int dpx = NCH > 1 ? it / NCH : it * PPI;
             const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
             r[u] = rbase[dpx];
-            gq[u] = ld_v4(tbase + dpx * CT + ch, r[u].pred & 15u);     // bins that scatter nothing are not even read
+            gq[u] = ZF ? ld_v4_hint(tbase + dpx * CT + ch, r[u].pred & 15u, pol_stream)
+                       : ld_v4(tbase + dpx * CT + ch, r[u].pred & 15u);     // bins that scatter nothing are not even read
         }
         uint32_t any = 0;
 #pragma unroll
@@ -409,6 +494,13 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
                 const int it = it0 + u;
                 const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
                 float* d = gbase + (long long)r[u].pix * CT + ch;
+                if (ZF) {
+                    if (r[u].pred & 1u) red_add_v4_hint(d, r[u].wlt, gq[u], pol_keep);
+                    if (r[u].pred & 2u) red_add_v4_hint(d + CT, r[u].wrt, gq[u], pol_keep);
+                    if (r[u].pred & 4u) red_add_v4_hint(d + rowC + CT, r[u].wrb, gq[u], pol_keep);
+                    if (r[u].pred & 8u) red_add_v4_hint(d + rowC, r[u].wlb, gq[u], pol_keep);
+                    continue;
+                }
                 if (r[u].pred & 1u) red_add_v4(d, r[u].wlt, gq[u]);
                 if (r[u].pred & 2u) red_add_v4(d + CT, r[u].wrt, gq[u]);
                 if (r[u].pred & 4u) red_add_v4(d + rowC + CT, r[u].wrb, gq[u]);
@@ -431,6 +523,97 @@ static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl
     }
     p.tiles = (bins + 63) / 64;
     return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
+}
+
+// ---- zero + scatter in one pass: pre-pass over the RoI rows ----------------------------------------------------
+// One CTA.  ok = every batch index is in [0, B), the rows are grouped by image in non-decreasing order and no image has
+// more than max_per_image RoIs.  rank[n] = position of RoI n inside its image, count[b], the list of images without
+// RoIs, order[] / pos[] = the images with RoIs in ascending order and each image's position in that list,
+// meta = {ok, n_empty, lookahead, n_images_with_rois}; arrived[] is cleared.
+__global__ void __launch_bounds__(1024) bwd_group_kernel(const float* __restrict__ rois, int N, int B, int max_per_image, int lookahead,
+                                                          int* __restrict__ rank, int* __restrict__ count, int* __restrict__ first,
+                                                          int* __restrict__ arrived, int* __restrict__ empty, int* __restrict__ order,
+                                                          int* __restrict__ pos, int* __restrict__ meta) {
+    __shared__ int bad, n_empty;
+    if (threadIdx.x == 0) { bad = 0; n_empty = 0; }
+    for (int b = threadIdx.x; b < B; b += blockDim.x) { count[b] = 0; first[b] = 0; arrived[b] = 0; }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float fb = __ldg(rois + (size_t)n * 6);
+        const int b = __float2int_rz(fb);
+        if (!(fb >= 0.0f) || b >= B) { bad = 1; continue; }
+        const int prev = n > 0 ? __float2int_rz(__ldg(rois + (size_t)(n - 1) * 6)) : -1;
+        if (prev > b) bad = 1;
+        if (prev != b) first[b] = n;
+        atomicAdd(count + b, 1);
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N && !bad; n += blockDim.x) {
+        const int b = __float2int_rz(__ldg(rois + (size_t)n * 6));
+        rank[n] = n - first[b];
+    }
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        if (count[b] > max_per_image) bad = 1;
+        if (count[b] == 0) empty[atomicAdd(&n_empty, 1)] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int k = 0;
+        for (int b = 0; b < B; ++b)
+            if (count[b] > 0) { order[k] = b; pos[b] = k; ++k; }
+        meta[0] = bad ? 0 : 1; meta[1] = n_empty; meta[2] = lookahead; meta[3] = k;
+    }
+}
+
+// runs between the pre-pass and the scatter: does nothing when the pre-pass said ok, otherwise it is the memset
+__global__ void __launch_bounds__(256) bwd_zero_unless_ok_kernel(float4* __restrict__ dst, size_t n4, const int* __restrict__ meta) {
+    if (__ldg(meta) != 0) return;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) dst[i] = z;
+}
+
+template <int CT>
+static cudaError_t launch_bwd_zero_fused_ct(BwdParams& p, cudaStream_t s, bool pdl) {
+    const int bins = p.PH * p.PW;
+    p.tiles = (bins + 255) / 256;
+    return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 256, 4, true>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
+}
+
+cudaError_t launch_bwd_nhwc_zero_fused(const BwdParams& p0, cudaStream_t s) {
+    BwdParams p = p0;
+    const size_t map_bytes = (size_t)p.B * p.C * p.H * p.W * sizeof(float);
+    const bool shape_ok = (p.C == 32 || p.C == 64 || p.C == 128 || p.C == 256) && p.N > 0 && p.B <= 4096 &&
+                          ((reinterpret_cast<uintptr_t>(p.top_diff) | reinterpret_cast<uintptr_t>(p.bottom_diff)) % 16 == 0) &&
+                          ((size_t)p.H * p.W * p.C) % 4 == 0 && g_tuning.bwd_dedupe != 2 && g_tuning.bwd_zero_fused != 0;
+    // worth it only when the map does not stay in L2 between a memset and the scatter
+    if (!shape_ok || map_bytes < (size_t)96 << 20) return cudaErrorNotSupported;
+    const int tiles = (p.PH * p.PW + 255) / 256;
+    const int max_per_image = 512 / tiles;                 // at most 512 CTAs wait for each other (592+ are resident)
+    if (max_per_image < 1) return cudaErrorNotSupported;
+    int* scratch = nullptr;
+    const size_t ints = (size_t)p.N + 6 * (size_t)p.B + 4;
+    // how many images ahead the map is zeroed: the zeroed-ahead maps plus the one being scattered must stay in L2
+    const size_t img_bytes = map_bytes / (size_t)p.B;
+    const int lookahead = 3 * img_bytes <= ((size_t)100 << 20) ? 2 : 2 * img_bytes <= ((size_t)100 << 20) ? 1 : 0;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), ints * sizeof(int), s);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return cudaErrorNotSupported; }
+    int* rank = scratch; int* count = rank + p.N; int* first = count + p.B; int* arrived = first + p.B;
+    int* empty = arrived + p.B; int* order = empty + p.B; int* pos = order + p.B; int* meta = pos + p.B;
+    bwd_group_kernel<<<1, 1024, 0, s>>>(p.rois, p.N, p.B, max_per_image, lookahead, rank, count, first, arrived, empty, order, pos, meta);
+    bwd_zero_unless_ok_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4*>(p.bottom_diff), map_bytes / 16, meta);
+    p.zf_rank = rank; p.zf_count = count; p.zf_arrived = arrived; p.zf_empty = empty; p.zf_meta = meta; p.zf_order = order; p.zf_pos = pos;
+    p.cgroups = 1;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        switch (p.C) {
+            case 32:  e = launch_bwd_zero_fused_ct<32>(p, s, false); break;
+            case 64:  e = launch_bwd_zero_fused_ct<64>(p, s, false); break;
+            case 128: e = launch_bwd_zero_fused_ct<128>(p, s, false); break;
+            default:  e = launch_bwd_zero_fused_ct<256>(p, s, false); break;
+        }
+    }
+    (void)cudaFreeAsync(scratch, s);
+    return e;
 }
 
 cudaError_t launch_bwd_nhwc(const BwdParams& p0, cudaStream_t s) {

@@ -22,7 +22,7 @@
 
 namespace rroi {
 
-Tuning g_tuning = {0, 0, 0, 1, 0};
+Tuning g_tuning = {0, 0, 0, 1, 0, 0};
 
 // code word of a bin
 enum : uint32_t {

@@ -36,6 +36,15 @@ struct BwdParams {
     int idx_mode;
     int tiles;
     int cgroups;
+    // fused zero-fill (channels-last packed kernel only; see rroi_bwd.cu "zero + scatter in one pass"): per-RoI rank
+    // inside its image, per-image RoI count, per-image arrival counter, list of images without RoIs, {ok, n_empty}
+    const int* zf_rank;
+    const int* zf_count;
+    int* zf_arrived;
+    const int* zf_empty;
+    const int* zf_meta;
+    const int* zf_order;
+    const int* zf_pos;
 };
 
 // Tunables a caller (bench sweeps, tests) may override through rroi_b200_set_tuning(); 0 = default.
@@ -44,6 +53,7 @@ struct Tuning {
     int nhwc_unroll;   // NHWC forward variant 0..5 (bins per warp x bins in flight), see launch_fwd_nhwc_vec
     int use_pdl;       // launch with programmatic stream serialization
     int bwd_dedupe;    // warp-level merge of equal sample points before the atomics (NCHW backward)
+    int bwd_zero_fused; // 1 = one-pass zero + scatter backward for maps >= 96 MB (measured slower than memset + scatter: opt-in)
     int nchw_tma;      // 0 = NCHW forward gathers through L1 (default); 1 = stages its footprint with TMA box loads; 2..5 = same, box index >= value - 2
 };
 extern Tuning g_tuning;
@@ -54,6 +64,9 @@ cudaError_t launch_fwd_nhwc(const FwdParams& p, cudaStream_t s);
 cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p, cudaStream_t s);
 cudaError_t launch_bwd_nchw(const BwdParams& p, cudaStream_t s);
 cudaError_t launch_bwd_nhwc(const BwdParams& p, cudaStream_t s);
+// channels-last backward that also defines the whole gradient map (replaces cudaMemsetAsync + launch_bwd_nhwc when the
+// map is much larger than L2); returns cudaErrorNotSupported when the shape is not eligible (caller falls back)
+cudaError_t launch_bwd_nhwc_zero_fused(const BwdParams& p, cudaStream_t s);
 // the reference-layout backward that honours caller-supplied [N,C,PH,PW] centres element by element
 cudaError_t launch_bwd_legacy(const BwdParams& p, cudaStream_t s);
 

@@ -40,6 +40,7 @@ typedef struct CUstream_st* cudaStream_t;   /* same definition as the CUDA runti
 #define RROI_B200_TUNE_NHWC_UNROLL  1   /* NHWC forward variant: 0 = auto, 1..6 = fixed tile size x loads in flight  */
 #define RROI_B200_TUNE_USE_PDL      2   /* 1: launch with programmatic dependent launch                       */
 #define RROI_B200_TUNE_BWD_DEDUPE   3   /* NCHW: 1 (default) warp-merge equal sample points, 0 off; 2 = generic NHWC kernel */
+#define RROI_B200_TUNE_BWD_ZERO_FUSED 5 /* channels-last backward with zero_fill: 0 (default) memset + scatter; 1 = one-pass zero + scatter for maps >= 96 MB (measured slower) */
 #define RROI_B200_TUNE_NCHW_TMA     4   /* NCHW forward: 0 (default) gather kernel; 1 = stage each patch's footprint with TMA box loads; 2..5 = same with a minimum box size (sweeps) */
 
 /*

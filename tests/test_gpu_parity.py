@@ -342,3 +342,39 @@ def test_nchw_tma_staged_forward_equals_gather_kernel_and_oracle(oracle, cuda, C
         Hh.assert_bit_equal(got, want, "NCHW forward")
         Hh.assert_bit_equal(ix, wx[:, 0], "idx_x")
         Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")
+
+
+@pytest.mark.parametrize("order", ["grouped", "grouped_with_empty_images", "shuffled", "crowded_image"])
+def test_backward_zero_fill_fused_with_scatter(oracle, cuda, order):
+    """The opt-in one-pass backward (RROI_B200_TUNE_BWD_ZERO_FUSED = 1; zero-fill + per-image rendezvous + scatter in one
+    kernel, rroi_bwd.cu) on a map larger than 96 MB: taken when the RoIs are grouped by image; shuffled rows, or more
+    RoIs in one image than may wait for each other, fall back to a memset kernel + scatter inside the same call.
+    Either way every element of the gradient map is defined (the buffer starts as NaN) and equals the oracle's to 1e-4."""
+    import torch
+    from fots.pytorch_b200 import _cabi
+    from fots.pytorch_b200.rroi_align.functions.rroi_align import backward_raw
+    B, C, H, W, ph, pw, scale = 8, 64, 180, 320, 8, 64, 0.25          # 118 MB gradient map
+    per = {"grouped": [5, 3, 4, 2, 6, 1, 3, 4], "grouped_with_empty_images": [6, 0, 0, 5, 0, 7, 0, 0],
+           "shuffled": [3, 3, 3, 3, 3, 3, 3, 3], "crowded_image": [300, 2, 0, 1, 0, 0, 0, 1]}[order]
+    rois = np.concatenate([WL.random_rois(11 + i, n, i) for i, n in enumerate(per) if n > 0], 0)
+    if order == "shuffled":
+        rois = rois[np.random.default_rng(0).permutation(len(rois))]
+    N = rois.shape[0]
+    rng = np.random.default_rng(5)
+    top = rng.standard_normal((N, C, ph, pw), dtype=np.float32)
+    feats = np.zeros((B, C, H, W), np.float32)
+    _, ix, iy = oracle.forward(feats, rois, ph, pw, scale, threads=0)
+    want = oracle.backward(top, rois, ix, iy, (B, C, H, W), scale, threads=0)
+    g = torch.from_numpy(top).to(cuda).contiguous(memory_format=torch.channels_last)
+    r = torch.from_numpy(rois).to(cuda)
+    # poison the allocator's next block so that an element the kernel forgets to define shows up as NaN
+    poison = torch.full((B, C, H, W), float("nan"), device=cuda).contiguous(memory_format=torch.channels_last)
+    del poison
+    _cabi.set_tuning(_cabi.TUNE_BWD_ZERO_FUSED, 1)
+    try:
+        got = backward_raw(g, r, None, None, (B, C, H, W), scale, _cabi.LAYOUT_NHWC)
+        torch.cuda.synchronize()
+    finally:
+        _cabi.set_tuning(_cabi.TUNE_BWD_ZERO_FUSED, 0)
+    assert bool(torch.isfinite(got).all())
+    Hh.assert_close_rel(got.cpu().numpy(), want, 1e-4, "fused zero-fill backward (%s)" % order)
