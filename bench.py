@@ -51,6 +51,7 @@ def parse():
                          "launches are in flight; 0 = auto (64-bin tiles for one small launch at a time)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-streams", type=int, default=2, help="host-buffer sets / streams of the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
     ap.add_argument("--pipeline-steps", type=int, default=4)
@@ -305,13 +306,13 @@ def verify_outputs(wl, torch, cabi):
     return ok
 
 
-def e2e_leg(args, wl, torch, device, steps):
+def e2e_leg(args, wl, torch, device, steps, nbuf=None):
     """Same metric end to end through the public module API with HOST buffers: per step a pinned-host ->
     device copy of the step's features + RoIs, _RRoiAlign.forward, and a device -> pinned-host read of the
     pooled result.  Two streams alternate so the H2D of step i+1 overlaps the D2H of step i."""
     from fots.pytorch_b200 import _RRoiAlign
     fmt = torch.channels_last if wl.layout == "nhwc" else torch.contiguous_format
-    nbuf = 2
+    nbuf = nbuf or getattr(args, "e2e_streams", 2)
     mod = _RRoiAlign(wl.PH, wl.PW, wl.scale)
     h_feat = [wl.feats[i % wl.sets].cpu().contiguous(memory_format=fmt).pin_memory() for i in range(nbuf)]
     h_rois = [wl.rois[i % wl.sets].cpu().pin_memory() for i in range(nbuf)]

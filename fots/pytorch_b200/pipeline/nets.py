@@ -278,7 +278,44 @@ class CRNN(nn.Module):
         self.rnn = nn.Sequential(_BiLSTM(512, hidden, hidden), _BiLSTM(hidden, hidden, nclass))
 
     def forward(self, x):
-        f = self.cnn(x)
+        fast = getattr(self, "_b200", None)
+        if fast is not None and x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad):
+            f = self._cnn_b200(x).float()
+        else:
+            f = self.cnn(x)
         if f.size(2) != 1:
             raise ValueError("CRNN: input height must reduce to 1 (use PH = 32)")
         return self.rnn(f.squeeze(2).permute(2, 0, 1).contiguous())
+
+    # ---- B200 placement ------------------------------------------------------------------------
+    def to_b200(self, device="cuda"):
+        """Inference placement: every convolution gets its (eval-mode) BatchNorm folded into bf16 channels-last weights
+        and an fp32 bias, so that each of the seven layers is ONE convolution with bias + ReLU in the epilogue -- on the
+        tcgen05 kernel (csrc/conv_tc.cu) wherever Cin % 64 == 0 (six of the seven layers, 99 % of the FLOPs), on the
+        library for the 3-channel first layer.  The BiLSTMs stay cuDNN in fp32.  Call again after loading a checkpoint."""
+        self.to(device).eval()
+        packs = []
+        for i, (cout, k, pad, bn, pool) in enumerate(self.PLAN):
+            conv = getattr(self.cnn, "conv%d" % i)
+            w, b = conv.weight.detach().float(), conv.bias.detach().float()
+            if bn:
+                m = getattr(self.cnn, "batchnorm%d" % i)
+                scale = m.weight.detach().float() / torch.sqrt(m.running_var.detach().float() + m.eps)
+                w = w * scale.view(-1, 1, 1, 1)
+                b = (b - m.running_mean.detach().float()) * scale + m.bias.detach().float()
+            packs.append((w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), b.contiguous(), pad, pool))
+        self._b200 = packs
+        return self
+
+    @torch.no_grad()
+    def _cnn_b200(self, x):
+        y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        for w, b, pad, pool in self._b200:
+            if tc.ENABLED and w.size(1) % 64 == 0:
+                y = tc.conv2d(y, w, b, (pad, pad), 0.0)                      # conv + folded BN + bias + ReLU, one kernel
+            else:
+                y = torch.relu(F.conv2d(y, w, b.to(torch.bfloat16), 1, pad))
+            if pool is not None:
+                kh, kw, sh, sw, ph, pw = pool
+                y = F.max_pool2d(y, (kh, kw), (sh, sw), (ph, pw))
+        return y

@@ -294,3 +294,21 @@ def test_detector_postprocessing_gpu_decode_plus_host_merge(oracle, cuda):
     centres = got[0][:, :8].reshape(-1, 4, 2).mean(1) / 4.0
     for cx, cy in ((200, 100), (120, 150)):
         assert np.min(np.hypot(centres[:, 0] - cx, centres[:, 1] - cy)) < 2.0
+
+
+def test_crnn_on_tensor_cores_matches_fp32(cuda):
+    """Consumer B on the B200 inference path (CRNN.to_b200: BatchNorm folded, conv + bias + ReLU on the tcgen05 kernel
+    for six of the seven layers) against the same module in fp32 on torch's ops."""
+    from fots.pytorch_b200.pipeline import CRNN
+    torch.manual_seed(0)
+    net = CRNN(nclass=89).to(cuda).eval()
+    with torch.no_grad():
+        for m in net.modules():                       # non-trivial running statistics, so that the folding is exercised
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+        x = torch.randn(5, 3, 32, 128, device=cuda)
+        want = net(x)
+        got = net.to_b200(cuda)(x)
+    assert got.shape == want.shape == (128 // 4 + 1, 5, 89)
+    err = (got - want).abs()
+    assert float(err.mean()) < 0.03 * float(want.abs().mean()) + 2e-3 and float(err.max()) < 0.25 * float(want.abs().max()) + 2e-2
