@@ -15,6 +15,11 @@
 // -> bias/activation -> bf16 -> swizzled shared block -> TMA store).  Persistent: one CTA per SM walks the tile
 // list; the accumulator is double-buffered in TMEM (2 x BN columns) and the producer runs ahead across tile
 // boundaries, so the epilogue of tile i and the pipeline fill of tile i+1 hide behind the MMAs.
+// Tile shapes: 128 pixels x 256 channels; two 128-pixel sub-tiles x 128 or 64 channels; and, for 256-wide tiles with
+// enough work, CTA PAIRS (tcgen05 cta_group::2, clusters of two): 256 pixels x 256 channels per pair with half of the
+// weight tile staged by each CTA (see the PAIR notes at the kernel).  Optional epilogue: per-image per-channel sum and
+// sum of squares of the stored values (the statistics pass of the InstanceNorm that follows).
+// Also used by CRNN.to_b200 (tools/models.py:853-909) with the BatchNorms folded into weights and bias.
 #include "../../../include/fots_b200_pipeline.h"
 #include <cuda.h>
 #include <cuda_runtime.h>
