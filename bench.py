@@ -468,6 +468,40 @@ def pipeline_leg(args, torch, device, dist, world, rank):
             "flop_per_image": 221.7e9}
 
 
+def conv_leg(torch, device):
+    """Tensor-pipe evidence for the consumer/feeder convolutions: the hand-written tcgen05 implicit-GEMM
+    kernel (fots_b200_conv2d_nhwc_bf16, leaky-ReLU fused) on the recogniser's shapes at the 8-image micro-batch of the
+    pipeline (512 RoIs), timed with CUDA events over 20 launches after 3 warm-ups, against the measured dense bf16 peak."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    except Exception:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+    out = {"peak_tflops": peak, "peak_source": src, "bound": "tensor"}
+    shapes = [("conv8_conv9_256to256_cta_pairs", 512, 4, 64, 256, 256), ("conv7_128to256_cta_pairs", 512, 4, 64, 128, 256),
+              ("conv6_128to128", 512, 8, 64, 128, 128), ("layer0_1_64to64_360x640", 8, 360, 640, 64, 64)]
+    with torch.no_grad():
+        for name, N, H, W, cin, cout in shapes:
+            x = torch.randn(N, cin, H, W, device=device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            w = (torch.randn(cout, cin, 3, 3, device=device) / (cin * 9) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            for _ in range(3):
+                TC.conv2d(x, w, None, (1, 1), 0.01)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                TC.conv2d(x, w, None, (1, 1), 0.01)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 20 * 1e3
+            tf = 2.0 * N * H * W * cout * cin * 9 / us / 1e6
+            out[name] = {"us_per_launch": us, "tflops": tf, "frac": tf / peak}
+            del x, w
+    torch.cuda.empty_cache()
+    return out
+
+
 def pipeline_cpu_baseline(torch):
     """The reference's CPU path for the end-to-end step, on this box's host cores: the same architecture in fp32 on
     torch CPU (fots.pytorch_b200.pipeline.nets is output-identical to tools/models.py with shared weights) + the
@@ -644,6 +678,10 @@ def run_b200(args):
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                        "api": "fots.pytorch_b200._RRoiAlign(8,64,0.25)(features, rois) with pinned host buffers, 2 streams"}
         line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_seconds)
+        try:
+            line["conv_tc"] = conv_leg(torch, device)
+        except Exception as e:   # secondary evidence: never take the headline line down
+            line["conv_tc"] = {"error": repr(e)}
     if not args.no_pipeline and not args.no_extras:
         del wl
         torch.cuda.empty_cache()
