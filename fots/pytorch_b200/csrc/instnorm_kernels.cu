@@ -43,11 +43,20 @@ __global__ void __launch_bounds__(kThreads) in_stats_kernel(const Bf16x8* __rest
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0f;
     if (phase < nphase) {
         const Bf16x8* base = x + ((size_t)b * HW) * G + g;
-        for (int r = r0 + phase; r < r1; r += nphase) {
-            float f[8];
-            unpack8(ld8(base + (size_t)r * G), f);
+        constexpr int U = 4;                                  // rows in flight per thread (memory-level parallelism)
+        for (int r = r0 + phase; r < r1; r += U * nphase) {
+            Bf16x8 v[U];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+            for (int u = 0; u < U; ++u)
+                if (r + u * nphase < r1) v[u] = ld8(base + (size_t)(r + u * nphase) * G);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * nphase >= r1) break;
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+            }
         }
     }
     // reduce over the row phases that share a channel group
@@ -98,27 +107,48 @@ __global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __rest
     const int r1 = min(HW, r0 + rows_per_cta);
     const size_t plane = (size_t)b * HW;
     const int Gout = Cout / 8;
-    for (int r = r0 + phase; r < r1; r += nphase) {
-        float f[8], o[8];
-        unpack8(ld8(x + (plane + r) * G + g), f);
+    // this thread's 8 channels: coefficients in registers, U rows in flight (memory-level parallelism)
+    float sc[8], sh[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(f[i], scale[g * 8 + i], shift[g * 8 + i]);
-        if (kResidual) {
-            float rr[8];
-            unpack8(ld8(res + (plane + r) * G + g), rr);
+    for (int i = 0; i < 8; ++i) { sc[i] = scale[g * 8 + i]; sh[i] = shift[g * 8 + i]; }
+    const float* sc2 = scale + C + g * 8;                 // CReLU's second half: read from shared memory (saves 16 registers)
+    const float* sh2 = shift + C + g * 8;
+    constexpr int U = 4;
+    for (int r = r0 + phase; r < r1; r += U * nphase) {
+        Bf16x8 xv[U], rv[U];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += rr[i];
+        for (int u = 0; u < U; ++u) {
+            const int rr_ = r + u * nphase;
+            if (rr_ < r1) {
+                xv[u] = ld8(x + (plane + rr_) * G + g);
+                if (kResidual) rv[u] = ld8(res + (plane + rr_) * G + g);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * slope;
-        y[(plane + r) * Gout + g] = pack8(o);
-        if (kCRelu) {
+        for (int u = 0; u < U; ++u) {
+            const int rr_ = r + u * nphase;
+            if (rr_ >= r1) break;
+            float f[8], o[8];
+            unpack8(xv[u], f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float v = fmaf(f[i], scale[C + g * 8 + i], shift[C + g * 8 + i]);
-                o[i] = v > 0.0f ? v : v * slope;
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(f[i], sc[i], sh[i]);
+            if (kResidual) {
+                float rr[8];
+                unpack8(rv[u], rr);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += rr[i];
             }
-            y[(plane + r) * Gout + G + g] = pack8(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * slope;
+            y[(plane + rr_) * Gout + g] = pack8(o);
+            if (kCRelu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float v = fmaf(f[i], sc2[i], sh2[i]);
+                    o[i] = v > 0.0f ? v : v * slope;
+                }
+                y[(plane + rr_) * Gout + G + g] = pack8(o);
+            }
         }
     }
 }
