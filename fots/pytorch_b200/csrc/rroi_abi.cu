@@ -157,7 +157,7 @@ int rroi_b200_set_tuning(int key, int value) {
             if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.nchw_cg = value; return RROI_B200_OK;
         case RROI_B200_TUNE_NHWC_UNROLL:
-            if (value < 0 || value > 6) return RROI_B200_ERR_INVALID_ARG;
+            if (value < 0 || value > 7) return RROI_B200_ERR_INVALID_ARG;
             rroi::g_tuning.nhwc_unroll = value; return RROI_B200_OK;
         case RROI_B200_TUNE_USE_PDL:    rroi::g_tuning.use_pdl = value != 0; return RROI_B200_OK;
         case RROI_B200_TUNE_BWD_DEDUPE:

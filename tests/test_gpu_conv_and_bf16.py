@@ -35,7 +35,7 @@ def test_bf16_forward_is_the_rounded_fp32_forward(oracle, cuda, C, B, n_per, ph,
     rois[-1, 0] = B + 3                                          # batch index out of range -> zeros (the oracle,
     want[-1] = 0.0                                               # like the reference, would read out of bounds)
     want_bits = _bf16_bits(torch.from_numpy(want).to(torch.bfloat16))
-    for variant in (0, 1, 5):
+    for variant in (0, 1, 5, 7):          # 7: whole-RoI 512-bin tiles
         _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, variant)
         try:
             got = rroi_align_bf16(x, torch.from_numpy(rois).to(cuda), ph, pw, scale)

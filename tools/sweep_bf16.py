@@ -20,7 +20,7 @@ if __name__ == "__main__":
         for C in (64, 256):
             a = types.SimpleNamespace(channels=C, layout="nhwc", images=images, rois_per_image=64, sets=0, dtype="bf16")
             w = bench.Workload(a, dev, torch)
-            for variant in (5, 6, 7, 8, 9):
+            for variant in (5, 7, 0):
                 _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, variant)
                 steps = max(200, 20000 // images)
                 ms = bench.timed_steps(w, steps, 20, 500, torch, _cabi.lib(), _cabi, lambda: None, streams)
