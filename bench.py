@@ -4,13 +4,15 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]                  # product arm (default)
   python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # reference CPU arm
 
-One STEP = one RoIRotate forward over one batch of synthetic input in BASELINE.json configs[1]
-("cfg1"): a single 1280x720 image's shared feature map (180x320 at 1/4 scale), 64 random rotated
-RoIs, 8x64 pooled output, fp32.  `value` = output feature pixels (N*C*PH*PW, zero tail included)
-per second, whole job (all ranks), inputs resident in HBM.  Between steps the working set rotates over
---sets independent (feature map, RoIs, output) buffer sets whose total size exceeds the 126 MB L2,
-so every step reads its features from HBM.  The K timed steps are replayed from CUDA graphs and
-timed with CUDA events on the launching stream, bracketed by barrier + synchronize; max over ranks.
+One STEP = one batch of `--launches-per-step` (default 2010) independent RoIRotate requests in BASELINE.json
+configs[1] ("cfg1"): each request is a single 1280x720 image's shared feature map (180x320 at 1/4 scale), 64 random
+rotated RoIs, 8x64 pooled output, fp32 -- ONE forward launch through the C ABI per request, so a step is a fixed CUDA
+graph of 2010 launches (about 5 ms) and `--steps 20` times about 0.1 s.  `value` = output feature pixels
+(N*C*PH*PW, zero tail included) per second, whole job (all ranks), inputs resident in HBM; `roofline` is per launch.
+Consecutive requests use different (feature map, RoIs, output) buffer sets out of 67 whose total size is 12x the
+126 MB L2, so every launch reads its features from HBM, and are issued round-robin on `--streams` streams the way a
+serving pipeline keeps independent images in flight.  Timed with CUDA events on the launching stream, bracketed by
+barrier + synchronize; max over ranks.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -42,13 +44,17 @@ def parse():
     ap.add_argument("--images", type=int, default=1, help="images per step (cfg1 = 1)")
     ap.add_argument("--rois-per-image", type=int, default=64)
     ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough to exceed 3x L2)")
-    ap.add_argument("--graph-chunk", type=int, default=500)
+    ap.add_argument("--launches-per-step", type=int, default=0,
+                    help="requests (= forward launches) per step; 0 = 30 x the number of buffer sets (2010 for cfg1)")
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--rois-ready", type=int, default=1,
+                    help="RROI_B200_FLAG_ROIS_READY: the RoI rows are uploaded long before the launch (true for this bench)")
+    ap.add_argument("--concurrency", type=int, default=-1,
+                    help="rroi_b200_opts.concurrency hint; -1 = the number of streams")
     ap.add_argument("--streams", type=int, default=8,
                     help="independent steps (different images) are issued round-robin on this many streams")
-    ap.add_argument("--variant", type=int, default=5,
-                    help="NHWC kernel tile variant (rroi_b200_set_tuning): 5 = 256-bin tiles, best when several "
-                         "launches are in flight; 0 = auto (64-bin tiles for one small launch at a time)")
+    ap.add_argument("--variant", type=int, default=0,
+                    help="rroi_b200_opts.variant: 0 = automatic (from grid size and the concurrency hint)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-streams", type=int, default=2, help="host-buffer sets / streams of the e2e leg")
@@ -56,6 +62,9 @@ def parse():
     ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
     ap.add_argument("--pipeline-steps", type=int, default=4)
     ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-images", type=int, default=32, help="batch of the cfg3 training step")
+    ap.add_argument("--train-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -159,9 +168,10 @@ def ncu_traffic(key):
 # ----------------------------------------------------------------------------------------- workload
 
 class Workload:
-    """`sets` independent (features, rois, pooled) buffer sets of the cfg1 shape, resident on the device."""
+    """`sets` independent (features, rois, pooled) buffer sets of the cfg1 shape, resident on the device.
+    Every launch goes through the C ABI with per-call options (rroi_b200_opts); nothing is process-global."""
 
-    def __init__(self, args, device, torch):
+    def __init__(self, args, device, torch, cabi=None):
         import workloads as WL
         self.WL = WL
         self.C, self.H, self.W, self.PH, self.PW, self.scale = args.channels, 180, 320, 8, 64, 0.25
@@ -192,91 +202,111 @@ class Workload:
         self.feat_px_per_step = self.N * self.C * self.PH * self.PW
         self.out = [torch.empty((self.N, self.C, self.PH, self.PW), device=device, memory_format=fmt,
                                 dtype=torch.bfloat16 if self.bf16 else torch.float32) for _ in range(self.sets)]
+        self.backward = False
+        self.opts = None                  # ctypes rroi_b200_opts kept alive here; None = the library's defaults
+        self.xform = None                 # optional per-set transform tables (rroi_b200_roi_xform)
+
+    def set_opts(self, cabi, **kw):
+        self.opts = cabi.opts(**kw) if kw else None
+        return self
+
+    def enable_xform(self, torch, lib, stream):
+        self.xform = [torch.empty((self.N, 8), device=r.device) for r in self.rois]
+        for x, r in zip(self.xform, self.rois):
+            assert lib.rroi_b200_roi_xform(r.data_ptr(), x.data_ptr(), self.N, self.PH, self.scale, stream) == 0
 
     def enable_backward(self, torch):
-        """Allocate top_diff / bottom_diff per buffer set (tools/sweep.py --backward, not the headline)."""
+        """Allocate top_diff / bottom_diff per buffer set and compute the backward's algorithmic bytes:
+        4*C*sum V_n (top_diff of valid elements) + 4*B*C*H*W (the map is defined everywhere) + 2*4*C*U (RMW of the U
+        distinct pixels that receive gradient) + 24*N.  U comes from this library's own forward centres."""
+        from fots.pytorch_b200.rroi_align.functions.rroi_align import forward_raw
         self.gtop = [torch.randn_like(o) for o in self.out]
         self.gbot = [torch.empty_like(f) for f in self.feats]
         self.backward = True
+        self.alg_bytes_bwd, self.touched = [], []
+        for s in range(self.sets):
+            _, ix, iy, _ = forward_raw(self.feats[s], self.rois[s], self.PH, self.PW, self.scale, want_idx=True)
+            valid = torch.from_numpy(self.WL.valid_counts(self.rois_np[s], self.PH, self.PW) // self.PH).to(ix.device)
+            inside = torch.arange(self.PW, device=ix.device)[None, None, :] < valid[:, None, None]
+            b = self.rois[s][:, 0].long()[:, None, None].expand_as(ix)
+            keys = []
+            for fx, fy in ((torch.floor, torch.floor), (torch.ceil, torch.floor), (torch.ceil, torch.ceil), (torch.floor, torch.ceil)):
+                x, y = fx(ix).long(), fy(iy).long()
+                ok = inside & (x > 0) & (x < self.W - 1) & (y > 0) & (y < self.H - 1)      # kernel.cu:267-274
+                keys.append(((b * self.H + y) * self.W + x)[ok])
+            U = int(torch.unique(torch.cat(keys)).numel())
+            V = int(self.WL.valid_counts(self.rois_np[s], self.PH, self.PW).sum())
+            self.touched.append(U)
+            self.alg_bytes_bwd.append(4 * self.C * V + 4 * self.B * self.C * self.H * self.W + 8 * self.C * U + 24 * self.N)
 
     def launch_bwd(self, s, lib, cabi, stream):
-        st = lib.rroi_b200_backward(self.gtop[s].data_ptr(), self.rois[s].data_ptr(), None, None,
-                                    self.gbot[s].data_ptr(), self.N, self.B, self.C, self.H, self.W, self.PH,
-                                    self.PW, self.scale,
-                                    cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW, 1, stream)
+        st = lib.rroi_b200_backward_opt(self.gtop[s].data_ptr(), self.rois[s].data_ptr(), None, None,
+                                        self.gbot[s].data_ptr(), self.N, self.B, self.C, self.H, self.W, self.PH,
+                                        self.PW, self.scale,
+                                        cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW, 1,
+                                        cabi.opts_ref(self.opts), stream)
         if st != 0:
-            raise RuntimeError("rroi_b200_backward -> %d" % st)
+            raise RuntimeError("rroi_b200_backward_opt -> %d" % st)
 
     def launch(self, s, lib, cabi, stream):
-        """One step on buffer set s: exactly one kernel launch through the C ABI (rroi_b200_forward)."""
-        if getattr(self, "backward", False):
+        """One request on buffer set s: exactly one kernel launch through the C ABI (rroi_b200_forward_opt)."""
+        if self.backward:
             return self.launch_bwd(s, lib, cabi, stream)
+        xf = self.xform[s].data_ptr() if self.xform is not None else None
         if self.bf16:
-            st = lib.rroi_b200_forward_bf16(self.feats[s].data_ptr(), self.rois[s].data_ptr(), self.out[s].data_ptr(),
-                                            None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
-                                            self.scale, stream)
+            st = lib.rroi_b200_forward_bf16_opt(self.feats[s].data_ptr(), self.rois[s].data_ptr(), xf, self.out[s].data_ptr(),
+                                                None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
+                                                self.scale, cabi.opts_ref(self.opts), stream)
             if st != 0:
-                raise RuntimeError("rroi_b200_forward_bf16 -> %d" % st)
+                raise RuntimeError("rroi_b200_forward_bf16_opt -> %d" % st)
             return
-        st = lib.rroi_b200_forward(self.feats[s].data_ptr(), self.rois[s].data_ptr(), self.out[s].data_ptr(),
-                                   None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
-                                   self.scale, cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW,
-                                   stream)
+        st = lib.rroi_b200_forward_opt(self.feats[s].data_ptr(), self.rois[s].data_ptr(), xf, self.out[s].data_ptr(),
+                                       None, None, self.N, self.B, self.C, self.H, self.W, self.PH, self.PW,
+                                       self.scale, cabi.LAYOUT_NHWC if self.layout == "nhwc" else cabi.LAYOUT_NCHW,
+                                       cabi.opts_ref(self.opts), stream)
         if st != 0:
-            raise RuntimeError("rroi_b200_forward -> %d" % st)
+            raise RuntimeError("rroi_b200_forward_opt -> %d" % st)
 
 
-def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier, nstreams=1):
-    """W untimed warm-up steps, then exactly K steps replayed from CUDA graphs; returns elapsed ms.
+def launches_per_step_for(wl, want=0, target=2000):
+    """A multiple of the number of buffer sets (every step then starts on set 0 and one graph serves all steps)."""
+    if want > 0:
+        return max(wl.sets, (want // wl.sets) * wl.sets)
+    return wl.sets * max(1, int(round(target / wl.sets)))
 
-    With nstreams > 1 consecutive steps (independent images: different buffer sets) are captured on
-    parallel branches of the graph, the way a serving pipeline keeps several requests in flight."""
+
+def timed_steps(wl, steps, warmup, per_step, torch, lib, cabi, barrier, nstreams=1, launch=None):
+    """One step = ONE CUDA graph of `per_step` launches (independent requests on rotating buffer sets), captured on
+    `nstreams` parallel branches the way a serving pipeline keeps several images in flight.  W untimed warm-up steps
+    (>= 3), then exactly K replays timed with CUDA events on the launching stream; returns elapsed ms."""
+    launch = launch or (lambda s, st: wl.launch(s, lib, cabi, st))
     stream = torch.cuda.Stream()
     side = [torch.cuda.Stream() for _ in range(max(nstreams - 1, 0))]
-    graphs = {}
-    chunk = max(wl.sets, (chunk // wl.sets) * wl.sets)   # every chunk starts on buffer set 0: one graph is reused
-
-    def graph_for(n, first):
-        key = (n, first % wl.sets)
-        if key not in graphs:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                cap = torch.cuda.current_stream()
-                lanes = [cap] + side
-                fork = torch.cuda.Event()
-                fork.record(cap)
-                for sd in side:
-                    sd.wait_event(fork)
-                for i in range(n):
-                    wl.launch((first + i) % wl.sets, lib, cabi, lanes[i % len(lanes)].cuda_stream)
-                for sd in side:
-                    join = torch.cuda.Event()
-                    join.record(sd)
-                    cap.wait_event(join)
-            graphs[key] = g
-        return graphs[key]
-
-    def plan(total):
-        seq, done = [], 0
-        while done < total:
-            n = min(chunk, total - done)
-            seq.append(graph_for(n, done))
-            done += n
-        return seq
-
     with torch.cuda.stream(stream):
         for i in range(3):   # lazy module load etc. outside any capture
-            wl.launch(i % wl.sets, lib, cabi, stream.cuda_stream)
+            launch(i % wl.sets, stream.cuda_stream)
     stream.synchronize()
-    warm_seq, timed_seq = plan(max(warmup, 3)), plan(steps)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        cap = torch.cuda.current_stream()
+        lanes = [cap] + side
+        fork = torch.cuda.Event()
+        fork.record(cap)
+        for sd in side:
+            sd.wait_event(fork)
+        for i in range(per_step):
+            launch(i % wl.sets, lanes[i % len(lanes)].cuda_stream)
+        for sd in side:
+            join = torch.cuda.Event()
+            join.record(sd)
+            cap.wait_event(join)
     # clock ramp (untimed, before the W warm-up steps): ~0.3 s of the same work
     t_end = time.time() + 0.3
     with torch.cuda.stream(stream):
         while time.time() < t_end:
-            for g in timed_seq[:4]:
-                g.replay()
+            g.replay()
             stream.synchronize()
-        for g in warm_seq:
+        for _ in range(max(warmup, 3)):
             g.replay()
     stream.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,7 +314,7 @@ def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier, nstreams=1)
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for g in timed_seq:
+        for _ in range(steps):
             g.replay()
         e1.record(stream)
     torch.cuda.synchronize()
@@ -294,22 +324,19 @@ def timed_steps(wl, steps, warmup, chunk, torch, lib, cabi, barrier, nstreams=1)
 
 def verify_outputs(wl, torch, cabi):
     """After the timed region: every buffer set's pooled output (written by the graph replays, on whatever stream)
-    must equal a fresh single-launch result with the default kernel variant, bit for bit."""
+    must equal a fresh single launch with default options, bit for bit."""
     from fots.pytorch_b200.rroi_align.functions.rroi_align import forward_raw
-    keep = cabi.get_tuning(cabi.TUNE_NHWC_UNROLL)
-    cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, 0)
     ok = True
     for s in range(0, wl.sets, max(1, wl.sets // 8)):
         want, _, _, _ = forward_raw(wl.feats[s], wl.rois[s], wl.PH, wl.PW, wl.scale, want_idx=False)
         ok = ok and bool(torch.equal(want, wl.out[s]))
-    cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, keep)
     return ok
 
 
-def e2e_leg(args, wl, torch, device, steps, nbuf=None):
+def e2e_leg(args, wl, torch, device, steps, barrier, nbuf=None):
     """Same metric end to end through the public module API with HOST buffers: per step a pinned-host ->
     device copy of the step's features + RoIs, _RRoiAlign.forward, and a device -> pinned-host read of the
-    pooled result.  Two streams alternate so the H2D of step i+1 overlaps the D2H of step i."""
+    pooled result.  Two streams alternate so the H2D of step i+1 overlaps the D2H of step i.  Every rank runs it."""
     from fots.pytorch_b200 import _RRoiAlign
     fmt = torch.channels_last if wl.layout == "nhwc" else torch.contiguous_format
     nbuf = nbuf or getattr(args, "e2e_streams", 2)
@@ -332,47 +359,142 @@ def e2e_leg(args, wl, torch, device, steps, nbuf=None):
     for i in range(6):
         step(i)
     torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for i in range(steps):
         step(i)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    barrier()
     h2d = h_feat[0].numel() * 4 + h_rois[0].numel() * 4
     d2h = h_out[0].numel() * 4
     return dt, h2d, d2h
 
 
+def ref_gpu_kernel_leg(wl, torch, lib, cabi, steps=30):
+    """Baseline leg (like cpu_baseline): the reference's own CUDA kernel (rroi_align_kernel.cu compiled unmodified for
+    sm_100a into oracle/_ref) with the three zero-fills its Python wrapper issues
+    (functions/rroi_align.py:17-20), graph-replayed over the same rotating NCHW buffer sets.  Checker-side code: it is
+    only timed here, never part of the product path."""
+    import ctypes
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_rroi_sm100a.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libref_rroi_sm100a.so not built (needs /root/reference at build time)"}
+    R = ctypes.CDLL(path)
+    i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+    R.RROIAlignForwardLaucher.restype = i
+    R.RROIAlignForwardLaucher.argtypes = [vp, f, i, i, i, i, i, i, vp, vp, vp, vp, vp]
+    nsets = min(wl.sets, 24)                      # 24 x (14.7 + 3 x 8.4) MB = 0.96 GB = 7.6 x L2
+    feats = [wl.feats[s].contiguous() for s in range(nsets)]
+    outs = [[torch.empty((wl.N, wl.C, wl.PH, wl.PW), device=feats[0].device) for _ in range(3)] for _ in range(nsets)]
+
+    class Shim:
+        sets = nsets
+
+    def launch(s, st):
+        with torch.cuda.stream(torch.cuda.ExternalStream(st)):
+            for t in outs[s]:
+                t.zero_()
+        rc = R.RROIAlignForwardLaucher(feats[s].data_ptr(), wl.scale, wl.N, wl.H, wl.W, wl.C, wl.PH, wl.PW,
+                                       wl.rois[s].data_ptr(), outs[s][0].data_ptr(), outs[s][1].data_ptr(),
+                                       outs[s][2].data_ptr(), st)
+        assert rc == 1
+
+    per_step = nsets * 10
+    ms = timed_steps(Shim, steps, 3, per_step, torch, lib, cabi, lambda: None, 1, launch=launch)
+    us = ms / (steps * per_step) * 1e3
+    ms8 = timed_steps(Shim, steps, 3, per_step, torch, lib, cabi, lambda: None, 8, launch=launch)
+    us8 = ms8 / (steps * per_step) * 1e3
+    # product, same layout (NCHW), same protocol
+    same = {"sets": nsets}
+    return {"us_per_call_1stream": us, "us_per_call_8streams": us8, "mfeat_px_per_s_1stream": wl.feat_px_per_step / us,
+            "mfeat_px_per_s_8streams": wl.feat_px_per_step / us8, "layout": "nchw", "channels": wl.C, "rois": wl.N,
+            "includes": "3 zero-fill kernels + RROIAlignForward (atomicAdd into top_data / con_idx_x / con_idx_y)",
+            "protocol": "CUDA graph of %d calls over %d rotating buffer sets, %d replays" % (per_step, nsets, steps), **same}
+
+
 def variants_leg(args, torch, device, lib, cabi, peak):
     """Same harness on neighbouring configurations (not the headline): one stream, the reference NCHW layout,
-    the 256-channel FPN map, and cfg4's per-GPU batch.  Each entry: us per launch, Mfeat-px/s, roofline frac."""
+    the 256-channel FPN map, cfg4's per-GPU batch, and the backward.  Each entry: us per launch, Mfeat-px/s, roofline
+    fraction (forward: SURVEY 8d forward bytes; backward: top_diff + whole map + RMW of the touched pixels)."""
     import types
     out = {}
-    grid = [("serial_1stream", dict(channels=args.channels, layout=args.layout, images=1, streams=1)),
-            ("nchw_reference_layout", dict(channels=args.channels, layout="nchw", images=1, streams=args.streams)),
-            ("fpn_c256", dict(channels=256, layout=args.layout, images=1, streams=args.streams)),
-            ("cfg4_per_gpu_32img_2048rois", dict(channels=args.channels, layout=args.layout, images=32, streams=1)),
-            ("cfg4_per_gpu_nchw", dict(channels=args.channels, layout="nchw", images=32, streams=1)),
-            # the opt-in NCHW kernel that stages each patch's footprint with TMA box loads (DESIGN 4.3: not faster)
-            ("cfg4_per_gpu_nchw_tma_staged", dict(channels=args.channels, layout="nchw", images=32, streams=1, nchw_tma=1)),
-            # the inference pipeline's variant: bf16 map in, bf16 pooled out (half the bytes, same arithmetic)
-            ("bf16_io", dict(channels=args.channels, layout="nhwc", images=1, streams=args.streams, dtype="bf16")),
-            ("bf16_io_cfg4_per_gpu", dict(channels=args.channels, layout="nhwc", images=32, streams=1, dtype="bf16"))]
+    S = args.streams
+    grid = [
+        # the library's defaults (opts = NULL), one launch at a time on one stream: the latency-bound case
+        ("serial_1stream", dict(images=1, streams=1)),
+        ("serial_1stream_rois_ready", dict(images=1, streams=1, opts=dict(rois_ready=True))),
+        ("serial_1stream_rois_ready_xform_table", dict(images=1, streams=1, opts=dict(rois_ready=True), xform=True)),
+        # 8 streams with the library's defaults (no concurrency hint, no flag)
+        ("default_opts_%dstreams" % S, dict(images=1, streams=S)),
+        ("nchw_reference_layout", dict(layout="nchw", images=1, streams=S, opts=dict(concurrency=S, rois_ready=True))),
+        ("fpn_c256", dict(channels=256, images=1, streams=S, opts=dict(concurrency=S, rois_ready=True))),
+        ("cfg4_per_gpu_32img_2048rois", dict(images=32, streams=1)),
+        ("cfg4_per_gpu_nchw", dict(layout="nchw", images=32, streams=1)),
+        # the inference pipeline's variant: bf16 map in, bf16 pooled out (half the bytes, same arithmetic)
+        ("bf16_io", dict(images=1, streams=S, dtype="bf16", opts=dict(concurrency=S, rois_ready=True))),
+        ("bf16_io_cfg4_per_gpu", dict(images=32, streams=1, dtype="bf16")),
+        # backward (rroi_b200_backward_opt, zero_fill = 1: the gradient map is defined everywhere), cfg3/cfg4's per-GPU batch
+        ("backward_nhwc_cfg4", dict(images=32, streams=1, backward=True)),
+        ("backward_nhwc_cfg4_unchunked_memset", dict(images=32, streams=1, backward=True, opts=dict(zero_chunk_images=-1))),
+        ("backward_nchw_cfg4", dict(layout="nchw", images=32, streams=1, backward=True)),
+        ("backward_nhwc_cfg1", dict(images=1, streams=1, backward=True)),
+    ]
     for name, kw in grid:
-        cabi.set_tuning(cabi.TUNE_NHWC_UNROLL, 0 if kw["streams"] == 1 else max(args.variant, 0))
-        cabi.set_tuning(cabi.TUNE_NCHW_TMA, kw.get("nchw_tma", 0))
-        a = types.SimpleNamespace(channels=kw["channels"], layout=kw["layout"], images=kw["images"],
-                                  rois_per_image=args.rois_per_image, sets=0, dtype=kw.get("dtype", "fp32"))
+        a = types.SimpleNamespace(channels=kw.get("channels", args.channels), layout=kw.get("layout", args.layout),
+                                  images=kw["images"], rois_per_image=args.rois_per_image, sets=0, dtype=kw.get("dtype", "fp32"))
         w = Workload(a, device, torch)
-        steps = max(200, 20000 // kw["images"])
-        ms = timed_steps(w, steps, 20, args.graph_chunk, torch, lib, cabi, lambda: None, kw["streams"])
-        us = ms / steps * 1e3
-        alg = float(np.mean(w.alg_bytes))
+        w.set_opts(cabi, **kw.get("opts", {}))
+        if kw.get("xform"):
+            w.enable_xform(torch, lib, torch.cuda.current_stream().cuda_stream)
+        if kw.get("backward"):
+            w.enable_backward(torch)
+        torch.cuda.synchronize()
+        per_step = launches_per_step_for(w, target=max(8, 2000 // (kw["images"] * (4 if kw.get("backward") else 1))))
+        steps = 10
+        ms = timed_steps(w, steps, 3, per_step, torch, lib, cabi, lambda: None, kw["streams"])
+        us = ms / (steps * per_step) * 1e3
+        alg = float(np.mean(w.alg_bytes_bwd if kw.get("backward") else w.alg_bytes))
         out[name] = {"us_per_launch": us, "mfeat_px_per_s": w.feat_px_per_step / us, "alg_mb": alg / 1e6,
                      "achieved_gbs": alg / us / 1e3, "frac": alg / us / 1e3 / peak, "streams": kw["streams"],
-                     "layout": kw["layout"], "channels": kw["channels"], "rois": w.N, "dtype": kw.get("dtype", "fp32")}
+                     "layout": a.layout, "channels": a.channels, "rois": w.N, "dtype": a.dtype,
+                     "opts": kw.get("opts", {}), "launches_timed": steps * per_step}
+        if kw.get("backward"):
+            out[name]["touched_pixels"] = float(np.mean(w.touched))
         del w
         torch.cuda.empty_cache()
-    cabi.set_tuning(cabi.TUNE_NCHW_TMA, 0)
+    return out
+
+
+def train_leg(args, torch, device):
+    """BASELINE.json configs[3]: one full training step at batch 32, 1280x720 synthetic images, random-init FOTSNet --
+    bf16 autocast backbone / recogniser, fp32 RoIRotate forward AND backward kernels (through autograd), CTC loss
+    (torch's ctc_loss: warp-ctc is absent, parity unpinned), detection losses, Adam update.  ms per step, images/s."""
+    from fots.pytorch_b200.pipeline import FOTSNet
+    from fots.pytorch_b200.pipeline.train import TrainStep, synthetic_targets
+    torch.manual_seed(0)
+    B = args.train_images
+    net = FOTSNet(attention=True, nclass=89).to(device).to(memory_format=torch.channels_last)
+    step = TrainStep(net, lr=1e-4)
+    gen = torch.Generator(device=device).manual_seed(7)
+    images = torch.randn(B, 3, 720, 1280, device=device, generator=gen)
+    tgt = synthetic_targets(B, 64, 720, 1280, 89, device, seed=0)
+    losses = [step(images, tgt)["total"]]                      # warm-up (cuDNN autotune, allocator)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        losses.append(step(images, tgt)["total"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.train_steps
+    out = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "batch": B, "rois_per_image": 64, "steps": args.train_steps,
+           "losses": [float(x) for x in losses], "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+           "dtype": "bf16 autocast networks (cuDNN/cuBLAS under autograd), fp32 RoIRotate forward + backward kernels "
+                    "(rroi_b200_forward_opt / rroi_b200_backward_opt), fp32 master weights, Adam",
+           "loss": "dense EAST-style detection losses + F.ctc_loss(sum)/N (warp-ctc absent: parity unpinned)"}
+    del net, step, images, tgt
+    torch.cuda.empty_cache()
     return out
 
 
@@ -627,68 +749,90 @@ def run_b200(args):
         barrier = lambda: None
     from fots.pytorch_b200 import _cabi
     lib = _cabi.lib()
-    _cabi.set_tuning(_cabi.TUNE_USE_PDL, args.pdl)
 
-    steps = args.steps if args.steps is not None else 100000
-    warmup = args.warmup if args.warmup is not None else 1000
+    steps = args.steps if args.steps is not None else 50
+    warmup = args.warmup if args.warmup is not None else 5
     wl = Workload(args, device, torch)
+    conc = args.streams if args.concurrency < 0 else args.concurrency
+    head_opts = dict(pdl=bool(args.pdl), rois_ready=bool(args.rois_ready), concurrency=conc, variant=max(args.variant, 0))
+    wl.set_opts(_cabi, **head_opts)
+    per_step = launches_per_step_for(wl, args.launches_per_step)
     sampler = ClockSampler(local)
     sampler.start()
-    _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, max(args.variant, 0))
-    ms = timed_steps(wl, steps, warmup, args.graph_chunk, torch, lib, _cabi, barrier, args.streams)
+    ms = timed_steps(wl, steps, warmup, per_step, torch, lib, _cabi, barrier, args.streams)
     clocks = sampler.finish()
     verified = verify_outputs(wl, torch, _cabi)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = wl.feat_px_per_step * steps * world / (ms_max * 1e-3) / 1e6
+    launches = steps * per_step
+    value = wl.feat_px_per_step * launches * world / (ms_max * 1e-3) / 1e6
 
     peak, peak_src = measured_peak_gbs()
     alg = float(np.mean(wl.alg_bytes))
-    launch_us = ms / steps * 1e3
+    launch_us = ms / launches * 1e3
     achieved = alg / (launch_us * 1e-6) / 1e9
-    tile = {5: 256, 4: 256, 3: 128, 2: 128}.get(max(args.variant, 0), 64)
-    kname = ("rroi_fwd_nhwc_packed_kernel<%d,%d,2>" % (wl.C, tile)) if wl.layout == "nhwc" and wl.C in (32, 64, 128, 256) \
-        else "rroi_fwd_%s_kernel" % wl.layout
+    kname = "rroi_fwd_nhwc_packed_kernel<%d,256,2> (auto: 256-bin tiles under the concurrency hint)" % wl.C \
+        if wl.layout == "nhwc" and wl.C in (32, 64, 128, 256) and args.variant <= 0 else "rroi_fwd_%s (variant %d)" % (wl.layout, args.variant)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg1 (BASELINE.json configs[1]): %dx%dx180x320 fp32 feature map per step, %d random rotated RoIs, "
-                               "8x64 pooled output, RoIRotate forward only" % (wl.B, wl.C, wl.N),
+        "config": {"workload": "cfg1 (BASELINE.json configs[1]) x %d independent requests per step: each request = one %dx%dx180x320 "
+                               "fp32 feature map, %d random rotated RoIs, 8x64 pooled output, ONE RoIRotate forward launch" %
+                               (per_step, wl.B, wl.C, wl.N),
                    "layout": "channels_last (NHWC in HBM)" if wl.layout == "nhwc" else "NCHW (reference layout)",
-                   "images_per_step": wl.B, "rois_per_step": wl.N, "channels": wl.C,
+                   "launches_per_step": per_step, "images_per_step": wl.B * per_step, "rois_per_launch": wl.N, "channels": wl.C,
                    "l2": "inputs larger than L2: %d rotating buffer sets, %.0f MB working set vs 126 MB L2" % (wl.sets, wl.working_set_mb),
-                   "launch": "CUDA graphs of %d steps, PDL=%d, %d stream(s)" % (min(args.graph_chunk, steps), args.pdl, args.streams),
+                   "launch": "one CUDA graph of %d launches per step, %d stream(s)" % (per_step, args.streams),
+                   "opts": "rroi_b200_forward_opt with per-call rroi_b200_opts %r (no process-global tuning)" % head_opts,
                    "parallelism": "image-sharded, %d rank(s), no data-path collective in RoIRotate" % world},
-        "gpu_launches": steps,
+        "gpu_launches": launches,
         "verified": verified,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("%s_c%d" % (wl.layout, wl.C)),
                      "algorithmic_bytes_per_launch": alg, "avg_launch_us": launch_us, "peak_source": peak_src},
     }
+    if not args.no_extras:
+        # end to end through the public module with host buffers: EVERY rank runs it, value = whole-job aggregate
+        dt, h2d, d2h = e2e_leg(args, wl, torch, device, args.e2e_steps, barrier)
+        te = torch.tensor([dt], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": wl.feat_px_per_step * args.e2e_steps * world / float(te.item()) / 1e6, "unit": UNIT,
+                       "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
+                       "ranks": world,
+                       "api": "fots.pytorch_b200._RRoiAlign(8,64,0.25)(features, rois) with pinned host buffers, 2 streams, on every rank"}
     if rank == 0 and not args.no_extras:
         line["variants"] = variants_leg(args, torch, device, lib, _cabi, peak)
-        _cabi.set_tuning(_cabi.TUNE_USE_PDL, args.pdl)
-        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, 0)
-        dt, h2d, d2h = e2e_leg(args, wl, torch, device, args.e2e_steps)
-        line["e2e"] = {"value": wl.feat_px_per_step * args.e2e_steps / dt / 1e6, "unit": UNIT,
-                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-                       "api": "fots.pytorch_b200._RRoiAlign(8,64,0.25)(features, rois) with pinned host buffers, 2 streams"}
-        line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_seconds)
+        try:
+            line["ref_gpu_kernel"] = ref_gpu_kernel_leg(wl, torch, lib, _cabi)
+            nchw = line["variants"].get("nchw_reference_layout")
+            if nchw and "us_per_call_8streams" in line["ref_gpu_kernel"]:
+                line["ref_gpu_kernel"]["speedup_same_layout_8streams"] = line["ref_gpu_kernel"]["us_per_call_8streams"] / nchw["us_per_launch"]
+                line["ref_gpu_kernel"]["speedup_headline_layout"] = line["ref_gpu_kernel"]["us_per_call_8streams"] / launch_us
+        except Exception as e:
+            line["ref_gpu_kernel"] = {"error": repr(e)}
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg(wl, args.cpu_seconds)
         try:
             line["conv_tc"] = conv_leg(torch, device)
         except Exception as e:   # secondary evidence: never take the headline line down
             line["conv_tc"] = {"error": repr(e)}
+    del wl
+    torch.cuda.empty_cache()
     if not args.no_pipeline and not args.no_extras:
-        del wl
-        torch.cuda.empty_cache()
         try:
             line["pipeline"] = pipeline_leg(args, torch, device, dist, world, rank)
         except Exception as e:   # the headline line must survive a failure of the secondary leg
             line["pipeline"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and not args.no_train and not args.no_extras:
+        try:
+            line.setdefault("pipeline", {})["train_step"] = train_leg(args, torch, device)
+        except Exception as e:
+            line.setdefault("pipeline", {})["train_step"] = {"error": repr(e)}
     if dist is not None:
         dist.barrier(device_ids=[local])
         dist.destroy_process_group()

@@ -18,27 +18,46 @@ ERR_CUDA = -3
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 
-TUNE_NCHW_CG = 0
-TUNE_NHWC_UNROLL = 1
-TUNE_USE_PDL = 2
-TUNE_BWD_DEDUPE = 3
-TUNE_NCHW_TMA = 4
-TUNE_BWD_ZERO_FUSED = 5
+FLAG_NO_PDL = 1
+FLAG_ROIS_READY = 2
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+
+
+class Opts(ctypes.Structure):
+    """rroi_b200_opts (include/rroi_align_b200.h): per-call launch options.  The library keeps no tuning state."""
+    _fields_ = [("size", ctypes.c_uint), ("flags", ctypes.c_uint), ("concurrency", ctypes.c_int),
+                ("variant", ctypes.c_int), ("nchw_cg", ctypes.c_int), ("bwd_mode", ctypes.c_int),
+                ("nchw_tma", ctypes.c_int), ("zero_chunk_images", ctypes.c_int)]
+
+
+def opts(pdl=True, rois_ready=False, concurrency=0, variant=0, nchw_cg=0, bwd_mode=0, nchw_tma=0, zero_chunk_images=0):
+    """Build an rroi_b200_opts; pass the result (or None = defaults) as `opts` to the *_opt entry points."""
+    o = Opts()
+    o.size = ctypes.sizeof(Opts)
+    o.flags = (0 if pdl else FLAG_NO_PDL) | (FLAG_ROIS_READY if rois_ready else 0)
+    o.concurrency, o.variant, o.nchw_cg = int(concurrency), int(variant), int(nchw_cg)
+    o.bwd_mode, o.nchw_tma, o.zero_chunk_images = int(bwd_mode), int(nchw_tma), int(zero_chunk_images)
+    return o
+
+
+def opts_ref(o):
+    return ctypes.byref(o) if o is not None else None
+
 
 # every symbol include/*.h declares
 EXPORTS = (
     "RROIAlignForwardLaucher", "RROIAlignBackwardLaucher",
     "rroi_b200_forward", "rroi_b200_backward", "rroi_b200_expand_idx", "rroi_b200_forward_bf16",
-    "rroi_b200_set_tuning", "rroi_b200_get_tuning", "rroi_b200_last_cuda_error",
+    "rroi_b200_forward_opt", "rroi_b200_backward_opt", "rroi_b200_forward_bf16_opt", "rroi_b200_roi_xform",
+    "rroi_b200_last_cuda_error",
     "rroi_b200_strerror", "rroi_b200_abi_version", "rroi_b200_build_info",
     # include/fots_b200_pipeline.h
     "fots_b200_boxes_to_rois", "fots_b200_ctc_greedy", "fots_b200_instnorm_nhwc_bf16",
     "fots_b200_fpn_merge_nhwc_bf16", "fots_b200_decode_candidates",
     "fots_b200_conv2d_nhwc_bf16", "fots_b200_conv_set_tile", "fots_b200_conv2d_stats_nhwc_bf16",
     "fots_b200_instnorm_apply_nhwc_bf16", "fots_b200_merge_candidates_host",
-    "fots_b200_stem_conv3x3_c3_c16", "fots_b200_maxpool_h2_nhwc_bf16",
+    "fots_b200_stem_conv3x3_c3_c16", "fots_b200_stem_conv3x3_c3_c16_u8", "fots_b200_maxpool_h2_nhwc_bf16",
 )
 
 _lib = None
@@ -72,10 +91,15 @@ def lib():
     L.rroi_b200_backward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, i, vp]
     L.rroi_b200_expand_idx.restype = i
     L.rroi_b200_expand_idx.argtypes = [vp, vp, i, i, i, i, vp]
-    L.rroi_b200_set_tuning.restype = i
-    L.rroi_b200_set_tuning.argtypes = [i, i]
-    L.rroi_b200_get_tuning.restype = i
-    L.rroi_b200_get_tuning.argtypes = [i]
+    op = ctypes.POINTER(Opts)
+    L.rroi_b200_forward_opt.restype = i
+    L.rroi_b200_forward_opt.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, op, vp]
+    L.rroi_b200_forward_bf16_opt.restype = i
+    L.rroi_b200_forward_bf16_opt.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, op, vp]
+    L.rroi_b200_backward_opt.restype = i
+    L.rroi_b200_backward_opt.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f, i, i, op, vp]
+    L.rroi_b200_roi_xform.restype = i
+    L.rroi_b200_roi_xform.argtypes = [vp, vp, i, i, f, vp]
     L.rroi_b200_last_cuda_error.restype = i
     L.rroi_b200_strerror.restype = ctypes.c_char_p
     L.rroi_b200_strerror.argtypes = [i]
@@ -95,14 +119,6 @@ def check(status, what):
         if status == ERR_CUDA:
             msg += " [cudaError_t=%d]" % L.rroi_b200_last_cuda_error()
         raise RRoiAlignError("%s failed: %s" % (what, msg))
-
-
-def set_tuning(key, value):
-    check(lib().rroi_b200_set_tuning(int(key), int(value)), "rroi_b200_set_tuning(%d,%d)" % (key, value))
-
-
-def get_tuning(key):
-    return lib().rroi_b200_get_tuning(int(key))
 
 
 def build_info():

@@ -4,6 +4,7 @@
 #include "rroi_kernels.cuh"
 
 #include <atomic>
+#include <cstring>
 
 namespace {
 
@@ -19,6 +20,25 @@ int cuda_status(cudaError_t e) {
 bool dims_ok(int n, int b, int c, int h, int w, int ph, int pw) {
     return n >= 0 && b > 0 && c > 0 && h > 0 && w > 0 && ph > 0 && pw > 0 &&
            (long long)ph * pw <= 0x7fffffffLL && (long long)b * h * w <= 0x7fffffffLL;
+}
+
+// rroi_b200_opts -> rroi::Opts.  false = malformed (unknown flag, value out of range).
+bool parse_opts(const rroi_b200_opts* in, rroi::Opts* out) {
+    *out = rroi::Opts();
+    if (!in) return true;
+    rroi_b200_opts o = {};
+    const size_t have = in->size < sizeof(o) ? in->size : sizeof(o);
+    if (have < 2 * sizeof(unsigned int)) return false;
+    memcpy(&o, in, have);                                  // fields the caller's (older) header does not have read as 0
+    if (o.flags & ~(RROI_B200_FLAG_NO_PDL | RROI_B200_FLAG_ROIS_READY)) return false;
+    if (o.concurrency < 0 || o.variant < 0 || o.variant > 32) return false;
+    if (o.nchw_cg != 0 && o.nchw_cg != 1 && o.nchw_cg != 2 && o.nchw_cg != 4 && o.nchw_cg != 8 && o.nchw_cg != 16) return false;
+    if (o.bwd_mode < 0 || o.bwd_mode > 3 || o.nchw_tma < 0 || o.nchw_tma > 5 || o.zero_chunk_images < -1) return false;
+    out->pdl = !(o.flags & RROI_B200_FLAG_NO_PDL);
+    out->rois_ready = (o.flags & RROI_B200_FLAG_ROIS_READY) != 0 && out->pdl;
+    out->concurrency = o.concurrency; out->variant = o.variant; out->nchw_cg = o.nchw_cg;
+    out->bwd_mode = o.bwd_mode; out->nchw_tma = o.nchw_tma; out->zero_chunk_images = o.zero_chunk_images;
+    return true;
 }
 
 __global__ void expand_idx_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t bins, int C, size_t total) {
@@ -46,7 +66,7 @@ int RROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale,
     p.C = channels; p.H = height; p.W = width; p.PH = pooled_height; p.PW = pooled_width;
     p.scale = spatial_scale;
     p.idx_mode = con_idx_x ? rroi::IDX_FULL : rroi::IDX_NONE;
-    const int st = cuda_status(rroi::launch_fwd_nchw(p, stream));
+    const int st = cuda_status(rroi::launch_fwd_nchw(p, rroi::Opts(), stream));
     return st == RROI_B200_OK ? 1 : st;
 }
 
@@ -62,37 +82,55 @@ int RROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, c
     p.top_diff = top_diff; p.rois = bottom_rois; p.bottom_diff = bottom_diff; p.idx_x = con_idx_x; p.idx_y = con_idx_y;
     p.N = num_rois; p.B = batch_size; p.C = channels; p.H = height; p.W = width;
     p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale; p.idx_mode = rroi::IDX_FULL;
-    const int st = cuda_status(rroi::launch_bwd_legacy(p, stream));
+    p.img_lo = -0x7fffffff; p.img_hi = 0x7fffffff;
+    const int st = cuda_status(rroi::launch_bwd_legacy(p, rroi::Opts(), stream));
     return st == RROI_B200_OK ? 1 : st;
 }
 
-int rroi_b200_forward(const float* features, const float* rois, float* pooled, float* idx_x, float* idx_y,
-                      int num_rois, int batch, int channels, int height, int width,
-                      int pooled_height, int pooled_width, float spatial_scale, int layout,
-                      cudaStream_t stream) {
+int rroi_b200_forward_opt(const float* features, const float* rois, const float* xform, float* pooled,
+                          float* idx_x, float* idx_y, int num_rois, int batch, int channels, int height, int width,
+                          int pooled_height, int pooled_width, float spatial_scale, int layout,
+                          const rroi_b200_opts* opts, cudaStream_t stream) {
+    rroi::Opts o;
+    if (!parse_opts(opts, &o)) return RROI_B200_ERR_INVALID_ARG;
     if (!features || !pooled || (num_rois > 0 && !rois) || ((idx_x == nullptr) != (idx_y == nullptr)))
         return RROI_B200_ERR_INVALID_ARG;
     if (!dims_ok(num_rois, batch, channels, height, width, pooled_height, pooled_width)) return RROI_B200_ERR_INVALID_ARG;
     if (layout != RROI_B200_LAYOUT_NCHW && layout != RROI_B200_LAYOUT_NHWC) return RROI_B200_ERR_INVALID_ARG;
+    if (xform && (reinterpret_cast<uintptr_t>(xform) & 15)) return RROI_B200_ERR_INVALID_ARG;
     if (num_rois == 0) return RROI_B200_OK;
     rroi::FwdParams p = {};
     p.feat = features; p.rois = rois; p.out = pooled; p.idx_x = idx_x; p.idx_y = idx_y;
     p.N = num_rois; p.B = batch; p.C = channels; p.H = height; p.W = width;
     p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale;
     p.idx_mode = idx_x ? rroi::IDX_COMPACT : rroi::IDX_NONE;
-    const cudaError_t e = layout == RROI_B200_LAYOUT_NCHW ? rroi::launch_fwd_nchw(p, stream) : rroi::launch_fwd_nhwc(p, stream);
+    p.xform = xform; p.early = o.rois_ready ? 1 : 0;
+    const cudaError_t e = layout == RROI_B200_LAYOUT_NCHW ? rroi::launch_fwd_nchw(p, o, stream) : rroi::launch_fwd_nhwc(p, o, stream);
     if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
+    if (e == cudaErrorInvalidValue && o.variant != 0) { (void)cudaGetLastError(); return RROI_B200_ERR_INVALID_ARG; }   // unknown variant
     return cuda_status(e);
 }
 
-int rroi_b200_forward_bf16(const void* features, const float* rois, void* pooled, float* idx_x, float* idx_y,
-                           int num_rois, int batch, int channels, int height, int width,
-                           int pooled_height, int pooled_width, float spatial_scale, cudaStream_t stream) {
+int rroi_b200_forward(const float* features, const float* rois, float* pooled, float* idx_x, float* idx_y,
+                      int num_rois, int batch, int channels, int height, int width,
+                      int pooled_height, int pooled_width, float spatial_scale, int layout,
+                      cudaStream_t stream) {
+    return rroi_b200_forward_opt(features, rois, nullptr, pooled, idx_x, idx_y, num_rois, batch, channels, height, width,
+                                 pooled_height, pooled_width, spatial_scale, layout, nullptr, stream);
+}
+
+int rroi_b200_forward_bf16_opt(const void* features, const float* rois, const float* xform, void* pooled,
+                               float* idx_x, float* idx_y, int num_rois, int batch, int channels, int height,
+                               int width, int pooled_height, int pooled_width, float spatial_scale,
+                               const rroi_b200_opts* opts, cudaStream_t stream) {
+    rroi::Opts o;
+    if (!parse_opts(opts, &o)) return RROI_B200_ERR_INVALID_ARG;
     if (!features || !pooled || (num_rois > 0 && !rois) || ((idx_x == nullptr) != (idx_y == nullptr)))
         return RROI_B200_ERR_INVALID_ARG;
     if (!dims_ok(num_rois, batch, channels, height, width, pooled_height, pooled_width)) return RROI_B200_ERR_INVALID_ARG;
     if (channels != 32 && channels != 64 && channels != 128 && channels != 256) return RROI_B200_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(features) | reinterpret_cast<uintptr_t>(pooled)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    if (xform && (reinterpret_cast<uintptr_t>(xform) & 15)) return RROI_B200_ERR_INVALID_ARG;
     if (num_rois == 0) return RROI_B200_OK;
     rroi::FwdParams p = {};
     p.feat = static_cast<const float*>(features); p.rois = rois; p.out = static_cast<float*>(pooled);
@@ -100,15 +138,25 @@ int rroi_b200_forward_bf16(const void* features, const float* rois, void* pooled
     p.N = num_rois; p.B = batch; p.C = channels; p.H = height; p.W = width;
     p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale;
     p.idx_mode = idx_x ? rroi::IDX_COMPACT : rroi::IDX_NONE;
-    const cudaError_t e = rroi::launch_fwd_nhwc_bf16(p, stream);
+    p.xform = xform; p.early = o.rois_ready ? 1 : 0;
+    const cudaError_t e = rroi::launch_fwd_nhwc_bf16(p, o, stream);
     if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
     return cuda_status(e);
 }
 
-int rroi_b200_backward(const float* top_diff, const float* rois, const float* idx_x, const float* idx_y,
-                       float* bottom_diff, int num_rois, int batch, int channels, int height, int width,
-                       int pooled_height, int pooled_width, float spatial_scale, int layout,
-                       int zero_fill, cudaStream_t stream) {
+int rroi_b200_forward_bf16(const void* features, const float* rois, void* pooled, float* idx_x, float* idx_y,
+                           int num_rois, int batch, int channels, int height, int width,
+                           int pooled_height, int pooled_width, float spatial_scale, cudaStream_t stream) {
+    return rroi_b200_forward_bf16_opt(features, rois, nullptr, pooled, idx_x, idx_y, num_rois, batch, channels, height,
+                                      width, pooled_height, pooled_width, spatial_scale, nullptr, stream);
+}
+
+int rroi_b200_backward_opt(const float* top_diff, const float* rois, const float* idx_x, const float* idx_y,
+                           float* bottom_diff, int num_rois, int batch, int channels, int height, int width,
+                           int pooled_height, int pooled_width, float spatial_scale, int layout, int zero_fill,
+                           const rroi_b200_opts* opts, cudaStream_t stream) {
+    rroi::Opts o;
+    if (!parse_opts(opts, &o)) return RROI_B200_ERR_INVALID_ARG;
     if (!bottom_diff || (num_rois > 0 && (!rois || !top_diff)) || ((idx_x == nullptr) != (idx_y == nullptr)))
         return RROI_B200_ERR_INVALID_ARG;
     if (!dims_ok(num_rois, batch, channels, height, width, pooled_height, pooled_width)) return RROI_B200_ERR_INVALID_ARG;
@@ -118,24 +166,29 @@ int rroi_b200_backward(const float* top_diff, const float* rois, const float* id
     p.N = num_rois; p.B = batch; p.C = channels; p.H = height; p.W = width;
     p.PH = pooled_height; p.PW = pooled_width; p.scale = spatial_scale;
     p.idx_mode = idx_x ? rroi::IDX_COMPACT : rroi::IDX_NONE;
-    if (zero_fill && num_rois > 0 && layout == RROI_B200_LAYOUT_NHWC) {
-        // large maps: zero-fill and scatter in ONE pass over the map (rroi_bwd.cu); not eligible -> memset + scatter below
-        const cudaError_t e = rroi::launch_bwd_nhwc_zero_fused(p, stream);
-        if (e == cudaSuccess) return RROI_B200_OK;
-        if (e != cudaErrorNotSupported) {
-            if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
-            return cuda_status(e);
-        }
-    }
-    if (zero_fill) {
-        const size_t bytes = (size_t)batch * channels * height * width * sizeof(float);
-        const cudaError_t e = cudaMemsetAsync(bottom_diff, 0, bytes, stream);
-        if (e != cudaSuccess) return cuda_status(e);
-    }
-    if (num_rois == 0) return RROI_B200_OK;
-    const cudaError_t e = layout == RROI_B200_LAYOUT_NCHW ? rroi::launch_bwd_nchw(p, stream) : rroi::launch_bwd_nhwc(p, stream);
+    p.img_lo = -0x7fffffff; p.img_hi = 0x7fffffff;
+    const bool nhwc = layout == RROI_B200_LAYOUT_NHWC;
+    cudaError_t e;
+    if (zero_fill) e = rroi::launch_bwd_zero_scatter(p, o, nhwc, stream);
+    else if (num_rois == 0) return RROI_B200_OK;
+    else e = nhwc ? rroi::launch_bwd_nhwc(p, o, stream) : rroi::launch_bwd_nchw(p, o, stream);
     if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); return RROI_B200_ERR_TOO_LARGE; }
     return cuda_status(e);
+}
+
+int rroi_b200_backward(const float* top_diff, const float* rois, const float* idx_x, const float* idx_y,
+                       float* bottom_diff, int num_rois, int batch, int channels, int height, int width,
+                       int pooled_height, int pooled_width, float spatial_scale, int layout,
+                       int zero_fill, cudaStream_t stream) {
+    return rroi_b200_backward_opt(top_diff, rois, idx_x, idx_y, bottom_diff, num_rois, batch, channels, height, width,
+                                  pooled_height, pooled_width, spatial_scale, layout, zero_fill, nullptr, stream);
+}
+
+int rroi_b200_roi_xform(const float* rois, float* xform, int num_rois, int pooled_height, float spatial_scale,
+                        cudaStream_t stream) {
+    if (num_rois < 0 || pooled_height <= 0 || (num_rois > 0 && (!rois || !xform))) return RROI_B200_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(xform) & 15) return RROI_B200_ERR_INVALID_ARG;
+    return cuda_status(rroi::launch_roi_xform(rois, xform, num_rois, pooled_height, spatial_scale, stream));
 }
 
 int rroi_b200_expand_idx(const float* idx_compact, float* idx_full, int num_rois, int channels,
@@ -151,38 +204,6 @@ int rroi_b200_expand_idx(const float* idx_compact, float* idx_full, int num_rois
     return cuda_status(cudaGetLastError());
 }
 
-int rroi_b200_set_tuning(int key, int value) {
-    switch (key) {
-        case RROI_B200_TUNE_NCHW_CG:
-            if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return RROI_B200_ERR_INVALID_ARG;
-            rroi::g_tuning.nchw_cg = value; return RROI_B200_OK;
-        case RROI_B200_TUNE_NHWC_UNROLL:
-            if (value < 0 || value > 7) return RROI_B200_ERR_INVALID_ARG;
-            rroi::g_tuning.nhwc_unroll = value; return RROI_B200_OK;
-        case RROI_B200_TUNE_USE_PDL:    rroi::g_tuning.use_pdl = value != 0; return RROI_B200_OK;
-        case RROI_B200_TUNE_BWD_DEDUPE:
-            if (value < 0 || value > 2) return RROI_B200_ERR_INVALID_ARG;
-            rroi::g_tuning.bwd_dedupe = value; return RROI_B200_OK;
-        case RROI_B200_TUNE_BWD_ZERO_FUSED: rroi::g_tuning.bwd_zero_fused = value != 0; return RROI_B200_OK;
-        case RROI_B200_TUNE_NCHW_TMA:
-            if (value < 0 || value > 5) return RROI_B200_ERR_INVALID_ARG;
-            rroi::g_tuning.nchw_tma = value; return RROI_B200_OK;
-        default: return RROI_B200_ERR_INVALID_ARG;
-    }
-}
-
-int rroi_b200_get_tuning(int key) {
-    switch (key) {
-        case RROI_B200_TUNE_NCHW_CG:     return rroi::g_tuning.nchw_cg;
-        case RROI_B200_TUNE_NHWC_UNROLL: return rroi::g_tuning.nhwc_unroll;
-        case RROI_B200_TUNE_USE_PDL:     return rroi::g_tuning.use_pdl;
-        case RROI_B200_TUNE_BWD_DEDUPE:  return rroi::g_tuning.bwd_dedupe;
-        case RROI_B200_TUNE_NCHW_TMA:    return rroi::g_tuning.nchw_tma;
-        case RROI_B200_TUNE_BWD_ZERO_FUSED: return rroi::g_tuning.bwd_zero_fused;
-        default: return -1;
-    }
-}
-
 int rroi_b200_last_cuda_error(void) { return g_last_cuda_error.load(); }
 
 const char* rroi_b200_strerror(int status) {
@@ -195,7 +216,7 @@ const char* rroi_b200_strerror(int status) {
     }
 }
 
-int rroi_b200_abi_version(void) { return 1; }
+int rroi_b200_abi_version(void) { return 2; }
 
 const char* rroi_b200_build_info(void) {
 #define RROI_STR2(x) #x

@@ -47,6 +47,13 @@ __device__ __forceinline__ ScatterGeom scatter_geom(float cx, float cy, bool in,
 
 __device__ __forceinline__ void red_add(float* addr, float v) { atomicAdd(addr, v); }
 
+// Chunked zero-fill + scatter (launch_bwd_zero_scatter): one scatter launch only handles the RoIs whose image lies in
+// [img_lo, img_hi); CTAs of other RoIs leave at once (CTA-uniform: every thread reads the same word).
+__device__ __forceinline__ bool in_image_window(const BwdParams& p, int n) {
+    const int b = __float2int_rz(__ldg(p.rois + (size_t)n * 6));
+    return b >= p.img_lo && b < p.img_hi;
+}
+
 // ------------------------------------------------------------------------------------------ NCHW
 constexpr int kBlock = 256;
 
@@ -61,6 +68,7 @@ __global__ void __launch_bounds__(kBlock) rroi_bwd_nchw_kernel(const BwdParams p
 
     pdl_wait();
     pdl_launch_dependents();
+    if (!in_image_window(p, n)) return;
     if (threadIdx.x < 32) {
         RoiXform X;
         if (p.idx_mode == IDX_NONE) {
@@ -165,16 +173,16 @@ static int pick_cg(int want, int C) {
     return cg;
 }
 
-cudaError_t launch_bwd_nchw(const BwdParams& p0, cudaStream_t s) {
+cudaError_t launch_bwd_nchw(const BwdParams& p0, const Opts& o, cudaStream_t s) {
     BwdParams p = p0;
-    const int cg = pick_cg(g_tuning.nchw_cg, p.C);
+    const int cg = pick_cg(o.nchw_cg, p.C);
     const int bins = p.PH * p.PW;
     p.tiles = (bins + kBlock - 1) / kBlock;
     p.cgroups = (p.C + cg - 1) / cg;
     const long long grid = (long long)p.N * p.cgroups * p.tiles;
-    const bool pdl = g_tuning.use_pdl != 0;
-    return g_tuning.bwd_dedupe ? launch_bwd_nchw_cg<true>(p, cg, grid, s, pdl)
-                               : launch_bwd_nchw_cg<false>(p, cg, grid, s, pdl);
+    const bool pdl = o.pdl;
+    return o.bwd_mode != 3 ? launch_bwd_nchw_cg<true>(p, cg, grid, s, pdl)
+                           : launch_bwd_nchw_cg<false>(p, cg, grid, s, pdl);
 }
 
 // ------------------------------------------------------------------------------------------ legacy
@@ -207,11 +215,11 @@ __global__ void __launch_bounds__(kBlock) rroi_bwd_legacy_kernel(const BwdParams
     }
 }
 
-cudaError_t launch_bwd_legacy(const BwdParams& p, cudaStream_t s) {
+cudaError_t launch_bwd_legacy(const BwdParams& p, const Opts& o, cudaStream_t s) {
     const size_t total = (size_t)p.N * p.C * p.PH * p.PW;
     long long grid = (long long)((total + kBlock - 1) / kBlock);
     if (grid > (1LL << 30)) grid = 1LL << 30;
-    return launch_1d(rroi_bwd_legacy_kernel, grid, kBlock, p, s, g_tuning.use_pdl != 0);
+    return launch_1d(rroi_bwd_legacy_kernel, grid, kBlock, p, s, o.pdl);
 }
 
 // ------------------------------------------------------------------------------------------ NHWC
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(kBlock) rroi_bwd_nhwc_kernel(const BwdParams p
 
     pdl_wait();
     pdl_launch_dependents();
+    if (!in_image_window(p, n)) return;
     if (threadIdx.x < 32) {
         RoiXform X;
         if (p.idx_mode == IDX_NONE) {
@@ -326,52 +335,7 @@ __device__ __forceinline__ float4 ld_v4(const float* ptr, uint32_t pred) {
 
 constexpr int kPackWarps = 8;
 
-// L2 eviction-priority variants for the one-pass (ZF) kernel: the gradient map of the images in flight should stay in
-// L2 (evict_last) while top_diff streams through once (evict_first).
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ float4 ld_v4_hint(const float* ptr, uint32_t pred, uint64_t pol) {
-    float4 r;
-    asm volatile(
-        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
-        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
-        "@q ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
-        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-        : "l"(ptr), "r"(pred), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ void red_add_v4_hint(float* addr, float w, const float4& g, uint64_t pol) {
-    const float a = __fmul_rn(w, g.x), b = __fmul_rn(w, g.y), c = __fmul_rn(w, g.z), d = __fmul_rn(w, g.w);
-    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void st_zero_v4_hint(float4* addr, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(addr), "f"(0.0f), "l"(pol) : "memory");
-}
-
-// ZF (zero + scatter in one pass, opt-in: RROI_B200_TUNE_BWD_ZERO_FUSED = 1).  The gradient map has to be defined
-// everywhere, and with a separate memset every touched line of a map larger than L2 crosses DRAM three times (zero
-// written, read back by the first RED, final value written).  Here the map is zeroed by the scatter kernel itself,
-// image by image and `lookahead` images ahead of the scatter front: the CTAs of the j-th image that has RoIs zero the
-// map of image j + LA (the first team also images 0..LA), then wait on a per-image counter until THEIR image has been
-// zeroed -- by the team of image j - LA, whose CTAs have smaller block indices and are long done -- and scatter.  RoIs
-// must be grouped by image (checked by a one-CTA pre-pass, which also ranks the RoIs inside their image); if they are
-// not, a memset kernel runs instead and the scatter proceeds as usual.  Zero stores and REDs carry an L2 evict_last
-// policy, the top_diff stream evict_first.
-// MEASURED (tools/sweep_bwd.py, B200): correct (tests/test_gpu_parity.py::test_backward_zero_fill_fused_with_scatter)
-// but SLOWER than cudaMemsetAsync + scatter: 181 vs 159 us (C=64, 32 images, 472 MB map), 785 vs 624 us (C=256);
-// without the eviction hints 197 us, with a same-image rendezvous instead of the look-ahead 181 us.  The DRAM bytes it
-// saves (~400 MB) do not pay for pushing 472 MB of zero stores through the SMs' store path next to the RED traffic:
-// the copy-engine memset runs at the full 6.3 TB/s and the scatter alone is latency- rather than DRAM-bound (ncu:
-// 4.2 TB/s).  Kept opt-in for the record.
-template <int CT, int TILE, int UN, bool ZF = false>
+template <int CT, int TILE, int UN>
 __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(const BwdParams p) {
     constexpr int LPP = CT / 4;
     constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;
@@ -389,45 +353,7 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
 
     pdl_wait();
     pdl_launch_dependents();
-    const bool zf = ZF && __ldg(p.zf_meta) != 0;          // 0: the pre-pass refused (RoIs not grouped, ...): a memset kernel ran
-    const uint64_t pol_keep = ZF ? l2_policy_evict_last() : 0ull, pol_stream = ZF ? l2_policy_evict_first() : 0ull;
-    if (zf) {
-        // Pipelined over the images that have RoIs (position j in p.zf_order): the CTAs of image j zero the map of image
-        // j + LA (the first team also zeroes images 0..LA), then wait until THEIR image has been zeroed -- by the team of
-        // image j - LA, whose CTAs have smaller block indices and finished long ago -- and scatter.
-        const int LA = __ldg(p.zf_meta + 2), n_img = __ldg(p.zf_meta + 3);
-        const int b = __float2int_rz(__ldg(p.rois + (size_t)n * 6));
-        const int j = __ldg(p.zf_pos + b);
-        const int mine = __ldg(p.zf_rank + n) * p.tiles + tile;               // this CTA's rank among its image's CTAs
-        const int team = __ldg(p.zf_count + b) * p.tiles;
-        const size_t map4 = (size_t)p.H * p.W * CT / 4;                        // float4 per image
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int t_first = j == 0 ? 0 : j + LA, t_last = j + LA;              // positions this team zeroes
-        for (int t = t_first; t <= t_last && t < n_img; ++t) {
-            const int tb = __ldg(p.zf_order + t);
-            float4* img = reinterpret_cast<float4*>(p.bottom_diff) + (size_t)tb * map4;
-            for (size_t i = (size_t)mine * (kPackWarps * 32) + threadIdx.x; i < map4; i += (size_t)team * (kPackWarps * 32)) st_zero_v4_hint(img + i, pol_keep);
-        }
-        // images nobody scatters into: shared by the whole grid
-        const int n_empty = __ldg(p.zf_meta + 1);
-        for (int e = 0; e < n_empty; ++e) {
-            float4* eimg = reinterpret_cast<float4*>(p.bottom_diff) + (size_t)__ldg(p.zf_empty + e) * map4;
-            for (size_t i = (size_t)blockIdx.x * (kPackWarps * 32) + threadIdx.x; i < map4; i += (size_t)gridDim.x * (kPackWarps * 32)) eimg[i] = z;
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int t = t_first; t <= t_last && t < n_img; ++t) atomicAdd(p.zf_arrived + __ldg(p.zf_order + t), 1);
-            const int zeroer = j <= LA ? 0 : j - LA;                           // position of the team that zeroes image j
-            const int need = __ldg(p.zf_count + __ldg(p.zf_order + zeroer)) * p.tiles;
-            int seen;
-            do {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.zf_arrived + b) : "memory");
-                if (seen < need) __nanosleep(64);
-            } while (seen < need);
-        }
-        __syncthreads();
-    }
+    if (!in_image_window(p, n)) return;
     if (warp == 0) {
         RoiXform X;
         if (p.idx_mode == IDX_NONE) {
@@ -482,8 +408,7 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
             const int dpx = NCH > 1 ? it / NCH : it * PPI;
             const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
             r[u] = rbase[dpx];
-            gq[u] = ZF ? ld_v4_hint(tbase + dpx * CT + ch, r[u].pred & 15u, pol_stream)
-                       : ld_v4(tbase + dpx * CT + ch, r[u].pred & 15u);     // bins that scatter nothing are not even read
+            gq[u] = ld_v4(tbase + dpx * CT + ch, r[u].pred & 15u);     // bins that scatter nothing are not even read
         }
         uint32_t any = 0;
 #pragma unroll
@@ -494,13 +419,6 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
                 const int it = it0 + u;
                 const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
                 float* d = gbase + (long long)r[u].pix * CT + ch;
-                if (ZF) {
-                    if (r[u].pred & 1u) red_add_v4_hint(d, r[u].wlt, gq[u], pol_keep);
-                    if (r[u].pred & 2u) red_add_v4_hint(d + CT, r[u].wrt, gq[u], pol_keep);
-                    if (r[u].pred & 4u) red_add_v4_hint(d + rowC + CT, r[u].wrb, gq[u], pol_keep);
-                    if (r[u].pred & 8u) red_add_v4_hint(d + rowC, r[u].wlb, gq[u], pol_keep);
-                    continue;
-                }
                 if (r[u].pred & 1u) red_add_v4(d, r[u].wlt, gq[u]);
                 if (r[u].pred & 2u) red_add_v4(d + CT, r[u].wrt, gq[u]);
                 if (r[u].pred & 4u) red_add_v4(d + rowC + CT, r[u].wrb, gq[u]);
@@ -510,8 +428,130 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
     }
 }
 
+// ---------------------------------------------------------------------------- NHWC, packed, pre-summed per pixel
+// The scatter above issues one vector reduction per (bin, tap): about 739 per RoI on the benchmark draw, landing on only
+// about 386 distinct pixels, because neighbouring bins (pitch 0.5 .. 2 px) share taps -- and the L2 reduction path, not
+// DRAM, is what bounds it (24 M lane-level red.v4 for cfg4's per-GPU batch).  Here the CTA first GROUPS its taps by
+// pixel: one thread per bin computes the scatter geometry and inserts each of its <= 4 (pixel, weight) entries into a
+// shared-memory hash table keyed by the pixel index (open addressing, atomicCAS), chaining the entries of one pixel
+// in a linked list (atomicExch on the slot's head).  Then the warps walk the DISTINCT pixels: lanes = channel vectors,
+// every entry of the pixel's list is one coalesced 128-bit load of top_diff (L1 hits: the CTA's 256 bins are 64 KB)
+// and one FMA into a register accumulator, and the pixel receives ONE red.global.add.v4.f32.  Half the reductions for
+// about twice the (cheap, cached) loads.  The order in which a pixel's contributions are summed is unspecified, as with
+// the reference's atomics; parity is to 1e-4.
+template <int CT, int TILE>
+__global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_presum_kernel(const BwdParams p) {
+    constexpr int LPP = CT / 4;
+    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;           // pixels per warp iteration
+    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;            // 32-lane channel chunks per pixel
+    constexpr int HSZ = 8 * TILE;                           // hash slots: load factor <= 1/2
+    constexpr int NE = 4 * TILE;                            // entries: (bin, tap)
+    __shared__ RoiXform sX;
+    __shared__ int hkey[HSZ];                               // pixel index + 1; 0 = free
+    __shared__ int hhead[HSZ];                              // first entry of the pixel's list, -1 = none
+    __shared__ int enext[NE];
+    __shared__ float ew[NE];
+    __shared__ int uniq[NE];                                // occupied slots, in insertion order
+    __shared__ int nuniq;
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+    const int bin0 = tile * TILE;
+
+    pdl_wait();
+    pdl_launch_dependents();
+    if (!in_image_window(p, n)) return;
+    for (int i = threadIdx.x; i < HSZ; i += kPackWarps * 32) { hkey[i] = 0; hhead[i] = -1; }
+    if (threadIdx.x == 0) nuniq = 0;
+    if (warp == 0) {
+        RoiXform X;
+        if (p.idx_mode == IDX_NONE) {
+            X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        } else {
+            const float* roi = p.rois + (size_t)n * 6;
+            X.batch = __float2int_rz(__ldg(roi));
+            X.rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
+        }
+        if (lane == 0) sX = X;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TILE; t += kPackWarps * 32) {
+        const int bin = bin0 + t;
+        if (bin >= bins) continue;
+        const RoiXform X = sX;
+        const int ph = bin / p.PW, pw = bin - ph * p.PW;
+        const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+        float cx, cy;
+        if (p.idx_mode == IDX_NONE) bin_center(X, ph, pw, (float)(p.W - 1), (float)(p.H - 1), cx, cy);
+        else { cx = __ldg(p.idx_x + (size_t)n * bins + bin); cy = __ldg(p.idx_y + (size_t)n * bins + bin); }
+        const bool in = batch_ok & !(X.rpw < (float)pw);
+        const ScatterGeom g = scatter_geom<false>(cx, cy, in, p.H, p.W);
+        const int base = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+        // a tap with non-zero weight is a distinct pixel: rt/rb only when r == l + 1, lb/rb only when b == t + 1
+        const bool s[4] = {g.p_lt && g.wlt != 0.f, g.p_rt && g.wrt != 0.f && g.r == g.l + 1,
+                           g.p_rb && g.wrb != 0.f && g.r == g.l + 1 && g.b == g.t + 1, g.p_lb && g.wlb != 0.f && g.b == g.t + 1};
+        const int pixk[4] = {base, base + 1, base + p.W + 1, base + p.W};
+        const float wk[4] = {g.wlt, g.wrt, g.wrb, g.wlb};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!s[k]) continue;
+            const int key = pixk[k] + 1;
+            unsigned h = ((unsigned)pixk[k] * 2654435761u) >> 8;
+            for (;;) {
+                h &= HSZ - 1;
+                const int old = atomicCAS(&hkey[h], 0, key);
+                if (old == 0) { uniq[atomicAdd(&nuniq, 1)] = (int)h; break; }
+                if (old == key) break;
+                ++h;
+            }
+            const int e = t * 4 + k;
+            ew[e] = wk[k];
+            enext[e] = atomicExch(&hhead[h], e);
+        }
+    }
+    __syncthreads();
+
+    const int sub = LPP >= 32 ? 0 : lane / LPP;
+    const int cvl = LPP >= 32 ? lane : lane % LPP;
+    const int units = nuniq * NCH;                                   // (pixel, 128-channel chunk)
+    const float* tbase = p.top_diff + ((size_t)n * bins + bin0) * CT + cvl * 4;
+    float* gbase = p.bottom_diff + cvl * 4;
+    for (int u0 = warp * PPI; u0 < units; u0 += kPackWarps * PPI) {
+        const int u = u0 + sub;
+        const bool live = u < units;
+        const int slot = live ? uniq[u / NCH] : 0;
+        const int ch = NCH > 1 ? (u % NCH) * 128 : 0;
+        int e = live ? hhead[slot] : -1;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        while (__any_sync(0xffffffffu, e >= 0)) {
+            // up to four entries of the list per round: their loads are issued together
+            int ee[4];
+            float ww[4];
+            float4 gq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ee[k] = e;
+                ww[k] = e >= 0 ? ew[e] : 0.0f;
+                e = e >= 0 ? enext[e] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gq[k] = ld_v4(tbase + (size_t)((ee[k] >= 0 ? ee[k] : 0) >> 2) * CT + ch, ee[k] >= 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc.x = __fmaf_rn(ww[k], gq[k].x, acc.x); acc.y = __fmaf_rn(ww[k], gq[k].y, acc.y);
+                acc.z = __fmaf_rn(ww[k], gq[k].z, acc.z); acc.w = __fmaf_rn(ww[k], gq[k].w, acc.w);
+            }
+        }
+        if (live) {
+            float* d = gbase + (long long)(hkey[slot] - 1) * CT + ch;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+        }
+    }
+}
+
 template <int CT>
-static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl) {
+static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl, int mode) {
     const int bins = p.PH * p.PW;
     constexpr int PPI = CT >= 128 ? 1 : 128 / CT;
     constexpr int NCH = CT > 128 ? CT / 128 : 1;
@@ -519,120 +559,114 @@ static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl
     const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
     if (ctas256 >= 148 * 4) {
         p.tiles = (bins + 255) / 256;
+        // large launches are bound by the L2 reduction path: group the taps by pixel first (bwd_mode 1 = plain scatter)
+        if (mode != 1) return launch_1d(rroi_bwd_nhwc_presum_kernel<CT, 256>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
         return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 256, 4>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
     }
     p.tiles = (bins + 63) / 64;
     return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
 }
 
-// ---- zero + scatter in one pass: pre-pass over the RoI rows ----------------------------------------------------
-// One CTA.  ok = every batch index is in [0, B), the rows are grouped by image in non-decreasing order and no image has
-// more than max_per_image RoIs.  rank[n] = position of RoI n inside its image, count[b], the list of images without
-// RoIs, order[] / pos[] = the images with RoIs in ascending order and each image's position in that list,
-// meta = {ok, n_empty, lookahead, n_images_with_rois}; arrived[] is cleared.
-__global__ void __launch_bounds__(1024) bwd_group_kernel(const float* __restrict__ rois, int N, int B, int max_per_image, int lookahead,
-                                                          int* __restrict__ rank, int* __restrict__ count, int* __restrict__ first,
-                                                          int* __restrict__ arrived, int* __restrict__ empty, int* __restrict__ order,
-                                                          int* __restrict__ pos, int* __restrict__ meta) {
-    __shared__ int bad, n_empty;
-    if (threadIdx.x == 0) { bad = 0; n_empty = 0; }
-    for (int b = threadIdx.x; b < B; b += blockDim.x) { count[b] = 0; first[b] = 0; arrived[b] = 0; }
-    __syncthreads();
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const float fb = __ldg(rois + (size_t)n * 6);
-        const int b = __float2int_rz(fb);
-        if (!(fb >= 0.0f) || b >= B) { bad = 1; continue; }
-        const int prev = n > 0 ? __float2int_rz(__ldg(rois + (size_t)(n - 1) * 6)) : -1;
-        if (prev > b) bad = 1;
-        if (prev != b) first[b] = n;
-        atomicAdd(count + b, 1);
-    }
-    __syncthreads();
-    for (int n = threadIdx.x; n < N && !bad; n += blockDim.x) {
-        const int b = __float2int_rz(__ldg(rois + (size_t)n * 6));
-        rank[n] = n - first[b];
-    }
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        if (count[b] > max_per_image) bad = 1;
-        if (count[b] == 0) empty[atomicAdd(&n_empty, 1)] = b;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int k = 0;
-        for (int b = 0; b < B; ++b)
-            if (count[b] > 0) { order[k] = b; pos[b] = k; ++k; }
-        meta[0] = bad ? 0 : 1; meta[1] = n_empty; meta[2] = lookahead; meta[3] = k;
-    }
-}
-
-// runs between the pre-pass and the scatter: does nothing when the pre-pass said ok, otherwise it is the memset
-__global__ void __launch_bounds__(256) bwd_zero_unless_ok_kernel(float4* __restrict__ dst, size_t n4, const int* __restrict__ meta) {
-    if (__ldg(meta) != 0) return;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) dst[i] = z;
-}
-
-template <int CT>
-static cudaError_t launch_bwd_zero_fused_ct(BwdParams& p, cudaStream_t s, bool pdl) {
-    const int bins = p.PH * p.PW;
-    p.tiles = (bins + 255) / 256;
-    return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 256, 4, true>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
-}
-
-cudaError_t launch_bwd_nhwc_zero_fused(const BwdParams& p0, cudaStream_t s) {
-    BwdParams p = p0;
-    const size_t map_bytes = (size_t)p.B * p.C * p.H * p.W * sizeof(float);
-    const bool shape_ok = (p.C == 32 || p.C == 64 || p.C == 128 || p.C == 256) && p.N > 0 && p.B <= 4096 &&
-                          ((reinterpret_cast<uintptr_t>(p.top_diff) | reinterpret_cast<uintptr_t>(p.bottom_diff)) % 16 == 0) &&
-                          ((size_t)p.H * p.W * p.C) % 4 == 0 && g_tuning.bwd_dedupe != 2 && g_tuning.bwd_zero_fused != 0;
-    // worth it only when the map does not stay in L2 between a memset and the scatter
-    if (!shape_ok || map_bytes < (size_t)96 << 20) return cudaErrorNotSupported;
-    const int tiles = (p.PH * p.PW + 255) / 256;
-    const int max_per_image = 512 / tiles;                 // at most 512 CTAs wait for each other (592+ are resident)
-    if (max_per_image < 1) return cudaErrorNotSupported;
-    int* scratch = nullptr;
-    const size_t ints = (size_t)p.N + 6 * (size_t)p.B + 4;
-    // how many images ahead the map is zeroed: the zeroed-ahead maps plus the one being scattered must stay in L2
-    const size_t img_bytes = map_bytes / (size_t)p.B;
-    const int lookahead = 3 * img_bytes <= ((size_t)100 << 20) ? 2 : 2 * img_bytes <= ((size_t)100 << 20) ? 1 : 0;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), ints * sizeof(int), s);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); return cudaErrorNotSupported; }
-    int* rank = scratch; int* count = rank + p.N; int* first = count + p.B; int* arrived = first + p.B;
-    int* empty = arrived + p.B; int* order = empty + p.B; int* pos = order + p.B; int* meta = pos + p.B;
-    bwd_group_kernel<<<1, 1024, 0, s>>>(p.rois, p.N, p.B, max_per_image, lookahead, rank, count, first, arrived, empty, order, pos, meta);
-    bwd_zero_unless_ok_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4*>(p.bottom_diff), map_bytes / 16, meta);
-    p.zf_rank = rank; p.zf_count = count; p.zf_arrived = arrived; p.zf_empty = empty; p.zf_meta = meta; p.zf_order = order; p.zf_pos = pos;
-    p.cgroups = 1;
-    e = cudaGetLastError();
-    if (e == cudaSuccess) {
-        switch (p.C) {
-            case 32:  e = launch_bwd_zero_fused_ct<32>(p, s, false); break;
-            case 64:  e = launch_bwd_zero_fused_ct<64>(p, s, false); break;
-            case 128: e = launch_bwd_zero_fused_ct<128>(p, s, false); break;
-            default:  e = launch_bwd_zero_fused_ct<256>(p, s, false); break;
-        }
-    }
-    (void)cudaFreeAsync(scratch, s);
-    return e;
-}
-
-cudaError_t launch_bwd_nhwc(const BwdParams& p0, cudaStream_t s) {
+cudaError_t launch_bwd_nhwc(const BwdParams& p0, const Opts& o, cudaStream_t s) {
     BwdParams p = p0;
     const int bins = p.PH * p.PW;
     p.tiles = (bins + kTilePix - 1) / kTilePix;
     p.cgroups = 1;
     const long long grid = (long long)p.N * p.tiles;
-    const bool pdl = g_tuning.use_pdl != 0;
+    const bool pdl = o.pdl;
     const bool vec = (p.C % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.top_diff) | reinterpret_cast<uintptr_t>(p.bottom_diff)) % 16 == 0);
-    if (vec && g_tuning.bwd_dedupe != 2) {      // TUNE_BWD_DEDUPE = 2 selects the generic kernel (A/B measurements)
-        if (p.C == 32)  return launch_bwd_nhwc_packed<32>(p, s, pdl);
-        if (p.C == 64)  return launch_bwd_nhwc_packed<64>(p, s, pdl);
-        if (p.C == 128) return launch_bwd_nhwc_packed<128>(p, s, pdl);
-        if (p.C == 256) return launch_bwd_nhwc_packed<256>(p, s, pdl);
+    if (vec && o.bwd_mode != 2) {      // opts.bwd_mode = 2 selects the generic kernel (A/B measurements)
+        if (p.C == 32)  return launch_bwd_nhwc_packed<32>(p, s, pdl, o.bwd_mode);
+        if (p.C == 64)  return launch_bwd_nhwc_packed<64>(p, s, pdl, o.bwd_mode);
+        if (p.C == 128) return launch_bwd_nhwc_packed<128>(p, s, pdl, o.bwd_mode);
+        if (p.C == 256) return launch_bwd_nhwc_packed<256>(p, s, pdl, o.bwd_mode);
     }
     return vec ? launch_1d(rroi_bwd_nhwc_kernel<true>, grid, kBlock, p, s, pdl)
                : launch_1d(rroi_bwd_nhwc_kernel<false>, grid, kBlock, p, s, pdl);
+}
+
+// --------------------------------------------------------------------- zero-fill + scatter, chunked by image
+// The gradient map must be defined everywhere, so zero_fill means 4*B*C*H*W bytes of stores in front of the scatter.
+// With one memset of a map much larger than L2 (cfg3/cfg4: 472 MB vs 126 MB) every line a RoI touches crosses DRAM
+// three times: written as zero, evicted, read back by the first reduction, written again.  Here the map is cleared in
+// chunks of a few images on a side stream and each chunk's RoIs are scattered (image window [img_lo, img_hi) of the
+// scatter kernels) as soon as ITS chunk is clear: the reductions hit lines that are still dirty in L2, and the
+// zero-fill of the next chunks (DRAM-write-bound) overlaps the scatter of this one (L2-reduction-bound).  The side
+// stream runs at most two chunks ahead of the scatter so the cleared lines are not evicted before they are used.
+// No assumption on the order of the RoI rows: a scatter launch skips (CTA-uniform early exit) every RoI outside its
+// window.  Streams and events are cached per host thread and device, so concurrent callers never share them.
+namespace {
+
+struct SideLane {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr;
+    cudaEvent_t zeroed[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t scattered[3] = {nullptr, nullptr, nullptr};
+    bool ok = false;
+};
+
+SideLane* side_lane() {
+    thread_local SideLane lanes[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideLane& L = lanes[dev];
+    if (!L.ok) {
+        if (cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        bool good = cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 3 && good; ++i)
+            good = cudaEventCreateWithFlags(&L.zeroed[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&L.scattered[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!good) return nullptr;
+        L.ok = true;
+    }
+    return &L;
+}
+
+}  // namespace
+
+cudaError_t launch_bwd_zero_scatter(const BwdParams& p0, const Opts& o, bool nhwc, cudaStream_t s) {
+    BwdParams p = p0;
+    const size_t img_bytes = (size_t)p.C * p.H * p.W * sizeof(float);
+    const size_t map_bytes = img_bytes * (size_t)p.B;
+    auto scatter = [&](int lo, int hi) {
+        p.img_lo = lo; p.img_hi = hi;
+        return nhwc ? launch_bwd_nhwc(p, o, s) : launch_bwd_nchw(p, o, s);
+    };
+    // MEASURED on B200 (profiles/r02_sweep_bwd.txt, cfg4's per-GPU batch, C = 64): one memset + one scatter 159 us; chunks
+    // of 8 / 4 / 2 / 1 images 184 / 208 / 266 / 408 us -- every chunk costs about 7 us of cross-stream hand-over and the
+    // scatter gains nothing from L2-resident zeros because it is bound by the reduction path, not by DRAM.  So the
+    // chunked form is opt-in (opts.zero_chunk_images > 0) and the default is the plain memset + scatter.
+    const int per = o.zero_chunk_images;
+    SideLane* L = nullptr;
+    if (per > 0 && per < p.B && map_bytes > ((size_t)96 << 20) && p.N > 0) L = side_lane();
+    if (!L) {                                              // small map (stays in L2 anyway), or asked for: memset, scatter
+        cudaError_t e = cudaMemsetAsync(p.bottom_diff, 0, map_bytes, s);
+        if (e != cudaSuccess || p.N == 0) return e;
+        return scatter(0, 0x7fffffff);
+    }
+    const int chunks = (p.B + per - 1) / per;
+    cudaError_t e = cudaEventRecord(L->fork, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(L->side, L->fork, 0);
+    auto clear = [&](int g) -> cudaError_t {               // on the side stream; at most two chunks ahead of the scatter
+        cudaError_t ee = cudaSuccess;
+        if (g >= 3) ee = cudaStreamWaitEvent(L->side, L->scattered[(g - 3) % 3], 0);
+        const int lo = g * per, hi = lo + per < p.B ? lo + per : p.B;
+        if (ee == cudaSuccess) ee = cudaMemsetAsync(reinterpret_cast<char*>(p.bottom_diff) + (size_t)lo * img_bytes, 0, (size_t)(hi - lo) * img_bytes, L->side);
+        if (ee == cudaSuccess) ee = cudaEventRecord(L->zeroed[g % 3], L->side);
+        return ee;
+    };
+    // Event slots are reused round-robin (3 each way); a cudaStreamWaitEvent captures the record that precedes it in host
+    // order, so each wait below is issued before its slot is recorded again.
+    for (int g = 0; g < chunks && g < 2 && e == cudaSuccess; ++g) e = clear(g);
+    for (int g = 0; g < chunks && e == cudaSuccess; ++g) {
+        e = cudaStreamWaitEvent(s, L->zeroed[g % 3], 0);
+        const int lo = g * per, hi = g + 1 == chunks ? 0x7fffffff : lo + per;     // the last window also takes batch >= B (no-ops)
+        if (e == cudaSuccess) e = scatter(g == 0 ? -0x7fffffff : lo, hi);
+        if (e == cudaSuccess) e = cudaEventRecord(L->scattered[g % 3], s);
+        if (e == cudaSuccess && g + 2 < chunks) e = clear(g + 2);
+    }
+    return e;
 }
 
 }  // namespace rroi

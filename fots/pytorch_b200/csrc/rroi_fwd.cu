@@ -22,7 +22,47 @@
 
 namespace rroi {
 
-Tuning g_tuning = {0, 0, 0, 1, 0, 0};
+// The per-RoI transform: from the caller's table (rroi_b200_roi_xform) when there is one, else computed here.
+__device__ __forceinline__ RoiXform get_xform(const FwdParams& p, int n) {
+    if (p.xform) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.xform) + 2 * (size_t)n);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.xform) + 2 * (size_t)n + 1);
+        RoiXform X;
+        X.M00 = a.x; X.M01 = a.y; X.M02 = a.z; X.M10 = a.w; X.M11 = b.x; X.M12 = b.y; X.rpw = b.z; X.batch = __float_as_int(b.w);
+        return X;
+    }
+    return roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+}
+
+// CTA prologue of the block-level kernels: warp 0 fetches the transform into shared memory.  With p.early (the caller
+// vouches that the RoI rows are older than the preceding kernel) that happens before the grid dependency resolves.
+__device__ __forceinline__ void cta_xform_prologue(const FwdParams& p, int n, RoiXform* sX) {
+    if (!p.early) pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x < 32) {
+        const RoiXform X = get_xform(p, n);
+        if (threadIdx.x == 0) *sX = X;
+    }
+    if (p.early) pdl_wait();
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) roi_xform_kernel(const float* __restrict__ rois, float* __restrict__ xform, int N, int PH, float scale) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const RoiXform X = roi_xform(rois + (size_t)n * 6, scale, PH);
+    float4* o = reinterpret_cast<float4*>(xform) + 2 * (size_t)n;
+    o[0] = make_float4(X.M00, X.M01, X.M02, X.M10);
+    o[1] = make_float4(X.M11, X.M12, X.rpw, __int_as_float(X.batch));
+}
+
+cudaError_t launch_roi_xform(const float* rois, float* xform, int N, int PH, float scale, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    roi_xform_kernel<<<(N + 127) / 128, 128, 0, s>>>(rois, xform, N, PH, scale);
+    return cudaGetLastError();
+}
 
 // code word of a bin
 enum : uint32_t {
@@ -75,13 +115,7 @@ __global__ void __launch_bounds__(kNchwBlock) rroi_fwd_nchw_kernel(const FwdPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bins = p.PH * p.PW;
 
-    pdl_wait();
-    pdl_launch_dependents();
-    if (warp == 0) {
-        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        if (lane == 0) sX = X;
-    }
-    __syncthreads();
+    cta_xform_prologue(p, n, &sX);
     const RoiXform X = sX;
     const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
     if (threadIdx.x < kPatch * kPatch) {
@@ -193,10 +227,11 @@ rroi_fwd_nchw_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bins = p.PH * p.PW;
 
-    pdl_wait();
+    if (!p.early) pdl_wait();
     pdl_launch_dependents();
     if (warp == 0) {
-        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        const RoiXform X = get_xform(p, n);
+        if (p.early) pdl_wait();
         if (lane == 0) {
             sX = X;
             bb[0] = INT_MAX; bb[1] = INT_MAX; bb[2] = INT_MIN; bb[3] = INT_MIN;
@@ -408,28 +443,37 @@ static bool make_nchw_maps(const FwdParams& p, NchwTmaMaps* out) {
     return true;
 }
 
-cudaError_t launch_fwd_nchw(const FwdParams& p0, cudaStream_t s) {
+// cudaFuncSetAttribute is per device: remember per device ordinal which devices have been opted in (the attribute
+// call itself is idempotent, so a benign race between threads only repeats it)
+static cudaError_t tma_kernel_smem_optin() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(rroi_fwd_nchw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTmaStageBytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
+cudaError_t launch_fwd_nchw(const FwdParams& p0, const Opts& o, cudaStream_t s) {
     FwdParams p = p0;
     p.tiles = ((p.PH + kPatch - 1) / kPatch) * ((p.PW + kPatch - 1) / kPatch);
     p.cgroups = 1;
     const long long grid = (long long)p.N * p.tiles;
-    const bool pdl = g_tuning.use_pdl != 0;
+    const bool pdl = o.pdl;
     // Measured on B200: the TMA-staged kernel is bit-identical but not faster than the gather kernel
     // (5.46 vs 5.54 us on cfg1, 179.8 vs 183.2 us on cfg4's per-GPU batch) -- the boxes over-fetch 3-4x from L2, which
     // trades the L1-wavefront bound for an L2-bandwidth bound -- and it costs four tensor-map encodes per call on the
-    // host, so it is opt-in (RROI_B200_TUNE_NCHW_TMA >= 1).
-    if (g_tuning.nchw_tma >= 1 && p.B != 0x7fffffff) {      // the legacy launcher does not know the batch size
-        p.cgroups = g_tuning.nchw_tma >= 2 ? g_tuning.nchw_tma : 1;
+    // host, so it is opt-in (opts.nchw_tma >= 1).
+    if (o.nchw_tma >= 1 && p.B != 0x7fffffff) {      // the legacy launcher does not know the batch size
+        p.cgroups = o.nchw_tma >= 2 ? o.nchw_tma : 1;
         NchwTmaMaps maps;
         if (make_nchw_maps(p, &maps)) {
             if (grid <= 0) return cudaSuccess;
             if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-            static bool attr = false;
-            if (!attr) {
-                const cudaError_t e = cudaFuncSetAttribute(rroi_fwd_nchw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTmaStageBytes);
-                if (e != cudaSuccess) return e;
-                attr = true;
-            }
+            const cudaError_t ea = tma_kernel_smem_optin();
+            if (ea != cudaSuccess) return ea;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid);
             cfg.blockDim = dim3(kNchwBlock);
@@ -443,7 +487,7 @@ cudaError_t launch_fwd_nchw(const FwdParams& p0, cudaStream_t s) {
             return cudaLaunchKernelEx(&cfg, rroi_fwd_nchw_tma_kernel, p, maps.m[0], maps.m[1], maps.m[2], maps.m[3]);
         }
     }
-    switch (g_tuning.nchw_cg) {     // channels in flight per lane
+    switch (o.nchw_cg) {     // channels in flight per lane
         case 1:  return launch_1d(rroi_fwd_nchw_kernel<1>, grid, kNchwBlock, p, s, pdl);
         case 2:  return launch_1d(rroi_fwd_nchw_kernel<2>, grid, kNchwBlock, p, s, pdl);
         case 8:  return launch_1d(rroi_fwd_nchw_kernel<8>, grid, kNchwBlock, p, s, pdl);
@@ -541,13 +585,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_kernel(const Fw
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bins = p.PH * p.PW;
 
-    pdl_wait();
-    pdl_launch_dependents();
-    if (warp == 0) {
-        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        if (lane == 0) sX = X;
-    }
-    __syncthreads();
+    cta_xform_prologue(p, n, &sX);
 
     // ---- geometry: lane j <-> bin bin0 + j
     const int bin0 = (tile * kNhwcWarps + warp) * PPW;
@@ -675,13 +713,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_packed_kernel(c
     const int bins = p.PH * p.PW;
     const int bin0 = tile * TILE;
 
-    pdl_wait();
-    pdl_launch_dependents();
-    if (warp == 0) {
-        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        if (lane == 0) sX = X;
-    }
-    __syncthreads();
+    cta_xform_prologue(p, n, &sX);
     for (int t = threadIdx.x; t < TILE; t += kNhwcWarps * 32) {
         BinRec r;
         r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
@@ -774,23 +806,307 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_packed_kernel(c
     }
 }
 
-template <int CT>
-static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, bool pdl, int variant) {
+// ------------------------------------------------------------------------- NHWC, packed, warp-autonomous
+// Same lanes, records and blend as the block-level kernel above, but every WARP is its own unit of work: it owns
+// BPW consecutive bins of one RoI, evaluates the RoI transform itself (all lanes redundantly -- no shared-memory
+// broadcast), computes its bins' geometry lane-parallel into its private slice of shared memory and starts loading
+// after a __syncwarp().  No __syncthreads() anywhere: a single small launch (cfg1: 64 RoIs) is a pure latency chain
+// RoI row -> transform -> geometry -> taps -> store, and the two block barriers of the block-level kernel made
+// every warp wait for the slowest one twice (ncu: barrier = 5.1 of 17 stall cycles per issued instruction).
+// With p.early (RROI_B200_FLAG_ROIS_READY) the whole prologue runs before griddepcontrol.wait, i.e. while the
+// previous kernel in the stream drains; only the feature reads and the stores wait for the grid dependency.
+template <int CT, int BPW, int UN>
+__global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_warp_kernel(const FwdParams p) {
+    constexpr int LPP = CT / 4;
+    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;
+    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;
+    constexpr int ITERS = BPW * NCH / PPI;
+    static_assert(ITERS > 0 && ITERS % UN == 0 && BPW % PPI == 0, "segment shape");
+    __shared__ BinRec rec[kNhwcWarps][BPW];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * kNhwcWarps + warp;       // global warp = (RoI, segment)
+    const int n = (int)(gw / p.tiles);
     const int bins = p.PH * p.PW;
-    auto go = [&](auto kernel, int tile) {
+    const int bin0 = (int)(gw - (long long)n * p.tiles) * BPW;
+    if (!p.early) pdl_wait();
+    pdl_launch_dependents();
+    if (n >= p.N) return;                                                  // warp-uniform (ragged last CTA)
+
+    const RoiXform X = get_xform(p, n);                                    // every lane: same addresses, same result
+    const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+    float ccx[(BPW + 31) / 32], ccy[(BPW + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (BPW + 31) / 32; ++k) {
+        const int t = k * 32 + lane;
+        ccx[k] = 0.0f; ccy[k] = 0.0f;
+        if (t < BPW) {
+            BinRec r;
+            r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
+            const int bin = bin0 + t;
+            if (bin < bins) {
+                const int ph = bin / p.PW, pw = bin - ph * p.PW;
+                const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+                const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+                r.pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+                r.code = C_LIVE;
+                if (in) {
+                    const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+                    const bool l_lt = g.flags & TAP_LT;
+                    const bool l_rt = (g.flags & TAP_RT) && two_c;
+                    const bool l_lb = (g.flags & TAP_LB) && two_r;
+                    const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+                    r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+                    r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+                    r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+                    r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+                    r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+                    ccx[k] = g.cx; ccy[k] = g.cy;
+                }
+            }
+            rec[warp][t] = r;
+        }
+    }
+    __syncwarp();
+    if (p.early) pdl_wait();                                               // nothing above touched the caller's outputs
+    if (p.idx_mode == IDX_COMPACT) {
+#pragma unroll
+        for (int k = 0; k < (BPW + 31) / 32; ++k) {
+            const int t = k * 32 + lane;
+            if (t < BPW && bin0 + t < bins) {
+                p.idx_x[(size_t)n * bins + bin0 + t] = ccx[k];
+                p.idx_y[(size_t)n * bins + bin0 + t] = ccy[k];
+            }
+        }
+    }
+
+    const int sub = LPP >= 32 ? 0 : lane / LPP;
+    const int cvl = LPP >= 32 ? lane : lane % LPP;
+    const long long rowC = (long long)p.W * CT;
+    const float* fbase = p.feat + cvl * 4;
+    float* obase = p.out + ((size_t)n * bins + bin0 + (NCH > 1 ? 0 : sub)) * CT + cvl * 4;
+    const BinRec* rbase = rec[warp] + (NCH > 1 ? 0 : sub);
+
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += UN) {
+        float4 lt[UN], rt[UN], lb[UN], rb[UN];
+        BinRec r[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int it = it0 + u;
+            r[u] = rbase[NCH > 1 ? it / NCH : it * PPI];
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int it = it0 + u;
+            const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+            const float* s = fbase + (long long)r[u].pix * CT + ch;
+            const float* s2 = s + rowC;
+            lt[u] = ldg_pred_v4(s, r[u].code & C_LT);
+            rt[u] = ldg_pred_v4(s + CT, r[u].code & C_RT);
+            lb[u] = ldg_pred_v4(s2, r[u].code & C_LB);
+            rb[u] = ldg_pred_v4(s2 + CT, r[u].code & C_RB);
+        }
+        uint32_t any_live = 0;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) any_live |= r[u].code;
+        if (any_live & C_LIVE) {                         // own basic block: keeps the UN iterations' loads batched
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int it = it0 + u;
+                const int dpx = NCH > 1 ? it / NCH : it * PPI;
+                const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+                const float wlt = r[u].wlt, wrt = r[u].wrt, wrb = r[u].wrb, wlb = r[u].wlb;
+                float4 o;
+                float v;
+                v = __fmaf_rn(lt[u].x, wlt, 0.0f); v = __fmaf_rn(rt[u].x, wrt, v); v = __fmaf_rn(wrb, rb[u].x, v); o.x = __fmaf_rn(lb[u].x, wlb, v);
+                v = __fmaf_rn(lt[u].y, wlt, 0.0f); v = __fmaf_rn(rt[u].y, wrt, v); v = __fmaf_rn(wrb, rb[u].y, v); o.y = __fmaf_rn(lb[u].y, wlb, v);
+                v = __fmaf_rn(lt[u].z, wlt, 0.0f); v = __fmaf_rn(rt[u].z, wrt, v); v = __fmaf_rn(wrb, rb[u].z, v); o.z = __fmaf_rn(lb[u].z, wlb, v);
+                v = __fmaf_rn(lt[u].w, wlt, 0.0f); v = __fmaf_rn(rt[u].w, wrt, v); v = __fmaf_rn(wrb, rb[u].w, v); o.w = __fmaf_rn(lb[u].w, wlb, v);
+                if (r[u].code & C_LIVE) *reinterpret_cast<float4*>(obase + dpx * CT + ch) = o;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------- NHWC, packed, warp-autonomous, taps staged in shared memory
+// The register-staged kernels above keep UN iterations' taps (UN x 4 float4 per lane) in flight and need ITERS / UN
+// dependent DRAM round trips per warp; more in flight costs registers, i.e. occupancy.  Here every tap of the warp's
+// BPW bins is fetched by cp.async (LDGSTS, 16 bytes per lane) straight into the warp's slice of shared memory: all
+// 4 * ITERS warp-level copies are issued back to back (no registers held, no scoreboard stall between them), taps
+// that are not loaded are zero-filled by the copy itself (src-size 0), and after ONE cp.async.wait_all the blend
+// reads LDS.128 x 4 -> 16 FFMA -> STG.128 per lane and iteration, branch-free.  One DRAM round trip per warp instead
+// of ITERS / UN -- what a single small launch (cfg1: a pure latency chain) wants.  Same records, same FFMA order:
+// bit-identical to the other kernels.  BPW * CT * 16 bytes of shared memory per warp.
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const float* src, uint32_t pred) {
+    const uint32_t n = pred ? 16u : 0u;                                    // 0: nothing is read, 16 zero bytes are written
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+
+template <int CT, int BPW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rroi_fwd_nhwc_stage_kernel(const FwdParams p) {
+    constexpr int LPP = CT / 4;
+    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;
+    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;
+    constexpr int ITERS = BPW * NCH / PPI;
+    static_assert(ITERS > 0 && BPW % PPI == 0 && BPW <= 32, "segment shape");
+    extern __shared__ __align__(16) uint8_t stage_raw[];                   // [WARPS][ITERS][4 taps][32 lanes] float4, then the records
+    float4* const stage = reinterpret_cast<float4*>(stage_raw);
+    BinRec* const recs = reinterpret_cast<BinRec*>(stage_raw + (size_t)WARPS * ITERS * 4 * 32 * sizeof(float4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * WARPS + warp;
+    const int n = (int)(gw / p.tiles);
+    const int bins = p.PH * p.PW;
+    const int bin0 = (int)(gw - (long long)n * p.tiles) * BPW;
+    if (!p.early) pdl_wait();
+    pdl_launch_dependents();
+    if (n >= p.N) return;
+
+    BinRec* const rec = recs + warp * BPW;
+    float ccx = 0.0f, ccy = 0.0f;
+    {
+        const RoiXform X = get_xform(p, n);
+        const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+        if (lane < BPW) {
+            BinRec r;
+            r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
+            const int bin = bin0 + lane;
+            if (bin < bins) {
+                const int ph = bin / p.PW, pw = bin - ph * p.PW;
+                const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+                const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
+                r.pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
+                r.code = C_LIVE;
+                if (in) {
+                    const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+                    const bool l_lt = g.flags & TAP_LT;
+                    const bool l_rt = (g.flags & TAP_RT) && two_c;
+                    const bool l_lb = (g.flags & TAP_LB) && two_r;
+                    const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+                    r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+                    r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+                    r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+                    r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+                    r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+                    ccx = g.cx; ccy = g.cy;
+                }
+            }
+            rec[lane] = r;
+        }
+    }
+    __syncwarp();
+    if (p.early) pdl_wait();                                               // nothing above touched the caller's buffers
+    if (p.idx_mode == IDX_COMPACT && lane < BPW && bin0 + lane < bins) {
+        p.idx_x[(size_t)n * bins + bin0 + lane] = ccx;
+        p.idx_y[(size_t)n * bins + bin0 + lane] = ccy;
+    }
+
+    const int sub = LPP >= 32 ? 0 : lane / LPP;
+    const int cvl = LPP >= 32 ? lane : lane % LPP;
+    const long long rowC = (long long)p.W * CT;
+    const float* fbase = p.feat + cvl * 4;
+    float4* const wstage = stage + (size_t)warp * ITERS * 4 * 32 + lane;
+    const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(wstage);
+    const BinRec* rbase = rec + (NCH > 1 ? 0 : sub);
+
+    // ---- issue every tap of every iteration ----
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const BinRec r = rbase[NCH > 1 ? it / NCH : it * PPI];
+        const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+        const uint32_t any = r.code & (C_LT | C_RT | C_LB | C_RB);
+        const float* s = fbase + (any ? (long long)r.pix * CT + ch : 0);   // a valid address even when nothing is read
+        const float* s2 = s + (any ? rowC : 0);
+        const uint32_t d = wstage_s + (uint32_t)(it * 4 * 32 * sizeof(float4));
+        cp_async_16_zfill(d, s, r.code & C_LT);
+        cp_async_16_zfill(d + 32 * sizeof(float4), (r.code & C_RT) ? s + CT : s, r.code & C_RT);
+        cp_async_16_zfill(d + 64 * sizeof(float4), (r.code & C_LB) ? s2 : s, r.code & C_LB);
+        cp_async_16_zfill(d + 96 * sizeof(float4), (r.code & C_RB) ? s2 + CT : s, r.code & C_RB);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    // ---- blend from shared memory (each lane reads back exactly the 16 bytes it copied) ----
+    float* obase = p.out + ((size_t)n * bins + bin0 + (NCH > 1 ? 0 : sub)) * CT + cvl * 4;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int dpx = NCH > 1 ? it / NCH : it * PPI;
+        const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
+        const BinRec r = rbase[dpx];
+        const float4 lt = wstage[it * 128], rt = wstage[it * 128 + 32], lb = wstage[it * 128 + 64], rb = wstage[it * 128 + 96];
+        const float wlt = r.wlt, wrt = r.wrt, wrb = r.wrb, wlb = r.wlb;
+        float4 o;
+        float v;
+        v = __fmaf_rn(lt.x, wlt, 0.0f); v = __fmaf_rn(rt.x, wrt, v); v = __fmaf_rn(wrb, rb.x, v); o.x = __fmaf_rn(lb.x, wlb, v);
+        v = __fmaf_rn(lt.y, wlt, 0.0f); v = __fmaf_rn(rt.y, wrt, v); v = __fmaf_rn(wrb, rb.y, v); o.y = __fmaf_rn(lb.y, wlb, v);
+        v = __fmaf_rn(lt.z, wlt, 0.0f); v = __fmaf_rn(rt.z, wrt, v); v = __fmaf_rn(wrb, rb.z, v); o.z = __fmaf_rn(lb.z, wlb, v);
+        v = __fmaf_rn(lt.w, wlt, 0.0f); v = __fmaf_rn(rt.w, wrt, v); v = __fmaf_rn(wrb, rb.w, v); o.w = __fmaf_rn(lb.w, wlb, v);
+        if (r.code & C_LIVE) *reinterpret_cast<float4*>(obase + dpx * CT + ch) = o;
+    }
+}
+
+// shared memory of one CTA of the staged kernel; opted in per device on first use (idempotent attribute)
+template <int CT, int BPW, int WARPS>
+static cudaError_t launch_stage(FwdParams& p, cudaStream_t s, bool pdl) {
+    constexpr int PPI = CT >= 128 ? 1 : 128 / CT, NCH = CT > 128 ? CT / 128 : 1, ITERS = BPW * NCH / PPI;
+    constexpr size_t smem = (size_t)WARPS * ITERS * 4 * 32 * 16 + (size_t)WARPS * BPW * sizeof(BinRec);
+    static_assert(smem <= 227 * 1024, "shared memory per CTA");
+    const int bins = p.PH * p.PW;
+    p.tiles = (bins + BPW - 1) / BPW;
+    const long long warps = (long long)p.N * p.tiles, grid = (warps + WARPS - 1) / WARPS;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024) {
+        static bool done[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            e = cudaFuncSetAttribute(rroi_fwd_nhwc_stage_kernel<CT, BPW, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, rroi_fwd_nhwc_stage_kernel<CT, BPW, WARPS>, p);
+}
+
+template <int CT>
+static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, const Opts& o) {
+    const int bins = p.PH * p.PW;
+    const bool pdl = o.pdl;
+    auto go = [&](auto kernel, int tile) {               // block-level kernels: one CTA per (RoI, tile)
         p.tiles = (bins + tile - 1) / tile;
         return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, pdl);
+    };
+    auto gow = [&](auto kernel, int bpw) {               // warp-autonomous kernels: p.tiles = segments (warps) per RoI
+        p.tiles = (bins + bpw - 1) / bpw;
+        const long long warps = (long long)p.N * p.tiles;
+        return launch_1d(kernel, (warps + kNhwcWarps - 1) / kNhwcWarps, kNhwcWarps * 32, p, s, pdl);
     };
     constexpr int PPI = CT >= 128 ? 1 : 128 / CT;   // pixels per warp iteration
     constexpr int NCH = CT > 128 ? CT / 128 : 1;
     // UN chosen so that a 64-bin tile's per-warp iterations (8*NCH/PPI) are a multiple of it
     constexpr int I64 = 8 * NCH / PPI;
+    constexpr int I8 = 8 * NCH / PPI, I16 = 16 * NCH / PPI;          // iterations of an 8- / 16-bin warp segment
+    int variant = o.variant;
     if (variant == 0) {
-        // auto: small launches (about one wave of 64-bin CTAs or less) want many small CTAs; large ones
-        // amortise the per-CTA prologue (RoI transform, two barriers) over 256 bins.  Measured on B200:
-        // cfg1 (N=64) 5.2 us with 64-bin tiles vs 8.9 us with 256; N=2048 75.7 us with 256 vs 96.7 with 64.
+        // auto (measured on B200, profiles/r02_sweep_fwd.txt): a launch that has the GPU to itself and fills at most
+        // about one wave is a latency chain -> warp-autonomous 16-bin segments; large launches and launches that overlap
+        // with others (opts.concurrency) amortise the per-CTA prologue over 256 bins.
         const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
-        variant = ctas256 >= 148 * 4 ? 5 : 1;
+        const long long load = ctas256 * (o.concurrency > 1 ? o.concurrency : 1);
+        variant = load >= 148 * 4 ? 5 : 12;
     }
     switch (variant) {
         case 1:  return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
@@ -799,38 +1115,49 @@ static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, bool pdl
         case 4:  return go(rroi_fwd_nhwc_packed_kernel<CT, 256, 4>, 256);
         case 5:  return go(rroi_fwd_nhwc_packed_kernel<CT, 256, 2>, 256);
         case 6:  return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 4 ? 4 : I64)>, 64);
-        default: return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
+        case 11: return gow(rroi_fwd_nhwc_warp_kernel<CT, 8, (I8 >= 2 ? 2 : 1)>, 8);
+        case 12: return gow(rroi_fwd_nhwc_warp_kernel<CT, 16, (I16 >= 2 ? 2 : 1)>, 16);
+        case 13: return gow(rroi_fwd_nhwc_warp_kernel<CT, 16, (I16 >= 4 ? 4 : I16)>, 16);
+        case 14: return gow(rroi_fwd_nhwc_warp_kernel<CT, 32, 4>, 32);
+        case 15: return gow(rroi_fwd_nhwc_warp_kernel<CT, 64, 4>, 64);
+        case 16: return gow(rroi_fwd_nhwc_warp_kernel<CT, 32, 2>, 32);
+        case 17: return gow(rroi_fwd_nhwc_warp_kernel<CT, 8, (I8 >= 4 ? 4 : I8)>, 8);
+        // taps staged in shared memory by cp.async: (bins per warp, warps per CTA)
+        case 21: return launch_stage<CT, (CT <= 64 ? 8 : 4), 4>(p, s, pdl);
+        case 22: return launch_stage<CT, (CT <= 64 ? 8 : 4), 2>(p, s, pdl);
+        case 23: return launch_stage<CT, (CT <= 64 ? 16 : 8), 2>(p, s, pdl);
+        case 24: return launch_stage<CT, (CT <= 64 ? 4 : 2), 4>(p, s, pdl);
+        case 25: return launch_stage<CT, (CT <= 64 ? 8 : 4), 8>(p, s, pdl);
+        default: return cudaErrorInvalidValue;
     }
 }
 
 template <int CT, int VEC>
-static cudaError_t launch_fwd_nhwc_vec(FwdParams& p, cudaStream_t s, bool pdl, int variant) {
+static cudaError_t launch_fwd_nhwc_vec(FwdParams& p, cudaStream_t s, const Opts& o) {
     const int bins = p.PH * p.PW;
     auto go = [&](auto kernel, int ppw) {
         p.tiles = (bins + kNhwcWarps * ppw - 1) / (kNhwcWarps * ppw);
-        return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, pdl);
+        return launch_1d(kernel, (long long)p.N * p.tiles, kNhwcWarps * 32, p, s, o.pdl);
     };
-    switch (variant) {
+    switch (o.variant) {
         case 1:  return go(rroi_fwd_nhwc_kernel<CT, VEC, 8, 4>, 8);
         case 3:  return go(rroi_fwd_nhwc_kernel<CT, VEC, 32, 4>, 32);
         default: return go(rroi_fwd_nhwc_kernel<CT, VEC, 16, 4>, 16);
     }
 }
 
-cudaError_t launch_fwd_nhwc(const FwdParams& p0, cudaStream_t s) {
+cudaError_t launch_fwd_nhwc(const FwdParams& p0, const Opts& o, cudaStream_t s) {
     FwdParams p = p0;
     p.cgroups = 1;
-    const bool pdl = g_tuning.use_pdl != 0;
-    const int variant = g_tuning.nhwc_unroll;
     const bool al16 = (reinterpret_cast<uintptr_t>(p.feat) | reinterpret_cast<uintptr_t>(p.out)) % 16 == 0;
-    if (al16 && p.C == 32)  return launch_fwd_nhwc_packed<32>(p, s, pdl, variant);
-    if (al16 && p.C == 64)  return launch_fwd_nhwc_packed<64>(p, s, pdl, variant);
-    if (al16 && p.C == 128) return launch_fwd_nhwc_packed<128>(p, s, pdl, variant);
-    if (al16 && p.C == 256) return launch_fwd_nhwc_packed<256>(p, s, pdl, variant);
+    if (al16 && p.C == 32)  return launch_fwd_nhwc_packed<32>(p, s, o);
+    if (al16 && p.C == 64)  return launch_fwd_nhwc_packed<64>(p, s, o);
+    if (al16 && p.C == 128) return launch_fwd_nhwc_packed<128>(p, s, o);
+    if (al16 && p.C == 256) return launch_fwd_nhwc_packed<256>(p, s, o);
     // any other C: warp-per-bin kernel with run-time C, widest vector that divides it
-    if (al16 && p.C % 4 == 0 && p.C >= 128) return launch_fwd_nhwc_vec<0, 4>(p, s, pdl, variant);
-    if (al16 && p.C % 2 == 0 && p.C >= 64)  return launch_fwd_nhwc_vec<0, 2>(p, s, pdl, variant);
-    return launch_fwd_nhwc_vec<0, 1>(p, s, pdl, variant);
+    if (al16 && p.C % 4 == 0 && p.C >= 128) return launch_fwd_nhwc_vec<0, 4>(p, s, o);
+    if (al16 && p.C % 2 == 0 && p.C >= 64)  return launch_fwd_nhwc_vec<0, 2>(p, s, o);
+    return launch_fwd_nhwc_vec<0, 1>(p, s, o);
 }
 
 // ------------------------------------------------------------------------------ NHWC, bf16 -> bf16
@@ -898,13 +1225,7 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, MINB) rroi_fwd_nhwc_bf16_kern
     const int bins = p.PH * p.PW;
     const int bin0 = tile * TILE;
 
-    pdl_wait();
-    pdl_launch_dependents();
-    if (warp == 0) {
-        const RoiXform X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        if (lane == 0) sX = X;
-    }
-    __syncthreads();
+    cta_xform_prologue(p, n, &sX);
     for (int t = threadIdx.x; t < TILE; t += kNhwcWarps * 32) {
         BinRec r;
         r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
@@ -980,7 +1301,8 @@ __global__ void __launch_bounds__(kNhwcWarps * 32, MINB) rroi_fwd_nhwc_bf16_kern
 }
 
 template <int CT>
-static cudaError_t launch_fwd_nhwc_bf16_ct(FwdParams& p, cudaStream_t s, bool pdl) {
+static cudaError_t launch_fwd_nhwc_bf16_ct(FwdParams& p, cudaStream_t s, const Opts& o) {
+    const bool pdl = o.pdl;
     const int bins = p.PH * p.PW;
     auto go = [&](auto kernel, int tile) {
         p.tiles = (bins + tile - 1) / tile;
@@ -990,10 +1312,11 @@ static cudaError_t launch_fwd_nhwc_bf16_ct(FwdParams& p, cudaStream_t s, bool pd
     constexpr int I64 = 8 / PPI, I128 = 16 / PPI, I256 = 32 / PPI;   // per-warp iterations of a 64/128/256-bin tile
     constexpr int U64 = I64 >= 2 ? 2 : 1, U128 = I128 >= 2 ? 2 : 1, U256 = I256 >= 4 ? 4 : 2;
     const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
-    int variant = g_tuning.nhwc_unroll;                  // 0 = by grid size, like the fp32 kernel
+    int variant = o.variant;                             // 0 = by grid size, like the fp32 kernel
     // one small launch: 64-bin tiles; large grids: 256-bin tiles; very large grids: whole-RoI 512-bin tiles, which halve
     // the per-CTA prologues (measured +7 % at 2 048 RoIs, but -20 % on a 64-RoI launch)
-    if (variant == 0) variant = ctas256 < 148 * 4 ? 1 : ctas256 < 148 * 16 ? 5 : 7;
+    const long long load = ctas256 * (o.concurrency > 1 ? o.concurrency : 1);     // launches the caller overlaps with this one
+    if (variant == 0) variant = load < 148 * 4 ? 1 : ctas256 < 148 * 16 ? 5 : 7;
     // Measured on B200 (profiles/r01_sweep_bf16.txt): occupancy is what matters once the bytes per bin are halved --
     // 256-bin tiles, 2 iterations in flight, 64 registers (4 CTAs/SM) beat every wider-unrolled shape.
     switch (variant) {
@@ -1007,15 +1330,14 @@ static cudaError_t launch_fwd_nhwc_bf16_ct(FwdParams& p, cudaStream_t s, bool pd
     }
 }
 
-cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p0, cudaStream_t s) {
+cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p0, const Opts& o, cudaStream_t s) {
     FwdParams p = p0;
     p.cgroups = 1;
-    const bool pdl = g_tuning.use_pdl != 0;
     switch (p.C) {
-        case 32:  return launch_fwd_nhwc_bf16_ct<32>(p, s, pdl);
-        case 64:  return launch_fwd_nhwc_bf16_ct<64>(p, s, pdl);
-        case 128: return launch_fwd_nhwc_bf16_ct<128>(p, s, pdl);
-        case 256: return launch_fwd_nhwc_bf16_ct<256>(p, s, pdl);
+        case 32:  return launch_fwd_nhwc_bf16_ct<32>(p, s, o);
+        case 64:  return launch_fwd_nhwc_bf16_ct<64>(p, s, o);
+        case 128: return launch_fwd_nhwc_bf16_ct<128>(p, s, o);
+        case 256: return launch_fwd_nhwc_bf16_ct<256>(p, s, o);
         default:  return cudaErrorInvalidValue;
     }
 }

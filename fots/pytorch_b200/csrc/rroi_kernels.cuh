@@ -23,6 +23,8 @@ struct FwdParams {
     int idx_mode;
     int tiles;           // bin tiles per (RoI[, channel group])
     int cgroups;         // channel groups per RoI (NCHW kernels)
+    const float* xform;  // optional [N,8] RoiXform table (rroi_b200_roi_xform); null = compute from the RoI row
+    int early;           // 1: the RoI rows / xform table may be read before griddepcontrol.wait (Opts::rois_ready)
 };
 
 struct BwdParams {
@@ -36,39 +38,35 @@ struct BwdParams {
     int idx_mode;
     int tiles;
     int cgroups;
-    // fused zero-fill (channels-last packed kernel only; see rroi_bwd.cu "zero + scatter in one pass"): per-RoI rank
-    // inside its image, per-image RoI count, per-image arrival counter, list of images without RoIs, {ok, n_empty}
-    const int* zf_rank;
-    const int* zf_count;
-    int* zf_arrived;
-    const int* zf_empty;
-    const int* zf_meta;
-    const int* zf_order;
-    const int* zf_pos;
+    int img_lo, img_hi;     // only RoIs whose image index is in [img_lo, img_hi) scatter (chunked zero-fill + scatter)
 };
 
-// Tunables a caller (bench sweeps, tests) may override through rroi_b200_set_tuning(); 0 = default.
-struct Tuning {
-    int nchw_cg;       // channels per CTA in the NCHW kernels: 1,2,4,8,16
-    int nhwc_unroll;   // NHWC forward variant 0..5 (bins per warp x bins in flight), see launch_fwd_nhwc_vec
-    int use_pdl;       // launch with programmatic stream serialization
-    int bwd_dedupe;    // warp-level merge of equal sample points before the atomics (NCHW backward)
-    int bwd_zero_fused; // 1 = one-pass zero + scatter backward for maps >= 96 MB (measured slower than memset + scatter: opt-in)
-    int nchw_tma;      // 0 = NCHW forward gathers through L1 (default); 1 = stages its footprint with TMA box loads; 2..5 = same, box index >= value - 2
+// Per-call launch options (the C ABI's rroi_b200_opts, validated and with defaults filled in by rroi_abi.cu).
+// There is no process-global tuning state: two threads / streams that want different variants cannot race.
+struct Opts {
+    bool pdl = true;         // launch with programmatic stream serialization
+    bool rois_ready = false; // RROI_B200_FLAG_ROIS_READY: prologue (RoI rows -> transform -> geometry) may run before griddepcontrol.wait
+    int concurrency = 0;     // independent launches the caller keeps in flight (0/1 = alone)
+    int variant = 0;         // 0 = automatic; > 0 forces a forward kernel variant
+    int nchw_cg = 0;         // channels per lane / per CTA in the NCHW kernels: 1,2,4,8,16 (0 = default)
+    int bwd_mode = 0;        // 0 auto; 1 plain per-tap reductions; 2 generic channels-last kernel; 3 NCHW without the warp merge
+    int nchw_tma = 0;        // 0 = NCHW forward gathers through L1; 1 = TMA box staging; 2..5 = same, box index >= value - 2
+    int zero_chunk_images = 0; // backward zero_fill: images per zero/scatter chunk (0 auto, -1 whole map)
 };
-extern Tuning g_tuning;
 
-cudaError_t launch_fwd_nchw(const FwdParams& p, cudaStream_t s);
-cudaError_t launch_fwd_nhwc(const FwdParams& p, cudaStream_t s);
+cudaError_t launch_fwd_nchw(const FwdParams& p, const Opts& o, cudaStream_t s);
+cudaError_t launch_fwd_nhwc(const FwdParams& p, const Opts& o, cudaStream_t s);
 // bf16 features / bf16 pooled, channels-last, C in {32,64,128,256}; p.feat / p.out alias the bf16 buffers
-cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p, cudaStream_t s);
-cudaError_t launch_bwd_nchw(const BwdParams& p, cudaStream_t s);
-cudaError_t launch_bwd_nhwc(const BwdParams& p, cudaStream_t s);
-// channels-last backward that also defines the whole gradient map (replaces cudaMemsetAsync + launch_bwd_nhwc when the
-// map is much larger than L2); returns cudaErrorNotSupported when the shape is not eligible (caller falls back)
-cudaError_t launch_bwd_nhwc_zero_fused(const BwdParams& p, cudaStream_t s);
+cudaError_t launch_fwd_nhwc_bf16(const FwdParams& p, const Opts& o, cudaStream_t s);
+cudaError_t launch_bwd_nchw(const BwdParams& p, const Opts& o, cudaStream_t s);
+cudaError_t launch_bwd_nhwc(const BwdParams& p, const Opts& o, cudaStream_t s);
+// zero-fill of the whole gradient map + scatter, chunked by image and overlapped on a side stream when the map is much
+// larger than L2 (rroi_bwd.cu); plain cudaMemsetAsync + one scatter otherwise
+cudaError_t launch_bwd_zero_scatter(const BwdParams& p, const Opts& o, bool nhwc, cudaStream_t s);
 // the reference-layout backward that honours caller-supplied [N,C,PH,PW] centres element by element
-cudaError_t launch_bwd_legacy(const BwdParams& p, cudaStream_t s);
+cudaError_t launch_bwd_legacy(const BwdParams& p, const Opts& o, cudaStream_t s);
+// [N,8] transform table (rroi_b200_roi_xform)
+cudaError_t launch_roi_xform(const float* rois, float* xform, int N, int PH, float scale, cudaStream_t s);
 
 template <typename K, typename P>
 inline cudaError_t launch_1d(K kernel, long long grid, int block, const P& p, cudaStream_t s, bool pdl) {

@@ -36,8 +36,20 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return r;
 }
 
+// Input element: fp32 (the reference's preprocessed image, test.py:80-83) or the raw uint8 pixel, normalised here as
+// the reference does on the host (x / 128 - 1: exact in fp32, so both inputs give the same bf16 operand).
+__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4(const uint8_t* p) {
+    const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
+    return make_float4(fmaf((float)u.x, 0.0078125f, -1.0f), fmaf((float)u.y, 0.0078125f, -1.0f),
+                       fmaf((float)u.z, 0.0078125f, -1.0f), fmaf((float)u.w, 0.0078125f, -1.0f));
+}
+__device__ __forceinline__ float load1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load1(const uint8_t* p) { return fmaf((float)__ldg(p), 0.0078125f, -1.0f); }
+
+template <typename In>
 __global__ void __launch_bounds__(kThreads, 3)
-stem_conv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wgt, uint32_t* __restrict__ y,
+stem_conv_kernel(const In* __restrict__ x, const __nv_bfloat16* __restrict__ wgt, uint32_t* __restrict__ y,
                  double* __restrict__ stats, int B, int H, int W, int tiles_x, int tiles_y, int tiles_per_cta) {
     __shared__ __align__(16) __nv_bfloat16 tile[HALO_H * PITCH];
     __shared__ float red[32];                   // [16 channels][sum, sumsq] of one flush
@@ -105,7 +117,7 @@ stem_conv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ 
     // the MMAs and the epilogue.
     constexpr int VEC_ROW = (HALO_W * 3 + 1 + 3) / 4 + 1;          // 99
     constexpr int VEC_IT = (HALO_H * VEC_ROW + kThreads - 1) / kThreads;   // 4
-    const bool fast = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool fast = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & (4 * sizeof(In) - 1)) == 0);
     float4 pre[VEC_IT];
     auto tile_coords = [&](int tile_id, int& b, int& y0, int& x0) {
         b = tile_id / tiles_img;
@@ -116,7 +128,7 @@ stem_conv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ 
     auto prefetch = [&](int tile_id) {
         int b, y0, x0;
         tile_coords(tile_id, b, y0, x0);
-        const float* img = x + (size_t)b * H * W * 3;
+        const In* img = x + (size_t)b * H * W * 3;
 #pragma unroll
         for (int it = 0; it < VEC_IT; ++it) {
             const int i = it * kThreads + (int)threadIdx.x;
@@ -125,7 +137,7 @@ stem_conv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ 
             const long long f = (long long)x0 * 3 - 4 + 4 * v;          // first float of the vector inside its row
             pre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < HALO_H && yy >= 0 && yy < H && f >= 0 && f + 3 < (long long)W * 3)
-                pre[it] = __ldg(reinterpret_cast<const float4*>(img + (size_t)yy * W * 3 + f));
+                pre[it] = load4(img + (size_t)yy * W * 3 + f);
         }
     };
     auto commit = [&]() {                                            // registers -> bf16 shared tile
@@ -156,13 +168,13 @@ stem_conv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ 
             commit();
         } else {
             // generic path: element by element, zero outside the image
-            const float* img = x + (size_t)b * H * W * 3;
+            const In* img = x + (size_t)b * H * W * 3;
             for (int i = threadIdx.x; i < HALO_H * HALO_W * 3; i += kThreads) {
                 const int row = i / (HALO_W * 3), e = i - row * (HALO_W * 3);
                 const int px = e / 3, ch = e - px * 3;
                 const int yy = y0 - 1 + row, xx = x0 - 1 + px;
                 float v = 0.0f;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(img + ((size_t)yy * W + xx) * 3 + ch);
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = load1(img + ((size_t)yy * W + xx) * 3 + ch);
                 tile[row * PITCH + px * 4 + ch] = __float2bfloat16(v);
             }
         }
@@ -234,10 +246,10 @@ stem_conv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ 
 
 }  // namespace
 
-extern "C" int fots_b200_stem_conv3x3_c3_c16(const float* x, const void* w, void* y, double* stats, int B, int H, int W,
-                                             cudaStream_t stream) {
+template <typename In>
+static int stem_launch(const In* x, const void* w, void* y, double* stats, int B, int H, int W, cudaStream_t stream) {
     if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return RROI_B200_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(x) & 3)) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(x) & (sizeof(In) - 1))) return RROI_B200_ERR_INVALID_ARG;
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
     const long long total = (long long)tiles_x * tiles_y * B;
     if (total > 0x7fffffffLL) return RROI_B200_ERR_TOO_LARGE;
@@ -249,9 +261,19 @@ extern "C" int fots_b200_stem_conv3x3_c3_c16(const float* x, const void* w, void
     const long long ctas_wanted = 148LL * 6;
     const int per = (int)((total + ctas_wanted - 1) / ctas_wanted);
     const int grid = (int)((total + per - 1) / per);
-    stem_conv_kernel<<<grid, kThreads, 0, stream>>>(x, static_cast<const __nv_bfloat16*>(w), static_cast<uint32_t*>(y), stats,
-                                                    B, H, W, tiles_x, tiles_y, per);
+    stem_conv_kernel<In><<<grid, kThreads, 0, stream>>>(x, static_cast<const __nv_bfloat16*>(w), static_cast<uint32_t*>(y), stats,
+                                                        B, H, W, tiles_x, tiles_y, per);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
+}
+
+extern "C" int fots_b200_stem_conv3x3_c3_c16(const float* x, const void* w, void* y, double* stats, int B, int H, int W,
+                                             cudaStream_t stream) {
+    return stem_launch<float>(x, w, y, stats, B, H, W, stream);
+}
+
+extern "C" int fots_b200_stem_conv3x3_c3_c16_u8(const unsigned char* x, const void* w, void* y, double* stats, int B, int H, int W,
+                                                cudaStream_t stream) {
+    return stem_launch<uint8_t>(x, w, y, stats, B, H, W, stream);
 }

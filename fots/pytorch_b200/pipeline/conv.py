@@ -27,6 +27,8 @@ def _lib():
         L.fots_b200_conv2d_stats_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
         L.fots_b200_stem_conv3x3_c3_c16.restype = i
         L.fots_b200_stem_conv3x3_c3_c16.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+        L.fots_b200_stem_conv3x3_c3_c16_u8.restype = i
+        L.fots_b200_stem_conv3x3_c3_c16_u8.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.fots_b200_conv_set_tile.restype = i
         L.fots_b200_conv_set_tile.argtypes = [i]
         L._conv_bound = True
@@ -91,9 +93,10 @@ def apply(conv, x, slope=1.0):
 
 
 def stem_eligible(x, conv):
-    """The first layer: fp32 channels-last image, Conv2d(3, 16, 3, 1, 1, bias=False) with bf16 weights."""
+    """The first layer: fp32 (preprocessed) or uint8 (raw, normalised on load) channels-last image,
+    Conv2d(3, 16, 3, 1, 1, bias=False) with bf16 weights."""
     w = conv.weight
-    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.size(1) == 3
+    return (ENABLED and x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.dim() == 4 and x.size(1) == 3
             and x.is_contiguous(memory_format=torch.channels_last) and w.dtype == torch.bfloat16
             and tuple(w.shape) == (16, 3, 3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
@@ -108,8 +111,9 @@ def stem_conv_stats(x, weight):
     wk = weight.contiguous(memory_format=torch.channels_last)
     y = torch.empty((B, 16, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     ws = fused.workspace(x.device, B * 32)
+    fn = _lib().fots_b200_stem_conv3x3_c3_c16_u8 if x.dtype == torch.uint8 else _lib().fots_b200_stem_conv3x3_c3_c16
     with torch.cuda.device(x.device):
-        st = _lib().fots_b200_stem_conv3x3_c3_c16(x.data_ptr(), wk.data_ptr(), y.data_ptr(), ws.data_ptr(), B, H, W,
-                                                  torch.cuda.current_stream(x.device).cuda_stream)
+        st = fn(x.data_ptr(), wk.data_ptr(), y.data_ptr(), ws.data_ptr(), B, H, W,
+                torch.cuda.current_stream(x.device).cuda_stream)
     _cabi.check(st, "fots_b200_stem_conv3x3_c3_c16")
     return y, ws

@@ -162,6 +162,8 @@ class FOTSNet(nn.Module):
             y = fused.instnorm_act(y, bn.weight, bn.bias, bn.eps, 0.01, crelu=True, stats=ws)
             y = crelu1(conv1(y))
         else:
+            if x.dtype == torch.uint8:                   # raw image: the reference's host-side preprocessing (test.py:80-83)
+                x = x.float() / 128 - 1
             y = self.layer0(x)
         c1, _, c2, _ = self.layer0_1
         y = tc.apply(c1, y, 0.0)                        # conv + ReLU in one kernel on the inference path

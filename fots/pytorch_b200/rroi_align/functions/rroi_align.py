@@ -35,8 +35,21 @@ def _check_inputs(features, rois):
         raise ValueError("rroi_align: rois must be [N, 6] = [batch_idx, cx, cy, h, w, angle_deg]")
 
 
-def forward_raw(features, rois, pooled_height, pooled_width, spatial_scale, want_idx=True):
-    """One forward launch.  Returns (pooled, idx_x, idx_y, layout); idx_* are compact [N, PH, PW] or None."""
+def roi_xform(rois, pooled_height, spatial_scale):
+    """[N, 8] per-RoI transform table (rroi_b200_roi_xform) for `forward_raw(..., xform=...)`: a producer of RoI rows
+    can compute it once so that the forward's CTAs start at the bin geometry."""
+    rois = rois.contiguous()
+    out = torch.empty((rois.size(0), 8), dtype=torch.float32, device=rois.device)
+    with torch.cuda.device(rois.device):
+        st = _cabi.lib().rroi_b200_roi_xform(rois.data_ptr(), out.data_ptr(), rois.size(0), int(pooled_height),
+                                             float(spatial_scale), _stream(rois.device))
+        _cabi.check(st, "rroi_b200_roi_xform")
+    return out
+
+
+def forward_raw(features, rois, pooled_height, pooled_width, spatial_scale, want_idx=True, opts=None, xform=None):
+    """One forward launch.  Returns (pooled, idx_x, idx_y, layout); idx_* are compact [N, PH, PW] or None.
+    opts: _cabi.opts(...) per-call launch options (None = defaults); xform: optional table from roi_xform()."""
     _check_inputs(features, rois)
     ph, pw = int(pooled_height), int(pooled_width)
     if ph <= 0 or pw <= 0:
@@ -53,15 +66,15 @@ def forward_raw(features, rois, pooled_height, pooled_width, spatial_scale, want
         else:
             idx_x = idx_y = None
         if N > 0:
-            st = _cabi.lib().rroi_b200_forward(
-                features.data_ptr(), rois.data_ptr(), pooled.data_ptr(),
+            st = _cabi.lib().rroi_b200_forward_opt(
+                features.data_ptr(), rois.data_ptr(), xform.data_ptr() if xform is not None else None, pooled.data_ptr(),
                 idx_x.data_ptr() if want_idx else None, idx_y.data_ptr() if want_idx else None,
-                N, B, C, H, W, ph, pw, float(spatial_scale), layout, _stream(features.device))
-            _cabi.check(st, "rroi_b200_forward")
+                N, B, C, H, W, ph, pw, float(spatial_scale), layout, _cabi.opts_ref(opts), _stream(features.device))
+            _cabi.check(st, "rroi_b200_forward_opt")
     return pooled, idx_x, idx_y, layout
 
 
-def backward_raw(grad_output, rois, idx_x, idx_y, feature_size, spatial_scale, layout):
+def backward_raw(grad_output, rois, idx_x, idx_y, feature_size, spatial_scale, layout, opts=None):
     """One backward launch (+ the zero-fill of the gradient map).  Returns grad wrt features."""
     if not grad_output.is_cuda:
         raise RuntimeError("rroi_align backward: grad_output must be a CUDA tensor")  # reference :33
@@ -72,13 +85,13 @@ def backward_raw(grad_output, rois, idx_x, idx_y, feature_size, spatial_scale, l
     grad_output = _layout.as_layout(grad_output.float(), layout)
     with torch.cuda.device(grad_output.device):
         grad_input = _layout.empty((B, C, H, W), layout, grad_output)
-        st = _cabi.lib().rroi_b200_backward(
+        st = _cabi.lib().rroi_b200_backward_opt(
             grad_output.data_ptr() if N > 0 else None, rois.data_ptr() if N > 0 else None,
             idx_x.data_ptr() if idx_x is not None else None,
             idx_y.data_ptr() if idx_y is not None else None,
             grad_input.data_ptr(), N, B, C, H, W, ph, pw, float(spatial_scale), layout, 1,
-            _stream(grad_output.device))
-        _cabi.check(st, "rroi_b200_backward")
+            _cabi.opts_ref(opts), _stream(grad_output.device))
+        _cabi.check(st, "rroi_b200_backward_opt")
     return grad_input
 
 
@@ -114,7 +127,7 @@ def rroi_align(features, rois, pooled_height, pooled_width, spatial_scale):
     return _RRoiAlignOp.apply(features, rois, int(pooled_height), int(pooled_width), float(spatial_scale), None)
 
 
-def rroi_align_bf16(features, rois, pooled_height, pooled_width, spatial_scale):
+def rroi_align_bf16(features, rois, pooled_height, pooled_width, spatial_scale, opts=None):
     """Inference-only bf16 RoIRotate (rroi_b200_forward_bf16): bf16 channels-last features [B, C, H, W] ->
     bf16 channels-last pooled [N, C, PH, PW], C in {32, 64, 128, 256}.  Equal to
     rroi_align(features.float(), ...) rounded to bf16; not differentiable (training uses the fp32 op)."""
@@ -131,9 +144,10 @@ def rroi_align_bf16(features, rois, pooled_height, pooled_width, spatial_scale):
         pooled = torch.empty((N, C, ph, pw), dtype=torch.bfloat16, device=features.device,
                              memory_format=torch.channels_last)
         if N > 0:
-            st = _cabi.lib().rroi_b200_forward_bf16(features.data_ptr(), rois.data_ptr(), pooled.data_ptr(), None, None,
-                                                    N, B, C, H, W, ph, pw, float(spatial_scale), _stream(features.device))
-            _cabi.check(st, "rroi_b200_forward_bf16")
+            st = _cabi.lib().rroi_b200_forward_bf16_opt(features.data_ptr(), rois.data_ptr(), None, pooled.data_ptr(), None, None,
+                                                        N, B, C, H, W, ph, pw, float(spatial_scale), _cabi.opts_ref(opts),
+                                                        _stream(features.device))
+            _cabi.check(st, "rroi_b200_forward_bf16_opt")
     return pooled
 
 

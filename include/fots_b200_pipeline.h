@@ -150,6 +150,13 @@ int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const float* gamm
  */
 int fots_b200_stem_conv3x3_c3_c16(const float* x, const void* w, void* y, double* stats, int B, int H, int W,
                                   cudaStream_t stream);
+/*
+ * Same layer fed with the RAW image: x = uint8 [B, H, W, 3] as cv2.imread returns it; the reference's host-side
+ * preprocessing (test.py:80-83: images /= 128; images -= 1) is applied on load -- exact in fp32, so y and stats are
+ * bit-identical to the fp32 entry point on the preprocessed image, and the upload is a quarter of the bytes.
+ */
+int fots_b200_stem_conv3x3_c3_c16_u8(const unsigned char* x, const void* w, void* y, double* stats, int B, int H, int W,
+                                     cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 

@@ -3,8 +3,8 @@
  * fots/pytorch_b200/lib/librroi_b200.so.  Plain pointers and sizes; no torch types.
  *
  * All pointers are DEVICE pointers (fp32) owned by the caller.  Every entry point only enqueues
- * work on `stream` (no synchronisation), is re-entrant, and keeps no state besides the tuning
- * knobs.  RoI rows are [batch_idx, cx, cy, h, w, angle_deg] in input-image pixels
+ * work on `stream` (no synchronisation), is re-entrant and thread-safe, and keeps no mutable state:
+ * kernel variants are selected per call (rroi_b200_opts).  RoI rows are [batch_idx, cx, cy, h, w, angle_deg] in input-image pixels
  * (reference: rroi_align/src/rroi_align_kernel.cu:58-65).
  *
  * Reference interfaces replaced (file:line relative to chenjun2hao/FOTS.pytorch):
@@ -35,13 +35,36 @@ typedef struct CUstream_st* cudaStream_t;   /* same definition as the CUDA runti
 #define RROI_B200_LAYOUT_NCHW 0   /* features [B,C,H,W], pooled [N,C,PH,PW]  (reference layout) */
 #define RROI_B200_LAYOUT_NHWC 1   /* features [B,H,W,C], pooled [N,PH,PW,C]  (channels-last)     */
 
-/* ---- tuning keys for rroi_b200_set_tuning / rroi_b200_get_tuning ---- */
-#define RROI_B200_TUNE_NCHW_CG      0   /* channels per CTA in the NCHW kernels: 1,2,4,8,16 (0 = default 8) */
-#define RROI_B200_TUNE_NHWC_UNROLL  1   /* NHWC forward variant: 0 = auto, 1..6 = fixed tile size x loads in flight  */
-#define RROI_B200_TUNE_USE_PDL      2   /* 1: launch with programmatic dependent launch                       */
-#define RROI_B200_TUNE_BWD_DEDUPE   3   /* NCHW: 1 (default) warp-merge equal sample points, 0 off; 2 = generic NHWC kernel */
-#define RROI_B200_TUNE_BWD_ZERO_FUSED 5 /* channels-last backward with zero_fill: 0 (default) memset + scatter; 1 = one-pass zero + scatter for maps >= 96 MB (measured slower) */
-#define RROI_B200_TUNE_NCHW_TMA     4   /* NCHW forward: 0 (default) gather kernel; 1 = stage each patch's footprint with TMA box loads; 2..5 = same with a minimum box size (sweeps) */
+/*
+ * ---- per-call launch options (the *_opt entry points; NULL = all defaults) ----
+ * The library keeps NO mutable state: everything that selects a kernel variant travels with the call, so threads
+ * and streams that want different variants cannot race.  `size` must be sizeof(rroi_b200_opts) of the caller's
+ * header (the struct may grow at the end; missing fields read as 0).
+ */
+#define RROI_B200_FLAG_NO_PDL      1u   /* launch without programmatic dependent launch (default: with)            */
+#define RROI_B200_FLAG_ROIS_READY  2u   /* the RoI rows were complete in device memory before the kernel that      */
+                                        /* PRECEDES this launch on `stream` was enqueued (uploaded by a copy, or   */
+                                        /* written two or more kernels ago): the forward may then read them and    */
+                                        /* compute the per-RoI transform and the bin geometry while that kernel    */
+                                        /* still drains (before griddepcontrol.wait).  Never set it when the       */
+                                        /* immediately preceding kernel writes the RoI rows.                       */
+typedef struct rroi_b200_opts {
+    unsigned int size;         /* sizeof(rroi_b200_opts)                                                            */
+    unsigned int flags;        /* RROI_B200_FLAG_*                                                                  */
+    int concurrency;           /* independent RoIRotate launches the caller keeps in flight on OTHER streams /      */
+                               /* graph branches (0 or 1: this launch has the GPU to itself).  Picks the tile size: */
+                               /* one small launch alone wants many small CTAs, overlapping launches want fewer,    */
+                               /* larger ones.                                                                      */
+    int variant;               /* 0 = automatic (grid size + concurrency); > 0 forces a forward kernel variant      */
+                               /* (sweeps and parity tests; see launch_fwd_nhwc / launch_fwd_nchw)                  */
+    int nchw_cg;               /* NCHW kernels: channels in flight per lane / per CTA: 1,2,4,8,16 (0 = default)     */
+    int bwd_mode;              /* backward: 0 = automatic; 1 = plain per-tap reductions; 2 = generic (non-packed)   */
+                               /* channels-last kernel; NCHW: 3 = no warp-level merge of equal centres              */
+    int nchw_tma;              /* NCHW forward: 0 gather through L1 (default); 1 = stage the patch footprint with    */
+                               /* TMA box loads; 2..5 = same with a minimum box index (sweeps)                      */
+    int zero_chunk_images;     /* backward with zero_fill: images per zero-fill/scatter chunk (0 = automatic,       */
+                               /* -1 = one memset of the whole map, then one scatter)                               */
+} rroi_b200_opts;
 
 /*
  * Drop-in for rroi_align/src/rroi_align_kernel.h:8-12.  NCHW.  top_data / con_idx_x / con_idx_y are
@@ -107,12 +130,37 @@ int rroi_b200_backward(const float* top_diff, const float* rois, const float* id
                        int pooled_height, int pooled_width, float spatial_scale, int layout,
                        int zero_fill, cudaStream_t stream);
 
+/*
+ * The same three operations with per-call options (opts may be NULL = defaults = the entry points above).
+ *   xform   optional [num_rois,8] table written by rroi_b200_roi_xform for THESE rois / pooled_height / scale
+ *           (the forward then skips the per-RoI transform: fp64 divide, sinf, cosf, three fp32 divides); NULL = compute.
+ */
+int rroi_b200_forward_opt(const float* features, const float* rois, const float* xform, float* pooled,
+                          float* idx_x, float* idx_y, int num_rois, int batch, int channels, int height, int width,
+                          int pooled_height, int pooled_width, float spatial_scale, int layout,
+                          const rroi_b200_opts* opts, cudaStream_t stream);
+int rroi_b200_forward_bf16_opt(const void* features, const float* rois, const float* xform, void* pooled,
+                               float* idx_x, float* idx_y, int num_rois, int batch, int channels, int height,
+                               int width, int pooled_height, int pooled_width, float spatial_scale,
+                               const rroi_b200_opts* opts, cudaStream_t stream);
+int rroi_b200_backward_opt(const float* top_diff, const float* rois, const float* idx_x, const float* idx_y,
+                           float* bottom_diff, int num_rois, int batch, int channels, int height, int width,
+                           int pooled_height, int pooled_width, float spatial_scale, int layout, int zero_fill,
+                           const rroi_b200_opts* opts, cudaStream_t stream);
+
+/*
+ * Per-RoI affine transform table (rroi_align_kernel.cu:58-84 evaluated once per RoI instead of once per output
+ * element): xform [num_rois,8] = {M00, M01, M02, M10, M11, M12, roi_pooled_width, batch_idx (int bits)}.
+ * Bit-identical to what the forward computes itself; a producer of RoI rows (fots_b200_boxes_to_rois) can emit
+ * it so that the forward's CTAs start at the bin geometry.
+ */
+int rroi_b200_roi_xform(const float* rois, float* xform, int num_rois, int pooled_height, float spatial_scale,
+                        cudaStream_t stream);
+
 /* Expand compact centres [N,PH,PW] to the reference's [N,C,PH,PW] (ctx.idx_x / ctx.idx_y attribute parity). */
 int rroi_b200_expand_idx(const float* idx_compact, float* idx_full, int num_rois, int channels,
                          int pooled_height, int pooled_width, cudaStream_t stream);
 
-int         rroi_b200_set_tuning(int key, int value);   /* returns RROI_B200_OK or ERR_INVALID_ARG */
-int         rroi_b200_get_tuning(int key);              /* current value, or -1 for an unknown key  */
 int         rroi_b200_last_cuda_error(void);            /* cudaError_t of the last failed launch (per process) */
 const char* rroi_b200_strerror(int status);
 int         rroi_b200_abi_version(void);                /* bumped on any signature change */

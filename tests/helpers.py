@@ -42,17 +42,21 @@ def to_cuda(x, device, channels_last=False):
     return t
 
 
-def run_new_forward(feats, rois, ph, pw, scale, device, channels_last=False):
+def run_new_forward(feats, rois, ph, pw, scale, device, channels_last=False, opts=None, with_xform=False):
     """Product forward via fots.pytorch_b200 (-> rroi_b200_forward).  Returns numpy (out NCHW-logical,
     idx_x, idx_y compact [N,PH,PW])."""
     from fots.pytorch_b200.rroi_align.functions.rroi_align import forward_raw
     f = to_cuda(feats, device, channels_last)
     r = to_cuda(rois, device)
-    out, ix, iy, _ = forward_raw(f, r, ph, pw, scale, want_idx=True)
+    xf = None
+    if with_xform:
+        from fots.pytorch_b200.rroi_align.functions.rroi_align import roi_xform
+        xf = roi_xform(r, ph, scale)
+    out, ix, iy, _ = forward_raw(f, r, ph, pw, scale, want_idx=True, opts=opts, xform=xf)
     return out.cpu().numpy(), ix.cpu().numpy(), iy.cpu().numpy()
 
 
-def run_new_backward(top_diff, rois, idx, feature_size, scale, device, channels_last=False):
+def run_new_backward(top_diff, rois, idx, feature_size, scale, device, channels_last=False, opts=None):
     """Product backward via rroi_b200_backward.  idx = (idx_x, idx_y) compact numpy or None (recompute)."""
     from fots.pytorch_b200 import _cabi
     from fots.pytorch_b200.rroi_align.functions.rroi_align import backward_raw
@@ -62,7 +66,7 @@ def run_new_backward(top_diff, rois, idx, feature_size, scale, device, channels_
     if idx is not None:
         ix, iy = to_cuda(idx[0], device), to_cuda(idx[1], device)
     layout = _cabi.LAYOUT_NHWC if channels_last else _cabi.LAYOUT_NCHW
-    return backward_raw(g, r, ix, iy, tuple(feature_size), scale, layout).cpu().numpy()
+    return backward_raw(g, r, ix, iy, tuple(feature_size), scale, layout, opts=opts).cpu().numpy()
 
 
 def run_legacy_forward(feats, rois, ph, pw, scale, device, with_idx=True):

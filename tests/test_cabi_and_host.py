@@ -52,14 +52,21 @@ def test_argument_errors_without_gpu():
     assert L.rroi_b200_forward(fake, fake, fake, fake, None, 1, 1, 1, 1, 1, 1, 1, 1.0, 0, None) == _cabi.ERR_INVALID_ARG  # half an idx pair
     assert L.rroi_b200_forward(fake, fake, fake, None, None, 1, 1, 1, 1, 1, 1, 1, 1.0, 5, None) == _cabi.ERR_INVALID_ARG  # layout
     assert L.rroi_b200_forward(fake, fake, fake, None, None, 0, 1, 1, 1, 1, 1, 1, 1.0, 0, None) == _cabi.OK               # no RoIs: nothing to do
-    for k, v in ((_cabi.TUNE_NCHW_CG, 4), (_cabi.TUNE_NHWC_UNROLL, 2), (_cabi.TUNE_USE_PDL, 1), (_cabi.TUNE_BWD_DEDUPE, 0)):
-        old = _cabi.get_tuning(k)
-        _cabi.set_tuning(k, v)
-        assert _cabi.get_tuning(k) == v
-        _cabi.set_tuning(k, old)
-    with pytest.raises(_cabi.RRoiAlignError):
-        _cabi.set_tuning(_cabi.TUNE_NCHW_CG, 3)
-    assert _cabi.get_tuning(99) == -1
+    # per-call options are validated before anything touches CUDA; there is no process-global tuning state
+    assert not hasattr(L, "rroi_b200_set_tuning")
+    ok = _cabi.opts(concurrency=8, variant=5)
+    assert L.rroi_b200_forward_opt(fake, fake, None, fake, None, None, 0, 1, 1, 1, 1, 1, 1, 1.0, 0, ctypes.byref(ok), None) == _cabi.OK
+    for bad in (_cabi.opts(nchw_cg=3), _cabi.opts(variant=99), _cabi.opts(bwd_mode=7), _cabi.opts(nchw_tma=6), _cabi.opts(concurrency=-1)):
+        assert L.rroi_b200_forward_opt(fake, fake, None, fake, None, None, 0, 1, 1, 1, 1, 1, 1, 1.0, 0, ctypes.byref(bad), None) == _cabi.ERR_INVALID_ARG
+        assert L.rroi_b200_backward_opt(fake, fake, None, None, fake, 0, 1, 1, 1, 1, 1, 1, 1.0, 0, 0, ctypes.byref(bad), None) == _cabi.ERR_INVALID_ARG
+    flags = _cabi.opts()
+    flags.flags = 0x80
+    assert L.rroi_b200_forward_opt(fake, fake, None, fake, None, None, 0, 1, 1, 1, 1, 1, 1, 1.0, 0, ctypes.byref(flags), None) == _cabi.ERR_INVALID_ARG
+    short = _cabi.opts(variant=99)
+    short.size = 12                                    # an older caller whose struct ends before `variant`: reads as 0
+    assert L.rroi_b200_forward_opt(fake, fake, None, fake, None, None, 0, 1, 1, 1, 1, 1, 1, 1.0, 0, ctypes.byref(short), None) == _cabi.OK
+    assert L.rroi_b200_forward_opt(fake, fake, ctypes.c_void_p(8), fake, None, None, 1, 1, 1, 1, 1, 1, 1, 1.0, 0, None, None) == _cabi.ERR_INVALID_ARG  # misaligned xform
+    assert L.rroi_b200_roi_xform(None, None, 1, 8, 0.25, None) == _cabi.ERR_INVALID_ARG
     assert b"invalid" in L.rroi_b200_strerror(_cabi.ERR_INVALID_ARG)
 
 

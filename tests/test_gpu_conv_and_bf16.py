@@ -36,11 +36,8 @@ def test_bf16_forward_is_the_rounded_fp32_forward(oracle, cuda, C, B, n_per, ph,
     want[-1] = 0.0                                               # like the reference, would read out of bounds)
     want_bits = _bf16_bits(torch.from_numpy(want).to(torch.bfloat16))
     for variant in (0, 1, 5, 7):          # 7: whole-RoI 512-bin tiles
-        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, variant)
-        try:
-            got = rroi_align_bf16(x, torch.from_numpy(rois).to(cuda), ph, pw, scale)
-        finally:
-            _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, 0)
+        got = rroi_align_bf16(x, torch.from_numpy(rois).to(cuda), ph, pw, scale,
+                              opts=_cabi.opts(variant=variant, rois_ready=variant == 5))
         assert got.dtype == torch.bfloat16 and got.shape == (rois.shape[0], C, ph, pw)
         assert got.is_contiguous(memory_format=torch.channels_last)
         got_bits = _bf16_bits(got.contiguous())                  # logical NCHW order, like the oracle

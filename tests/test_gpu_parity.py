@@ -161,8 +161,9 @@ def test_ten_million_bins_index_parity_vs_reference_kernel(oracle, cuda):
     Hh.assert_bit_equal(out, ro, "10M-bin values")
 
 
-def test_full_size_properties(cuda):
-    """cfg4 per-GPU size (32 images x 64 RoIs, C=64, 180x320): size-independent properties.
+def test_full_size_properties(oracle, cuda):
+    """cfg4 per-GPU size (32 images x 64 RoIs, C=64, 180x320): the oracle itself on all 2 048 RoIs (values and centres
+    bit for bit, both layouts), then size-independent properties.
       * zero tail: every element with pw > rpw is exactly 0, and nothing else was left unwritten;
       * layout invariance: NHWC result == NCHW result bitwise;
       * linearity: f(a + b) ~= f(a) + f(b), f(2a) == 2 f(a) exactly (power-of-two scaling commutes);
@@ -179,6 +180,11 @@ def test_full_size_properties(cuda):
     fa, ix, iy, _ = forward_raw(a, rois, ph, pw, scale)
     fa_cl, _, _, _ = forward_raw(a.contiguous(memory_format=torch.channels_last), rois, ph, pw, scale)
     assert torch.equal(fa, fa_cl.contiguous())
+    want, wx, wy = oracle.forward(a.cpu().numpy(), rois_np, ph, pw, scale, threads=0)
+    Hh.assert_bit_equal(fa.cpu().numpy(), want, "cfg4-size forward vs oracle")
+    Hh.assert_bit_equal(ix.cpu().numpy(), wx[:, 0], "cfg4-size idx_x vs oracle")
+    Hh.assert_bit_equal(iy.cpu().numpy(), wy[:, 0], "cfg4-size idx_y vs oracle")
+    del want, wx, wy
     rpw = (rois[:, 4] * ph) / rois[:, 3]
     tail = torch.arange(pw, device=cuda)[None, :] > rpw[:, None]            # [N,PW]
     assert (fa.permute(0, 3, 1, 2)[tail] == 0).all()
@@ -219,35 +225,92 @@ def test_backward_dedupe_on_off_agree(cuda):
     rois[:, 3] = np.minimum(rois[:, 3], 6)          # bin pitch < 1 px -> long runs of equal centres
     out, ix, iy = Hh.run_new_forward(feats, rois, 8, 64, 0.25, cuda)
     g = np.random.default_rng(0).standard_normal(out.shape, dtype=np.float32)
-    try:
-        _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, 1)
-        a = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda)
-        _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, 0)
-        b = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda)
-    finally:
-        _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, 1)
+    a = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda)
+    b = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda, opts=_cabi.opts(bwd_mode=3))
     Hh.assert_close_rel(a, b, REL_BWD, "dedupe on vs off")
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256])
+def test_backward_presummed_per_pixel_matches_oracle_and_plain_scatter(oracle, cuda, C):
+    """Large channels-last launches group their taps by pixel in shared memory before the vector reductions
+    (rroi_bwd_nhwc_presum_kernel).  Against the oracle and against the plain per-tap scatter (opts.bwd_mode = 1), with
+    saved and with recomputed centres; the RoI mix includes sub-pixel bin pitch (dozens of taps on one pixel), boxes
+    over the border and an out-of-range image index."""
+    from fots.pytorch_b200 import _cabi
+    B, H, W, ph, pw, scale = 3, 45, 80, 8, 64, 0.25
+    rois = np.concatenate([WL.stress_rois(70 + C, 260, B, int(W / scale), int(H / scale)),
+                           np.concatenate([WL.random_rois(5 + i, 30, i, img_w=int(W / scale), img_h=int(H / scale)) for i in range(B)], 0)], 0)
+    rois[:40, 3] = np.minimum(rois[:40, 3], 5)                       # bin pitch << 1 px
+    feats = np.zeros((B, C, H, W), np.float32)
+    top = np.random.default_rng(C).standard_normal((len(rois), C, ph, pw), dtype=np.float32)
+    _, ix, iy = oracle.forward(feats, rois, ph, pw, scale, threads=0)
+    want = oracle.backward(top, rois, ix, iy, feats.shape, scale, threads=0)
+    assert len(rois) * ((ph * pw + 255) // 256) >= 148 * 4           # large enough for the pre-summed kernel
+    for idx in ((ix[:, 0], iy[:, 0]), None):
+        got = Hh.run_new_backward(top, rois, idx, feats.shape, scale, cuda, channels_last=True)
+        plain = Hh.run_new_backward(top, rois, idx, feats.shape, scale, cuda, channels_last=True, opts=_cabi.opts(bwd_mode=1))
+        Hh.assert_close_rel(got, want, REL_BWD, "pre-summed backward C=%d saved_idx=%s" % (C, idx is not None))
+        Hh.assert_close_rel(plain, want, REL_BWD, "plain scatter C=%d" % C)
+    rois[7, 0] = B + 1                                                # image that does not exist: contributes nothing
+    ok = rois[:, 0] < B
+    want2 = oracle.backward(top[ok], rois[ok], ix[ok], iy[ok], feats.shape, scale, threads=0)
+    got2 = Hh.run_new_backward(top, rois, None, feats.shape, scale, cuda, channels_last=True)
+    Hh.assert_close_rel(got2, want2, REL_BWD, "pre-summed backward with an out-of-range image index")
 
 
 @pytest.mark.parametrize("cg", [1, 2, 4, 8, 16])
 def test_tuning_variants_bit_exact(cuda, cg):
+    """Every per-call kernel variant (rroi_b200_opts.variant / nchw_cg, with and without programmatic dependent launch)
+    returns the bits of the default."""
     from fots.pytorch_b200 import _cabi
     feats, rois, ph, pw, scale = WL.cfg1({1: 24, 2: 64, 4: 128, 8: 256, 16: 40}[cg])   # templated and run-time C paths
     base = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda)
-    try:
-        _cabi.set_tuning(_cabi.TUNE_NCHW_CG, cg)
-        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, {1: 1, 2: 2, 4: 3, 8: 4, 16: 5}[cg])
-        _cabi.set_tuning(_cabi.TUNE_USE_PDL, cg % 4 == 0)
-        a = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda)
-        b = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda, channels_last=True)
-    finally:
-        _cabi.set_tuning(_cabi.TUNE_NCHW_CG, 0)
-        _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, 0)
-        _cabi.set_tuning(_cabi.TUNE_USE_PDL, 0)
+    o = _cabi.opts(nchw_cg=cg, variant={1: 1, 2: 2, 4: 3, 8: 4, 16: 5}[cg], pdl=cg % 4 == 0)
+    a = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda, opts=o)
+    b = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda, channels_last=True, opts=o)
     for x, y in zip(a, base):
         Hh.assert_bit_equal(x, y, "NCHW cg=%d" % cg)
     for x, y in zip(b, base):
         Hh.assert_bit_equal(x, y, "NHWC variant")
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256])
+@pytest.mark.parametrize("variant", [0, 1, 5, 6, 11, 12, 13, 14, 15, 16, 17, 21, 22, 23, 24, 25])
+def test_nhwc_packed_and_warp_autonomous_variants_bit_exact(oracle, cuda, C, variant):
+    """The block-level and the warp-autonomous channels-last kernels, with the RoI rows declared ready (prologue ahead
+    of the grid dependency), with a precomputed transform table, and under a concurrency hint: same bits as the oracle,
+    centres included; stress RoIs (border, huge angles, out-of-range batch index) on two images."""
+    from fots.pytorch_b200 import _cabi
+    B, H, W, ph, pw, scale = 2, 45, 80, 8, 64, 0.25
+    feats = WL.features(C + variant, B, C, H, W)
+    rois = np.concatenate([WL.stress_rois(50 + variant, 40, B, int(W / scale), int(H / scale)),
+                           WL.random_rois(9, 9, 1, img_w=int(W / scale), img_h=int(H / scale))], 0)
+    want, wx, wy = oracle.forward(feats, rois, ph, pw, scale, threads=0)
+    for kw, xf in ((dict(), False), (dict(rois_ready=True), False), (dict(), True), (dict(rois_ready=True, concurrency=8), True),
+                   (dict(pdl=False), False)):
+        got, ix, iy = Hh.run_new_forward(feats, rois, ph, pw, scale, cuda, channels_last=True,
+                                         opts=_cabi.opts(variant=variant, **kw), with_xform=xf)
+        Hh.assert_bit_equal(got, want, "variant %d %r xform=%s" % (variant, kw, xf))
+        Hh.assert_bit_equal(ix, wx[:, 0], "idx_x")
+        Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")
+    # ragged: bins not a multiple of any segment size, N not a multiple of the warps per CTA
+    r3 = rois[:3]
+    want3, wx3, _ = oracle.forward(feats, r3, 5, 13, scale, threads=0)
+    got3, ix3, _ = Hh.run_new_forward(feats, r3, 5, 13, scale, cuda, channels_last=True, opts=_cabi.opts(variant=variant))
+    Hh.assert_bit_equal(got3, want3, "ragged variant %d" % variant)
+    Hh.assert_bit_equal(ix3, wx3[:, 0], "ragged idx_x")
+
+
+def test_unknown_variant_and_bad_opts_are_rejected(cuda):
+    import torch
+    from fots.pytorch_b200 import _cabi
+    from fots.pytorch_b200.rroi_align.functions.rroi_align import forward_raw
+    f = torch.zeros(1, 64, 8, 8, device=cuda).contiguous(memory_format=torch.channels_last)
+    r = torch.tensor([[0, 10, 10, 8, 16, 0]], dtype=torch.float32, device=cuda)
+    with pytest.raises(_cabi.RRoiAlignError):
+        forward_raw(f, r, 8, 16, 1.0, opts=_cabi.opts(variant=9))
+    forward_raw(f, r, 8, 16, 1.0, opts=_cabi.opts(variant=12))
+    torch.cuda.synchronize()
 
 
 def test_module_api_and_function_attributes(oracle, cuda):
@@ -319,7 +382,7 @@ def test_error_behaviour(cuda):
 ])
 def test_nchw_tma_staged_forward_equals_gather_kernel_and_oracle(oracle, cuda, C, H, W, scale, rois):
     """The opt-in NCHW forward that stages each patch's footprint with TMA box loads (rroi_fwd_nchw_tma_kernel,
-    RROI_B200_TUNE_NCHW_TMA = 1, and 5 = largest box forced) must agree bit for bit with the gather kernel and with
+    rroi_b200_opts.nchw_tma = 1, and 5 = largest box forced) must agree bit for bit with the gather kernel and with
     the oracle, centres included."""
     from fots.pytorch_b200 import _cabi
     B = 2
@@ -333,23 +396,20 @@ def test_nchw_tma_staged_forward_equals_gather_kernel_and_oracle(oracle, cuda, C
     want, wx, wy = oracle.forward(feats, r, ph, pw, scale, threads=0)
     outs = []
     for mode in (0, 1, 5):
-        _cabi.set_tuning(_cabi.TUNE_NCHW_TMA, mode)
-        try:
-            outs.append(Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False))
-        finally:
-            _cabi.set_tuning(_cabi.TUNE_NCHW_TMA, 0)
+        outs.append(Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(nchw_tma=mode)))
     for got, ix, iy in outs:
         Hh.assert_bit_equal(got, want, "NCHW forward")
         Hh.assert_bit_equal(ix, wx[:, 0], "idx_x")
         Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")
 
 
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
 @pytest.mark.parametrize("order", ["grouped", "grouped_with_empty_images", "shuffled", "crowded_image"])
-def test_backward_zero_fill_fused_with_scatter(oracle, cuda, order):
-    """The opt-in one-pass backward (RROI_B200_TUNE_BWD_ZERO_FUSED = 1; zero-fill + per-image rendezvous + scatter in one
-    kernel, rroi_bwd.cu) on a map larger than 96 MB: taken when the RoIs are grouped by image; shuffled rows, or more
-    RoIs in one image than may wait for each other, fall back to a memset kernel + scatter inside the same call.
-    Either way every element of the gradient map is defined (the buffer starts as NaN) and equals the oracle's to 1e-4."""
+def test_backward_chunked_zero_fill_and_scatter(oracle, cuda, order, layout):
+    """zero_fill on a map larger than 96 MB: the gradient map is cleared in chunks of a few images on a side stream and
+    each chunk's RoIs are scattered as soon as its chunk is clear (launch_bwd_zero_scatter, rroi_bwd.cu), for any order
+    of the RoI rows.  Every element of the map is defined (the buffer starts as NaN) and equals the oracle's to 1e-4,
+    for the automatic chunk size, one image per chunk, three, and the unchunked memset + scatter."""
     import torch
     from fots.pytorch_b200 import _cabi
     from fots.pytorch_b200.rroi_align.functions.rroi_align import backward_raw
@@ -359,22 +419,24 @@ def test_backward_zero_fill_fused_with_scatter(oracle, cuda, order):
     rois = np.concatenate([WL.random_rois(11 + i, n, i) for i, n in enumerate(per) if n > 0], 0)
     if order == "shuffled":
         rois = rois[np.random.default_rng(0).permutation(len(rois))]
+        rois[0, 0] = B + 2                                                # and one row whose image does not exist
     N = rois.shape[0]
     rng = np.random.default_rng(5)
     top = rng.standard_normal((N, C, ph, pw), dtype=np.float32)
     feats = np.zeros((B, C, H, W), np.float32)
-    _, ix, iy = oracle.forward(feats, rois, ph, pw, scale, threads=0)
-    want = oracle.backward(top, rois, ix, iy, (B, C, H, W), scale, threads=0)
-    g = torch.from_numpy(top).to(cuda).contiguous(memory_format=torch.channels_last)
+    ok = rois[:, 0] < B
+    _, ix, iy = oracle.forward(feats, rois[ok], ph, pw, scale, threads=0)
+    want = oracle.backward(top[ok], rois[ok], ix, iy, (B, C, H, W), scale, threads=0)
+    fmt = torch.channels_last if layout == "nhwc" else torch.contiguous_format
+    lay = _cabi.LAYOUT_NHWC if layout == "nhwc" else _cabi.LAYOUT_NCHW
+    g = torch.from_numpy(top).to(cuda).contiguous(memory_format=fmt)
     r = torch.from_numpy(rois).to(cuda)
-    # poison the allocator's next block so that an element the kernel forgets to define shows up as NaN
-    poison = torch.full((B, C, H, W), float("nan"), device=cuda).contiguous(memory_format=torch.channels_last)
-    del poison
-    _cabi.set_tuning(_cabi.TUNE_BWD_ZERO_FUSED, 1)
-    try:
-        got = backward_raw(g, r, None, None, (B, C, H, W), scale, _cabi.LAYOUT_NHWC)
+    for chunk in (0, 1, 3, -1):
+        # poison the allocator's next block so that an element the kernel forgets to define shows up as NaN
+        poison = torch.full((B, C, H, W), float("nan"), device=cuda).contiguous(memory_format=fmt)
+        del poison
+        got = backward_raw(g, r, None, None, (B, C, H, W), scale, lay, opts=_cabi.opts(zero_chunk_images=chunk))
         torch.cuda.synchronize()
-    finally:
-        _cabi.set_tuning(_cabi.TUNE_BWD_ZERO_FUSED, 0)
-    assert bool(torch.isfinite(got).all())
-    Hh.assert_close_rel(got.cpu().numpy(), want, 1e-4, "fused zero-fill backward (%s)" % order)
+        assert bool(torch.isfinite(got).all())
+        Hh.assert_close_rel(got.cpu().numpy(), want, 1e-4, "chunked zero-fill backward (%s, %s, chunk %d)" % (order, layout, chunk))
+        del got

@@ -46,3 +46,27 @@ def test_new_forward_faster_than_reference_kernel(oracle, cuda, channels):
         json.dump(rec, fh)
     print(rec)
     assert t_nchw < t_ref and t_nhwc < t_ref
+
+
+def test_device_time_vs_reference_kernel_graph_replayed(oracle, cuda):
+    """Device time, not Python overhead: both sides replayed from CUDA graphs over rotating buffer sets larger than L2
+    (bench.py's ref_gpu_kernel leg).  The product must beat the reference kernel (+ its three zero-fills) by a wide
+    margin in the reference's own NCHW layout and by more in channels-last."""
+    import types
+    import torch
+    if not oracle.ref_gpu_available():
+        pytest.skip("oracle/_ref not built")
+    import bench
+    from fots.pytorch_b200 import _cabi
+    lib = _cabi.lib()
+    a = types.SimpleNamespace(channels=64, layout="nchw", images=1, rois_per_image=64, sets=24, dtype="fp32")
+    wl = bench.Workload(a, cuda, torch)
+    ref = bench.ref_gpu_kernel_leg(wl, torch, lib, _cabi, steps=5)
+    ms = bench.timed_steps(wl, 5, 3, 240, torch, lib, _cabi, lambda: None, 1)
+    us_nchw = ms / (5 * 240) * 1e3
+    rec = {"reference_kernel_us_1stream": ref["us_per_call_1stream"], "b200_nchw_us_1stream": us_nchw,
+           "speedup_nchw": ref["us_per_call_1stream"] / us_nchw}
+    with open(os.path.join(ROOT, "gpurun_out", "ref_kernel_device_time.json"), "w") as fh:
+        json.dump(rec, fh)
+    print(rec)
+    assert rec["speedup_nchw"] > 2.0

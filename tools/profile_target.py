@@ -29,17 +29,18 @@ if __name__ == "__main__":
     ap.add_argument("--backward", type=int, default=0)
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--nchw-tma", type=int, default=0)
+    ap.add_argument("--rois-ready", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--bwd-mode", type=int, default=0)
     a = ap.parse_args()
     args = types.SimpleNamespace(channels=a.channels, layout=a.layout, images=a.images, rois_per_image=64,
-                                 sets=0, graph_chunk=1, pdl=a.pdl, dtype=a.dtype)
+                                 sets=0, dtype=a.dtype)
     dev = torch.device("cuda:0")
     wl = bench.Workload(args, dev, torch)
     if a.backward:
         wl.enable_backward(torch)
-    _cabi.set_tuning(_cabi.TUNE_NCHW_CG, a.cg)
-    _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, a.variant)
-    _cabi.set_tuning(_cabi.TUNE_USE_PDL, a.pdl)
-    _cabi.set_tuning(_cabi.TUNE_NCHW_TMA, a.nchw_tma)
+    wl.set_opts(_cabi, nchw_cg=a.cg, variant=a.variant, pdl=bool(a.pdl), nchw_tma=a.nchw_tma, rois_ready=bool(a.rois_ready),
+                zero_chunk_images=a.chunk, bwd_mode=a.bwd_mode)
     st = torch.cuda.current_stream().cuda_stream
     for i in range(a.steps):
         wl.launch(i % wl.sets, _cabi.lib(), _cabi, st)

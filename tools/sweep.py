@@ -1,13 +1,11 @@
 #!/usr/bin/env python
 """GPU tuning sweep for the RoIRotate forward/backward kernels (development tool, run under gpurun).
 
-    python tools/sweep.py [--quick] > gpurun_out/sweep.txt
+    python tools/sweep.py fwd|bwd|bf16|nchw [...] > gpurun_out/sweep.txt
 
-Same timing harness as bench.py (rotating buffer sets > L2, CUDA graphs, CUDA events) over the grid
-layout x channels x RoIs-per-step x tuning knobs.  Prints one line per point and writes
-gpurun_out/sweep.json.
+Same timing harness as bench.py (rotating buffer sets > L2, one CUDA graph per step, CUDA events); every point passes
+its kernel choice through the per-call rroi_b200_opts.  Prints one line per point and appends to gpurun_out/sweep.json.
 """
-import argparse
 import json
 import os
 import sys
@@ -23,65 +21,113 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from fots.pytorch_b200 import _cabi  # noqa: E402
 
+RECS = []
 
-def point(layout, C, images, steps, cg=0, unroll=0, pdl=0, chunk=500, rois_per_image=64, streams=1, backward=False, dedupe=1):
-    args = types.SimpleNamespace(channels=C, layout=layout, images=images, rois_per_image=rois_per_image,
-                                 sets=0, graph_chunk=chunk, pdl=pdl)
+
+def point(layout="nhwc", C=64, images=1, streams=1, backward=False, dtype="fp32", xform=False, target=2000, steps=8, **opts):
+    args = types.SimpleNamespace(channels=C, layout=layout, images=images, rois_per_image=64, sets=0, dtype=dtype)
     dev = torch.device("cuda:0")
     wl = bench.Workload(args, dev, torch)
+    wl.set_opts(_cabi, **opts)
+    lib = _cabi.lib()
+    if xform:
+        wl.enable_xform(torch, lib, torch.cuda.current_stream().cuda_stream)
     if backward:
         wl.enable_backward(torch)
-    _cabi.set_tuning(_cabi.TUNE_BWD_DEDUPE, dedupe)
-    _cabi.set_tuning(_cabi.TUNE_NCHW_CG, cg)
-    _cabi.set_tuning(_cabi.TUNE_NHWC_UNROLL, unroll)
-    _cabi.set_tuning(_cabi.TUNE_USE_PDL, pdl)
-    ms = bench.timed_steps(wl, steps, 50, chunk, torch, _cabi.lib(), _cabi, lambda: None, streams)
-    us = ms / steps * 1e3
-    alg = float(np.mean(wl.alg_bytes))
+    torch.cuda.synchronize()
+    per_step = bench.launches_per_step_for(wl, target=max(8, target // (images * (4 if backward else 1))))
+    ms = bench.timed_steps(wl, steps, 3, per_step, torch, lib, _cabi, lambda: None, streams)
+    us = ms / (steps * per_step) * 1e3
+    alg = float(np.mean(wl.alg_bytes_bwd if backward else wl.alg_bytes))
     peak, _ = bench.measured_peak_gbs()
     gbs = alg / us / 1e3
-    rec = dict(layout=layout, C=C, images=images, rois=wl.N, cg=cg, unroll=unroll, pdl=pdl, chunk=chunk, streams=streams,
-               us_per_launch=us, alg_mb=alg / 1e6, gbs=gbs, frac=gbs / peak,
-               mfeat_px_s=wl.feat_px_per_step / us, sets=wl.sets)
-    if backward:
-        import workloads as WL
-        # SURVEY 8d backward bytes: read top_diff on valid elements + define the whole grad map + 24 N
-        # (the RMW of the touched pixels is L2 traffic, not counted)
-        alg = float(np.mean([4 * C * int(WL.valid_counts(r, 8, 64).sum()) + 24 * len(r) for r in wl.rois_np])) + 4.0 * images * C * 180 * 320
-        gbs = alg / us / 1e3
-        rec.update(alg_mb=alg / 1e6, gbs=gbs, frac=gbs / peak, backward=True, dedupe=dedupe)
-        print("BWD  ", end="")
-    print("%-5s C=%-3d img=%-3d N=%-5d cg=%-2d U=%d pdl=%d S=%d | %8.2f us  %7.1f GB/s  frac %.3f" % (
-        layout, C, images, wl.N, cg, unroll, pdl, streams, us, gbs, gbs / peak), flush=True)
+    rec = dict(layout=layout, C=C, images=images, rois=wl.N, streams=streams, backward=backward, dtype=dtype, xform=xform,
+               opts=opts, us_per_launch=us, alg_mb=alg / 1e6, gbs=gbs, frac=gbs / peak)
+    RECS.append(rec)
+    print("%s %-4s %-4s C=%-3d img=%-2d S=%d xf=%d %-60s | %8.2f us  %7.1f GB/s  frac %.3f" % (
+        "BWD" if backward else "FWD", layout, dtype, C, images, streams, int(xform), json.dumps(opts, sort_keys=True), us, gbs, gbs / peak),
+        flush=True)
     del wl
     torch.cuda.empty_cache()
     return rec
 
 
+def sweep_fwd():
+    for S in (1, 8):
+        for v in (1, 6, 5, 4, 11, 17, 12, 13, 16, 14, 15):
+            for early in (False, True):
+                point(streams=S, variant=v, rois_ready=early)
+        point(streams=S, variant=12, rois_ready=True, xform=True)
+        point(streams=S, variant=13, rois_ready=True, xform=True)
+        point(streams=S, variant=5, rois_ready=True, xform=True)
+        point(streams=S, variant=12, pdl=False)
+        point(streams=S)                                   # auto, no hints
+        point(streams=S, concurrency=S, rois_ready=True)   # auto with hints
+    for S in (2, 4):
+        for v in (5, 12, 13, 14):
+            point(streams=S, variant=v, rois_ready=True)
+    for v in (5, 4, 14, 15, 12):                           # large launches
+        point(images=8, variant=v)
+        point(images=32, variant=v)
+    point(images=32, variant=5, xform=True)
+    for v in (1, 5, 12, 13, 14):
+        point(C=256, streams=1, variant=v, rois_ready=True)
+        point(C=256, streams=8, variant=v, rois_ready=True)
+
+
+def sweep_bwd():
+    for chunk in (-1, 0, 1, 2, 3, 4, 6, 8):
+        point(images=32, backward=True, zero_chunk_images=chunk)
+    point(images=32, backward=True, zero_chunk_images=-1, bwd_mode=2)
+    point(images=32, backward=True, zero_chunk_images=2, bwd_mode=1)
+    for chunk in (-1, 0, 2):
+        point(images=32, C=256, backward=True, zero_chunk_images=chunk)
+        point(images=32, layout="nchw", backward=True, zero_chunk_images=chunk)
+        point(images=8, backward=True, zero_chunk_images=chunk)
+    point(images=1, backward=True)
+    point(images=1, layout="nchw", backward=True)
+
+
+def sweep_fwd2():
+    for S in (1, 2, 8):
+        for v in (1, 11, 13, 5, 21, 22, 23, 24, 25):
+            for early in (False, True):
+                point(streams=S, variant=v, rois_ready=early)
+        point(streams=S, variant=21, rois_ready=True, xform=True)
+        point(streams=S, variant=24, rois_ready=True, xform=True)
+    for v in (21, 22, 23, 25):
+        point(images=8, variant=v)
+        point(images=32, variant=v)
+        point(C=256, streams=1, variant=v, rois_ready=True)
+        point(C=256, streams=8, variant=v, rois_ready=True)
+
+
+def sweep_bwd2():
+    for images in (32, 8):
+        for C in (64, 256):
+            for mode in (0, 1):
+                point(images=images, C=C, backward=True, bwd_mode=mode)
+    point(images=32, backward=True, zero_chunk_images=8)
+
+
+def sweep_bf16():
+    for images, S in ((1, 8), (32, 1)):
+        for C in (64, 256):
+            for v in (5, 7, 0):
+                point(C=C, images=images, streams=S, dtype="bf16", variant=v, rois_ready=True, concurrency=S)
+
+
+def sweep_nchw():
+    for images, S in ((1, 1), (1, 8), (32, 1)):
+        for cg in (2, 4, 8):
+            point(layout="nchw", images=images, streams=S, nchw_cg=cg, rois_ready=True)
+        point(layout="nchw", images=images, streams=S, nchw_tma=1)
+
+
 if __name__ == "__main__":
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--quick", action="store_true")
-    a = ap.parse_args()
-    recs = []
-    steps = 5000 if a.quick else 20000
-    for C in (64, 256):
-        for pdl in (0, 1):
-            for U in (1, 2):
-                recs.append(point("nhwc", C, 1, steps, unroll=U, pdl=pdl))
-            for cg in (2, 4, 8):
-                recs.append(point("nchw", C, 1, steps, cg=cg, pdl=pdl))
-    for C in (64, 256):
-        for S in (2, 3, 4):
-            recs.append(point("nhwc", C, 1, steps, unroll=1, pdl=1, streams=S))
-            recs.append(point("nchw", C, 1, steps, cg=4, pdl=1, streams=S))
-    # batched steps (cfg2: 8 images, cfg4 per GPU: 32 images)
-    for images in (8, 32):
-        for layout, kw in (("nhwc", dict(unroll=3)), ("nhwc", dict(unroll=5)), ("nchw", dict(cg=2)), ("nchw", dict(cg=4)), ("nchw", dict(cg=8))):
-            recs.append(point(layout, 64, images, max(steps // images, 500), pdl=1, **kw))
-    for images in (1, 8, 32):
-        for layout, kws in (("nhwc", [dict()]), ("nchw", [dict(cg=8, dedupe=1), dict(cg=8, dedupe=0), dict(cg=4, dedupe=1), dict(cg=16, dedupe=1)])):
-            for kw in kws:
-                recs.append(point(layout, 64, images, max(steps // (4 * images), 200), pdl=1, backward=True, **kw))
+    which = sys.argv[1:] or ["fwd"]
+    for w in which:
+        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bf16": sweep_bf16, "nchw": sweep_nchw, "fwd2": sweep_fwd2, "bwd2": sweep_bwd2}[w]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w") as f:
-        json.dump(recs, f, indent=1)
+    with open(os.path.join(ROOT, "gpurun_out", "sweep_%s.json" % "_".join(which)), "w") as f:
+        json.dump(RECS, f, indent=1)
