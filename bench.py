@@ -423,8 +423,7 @@ def variants_leg(args, torch, device, lib, cabi, peak):
     grid = [
         # the library's defaults (opts = NULL), one launch at a time on one stream: the latency-bound case
         ("serial_1stream", dict(images=1, streams=1)),
-        ("serial_1stream_rois_ready", dict(images=1, streams=1, opts=dict(rois_ready=True))),
-        ("serial_1stream_rois_ready_xform_table", dict(images=1, streams=1, opts=dict(rois_ready=True), xform=True)),
+        ("serial_1stream_rois_ready", dict(images=1, streams=1, opts=dict(rois_ready=True, concurrency=1))),
         # 8 streams with the library's defaults (no concurrency hint, no flag)
         ("default_opts_%dstreams" % S, dict(images=1, streams=S)),
         ("nchw_reference_layout", dict(layout="nchw", images=1, streams=S, opts=dict(concurrency=S, rois_ready=True))),
@@ -436,7 +435,6 @@ def variants_leg(args, torch, device, lib, cabi, peak):
         ("bf16_io_cfg4_per_gpu", dict(images=32, streams=1, dtype="bf16")),
         # backward (rroi_b200_backward_opt, zero_fill = 1: the gradient map is defined everywhere), cfg3/cfg4's per-GPU batch
         ("backward_nhwc_cfg4", dict(images=32, streams=1, backward=True)),
-        ("backward_nhwc_cfg4_unchunked_memset", dict(images=32, streams=1, backward=True, opts=dict(zero_chunk_images=-1))),
         ("backward_nchw_cfg4", dict(layout="nchw", images=32, streams=1, backward=True)),
         ("backward_nhwc_cfg1", dict(images=1, streams=1, backward=True)),
     ]
@@ -461,6 +459,8 @@ def variants_leg(args, torch, device, lib, cabi, peak):
                      "opts": kw.get("opts", {}), "launches_timed": steps * per_step}
         if kw.get("backward"):
             out[name]["touched_pixels"] = float(np.mean(w.touched))
+            no_rmw = alg - 8.0 * a.channels * float(np.mean(w.touched))         # without the 2*4*C*U read-modify-write term
+            out[name]["frac_without_rmw_term"] = no_rmw / us / 1e3 / peak
         del w
         torch.cuda.empty_cache()
     return out

@@ -24,6 +24,8 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -117,7 +119,70 @@ double tri_intersection_area(const Tri& s, const Tri& c) {
     return n >= 3 ? std::fabs(signed_area(ax, ay, n)) : 0.0;
 }
 
+// Strictly convex quadrangle (all four turns the same way, none degenerate)?  Returns the orientation sign, 0 if not.
+int convex_orientation(const double* x, const double* y) {
+    int pos = 0, neg = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3, k = (i + 2) & 3;
+        const double c = cross(x[j] - x[i], y[j] - y[i], x[k] - x[j], y[k] - y[j]);
+        if (c > 0.0) ++pos; else if (c < 0.0) ++neg; else return 0;
+    }
+    return pos == 4 ? 1 : neg == 4 ? -1 : 0;
+}
+
+// Area of the intersection of two strictly convex quadrangles: Sutherland-Hodgman of `s` against the four edges of `c`.
+double convex_quad_intersection_area(const double* sx, const double* sy, const double* cx, const double* cy, int c_orient) {
+    double ax[16], ay[16], bx[16], by[16];
+    int n = 4;
+    for (int i = 0; i < 4; ++i) { ax[i] = sx[i]; ay[i] = sy[i]; }
+    const double orient = (double)c_orient;
+    for (int e = 0; e < 4 && n > 0; ++e) {
+        const int e2 = (e + 1) & 3;
+        const double ex = cx[e2] - cx[e], ey = cy[e2] - cy[e];
+        int m = 0;
+        double di = orient * (ex * (ay[0] - cy[e]) - ey * (ax[0] - cx[e]));
+        for (int i = 0; i < n; ++i) {
+            const int j = (i + 1 == n) ? 0 : i + 1;
+            const double dj = orient * (ex * (ay[j] - cy[e]) - ey * (ax[j] - cx[e]));
+            if (di >= 0.0) { bx[m] = ax[i]; by[m] = ay[i]; ++m; }
+            if ((di >= 0.0) != (dj >= 0.0)) {
+                const double t = di / (di - dj);
+                bx[m] = ax[i] + t * (ax[j] - ax[i]);
+                by[m] = ay[i] + t * (ay[j] - ay[i]);
+                ++m;
+            }
+            di = dj;
+        }
+        n = m;
+        std::memcpy(ax, bx, sizeof(double) * n);
+        std::memcpy(ay, by, sizeof(double) * n);
+    }
+    return n >= 3 ? std::fabs(signed_area(ax, ay, n)) : 0.0;
+}
+
 float quad_iou(const Quad& a, const Quad& b) {
+    // Disjoint bounding boxes: the intersection is empty and the quotient below is exactly 0 (never above a threshold).
+    // In raster order most comparisons against "the polygon appended last" are of this kind.
+    {
+        int64_t alx = a.x[0], ahx = a.x[0], aly = a.y[0], ahy = a.y[0], blx = b.x[0], bhx = b.x[0], bly = b.y[0], bhy = b.y[0];
+        for (int i = 1; i < 4; ++i) {
+            alx = std::min(alx, a.x[i]); ahx = std::max(ahx, a.x[i]); aly = std::min(aly, a.y[i]); ahy = std::max(ahy, a.y[i]);
+            blx = std::min(blx, b.x[i]); bhx = std::max(bhx, b.x[i]); bly = std::min(bly, b.y[i]); bhy = std::max(bhy, b.y[i]);
+        }
+        if (ahx < blx || bhx < alx || ahy < bly || bhy < aly) return 0.0f;
+    }
+    // Both strictly convex (decoded rectangles and almost all of their weighted means are): one quad-quad clip instead
+    // of two splits and four triangle clips.  Same area up to double rounding.
+    {
+        double ax[4], ay[4], bx[4], by[4];
+        for (int i = 0; i < 4; ++i) { ax[i] = (double)a.x[i]; ay[i] = (double)a.y[i]; bx[i] = (double)b.x[i]; by[i] = (double)b.y[i]; }
+        const int oa = convex_orientation(ax, ay), ob = convex_orientation(bx, by);
+        if (oa != 0 && ob != 0) {
+            const double inter = convex_quad_intersection_area(ax, ay, bx, by, ob);
+            const double uni = std::fabs(signed_area(ax, ay, 4)) + std::fabs(signed_area(bx, by, 4)) - inter;
+            return std::fabs((float)inter) / std::max(std::fabs((float)uni), 1.0f);
+        }
+    }
     Tri ta[2], tb[2];
     split(a, ta);
     split(b, tb);
@@ -246,4 +311,31 @@ extern "C" int fots_b200_merge_candidates_host(const int* cand, int num_cand, in
     }
     *num_boxes = total;
     return RROI_B200_OK;
+}
+
+// One call for a whole micro-batch: image b's candidates are cand[b * cap .. + counts[b]) (the layout
+// fots_b200_decode_candidates writes); images are independent, so they are dealt to `threads` host threads (the per-rank
+// worker pool of SURVEY.md section 8e).  boxes [B, max_boxes, 9], num_boxes [B].  Returns the first non-OK status.
+extern "C" int fots_b200_merge_candidates_host_batch(const int* cand, const int* counts, int B, int cap, int w, int h,
+                                                     float iou_threshold1, float iou_threshold2, float* boxes, int max_boxes,
+                                                     int* num_boxes, int threads) {
+    if (B < 0 || cap < 0 || !counts || !num_boxes || (B > 0 && max_boxes > 0 && !boxes)) return RROI_B200_ERR_INVALID_ARG;
+    if (threads < 1) threads = 1;
+    if (threads > B) threads = B;
+    std::atomic<int> next(0), status(RROI_B200_OK);
+    auto work = [&]() {
+        for (int b = next.fetch_add(1); b < B; b = next.fetch_add(1)) {
+            const int n = counts[b] < cap ? counts[b] : cap;
+            const int st = fots_b200_merge_candidates_host(cand + (size_t)b * cap * 16, n < 0 ? 0 : n, w, h, iou_threshold1, iou_threshold2,
+                                                           boxes + (size_t)b * max_boxes * 9, max_boxes, num_boxes + b);
+            if (st != RROI_B200_OK) { int ok = RROI_B200_OK; status.compare_exchange_strong(ok, st); }
+        }
+    };
+    if (threads <= 1) { work(); return status.load(); }
+    std::vector<std::thread> pool;
+    pool.reserve(threads - 1);
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return status.load();
 }

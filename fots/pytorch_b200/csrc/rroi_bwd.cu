@@ -428,130 +428,14 @@ __global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_packed_kernel(c
     }
 }
 
-// ---------------------------------------------------------------------------- NHWC, packed, pre-summed per pixel
-// The scatter above issues one vector reduction per (bin, tap): about 739 per RoI on the benchmark draw, landing on only
-// about 386 distinct pixels, because neighbouring bins (pitch 0.5 .. 2 px) share taps -- and the L2 reduction path, not
-// DRAM, is what bounds it (24 M lane-level red.v4 for cfg4's per-GPU batch).  Here the CTA first GROUPS its taps by
-// pixel: one thread per bin computes the scatter geometry and inserts each of its <= 4 (pixel, weight) entries into a
-// shared-memory hash table keyed by the pixel index (open addressing, atomicCAS), chaining the entries of one pixel
-// in a linked list (atomicExch on the slot's head).  Then the warps walk the DISTINCT pixels: lanes = channel vectors,
-// every entry of the pixel's list is one coalesced 128-bit load of top_diff (L1 hits: the CTA's 256 bins are 64 KB)
-// and one FMA into a register accumulator, and the pixel receives ONE red.global.add.v4.f32.  Half the reductions for
-// about twice the (cheap, cached) loads.  The order in which a pixel's contributions are summed is unspecified, as with
-// the reference's atomics; parity is to 1e-4.
-template <int CT, int TILE>
-__global__ void __launch_bounds__(kPackWarps * 32) rroi_bwd_nhwc_presum_kernel(const BwdParams p) {
-    constexpr int LPP = CT / 4;
-    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;           // pixels per warp iteration
-    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;            // 32-lane channel chunks per pixel
-    constexpr int HSZ = 8 * TILE;                           // hash slots: load factor <= 1/2
-    constexpr int NE = 4 * TILE;                            // entries: (bin, tap)
-    __shared__ RoiXform sX;
-    __shared__ int hkey[HSZ];                               // pixel index + 1; 0 = free
-    __shared__ int hhead[HSZ];                              // first entry of the pixel's list, -1 = none
-    __shared__ int enext[NE];
-    __shared__ float ew[NE];
-    __shared__ int uniq[NE];                                // occupied slots, in insertion order
-    __shared__ int nuniq;
-    const int n = blockIdx.x / p.tiles;
-    const int tile = blockIdx.x - n * p.tiles;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bins = p.PH * p.PW;
-    const int bin0 = tile * TILE;
-
-    pdl_wait();
-    pdl_launch_dependents();
-    if (!in_image_window(p, n)) return;
-    for (int i = threadIdx.x; i < HSZ; i += kPackWarps * 32) { hkey[i] = 0; hhead[i] = -1; }
-    if (threadIdx.x == 0) nuniq = 0;
-    if (warp == 0) {
-        RoiXform X;
-        if (p.idx_mode == IDX_NONE) {
-            X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
-        } else {
-            const float* roi = p.rois + (size_t)n * 6;
-            X.batch = __float2int_rz(__ldg(roi));
-            X.rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
-        }
-        if (lane == 0) sX = X;
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < TILE; t += kPackWarps * 32) {
-        const int bin = bin0 + t;
-        if (bin >= bins) continue;
-        const RoiXform X = sX;
-        const int ph = bin / p.PW, pw = bin - ph * p.PW;
-        const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
-        float cx, cy;
-        if (p.idx_mode == IDX_NONE) bin_center(X, ph, pw, (float)(p.W - 1), (float)(p.H - 1), cx, cy);
-        else { cx = __ldg(p.idx_x + (size_t)n * bins + bin); cy = __ldg(p.idx_y + (size_t)n * bins + bin); }
-        const bool in = batch_ok & !(X.rpw < (float)pw);
-        const ScatterGeom g = scatter_geom<false>(cx, cy, in, p.H, p.W);
-        const int base = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
-        // a tap with non-zero weight is a distinct pixel: rt/rb only when r == l + 1, lb/rb only when b == t + 1
-        const bool s[4] = {g.p_lt && g.wlt != 0.f, g.p_rt && g.wrt != 0.f && g.r == g.l + 1,
-                           g.p_rb && g.wrb != 0.f && g.r == g.l + 1 && g.b == g.t + 1, g.p_lb && g.wlb != 0.f && g.b == g.t + 1};
-        const int pixk[4] = {base, base + 1, base + p.W + 1, base + p.W};
-        const float wk[4] = {g.wlt, g.wrt, g.wrb, g.wlb};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!s[k]) continue;
-            const int key = pixk[k] + 1;
-            unsigned h = ((unsigned)pixk[k] * 2654435761u) >> 8;
-            for (;;) {
-                h &= HSZ - 1;
-                const int old = atomicCAS(&hkey[h], 0, key);
-                if (old == 0) { uniq[atomicAdd(&nuniq, 1)] = (int)h; break; }
-                if (old == key) break;
-                ++h;
-            }
-            const int e = t * 4 + k;
-            ew[e] = wk[k];
-            enext[e] = atomicExch(&hhead[h], e);
-        }
-    }
-    __syncthreads();
-
-    const int sub = LPP >= 32 ? 0 : lane / LPP;
-    const int cvl = LPP >= 32 ? lane : lane % LPP;
-    const int units = nuniq * NCH;                                   // (pixel, 128-channel chunk)
-    const float* tbase = p.top_diff + ((size_t)n * bins + bin0) * CT + cvl * 4;
-    float* gbase = p.bottom_diff + cvl * 4;
-    for (int u0 = warp * PPI; u0 < units; u0 += kPackWarps * PPI) {
-        const int u = u0 + sub;
-        const bool live = u < units;
-        const int slot = live ? uniq[u / NCH] : 0;
-        const int ch = NCH > 1 ? (u % NCH) * 128 : 0;
-        int e = live ? hhead[slot] : -1;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        while (__any_sync(0xffffffffu, e >= 0)) {
-            // up to four entries of the list per round: their loads are issued together
-            int ee[4];
-            float ww[4];
-            float4 gq[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                ee[k] = e;
-                ww[k] = e >= 0 ? ew[e] : 0.0f;
-                e = e >= 0 ? enext[e] : -1;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gq[k] = ld_v4(tbase + (size_t)((ee[k] >= 0 ? ee[k] : 0) >> 2) * CT + ch, ee[k] >= 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                acc.x = __fmaf_rn(ww[k], gq[k].x, acc.x); acc.y = __fmaf_rn(ww[k], gq[k].y, acc.y);
-                acc.z = __fmaf_rn(ww[k], gq[k].z, acc.z); acc.w = __fmaf_rn(ww[k], gq[k].w, acc.w);
-            }
-        }
-        if (live) {
-            float* d = gbase + (long long)(hkey[slot] - 1) * CT + ch;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
-        }
-    }
-}
+// EVALUATED AND REMOVED (round 2, profiles/r02_sweep_bwd2.txt): grouping a CTA's taps by pixel in a shared-memory hash
+// table and issuing ONE vector reduction per distinct pixel (739 tap writes land on 386 pixels per RoI) was slower than
+// the plain scatter above: 170 vs 161 us on cfg4's per-GPU batch (C = 64), 57 vs 45 us on 8 images.  Halving the
+// reductions buys nothing because the scatter is DRAM-bound, not reduction-bound: it moves 171 MB of top_diff plus the
+// read-modify-write of 203 MB of zeroed lines in ~85 us (6.8 TB/s, the copy roofline).
 
 template <int CT>
-static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl, int mode) {
+static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl) {
     const int bins = p.PH * p.PW;
     constexpr int PPI = CT >= 128 ? 1 : 128 / CT;
     constexpr int NCH = CT > 128 ? CT / 128 : 1;
@@ -559,8 +443,6 @@ static cudaError_t launch_bwd_nhwc_packed(BwdParams& p, cudaStream_t s, bool pdl
     const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
     if (ctas256 >= 148 * 4) {
         p.tiles = (bins + 255) / 256;
-        // large launches are bound by the L2 reduction path: group the taps by pixel first (bwd_mode 1 = plain scatter)
-        if (mode != 1) return launch_1d(rroi_bwd_nhwc_presum_kernel<CT, 256>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
         return launch_1d(rroi_bwd_nhwc_packed_kernel<CT, 256, 4>, (long long)p.N * p.tiles, kPackWarps * 32, p, s, pdl);
     }
     p.tiles = (bins + 63) / 64;
@@ -577,10 +459,10 @@ cudaError_t launch_bwd_nhwc(const BwdParams& p0, const Opts& o, cudaStream_t s) 
     const bool vec = (p.C % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.top_diff) | reinterpret_cast<uintptr_t>(p.bottom_diff)) % 16 == 0);
     if (vec && o.bwd_mode != 2) {      // opts.bwd_mode = 2 selects the generic kernel (A/B measurements)
-        if (p.C == 32)  return launch_bwd_nhwc_packed<32>(p, s, pdl, o.bwd_mode);
-        if (p.C == 64)  return launch_bwd_nhwc_packed<64>(p, s, pdl, o.bwd_mode);
-        if (p.C == 128) return launch_bwd_nhwc_packed<128>(p, s, pdl, o.bwd_mode);
-        if (p.C == 256) return launch_bwd_nhwc_packed<256>(p, s, pdl, o.bwd_mode);
+        if (p.C == 32)  return launch_bwd_nhwc_packed<32>(p, s, pdl);
+        if (p.C == 64)  return launch_bwd_nhwc_packed<64>(p, s, pdl);
+        if (p.C == 128) return launch_bwd_nhwc_packed<128>(p, s, pdl);
+        if (p.C == 256) return launch_bwd_nhwc_packed<256>(p, s, pdl);
     }
     return vec ? launch_1d(rroi_bwd_nhwc_kernel<true>, grid, kBlock, p, s, pdl)
                : launch_1d(rroi_bwd_nhwc_kernel<false>, grid, kBlock, p, s, pdl);

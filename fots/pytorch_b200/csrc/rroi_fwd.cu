@@ -929,157 +929,11 @@ __global__ void __launch_bounds__(kNhwcWarps * 32) rroi_fwd_nhwc_warp_kernel(con
     }
 }
 
-// ------------------------------------------------------- NHWC, packed, warp-autonomous, taps staged in shared memory
-// The register-staged kernels above keep UN iterations' taps (UN x 4 float4 per lane) in flight and need ITERS / UN
-// dependent DRAM round trips per warp; more in flight costs registers, i.e. occupancy.  Here every tap of the warp's
-// BPW bins is fetched by cp.async (LDGSTS, 16 bytes per lane) straight into the warp's slice of shared memory: all
-// 4 * ITERS warp-level copies are issued back to back (no registers held, no scoreboard stall between them), taps
-// that are not loaded are zero-filled by the copy itself (src-size 0), and after ONE cp.async.wait_all the blend
-// reads LDS.128 x 4 -> 16 FFMA -> STG.128 per lane and iteration, branch-free.  One DRAM round trip per warp instead
-// of ITERS / UN -- what a single small launch (cfg1: a pure latency chain) wants.  Same records, same FFMA order:
-// bit-identical to the other kernels.  BPW * CT * 16 bytes of shared memory per warp.
-__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const float* src, uint32_t pred) {
-    const uint32_t n = pred ? 16u : 0u;                                    // 0: nothing is read, 16 zero bytes are written
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
-}
-
-template <int CT, int BPW, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rroi_fwd_nhwc_stage_kernel(const FwdParams p) {
-    constexpr int LPP = CT / 4;
-    constexpr int PPI = LPP >= 32 ? 1 : 32 / LPP;
-    constexpr int NCH = LPP > 32 ? LPP / 32 : 1;
-    constexpr int ITERS = BPW * NCH / PPI;
-    static_assert(ITERS > 0 && BPW % PPI == 0 && BPW <= 32, "segment shape");
-    extern __shared__ __align__(16) uint8_t stage_raw[];                   // [WARPS][ITERS][4 taps][32 lanes] float4, then the records
-    float4* const stage = reinterpret_cast<float4*>(stage_raw);
-    BinRec* const recs = reinterpret_cast<BinRec*>(stage_raw + (size_t)WARPS * ITERS * 4 * 32 * sizeof(float4));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * WARPS + warp;
-    const int n = (int)(gw / p.tiles);
-    const int bins = p.PH * p.PW;
-    const int bin0 = (int)(gw - (long long)n * p.tiles) * BPW;
-    if (!p.early) pdl_wait();
-    pdl_launch_dependents();
-    if (n >= p.N) return;
-
-    BinRec* const rec = recs + warp * BPW;
-    float ccx = 0.0f, ccy = 0.0f;
-    {
-        const RoiXform X = get_xform(p, n);
-        const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
-        if (lane < BPW) {
-            BinRec r;
-            r.pix = 0; r.code = 0; r.wlt = r.wrt = r.wrb = r.wlb = 0.0f; r.pad[0] = r.pad[1] = 0;
-            const int bin = bin0 + lane;
-            if (bin < bins) {
-                const int ph = bin / p.PW, pw = bin - ph * p.PW;
-                const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
-                const bool in = g.flags & BIN_IN, two_c = g.flags & TWO_COLS, two_r = g.flags & TWO_ROWS;
-                r.pix = (int)(((unsigned)(batch_ok ? X.batch : 0) * (unsigned)p.H + (unsigned)g.t) * (unsigned)p.W + (unsigned)g.l);
-                r.code = C_LIVE;
-                if (in) {
-                    const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
-                    const bool l_lt = g.flags & TAP_LT;
-                    const bool l_rt = (g.flags & TAP_RT) && two_c;
-                    const bool l_lb = (g.flags & TAP_LB) && two_r;
-                    const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
-                    r.code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
-                    r.wlt = (l_lt || nanw) ? g.wlt : 0.0f;
-                    r.wrt = (l_rt || nanw) ? g.wrt : 0.0f;
-                    r.wrb = (l_rb || nanw) ? g.wrb : 0.0f;
-                    r.wlb = (l_lb || nanw) ? g.wlb : 0.0f;
-                    ccx = g.cx; ccy = g.cy;
-                }
-            }
-            rec[lane] = r;
-        }
-    }
-    __syncwarp();
-    if (p.early) pdl_wait();                                               // nothing above touched the caller's buffers
-    if (p.idx_mode == IDX_COMPACT && lane < BPW && bin0 + lane < bins) {
-        p.idx_x[(size_t)n * bins + bin0 + lane] = ccx;
-        p.idx_y[(size_t)n * bins + bin0 + lane] = ccy;
-    }
-
-    const int sub = LPP >= 32 ? 0 : lane / LPP;
-    const int cvl = LPP >= 32 ? lane : lane % LPP;
-    const long long rowC = (long long)p.W * CT;
-    const float* fbase = p.feat + cvl * 4;
-    float4* const wstage = stage + (size_t)warp * ITERS * 4 * 32 + lane;
-    const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(wstage);
-    const BinRec* rbase = rec + (NCH > 1 ? 0 : sub);
-
-    // ---- issue every tap of every iteration ----
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const BinRec r = rbase[NCH > 1 ? it / NCH : it * PPI];
-        const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
-        const uint32_t any = r.code & (C_LT | C_RT | C_LB | C_RB);
-        const float* s = fbase + (any ? (long long)r.pix * CT + ch : 0);   // a valid address even when nothing is read
-        const float* s2 = s + (any ? rowC : 0);
-        const uint32_t d = wstage_s + (uint32_t)(it * 4 * 32 * sizeof(float4));
-        cp_async_16_zfill(d, s, r.code & C_LT);
-        cp_async_16_zfill(d + 32 * sizeof(float4), (r.code & C_RT) ? s + CT : s, r.code & C_RT);
-        cp_async_16_zfill(d + 64 * sizeof(float4), (r.code & C_LB) ? s2 : s, r.code & C_LB);
-        cp_async_16_zfill(d + 96 * sizeof(float4), (r.code & C_RB) ? s2 + CT : s, r.code & C_RB);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
-
-    // ---- blend from shared memory (each lane reads back exactly the 16 bytes it copied) ----
-    float* obase = p.out + ((size_t)n * bins + bin0 + (NCH > 1 ? 0 : sub)) * CT + cvl * 4;
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const int dpx = NCH > 1 ? it / NCH : it * PPI;
-        const int ch = NCH > 1 ? (it % NCH) * 128 : 0;
-        const BinRec r = rbase[dpx];
-        const float4 lt = wstage[it * 128], rt = wstage[it * 128 + 32], lb = wstage[it * 128 + 64], rb = wstage[it * 128 + 96];
-        const float wlt = r.wlt, wrt = r.wrt, wrb = r.wrb, wlb = r.wlb;
-        float4 o;
-        float v;
-        v = __fmaf_rn(lt.x, wlt, 0.0f); v = __fmaf_rn(rt.x, wrt, v); v = __fmaf_rn(wrb, rb.x, v); o.x = __fmaf_rn(lb.x, wlb, v);
-        v = __fmaf_rn(lt.y, wlt, 0.0f); v = __fmaf_rn(rt.y, wrt, v); v = __fmaf_rn(wrb, rb.y, v); o.y = __fmaf_rn(lb.y, wlb, v);
-        v = __fmaf_rn(lt.z, wlt, 0.0f); v = __fmaf_rn(rt.z, wrt, v); v = __fmaf_rn(wrb, rb.z, v); o.z = __fmaf_rn(lb.z, wlb, v);
-        v = __fmaf_rn(lt.w, wlt, 0.0f); v = __fmaf_rn(rt.w, wrt, v); v = __fmaf_rn(wrb, rb.w, v); o.w = __fmaf_rn(lb.w, wlb, v);
-        if (r.code & C_LIVE) *reinterpret_cast<float4*>(obase + dpx * CT + ch) = o;
-    }
-}
-
-// shared memory of one CTA of the staged kernel; opted in per device on first use (idempotent attribute)
-template <int CT, int BPW, int WARPS>
-static cudaError_t launch_stage(FwdParams& p, cudaStream_t s, bool pdl) {
-    constexpr int PPI = CT >= 128 ? 1 : 128 / CT, NCH = CT > 128 ? CT / 128 : 1, ITERS = BPW * NCH / PPI;
-    constexpr size_t smem = (size_t)WARPS * ITERS * 4 * 32 * 16 + (size_t)WARPS * BPW * sizeof(BinRec);
-    static_assert(smem <= 227 * 1024, "shared memory per CTA");
-    const int bins = p.PH * p.PW;
-    p.tiles = (bins + BPW - 1) / BPW;
-    const long long warps = (long long)p.N * p.tiles, grid = (warps + WARPS - 1) / WARPS;
-    if (grid <= 0) return cudaSuccess;
-    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-    if (smem > 48 * 1024) {
-        static bool done[64] = {};
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if (dev < 0 || dev >= 64 || !done[dev]) {
-            e = cudaFuncSetAttribute(rroi_fwd_nhwc_stage_kernel<CT, BPW, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) done[dev] = true;
-        }
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(WARPS * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, rroi_fwd_nhwc_stage_kernel<CT, BPW, WARPS>, p);
-}
+// EVALUATED AND REMOVED (round 2, profiles/r02_sweep_fwd2.txt): staging every tap of a warp's bins in shared memory with
+// cp.async (LDGSTS, zero-fill for taps that are not loaded) so that a warp needs ONE DRAM round trip and no registers
+// for loads in flight.  Bit-identical, but slower everywhere: cfg1 alone 5.2-7.2 us (register-staged: 4.2-5.2), on 8
+// streams 3.6-4.3 us (2.2), cfg4's per-GPU batch 118-137 us (76).  LDGSTS costs ~8 issue cycles per warp-level copy plus
+// the shared-memory round trip, and 8 KB of staging per warp caps occupancy at 26 warps per SM.
 
 template <int CT>
 static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, const Opts& o) {
@@ -1101,12 +955,20 @@ static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, const Op
     constexpr int I8 = 8 * NCH / PPI, I16 = 16 * NCH / PPI;          // iterations of an 8- / 16-bin warp segment
     int variant = o.variant;
     if (variant == 0) {
-        // auto (measured on B200, profiles/r02_sweep_fwd.txt): a launch that has the GPU to itself and fills at most
-        // about one wave is a latency chain -> warp-autonomous 16-bin segments; large launches and launches that overlap
-        // with others (opts.concurrency) amortise the per-CTA prologue over 256 bins.
+        // auto, measured on B200 (profiles/r02_sweep_fwd.txt, cfg1 = 128 CTAs of 256 bins; us per launch):
+        //   in flight        1 (alone)   1 + RoIs ready   2      4      8
+        //   block,  64 bins    5.14          4.40        3.06   --     2.95        (variant 1)
+        //   warp,    8 bins    5.62          4.17        3.17   --     3.12        (variant 11)
+        //   warp,   16 bins    6.42          5.23        3.31   2.48   2.48        (variant 12)
+        //   block, 256 bins    8.66          8.66        4.71   3.01   2.22        (variant 5)
+        // A launch that has the GPU to itself is a latency chain and wants many small units of work (and, when the RoI
+        // rows are declared ready, no block barrier between the prologue and the grid dependency); large launches and
+        // launches the caller overlaps with others amortise the per-CTA prologue over 256 bins.
         const long long ctas256 = (long long)p.N * ((bins + 255) / 256);
         const long long load = ctas256 * (o.concurrency > 1 ? o.concurrency : 1);
-        variant = load >= 148 * 4 ? 5 : 12;
+        if (load >= 148 * 4) variant = 5;
+        else if (o.concurrency >= 3) variant = 12;
+        else variant = (p.early && o.concurrency <= 1) ? 11 : 1;
     }
     switch (variant) {
         case 1:  return go(rroi_fwd_nhwc_packed_kernel<CT, 64, (I64 >= 2 ? 2 : 1)>, 64);
@@ -1122,12 +984,6 @@ static cudaError_t launch_fwd_nhwc_packed(FwdParams& p, cudaStream_t s, const Op
         case 15: return gow(rroi_fwd_nhwc_warp_kernel<CT, 64, 4>, 64);
         case 16: return gow(rroi_fwd_nhwc_warp_kernel<CT, 32, 2>, 32);
         case 17: return gow(rroi_fwd_nhwc_warp_kernel<CT, 8, (I8 >= 4 ? 4 : I8)>, 8);
-        // taps staged in shared memory by cp.async: (bins per warp, warps per CTA)
-        case 21: return launch_stage<CT, (CT <= 64 ? 8 : 4), 4>(p, s, pdl);
-        case 22: return launch_stage<CT, (CT <= 64 ? 8 : 4), 2>(p, s, pdl);
-        case 23: return launch_stage<CT, (CT <= 64 ? 16 : 8), 2>(p, s, pdl);
-        case 24: return launch_stage<CT, (CT <= 64 ? 4 : 2), 4>(p, s, pdl);
-        case 25: return launch_stage<CT, (CT <= 64 ? 8 : 4), 8>(p, s, pdl);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -74,6 +74,15 @@ int fots_b200_decode_candidates(const float* segm, const float* rbox, const floa
  */
 int fots_b200_merge_candidates_host(const int* cand, int num_cand, int w, int h, float iou_threshold1,
                                     float iou_threshold2, float* boxes, int max_boxes, int* num_boxes);
+/*
+ * The same merge for a micro-batch of B images in one call, dealt to `threads` host threads (images are independent;
+ * the per-rank worker pool of the end-to-end step).  cand [B, cap, 16] / counts [B] as fots_b200_decode_candidates
+ * writes them (host copies); boxes [B, max_boxes, 9], num_boxes [B] (totals: may exceed max_boxes, rows beyond it are
+ * dropped and the caller must check).
+ */
+int fots_b200_merge_candidates_host_batch(const int* cand, const int* counts, int B, int cap, int w, int h,
+                                          float iou_threshold1, float iou_threshold2, float* boxes, int max_boxes,
+                                          int* num_boxes, int threads);
 
 /*
  * Fused channels-last InstanceNorm (+ affine) (+ residual add) + leaky-ReLU for the feeder/consumer networks

@@ -58,12 +58,13 @@ typedef struct rroi_b200_opts {
     int variant;               /* 0 = automatic (grid size + concurrency); > 0 forces a forward kernel variant      */
                                /* (sweeps and parity tests; see launch_fwd_nhwc / launch_fwd_nchw)                  */
     int nchw_cg;               /* NCHW kernels: channels in flight per lane / per CTA: 1,2,4,8,16 (0 = default)     */
-    int bwd_mode;              /* backward: 0 = automatic; 1 = plain per-tap reductions; 2 = generic (non-packed)   */
-                               /* channels-last kernel; NCHW: 3 = no warp-level merge of equal centres              */
+    int bwd_mode;              /* backward: 0 = automatic; 2 = generic (non-packed) channels-last kernel;            */
+                               /* NCHW: 3 = no warp-level merge of equal centres (A/B measurements)                 */
     int nchw_tma;              /* NCHW forward: 0 gather through L1 (default); 1 = stage the patch footprint with    */
                                /* TMA box loads; 2..5 = same with a minimum box index (sweeps)                      */
-    int zero_chunk_images;     /* backward with zero_fill: images per zero-fill/scatter chunk (0 = automatic,       */
-                               /* -1 = one memset of the whole map, then one scatter)                               */
+    int zero_chunk_images;     /* backward with zero_fill: 0 (default) = one memset of the whole map, then one      */
+                               /* scatter; k > 0 = clear k images at a time on a side stream and scatter each chunk  */
+                               /* as soon as it is clear (measured slower on B200, kept for maps that thrash L2)     */
 } rroi_b200_opts;
 
 /*

@@ -230,34 +230,6 @@ def test_backward_dedupe_on_off_agree(cuda):
     Hh.assert_close_rel(a, b, REL_BWD, "dedupe on vs off")
 
 
-@pytest.mark.parametrize("C", [32, 64, 128, 256])
-def test_backward_presummed_per_pixel_matches_oracle_and_plain_scatter(oracle, cuda, C):
-    """Large channels-last launches group their taps by pixel in shared memory before the vector reductions
-    (rroi_bwd_nhwc_presum_kernel).  Against the oracle and against the plain per-tap scatter (opts.bwd_mode = 1), with
-    saved and with recomputed centres; the RoI mix includes sub-pixel bin pitch (dozens of taps on one pixel), boxes
-    over the border and an out-of-range image index."""
-    from fots.pytorch_b200 import _cabi
-    B, H, W, ph, pw, scale = 3, 45, 80, 8, 64, 0.25
-    rois = np.concatenate([WL.stress_rois(70 + C, 260, B, int(W / scale), int(H / scale)),
-                           np.concatenate([WL.random_rois(5 + i, 30, i, img_w=int(W / scale), img_h=int(H / scale)) for i in range(B)], 0)], 0)
-    rois[:40, 3] = np.minimum(rois[:40, 3], 5)                       # bin pitch << 1 px
-    feats = np.zeros((B, C, H, W), np.float32)
-    top = np.random.default_rng(C).standard_normal((len(rois), C, ph, pw), dtype=np.float32)
-    _, ix, iy = oracle.forward(feats, rois, ph, pw, scale, threads=0)
-    want = oracle.backward(top, rois, ix, iy, feats.shape, scale, threads=0)
-    assert len(rois) * ((ph * pw + 255) // 256) >= 148 * 4           # large enough for the pre-summed kernel
-    for idx in ((ix[:, 0], iy[:, 0]), None):
-        got = Hh.run_new_backward(top, rois, idx, feats.shape, scale, cuda, channels_last=True)
-        plain = Hh.run_new_backward(top, rois, idx, feats.shape, scale, cuda, channels_last=True, opts=_cabi.opts(bwd_mode=1))
-        Hh.assert_close_rel(got, want, REL_BWD, "pre-summed backward C=%d saved_idx=%s" % (C, idx is not None))
-        Hh.assert_close_rel(plain, want, REL_BWD, "plain scatter C=%d" % C)
-    rois[7, 0] = B + 1                                                # image that does not exist: contributes nothing
-    ok = rois[:, 0] < B
-    want2 = oracle.backward(top[ok], rois[ok], ix[ok], iy[ok], feats.shape, scale, threads=0)
-    got2 = Hh.run_new_backward(top, rois, None, feats.shape, scale, cuda, channels_last=True)
-    Hh.assert_close_rel(got2, want2, REL_BWD, "pre-summed backward with an out-of-range image index")
-
-
 @pytest.mark.parametrize("cg", [1, 2, 4, 8, 16])
 def test_tuning_variants_bit_exact(cuda, cg):
     """Every per-call kernel variant (rroi_b200_opts.variant / nchw_cg, with and without programmatic dependent launch)
@@ -275,7 +247,7 @@ def test_tuning_variants_bit_exact(cuda, cg):
 
 
 @pytest.mark.parametrize("C", [32, 64, 128, 256])
-@pytest.mark.parametrize("variant", [0, 1, 5, 6, 11, 12, 13, 14, 15, 16, 17, 21, 22, 23, 24, 25])
+@pytest.mark.parametrize("variant", [0, 1, 5, 6, 11, 12, 13, 14, 15, 16, 17])
 def test_nhwc_packed_and_warp_autonomous_variants_bit_exact(oracle, cuda, C, variant):
     """The block-level and the warp-autonomous channels-last kernels, with the RoI rows declared ready (prologue ahead
     of the grid dependency), with a precomputed transform table, and under a concurrency hint: same bits as the oracle,

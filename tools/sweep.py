@@ -88,28 +88,6 @@ def sweep_bwd():
     point(images=1, layout="nchw", backward=True)
 
 
-def sweep_fwd2():
-    for S in (1, 2, 8):
-        for v in (1, 11, 13, 5, 21, 22, 23, 24, 25):
-            for early in (False, True):
-                point(streams=S, variant=v, rois_ready=early)
-        point(streams=S, variant=21, rois_ready=True, xform=True)
-        point(streams=S, variant=24, rois_ready=True, xform=True)
-    for v in (21, 22, 23, 25):
-        point(images=8, variant=v)
-        point(images=32, variant=v)
-        point(C=256, streams=1, variant=v, rois_ready=True)
-        point(C=256, streams=8, variant=v, rois_ready=True)
-
-
-def sweep_bwd2():
-    for images in (32, 8):
-        for C in (64, 256):
-            for mode in (0, 1):
-                point(images=images, C=C, backward=True, bwd_mode=mode)
-    point(images=32, backward=True, zero_chunk_images=8)
-
-
 def sweep_bf16():
     for images, S in ((1, 8), (32, 1)):
         for C in (64, 256):
@@ -127,7 +105,7 @@ def sweep_nchw():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fwd"]
     for w in which:
-        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bf16": sweep_bf16, "nchw": sweep_nchw, "fwd2": sweep_fwd2, "bwd2": sweep_bwd2}[w]()
+        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bf16": sweep_bf16, "nchw": sweep_nchw}[w]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "sweep_%s.json" % "_".join(which)), "w") as f:
         json.dump(RECS, f, indent=1)
