@@ -481,6 +481,7 @@ def train_leg(args, torch, device):
     tgt = synthetic_targets(B, 64, 720, 1280, 89, device, seed=0)
     losses = [step(images, tgt)["total"]]                      # warm-up (cuDNN autotune, allocator)
     torch.cuda.synchronize()
+    bad = [n for n, p in net.named_parameters() if p.grad is not None and not bool(torch.isfinite(p.grad).all())]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.train_steps):
@@ -489,7 +490,7 @@ def train_leg(args, torch, device):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.train_steps
     out = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "batch": B, "rois_per_image": 64, "steps": args.train_steps,
-           "losses": [float(x) for x in losses], "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+           "losses": [float(x) for x in losses], "nonfinite_grads_after_first_step": bad[:8], "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
            "dtype": "bf16 autocast networks (cuDNN/cuBLAS under autograd), fp32 RoIRotate forward + backward kernels "
                     "(rroi_b200_forward_opt / rroi_b200_backward_opt), fp32 master weights, Adam",
            "loss": "dense EAST-style detection losses + F.ctc_loss(sum)/N (warp-ctc absent: parity unpinned)"}
@@ -512,7 +513,9 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     per_gpu, micro = args.pipeline_images, 8
     batch = per_gpu * world
     gen = torch.Generator(device=device).manual_seed(100 + rank)
-    images = torch.randn(per_gpu, 3, 720, 1280, device=device, generator=gen)
+    # raw uint8 images [b, 720, 1280, 3] as cv2.imread returns them (viewed as channels-last [b, 3, 720, 1280]); the
+    # reference's x / 128 - 1 (test.py:80-83) is applied inside the stem kernel, so the host uploads a quarter of the bytes
+    images = torch.randint(0, 256, (per_gpu, 720, 1280, 3), device=device, generator=gen, dtype=torch.uint8).permute(0, 3, 1, 2)
     quads = torch.from_numpy(planted_quads(per_gpu, 64, seed0=rank * per_gpu)).to(device)
 
     local = pipe.capture(images, quads, micro)      # one CUDA graph for the rank-local part of the step
@@ -542,7 +545,7 @@ def pipeline_leg(args, torch, device, dist, world, rank):
 
     # the same step fed from pinned HOST images: H2D of the next step's images on a copy stream overlaps this step's
     # compute; the records come back to pinned host memory every step
-    host_imgs = [torch.empty(images.shape, dtype=images.dtype).pin_memory() for _ in range(2)]
+    host_imgs = [torch.empty((per_gpu, 720, 1280, 3), dtype=torch.uint8).pin_memory().permute(0, 3, 1, 2) for _ in range(2)]
     for hbuf in host_imgs:
         hbuf.copy_(images)
     stage = [torch.empty_like(images) for _ in range(2)]
@@ -577,16 +580,48 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     for _ in range(2):
         step_host()
     ms_host, _ = timed(step_host, args.pipeline_steps)
+    # ---- the same step WITH the detector post-processing inside (SURVEY 8d protocol): the head outputs are overwritten
+    # by seeded planted detection maps (64 boxes per image), GPU decode + host merge on this rank's thread pool,
+    # merged boxes -> RoIs (padded / cut to 64 per image from the planted set)
+    det_info = None
+    try:
+        import workloads as WL
+        from fots.pytorch_b200.pipeline.detect import host_threads as det_threads
+        q_np = planted_quads(micro, 64, seed0=rank * per_gpu)
+        maps8 = WL.planted_maps_from_quads(q_np, 180, 320, seed0=rank * per_gpu)
+        maps = [torch.from_numpy(np.concatenate([m] * (per_gpu // micro), 0)).to(device) for m in maps8]
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        threads = max(1, det_threads() // max(local_world, 1))
+        det = pipe.capture_with_detection(images, quads, override_maps=maps, micro=micro, threads=threads)
+        found = {}
+
+        def step_det():
+            rec, f = det()
+            found["n"] = f
+            return all_gather_records(rec, batch)
+
+        for _ in range(2):
+            step_det()
+        ms_det, _ = timed(step_det, args.pipeline_steps)
+        det_info = {"images_per_s": batch / (ms_det * 1e-3), "ms_per_step": ms_det, "host_threads_per_rank": threads,
+                    "boxes_found_per_image_mean": float(np.mean(found["n"])),
+                    "boxes": "head outputs overwritten by planted detection maps (64 boxes per image, SURVEY 8d), then "
+                             "fots_b200_decode_candidates (GPU) + fots_b200_merge_candidates_host_batch (host thread pool, "
+                             "overlapped with the backbone of the next 8-image micro-batch); images device-resident"}
+        del det, maps
+    except Exception as e:
+        det_info = {"error": repr(e)}
     cpu = pipeline_cpu_baseline(torch) if (rank == 0 and world == 1) else None      # N=1 only, like cpu_baseline
     return {"images_per_s": batch / (ms_host * 1e-3), "ms_per_step": ms_host, "cpu_baseline": cpu,
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
             "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
-            "dtype": "bf16: hand-written tcgen05 convolutions (conv6/8/9 incl. CTA pairs, layer0_1[0]) and mma.sync stem conv, "
-                     "cuDNN for the remaining convolutions, fused InstanceNorm / FPN-merge / max-pool kernels, "
-                     "bf16-in/bf16-out RoIRotate (fp32 arithmetic)",
+            "dtype": "uint8 images in (normalised on load by the stem kernel); bf16 activations: hand-written tcgen05 convolutions and "
+                     "mma.sync stem conv, library calls for the remaining convolutions, fused InstanceNorm / FPN-merge / max-pool "
+                     "kernels, bf16-in/bf16-out RoIRotate (fp32 arithmetic, == bf16(reference(float(features))) bit for bit)",
             "collective": "one all_gather of int32 [images, 64, 74] records per step" if world > 1 else "none (1 rank)",
-            "boxes": "planted (seeded) -- reference NMS is pathological on random-init maps, SURVEY 8d",
+            "boxes": "planted (seeded) boxes are an INPUT of this number; `with_detection` has the decode + merge inside the step",
+            "with_detection": det_info,
             "flop_per_image": 221.7e9}
 
 

@@ -45,6 +45,7 @@ struct ConvParams {
     int S;                                 // filter width (taps = R*S)
     int taps;
     int pad_h, pad_w;
+    int stride;                            // 1 or 2 (both spatial dims): input pixel = stride * output pixel + tap - pad
     int cout_tiles;                        // Cout / BN
     int chunk;                             // consecutive tiles per CTA visit
     float slope;                           // leaky slope; 1 = identity
@@ -283,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + MT * kABytes;
                     if (PAIR) {
                         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * kStageBytes);
-                        tma_load_4d_pair(a_dst, &map_x, full_bar(s), cc * BK, T.w0 + sx - P.pad_w, T.h0 + r - P.pad_h, T.n0);
+                        tma_load_4d_pair(a_dst, &map_x, full_bar(s), cc * BK, T.w0 * P.stride + sx - P.pad_w, T.h0 * P.stride + r - P.pad_h, T.n0);
                         tma_load_2d_pair(b_dst, &map_w, full_bar(s), kb * BK, T.c_out0 + (int)rank * (BN / 2));
                         if (rank != 0) mbar_arrive_even_cta(full_bar(s));
                         continue;
@@ -291,8 +292,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     mbar_expect_tx(full_bar(s), kStageBytes);
 #pragma unroll
                     for (int j = 0; j < MT; ++j)
-                        tma_load_4d(a_dst + j * kABytes, &map_x, full_bar(s), cc * BK, T.w0 + sx - P.pad_w,
-                                    T.h0 + j * P.sub_h + r - P.pad_h, T.n0 + j * P.sub_n);
+                        tma_load_4d(a_dst + j * kABytes, &map_x, full_bar(s), cc * BK, T.w0 * P.stride + sx - P.pad_w,
+                                    (T.h0 + j * P.sub_h) * P.stride + r - P.pad_h, T.n0 + j * P.sub_n);
                     tma_load_2d(b_dst, &map_w, full_bar(s), kb * BK, T.c_out0);
                 }
             }
@@ -501,11 +502,14 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool make_map_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bn, int bh, int bw) {
+// `stride` > 1 (input map of a strided convolution): the box spans stride * bw x stride * bh input pixels and the TMA
+// traversal stride (elementStrides) picks every stride-th of them, so shared memory receives the same bw x bh pixels --
+// the strided im2col gather is done by the copy engine.
+bool make_map_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bn, int bh, int bw, int stride = 1) {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+    const cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -526,17 +530,24 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
                    long long ctas, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * (MT * kABytes + (PAIR ? BN / 2 : BN) * BK * 2) + 2 * BM * 128 + 8 * (2 * STAGES + 5) + 1024;
     static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
-    static bool attr_set = false;           // per instantiation; benign race (idempotent)
-    if (!attr_set) {
+    // The shared-memory opt-in and the SM count are PER DEVICE: cache them per device ordinal (per instantiation; the
+    // attribute call is idempotent, so a race between host threads only repeats it).
+    static bool attr_set[64] = {};
+    static int sm_count[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cudaErrorInvalidDevice;
+    const bool cached = dev >= 0 && dev < 64;
+    if (!cached || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MT, BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (cached) attr_set[dev] = true;
     }
-    static int sms = 0;
+    int sms = cached ? sm_count[dev] : 0;
     if (sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
         sms = n;
+        if (cached) sm_count[dev] = n;
     }
     // persistent: one CTA per SM walks the tile list with stride gridDim.x
     if (PAIR) {
@@ -571,11 +582,12 @@ extern "C" int fots_b200_conv_set_tile(int bn) {
 }
 
 static int conv2d_impl(const void* x, const void* w, const float* bias, void* y, double* stats, int N, int H, int W,
-                       int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope, cudaStream_t stream) {
+                       int Cin, int Cout, int R, int S, int pad_h, int pad_w, float slope, cudaStream_t stream, int stride = 1) {
     if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || R <= 0 || S <= 0 || pad_h < 0 || pad_w < 0)
         return RROI_B200_ERR_INVALID_ARG;
-    if (Cin % BK != 0 || Cout % 64 != 0 || R > 7 || S > 7) return RROI_B200_ERR_INVALID_ARG;
-    const int Ho = H + 2 * pad_h - R + 1, Wo = W + 2 * pad_w - S + 1;
+    if (Cin % BK != 0 || Cout % 64 != 0 || R > 7 || S > 7 || (stride != 1 && stride != 2)) return RROI_B200_ERR_INVALID_ARG;
+    if (H + 2 * pad_h < R || W + 2 * pad_w < S) return RROI_B200_ERR_INVALID_ARG;
+    const int Ho = (H + 2 * pad_h - R) / stride + 1, Wo = (W + 2 * pad_w - S) / stride + 1;
     if (Ho <= 0 || Wo <= 0) return RROI_B200_ERR_INVALID_ARG;
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return RROI_B200_ERR_INVALID_ARG;
     if (bias && ((uintptr_t)bias & 15)) return RROI_B200_ERR_INVALID_ARG;
@@ -598,6 +610,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     long long best = -1;
     for (int tw = 128; tw >= 8; tw >>= 1)
         for (int th = 128 / tw; th >= 1; th >>= 1) {
+            if (tw * stride > 256 || th * stride > 256) continue;          // TMA box edge limit
             const int tn = 128 / (tw * th);
             const int ch = tn > 1 ? th : th * mt, cn = tn > 1 ? tn * mt : tn;
             const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + ch - 1) / ch) * ((N + cn - 1) / cn);
@@ -610,7 +623,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     P.cta_h = stack_n ? P.th : P.th * mt;  P.cta_n = stack_n ? P.tn * mt : P.tn;
     P.sub_h = stack_n ? 0 : P.th;          P.sub_n = stack_n ? P.tn : 0;
     P.n_tiles_w = (Wo + P.tw - 1) / P.tw; P.n_tiles_h = (Ho + P.cta_h - 1) / P.cta_h; P.n_tiles_n = (N + P.cta_n - 1) / P.cta_n;
-    P.cin_chunks = Cin / BK; P.S = S; P.taps = R * S; P.pad_h = pad_h; P.pad_w = pad_w;
+    P.cin_chunks = Cin / BK; P.S = S; P.taps = R * S; P.pad_h = pad_h; P.pad_w = pad_w; P.stride = stride;
     P.cout_tiles = Cout / bn; P.slope = slope; P.bias = bias;
     P.stats = stats; P.N = N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout;
     P.chunk = 1;
@@ -626,7 +639,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     }
 
     CUtensorMap mx, mw, my;
-    if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
+    if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw, stride)) return RROI_B200_ERR_INVALID_ARG;
     if (!make_map_weights(&mw, w, Cout, R * S * Cin, pair ? bn / 2 : bn)) return RROI_B200_ERR_INVALID_ARG;
     if (!make_map_nhwc(&my, y, N, Ho, Wo, Cout, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
 
@@ -650,4 +663,13 @@ extern "C" int fots_b200_conv2d_stats_nhwc_bf16(const void* x, const void* w, co
                                                 cudaStream_t stream) {
     if (!stats) return RROI_B200_ERR_INVALID_ARG;
     return conv2d_impl(x, w, bias, y, stats, N, H, W, Cin, Cout, R, S, pad_h, pad_w, 1.0f, stream);
+}
+
+// Same convolution with a spatial stride of 1 or 2 (tools/models.py:257-264 layer0_1's second convolution, :283-296 the
+// first block of every residual stage and its 1x1 down-sampling branch): the TMA tensor map's traversal stride gathers
+// every second input pixel, everything else is the kernel above.
+extern "C" int fots_b200_conv2d_strided_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                                                  int Cin, int Cout, int R, int S, int pad_h, int pad_w, int stride,
+                                                  float slope, cudaStream_t stream) {
+    return conv2d_impl(x, w, bias, y, nullptr, N, H, W, Cin, Cout, R, S, pad_h, pad_w, slope, stream, stride);
 }

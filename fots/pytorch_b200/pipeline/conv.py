@@ -15,6 +15,13 @@ ENABLED = os.environ.get("FOTS_B200_TC_CONV", "1") != "0"   # A/B switch against
 # on B200 (profiles/r01_conv_tc_bench.txt) the bare library convolution + a separate statistics pass is still a
 # little faster for these shapes (the statistics make the 4-warp epilogue the bottleneck), so the default is off.
 FUSE_STATS = os.environ.get("FOTS_B200_TC_STATS", "0") != "0"
+# How much of the networks runs on this kernel (A/B switch for the step-time sweeps, tools/profile_pipeline.py):
+#   0 = only the convolutions whose activation it fuses (conv6/8/9, layer0_1[0]);
+#   1 = + every other convolution of the recogniser (conv5/7/10_s in front of an InstanceNorm, conv11 with its 89 classes
+#       padded to 128 output channels): forward_ocr then contains no library call;
+#   2 = + the stride-1 3x3 convolutions of stages 1-2 and every 1x1 convolution of the feeder (FPN laterals, separable
+#       blocks' pointwise halves, up-convolutions).
+LEVEL = int(os.environ.get("FOTS_B200_TC_LEVEL", "1"))
 
 
 def _lib():
@@ -23,6 +30,8 @@ def _lib():
         i, f, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
         L.fots_b200_conv2d_nhwc_bf16.restype = i
         L.fots_b200_conv2d_nhwc_bf16.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, f, vp]
+        L.fots_b200_conv2d_strided_nhwc_bf16.restype = i
+        L.fots_b200_conv2d_strided_nhwc_bf16.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, f, vp]
         L.fots_b200_conv2d_stats_nhwc_bf16.restype = i
         L.fots_b200_conv2d_stats_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
         L.fots_b200_stem_conv3x3_c3_c16.restype = i
@@ -39,19 +48,26 @@ def set_tile(bn):
     _cabi.check(_lib().fots_b200_conv_set_tile(int(bn)), "fots_b200_conv_set_tile")
 
 
+def input_ok(x):
+    """bf16 channels-last CUDA activations outside autograd: what the kernel consumes."""
+    return (ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last) and not (torch.is_grad_enabled() and x.requires_grad))
+
+
 def eligible(x, conv):
     """True when `conv` (an nn.Conv2d) applied to `x` can run on the tensor-core kernel."""
     w = conv.weight
     return (ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 4
             and x.is_contiguous(memory_format=torch.channels_last)
-            and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1) and conv.groups == 1
             and conv.padding_mode == "zeros" and not isinstance(conv.padding, str)
             and w.size(1) % 64 == 0 and w.size(0) % 64 == 0 and w.size(2) <= 7 and w.size(3) <= 7
-            and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)))
+            and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad
+                                                  or (conv.bias is not None and conv.bias.requires_grad))))
 
 
-def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0, stats=False):
-    """act(conv2d(x, weight, bias, stride 1, padding)) -> bf16 channels-last [N, Cout, Ho, Wo].
+def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0, stats=False, stride=1):
+    """act(conv2d(x, weight, bias, stride (1 or 2), padding)) -> bf16 channels-last [N, Cout, Ho, Wo].
     x: bf16 channels-last [N, Cin, H, W]; weight: bf16 [Cout, Cin, R, S]; bias: fp32/bf16 [Cout] or None.
     stats=True (slope must be 1): returns (y, ws) where ws is the fp64 [N, Cout, 2] per-image sum / sum of squares
     of y accumulated by the epilogue, for fused.instnorm_act(y, ..., stats=ws)."""
@@ -60,13 +76,20 @@ def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0, stats=False):
     if Cin_w != Cin:
         raise ValueError("conv2d: weight expects %d input channels, x has %d" % (Cin_w, Cin))
     ph, pw = (padding, padding) if isinstance(padding, int) else padding
-    Ho, Wo = H + 2 * ph - R + 1, W + 2 * pw - S + 1
+    stride = stride[0] if isinstance(stride, (tuple, list)) else int(stride)
+    Ho, Wo = (H + 2 * ph - R) // stride + 1, (W + 2 * pw - S) // stride + 1
     wk = weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
     b = None if bias is None else bias.float().contiguous()
     y = torch.empty((N, Cout, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     with torch.cuda.device(x.device):
-        if stats:
+        if stride != 1:
+            if stats:
+                raise ValueError("conv2d: fused statistics are only available at stride 1")
+            st = _lib().fots_b200_conv2d_strided_nhwc_bf16(
+                x.data_ptr(), wk.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(),
+                N, H, W, Cin, Cout, R, S, ph, pw, stride, float(slope), stream)
+        elif stats:
             if slope != 1.0:
                 raise ValueError("conv2d: stats=True computes the statistics of the raw convolution (slope must be 1)")
             from . import fused
@@ -82,10 +105,10 @@ def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0, stats=False):
     return (y, ws) if stats else y
 
 
-def apply(conv, x, slope=1.0):
-    """conv(x) followed by leaky-ReLU(slope) through the tensor-core kernel when eligible, else torch."""
-    if eligible(x, conv):
-        return conv2d(x, conv.weight, conv.bias, conv.padding, slope)
+def apply(conv, x, slope=1.0, level=0):
+    """conv(x) followed by leaky-ReLU(slope) through the tensor-core kernel when eligible (and LEVEL >= level), else torch."""
+    if LEVEL >= level and eligible(x, conv):
+        return conv2d(x, conv.weight, conv.bias, conv.padding, slope, stride=conv.stride)
     y = conv(x)
     if slope == 1.0:
         return y

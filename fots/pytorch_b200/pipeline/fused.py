@@ -8,7 +8,6 @@ import torch
 
 from .. import _cabi
 
-_ws = {}
 
 
 def _lib():
@@ -27,9 +26,15 @@ def _lib():
     return L
 
 
-def eligible(x, residual=None):
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def eligible(x, residual=None, weight=None, bias=None):
+    """The fused kernels are inference-only: under autograd (grad mode on and ANY of the activation, the residual or the
+    norm's affine parameters requiring grad) the caller must take torch's differentiable ops."""
     ok = (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.size(1) % 8 == 0 and x.size(1) <= 1024
-          and x.is_contiguous(memory_format=torch.channels_last) and not (torch.is_grad_enabled() and x.requires_grad))
+          and x.is_contiguous(memory_format=torch.channels_last) and not _needs_grad(x, residual, weight, bias))
     if ok and residual is not None:
         ok = (residual.dtype == torch.bfloat16 and residual.shape == x.shape
               and residual.is_contiguous(memory_format=torch.channels_last))
@@ -37,14 +42,10 @@ def eligible(x, residual=None):
 
 
 def workspace(device, numel):
-    """fp64 statistics workspace [B, C, 2] of the current stream (one per stream: producer and consumer of the
-    statistics are consecutive launches on it)."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
-    ws = _ws.get(key)
-    if ws is None or ws.numel() < numel:
-        ws = torch.empty(max(numel, 1 << 16), dtype=torch.float64, device=device)
-        _ws[key] = ws
-    return ws
+    """fp64 statistics workspace [B, C, 2], allocated per call from torch's caching allocator (stream-ordered; inside a
+    CUDA-graph capture it belongs to that graph's pool).  No module-level cache: a buffer first allocated during a
+    capture must not be shared with eager work on a recycled stream handle."""
+    return torch.empty(max(int(numel), 1), dtype=torch.float64, device=device)
 
 
 def instnorm_act(x, weight, bias, eps, slope, residual=None, crelu=False, stats=None):

@@ -10,6 +10,8 @@ B200 notes: convolutions are cuDNN through torch; run the module under `torch.au
 with channels-last activations (`FOTSNet.to_b200()`), InstanceNorm statistics stay fp32 inside autocast, and the
 map handed to RoIRotate (`focr`) is returned as an fp32 channels-last tensor -- the layout the sampler wants.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -25,7 +27,7 @@ def _inorm(ch, affine=True):
 def _in_act(norm, x, slope, residual=None):
     """act(norm(x) [+ residual]) with leaky slope (0 = ReLU, 1 = none).  On the CUDA bf16 channels-last inference
     path this is ONE fused pair of kernels (statistics + apply); otherwise torch's ops."""
-    if fused.eligible(x, residual):
+    if fused.eligible(x, residual, norm.weight, norm.bias):
         return fused.instnorm_act(x, norm.weight, norm.bias, norm.eps, slope, residual)
     y = norm(x)
     if residual is not None:
@@ -33,16 +35,17 @@ def _in_act(norm, x, slope, residual=None):
     return y if slope == 1.0 else F.leaky_relu(y, slope)
 
 
-def _conv_in_act(conv, norm, x, slope, residual=None):
-    """act(norm(conv(x)) [+ residual]).  On the bf16 channels-last inference path the convolution runs on the
-    tcgen05 kernel, whose epilogue also accumulates the InstanceNorm statistics, so the normalisation is a single
-    pass over the convolution's output (opt-in, conv.FUSE_STATS); otherwise conv + _in_act."""
-    # Cout = 64 (stage 1) stays on the library: one 64-wide weight tile cannot feed the tensor pipe from L2 fast enough
-    if tc.FUSE_STATS and tc.eligible(x, conv) and 128 <= conv.out_channels <= 1024:
-        y, ws = tc.conv2d(x, conv.weight, conv.bias, conv.padding, 1.0, stats=True)
-        if fused.eligible(y, residual):
-            return fused.instnorm_act(y, norm.weight, norm.bias, norm.eps, slope, residual, stats=ws)
-        return _in_act(norm, y, slope, residual)
+def _conv_in_act(conv, norm, x, slope, residual=None, level=1):
+    """act(norm(conv(x)) [+ residual]).  On the bf16 channels-last inference path (and conv.LEVEL >= level) the
+    convolution runs on the tcgen05 kernel; with conv.FUSE_STATS its epilogue also accumulates the InstanceNorm
+    statistics, so the normalisation is a single pass over the convolution's output; otherwise conv + _in_act."""
+    if tc.LEVEL >= level and tc.eligible(x, conv):
+        if tc.FUSE_STATS and 128 <= conv.out_channels <= 1024 and conv.stride == (1, 1):
+            y, ws = tc.conv2d(x, conv.weight, conv.bias, conv.padding, 1.0, stats=True)
+            if fused.eligible(y, residual, norm.weight, norm.bias):
+                return fused.instnorm_act(y, norm.weight, norm.bias, norm.eps, slope, residual, stats=ws)
+            return _in_act(norm, y, slope, residual)
+        return _in_act(norm, tc.conv2d(x, conv.weight, conv.bias, conv.padding, 1.0, stride=conv.stride), slope, residual)
     return _in_act(norm, conv(x), slope, residual)
 
 
@@ -54,7 +57,7 @@ class _CReLUNorm(nn.Module):
         self.bn = _inorm(2 * ch)
 
     def forward(self, x):
-        if fused.eligible(x):
+        if fused.eligible(x, None, self.bn.weight, self.bn.bias):
             return fused.instnorm_act(x, self.bn.weight, self.bn.bias, self.bn.eps, 0.01, crelu=True)
         return F.leaky_relu(self.bn(torch.cat((x, -x), 1)), 0.01)
 
@@ -77,8 +80,8 @@ class _ResIN(nn.Module):
 
     def forward(self, x):
         res = x if self.downsample is None else self.downsample(x)
-        y = _conv_in_act(self.conv1, self.bn1, x, 0.0)
-        return _conv_in_act(self.conv2, self.bn2, y, 0.0, res)
+        y = _conv_in_act(self.conv1, self.bn1, x, 0.0, level=2)
+        return _conv_in_act(self.conv2, self.bn2, y, 0.0, res, level=2)
 
 
 class _ResSepIN(nn.Module):
@@ -98,9 +101,9 @@ class _ResSepIN(nn.Module):
     def forward(self, x):
         res = x if self.downsample is None else self.downsample(x)
         s1, s2 = self.conv_sep1, self.conv2
-        y = _in_act(s1[2], s1[1](s1[0](x)), 0.01)
+        y = _in_act(s1[2], tc.apply(s1[1], s1[0](x), 1.0, level=2), 0.01)      # pointwise halves: 1x1 GEMMs on the tcgen05 kernel
         y = _in_act(s2[1], s2[0](y), 0.01)
-        return _in_act(s2[4], s2[3](y), 0.01, res)
+        return _in_act(s2[4], tc.apply(s2[3], y, 1.0, level=2), 0.01, res)
 
 
 def _up(x, like):
@@ -167,7 +170,7 @@ class FOTSNet(nn.Module):
             y = self.layer0(x)
         c1, _, c2, _ = self.layer0_1
         y = tc.apply(c1, y, 0.0)                        # conv + ReLU in one kernel on the inference path
-        return F.relu(c2(y))
+        return tc.apply(c2, y, 0.0, level=1)            # stride 2: the TMA traversal stride gathers every second pixel
 
     def _gate(self, x, like):
         return _up(torch.sigmoid(self.conv_attenton(x)), like)
@@ -186,15 +189,17 @@ class FOTSNet(nn.Module):
         s3 = self.layer1(self.drop1(focr))
         s2 = self.layer2(s3)
         s1 = self.layer3(s2)
-        f1, f2, f3 = self.feature1(s3), self.feature2(s2), self.feature3(s1)
-        f4 = self.feature4(self.drop1(self.layer4(s1)))
+        pw = lambda conv, t: tc.apply(conv, t, 1.0, level=2)              # 1x1 laterals
+        f1, f2, f3 = pw(self.feature1, s3), pw(self.feature2, s2), pw(self.feature3, s1)
+        f4 = pw(self.feature4, self.drop1(self.layer4(s1)))
         if fused.merge_eligible(f1, f2, f3, f4):
             # inference fast path: each merge step is one fused kernel (upsample + attention gate + add)
             att = self.conv_attenton if self.attention else (lambda t: None)
             x = fused.fpn_merge(a_lo=f4, b_hi=f3, gate_logits_lo=att(f4))
-            f2 = fused.fpn_merge(c_hi=self.upconv1(fused.fpn_merge(a_lo=x, size=f2.shape[2:])), b_hi=f2,
+            up = lambda seq, t: pw(seq[1], seq[0](t))                   # depthwise 3x3 (library) + pointwise 1x1
+            f2 = fused.fpn_merge(c_hi=up(self.upconv1, fused.fpn_merge(a_lo=x, size=f2.shape[2:])), b_hi=f2,
                                  gate_logits_lo=att(x))
-            x = fused.fpn_merge(c_hi=self.upconv2(fused.fpn_merge(a_lo=f2, size=f1.shape[2:])), b_hi=f1,
+            x = fused.fpn_merge(c_hi=up(self.upconv2, fused.fpn_merge(a_lo=f2, size=f1.shape[2:])), b_hi=f1,
                                 gate_logits_lo=att(f2))
         elif self.attention:
             x = _up(f4, f3) + f3 * _up(torch.sigmoid(self.conv_attenton(f4)).expand_as(f4), f3)
@@ -217,7 +222,9 @@ class FOTSNet(nn.Module):
             return fused.maxpool_h2(x)
         return self.max2(x)
 
-    def forward_ocr(self, x):
+    def forward_ocr(self, x, log_probs=True):
+        """log_probs=False returns the raw class scores [N, nclass, T] (fp32): the greedy decode only needs the arg-max,
+        so the inference step skips the log-softmax pass (tools/ocr_utils.py:183 takes the arg-max of it)."""
         # tc.apply = conv + leaky-ReLU in one tcgen05 kernel on the bf16 channels-last inference path, torch otherwise
         x = _conv_in_act(self.conv5, self.batch5, x, 0.01)
         x = tc.apply(self.conv6, tc.apply(self.conv6, x, 0.01), 0.01)
@@ -225,8 +232,14 @@ class FOTSNet(nn.Module):
         x = tc.apply(self.conv8, tc.apply(self.conv8, x, 0.01), 0.01)
         x = tc.apply(self.conv9, tc.apply(self.conv9, x, 0.01), 0.01)
         x = _conv_in_act(self.conv10_s, self.batch10_s, self._max2(x), 0.01)
-        x = self.conv11(self.drop1(x)).squeeze(2)            # [N, nclass, T]
-        return F.log_softmax(x.float(), dim=1)
+        pad = getattr(self, "_conv11_pad", None)
+        if tc.LEVEL >= 1 and pad is not None and not self.training and tc.input_ok(x) and x.size(1) % 64 == 0:
+            # the classifier as a 1x1 convolution on the tcgen05 kernel: nclass padded to a multiple of 64 output channels
+            x = tc.conv2d(x, pad[0], pad[1], (0, 0), 1.0)[:, :self.conv11.out_channels]
+        else:
+            x = self.conv11(self.drop1(x))
+        x = x.squeeze(2).float()                             # [N, nclass, T]
+        return F.log_softmax(x, dim=1) if log_probs else x
 
     # ---- B200 placement ------------------------------------------------------------------------
     def to_b200(self, device="cuda", inference=False):
@@ -235,11 +248,20 @@ class FOTSNet(nn.Module):
         re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
         batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
         self.to(device=device, memory_format=torch.channels_last)
+        self._conv11_pad = None
         if inference:
             for m in self.modules():
                 if isinstance(m, nn.Conv2d):
                     m.to(dtype=torch.bfloat16)
             self.eval()
+            # classifier weights with the class dimension padded to a multiple of 64 (zero rows), bias in fp32
+            c11 = self.conv11
+            cpad = (c11.out_channels + 63) // 64 * 64
+            w = torch.zeros((cpad, c11.in_channels, 1, 1), dtype=torch.bfloat16, device=c11.weight.device)
+            w[:c11.out_channels] = c11.weight.detach()
+            bias = torch.zeros((cpad,), dtype=torch.float32, device=w.device)
+            bias[:c11.out_channels] = c11.bias.detach().float()
+            self._conv11_pad = (w.contiguous(memory_format=torch.channels_last), bias)
         return self
 
 
@@ -280,21 +302,35 @@ class CRNN(nn.Module):
         self.rnn = nn.Sequential(_BiLSTM(512, hidden, hidden), _BiLSTM(hidden, hidden, nclass))
 
     def forward(self, x):
+        # the folded-BatchNorm bf16 path is a frozen inference snapshot of the weights: never under training or autograd
         fast = getattr(self, "_b200", None)
-        if fast is not None and x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad):
-            f = self._cnn_b200(x).float()
-        else:
-            f = self.cnn(x)
+        if fast is not None and x.is_cuda and not self.training and not (
+                torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            f = self._cnn_b200(x)
+            if f.size(2) != 1:
+                raise ValueError("CRNN: input height must reduce to 1 (use PH = 32)")
+            seq = f.squeeze(2).permute(2, 0, 1).contiguous()             # [T, N, 512] bf16
+            if self._rnn_b200 is not None:
+                # both BiLSTMs + embeddings on the hand-written kernels (csrc/lstm_kernels.cu): fp32 [T, N, nclass]
+                return self._rnn_b200[1](self._rnn_b200[0](seq))
+            return self.rnn(seq.float())
+        f = self.cnn(x)
         if f.size(2) != 1:
             raise ValueError("CRNN: input height must reduce to 1 (use PH = 32)")
         return self.rnn(f.squeeze(2).permute(2, 0, 1).contiguous())
+
+    def train(self, mode=True):
+        if mode:
+            self._b200 = self._rnn_b200 = None   # the folded weights are stale as soon as the parameters may change
+        return super().train(mode)
 
     # ---- B200 placement ------------------------------------------------------------------------
     def to_b200(self, device="cuda"):
         """Inference placement: every convolution gets its (eval-mode) BatchNorm folded into bf16 channels-last weights
         and an fp32 bias, so that each of the seven layers is ONE convolution with bias + ReLU in the epilogue -- on the
         tcgen05 kernel (csrc/conv_tc.cu) wherever Cin % 64 == 0 (six of the seven layers, 99 % of the FLOPs), on the
-        library for the 3-channel first layer.  The BiLSTMs stay cuDNN in fp32.  Call again after loading a checkpoint."""
+        library for the 3-channel first layer.  The two BiLSTMs + embeddings run on csrc/lstm_kernels.cu (bf16 weights,
+        fp32 state; FOTS_B200_LSTM=0 keeps cuDNN for A/B timing).  Call again after loading a checkpoint."""
         self.to(device).eval()
         packs = []
         for i, (cout, k, pad, bn, pool) in enumerate(self.PLAN):
@@ -307,6 +343,10 @@ class CRNN(nn.Module):
                 b = (b - m.running_mean.detach().float()) * scale + m.bias.detach().float()
             packs.append((w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), b.contiguous(), pad, pool))
         self._b200 = packs
+        self._rnn_b200 = None
+        if os.environ.get("FOTS_B200_LSTM", "1") != "0":
+            from .lstm import BiLSTMPack
+            self._rnn_b200 = [BiLSTMPack(self.rnn[0]), BiLSTMPack(self.rnn[1])]
         return self
 
     @torch.no_grad()

@@ -144,6 +144,10 @@ int fots_b200_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, 
 int fots_b200_conv2d_stats_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, double* stats,
                                      int N, int H, int W, int Cin, int Cout, int R, int S, int pad_h, int pad_w,
                                      cudaStream_t stream);
+/* The same convolution with spatial stride 1 or 2: y [N, (H + 2 pad_h - R) / stride + 1, (W + 2 pad_w - S) / stride + 1, Cout]. */
+int fots_b200_conv2d_strided_nhwc_bf16(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                                       int Cin, int Cout, int R, int S, int pad_h, int pad_w, int stride, float slope,
+                                       cudaStream_t stream);
 /* fots_b200_instnorm_nhwc_bf16 without its statistics pass: `stats` [B, C, 2] comes from the call above. */
 int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
                                        const void* residual, const double* stats, int B, int HW, int C,
@@ -166,6 +170,23 @@ int fots_b200_stem_conv3x3_c3_c16(const float* x, const void* w, void* y, double
  */
 int fots_b200_stem_conv3x3_c3_c16_u8(const unsigned char* x, const void* w, void* y, double* stats, int B, int H, int W,
                                      cudaStream_t stream);
+/*
+ * Consumer B's recurrent half (tools/models.py:17-33 BidirectionalLSTM = nn.LSTM(bidirectional) + nn.Linear; :898-909).
+ * csrc/lstm_kernels.cu.  One layer = gemm (input projections of all time steps, both directions) -> recurrent kernel
+ * (the whole time loop of both directions in one launch) -> gemm (the embedding Linear).
+ *
+ * fots_b200_gemm_bf16w:  C[M, N] fp32 = A[M, K] * W[N, K]^T + bias[N]
+ *   A  bf16 (a_is_f32 = 0) or fp32 (a_is_f32 = 1: split into bf16 hi + lo parts, two tensor-core products, so nothing
+ *      of an fp32 activation is lost); W bf16 [N, K] as nn.Linear / nn.LSTM store their weights; bias fp32 or NULL;
+ *      K % 32 == 0; A and W 16-byte aligned.
+ * fots_b200_bilstm_recurrent:  H must be 256 (the CRNN's hidden size).
+ *   G    fp32 [T, N, 2, 4H]  x_t * W_ih^T + b_ih + b_hh for (forward, reverse), gate order i, f, g, o (nn.LSTM)
+ *   Whh  bf16 [2, 4H, H]     weight_hh_l0, weight_hh_l0_reverse
+ *   Y    fp32 [T, N, 2H]     h_t, forward direction in [.., :H], reverse in [.., H:]  (what nn.LSTM returns), h_0 = c_0 = 0
+ */
+int fots_b200_gemm_bf16w(const void* A, int a_is_f32, const void* W, const float* bias, float* C, int M, int N, int K,
+                         cudaStream_t stream);
+int fots_b200_bilstm_recurrent(const float* G, const void* Whh, float* Y, int T, int N, int H, cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 

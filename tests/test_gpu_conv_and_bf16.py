@@ -103,6 +103,43 @@ def test_tcgen05_conv_matches_torch_fp32(cuda, case, bn):
     assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
 
 
+STRIDED_CASES = [
+    # N, H, W, Cin, Cout, R, S, pad, bias, slope
+    (2, 36, 64, 64, 64, 3, 3, 1, False, 0.0),            # layer0_1's second convolution (stride 2, ReLU), even sizes
+    (1, 45, 81, 64, 128, 3, 3, 1, True, 1.0),            # first block of a stage: odd sizes, ragged tiles
+    (3, 23, 37, 128, 256, 1, 1, 0, True, 1.0),           # 1x1 stride-2 down-sampling branch (BatchNorm folded into bias)
+    (2, 7, 9, 64, 64, 3, 3, 1, False, 1.0),              # output smaller than one tile
+    (1, 360, 640, 64, 64, 3, 3, 1, False, 0.0),          # full 720p size of layer0_1[1]
+]
+
+
+@pytest.mark.parametrize("case", STRIDED_CASES)
+@pytest.mark.parametrize("bn", [0, 64, 256])
+def test_tcgen05_conv_stride2_matches_torch_fp32(cuda, case, bn):
+    """Stride 2 through the TMA tensor map's traversal stride (fots_b200_conv2d_strided_nhwc_bf16): every second input
+    pixel is gathered by the copy engine, the rest is the stride-1 kernel."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    N, H, W, Cin, Cout, R, S, pad, bias, slope = case
+    if bn and Cout % bn:
+        pytest.skip("Cout is not a multiple of the forced tile")
+    g = torch.Generator().manual_seed(N * 17 + H + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, R, S, generator=g) / (Cin * R * S) ** 0.5).to(cuda).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g).to(cuda) if bias else None
+    TC.set_tile(bn)
+    try:
+        y = TC.conv2d(x, w, b, (pad, pad), slope, stride=2)
+    finally:
+        TC.set_tile(0)
+    ref = F.conv2d(x.float(), w.float(), b, 2, (pad, pad))
+    if slope != 1.0:
+        ref = F.leaky_relu(ref, slope)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    err = (y.float() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3 * float(ref.abs().max())
+    assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
+
+
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R,S,ph,pw", [(3, 8, 64, 64, 128, 3, 3, 1, 1), (5, 2, 64, 256, 256, 2, 3, 0, 1),
                                                        (2, 45, 80, 64, 64, 3, 3, 1, 1), (2, 23, 37, 128, 192, 3, 3, 1, 1),
                                                        (7, 3, 5, 64, 64, 3, 3, 1, 1)])

@@ -143,3 +143,23 @@ def planted_detection_maps(h, w, boxes, seed=0, noise=0.15):
         angle[0][inside] = sa
         angle[1][inside] = ca
     return seg, rbox.astype(np.float32), angle.astype(np.float32)
+
+
+def planted_maps_from_quads(quads, h, w, seed0=0):
+    """Detection maps (SURVEY 8d protocol) for a batch of planted quads [b, R, >=8] in IMAGE pixels (corner order of
+    fots.pytorch_b200.pipeline.infer.planted_quads: p0->p1 height edge, p1->p2 width edge) at 1/4 scale:
+    (seg [b,1,h,w], rbox [b,4,h,w], angle [b,2,h,w]) float32."""
+    b = quads.shape[0]
+    seg = np.zeros((b, 1, h, w), np.float32)
+    rbox = np.zeros((b, 4, h, w), np.float32)
+    ang = np.zeros((b, 2, h, w), np.float32)
+    for i in range(b):
+        boxes = []
+        for q in quads[i]:
+            p4 = np.asarray(q[:8], np.float64).reshape(4, 2) / 4.0
+            c = p4.mean(0)
+            dw, dh = p4[2] - p4[1], p4[1] - p4[0]
+            boxes.append((c[0], c[1], float(np.hypot(*dw)), float(np.hypot(*dh)), float(np.arctan2(dw[1], dw[0]))))
+        s, r, a = planted_detection_maps(h, w, boxes, seed=seed0 + i)
+        seg[i, 0], rbox[i], ang[i] = s, r, a
+    return seg, rbox, ang

@@ -34,3 +34,20 @@ if __name__ == "__main__":
         net.to_b200(dev)
         print("to_b200 (folded BN, tcgen05 conv + bias + ReLU) %.2f ms" % t(lambda: net(x)))
         print("  cnn part only %.2f ms" % t(lambda: net._cnn_b200(x)))
+        seq = net._cnn_b200(x).squeeze(2).permute(2, 0, 1).contiguous()
+        print("  BiLSTM x2 + embeddings, hand-written kernels (csrc/lstm_kernels.cu) %.3f ms" % t(lambda: net._rnn_b200[1](net._rnn_b200[0](seq))))
+        seqf = seq.float()
+        print("  BiLSTM x2 + embeddings, cuDNN nn.LSTM fp32 + cuBLAS %.3f ms" % t(lambda: net.rnn(seqf)))
+        from fots.pytorch_b200.pipeline.lstm import gemm
+        p0 = net._rnn_b200[0]
+        g = gemm(seq.view(-1, 512), p0.w_ih, p0.b)
+        print("    layer 1 input-projection GEMM %.3f ms" % t(lambda: gemm(seq.view(-1, 512), p0.w_ih, p0.b)))
+        import ctypes
+        from fots.pytorch_b200 import _cabi
+        y = torch.empty((seq.size(0), seq.size(1), 512), device=dev)
+        L = _cabi.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        print("    layer 1 recurrent kernel (T = %d, N = %d) %.3f ms" % (seq.size(0), seq.size(1), t(lambda: L.fots_b200_bilstm_recurrent(
+            g.data_ptr(), p0.w_hh.data_ptr(), y.data_ptr(), seq.size(0), seq.size(1), 256, st))))
+        net._rnn_b200 = None
+        print("to_b200 with the cuDNN LSTMs %.2f ms" % t(lambda: net(x)))
