@@ -406,6 +406,264 @@ rroi_fwd_nchw_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap 
     }
 }
 
+// ------------------------------------------------------------------------- NCHW, row segments staged
+// The bounding-box staging above over-fetches 3-4x (a rotated footprint fills half of its box, plus alignment slack and
+// box-size quantisation); the gather kernel is bound by L1 wavefronts (7.8 sectors per 32-lane request).  This kernel
+// stages exactly the ROW SEGMENTS the tile touches: CTA = one RoI x an 8 (ph) x 32 (pw) block of bins, thread = bin.
+//   1. every thread computes its bin's geometry (registers);
+//   2. the CTA builds, once, the list of 16-byte granules (4 pixels) of its footprint: per image row the span
+//      [min x, max x] of the taps that are loaded, widened to granule boundaries (shared-memory atomicMin/Max, a warp
+//      scan for the offsets, a table plane-offset-of-granule);
+//   3. for every group of channels the granules are copied plane by plane with cp.async (16 bytes per thread, consecutive
+//      threads = consecutive granules of a row: fully coalesced, every fetched byte within one granule of a tap),
+//      double-buffered over the channel groups;
+//   4. the blend reads its four taps from shared memory (predicated: an unloaded tap is 0, as in the gather kernel),
+//      same 4-FFMA chain, and stores 32 consecutive pw per warp (128-byte coalesced).
+// Tiles whose footprint does not fit (more than 96 rows or 20 KB per channel) or planes whose rows are not 16-byte
+// aligned take the gather loop inside the same kernel.  Bit-identical to the gather kernel and the oracle.
+constexpr int kRowsMax = 96;                      // image rows a tile's footprint may span
+constexpr int kStageFloats = 5120;                // floats per stage (20 KB); two stages
+constexpr int kGranMax = kStageFloats / 4;        // granules of one channel
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256) rroi_fwd_nchw_rows_kernel(const FwdParams p) {
+    __shared__ __align__(16) float stage[2][kStageFloats];
+    __shared__ int gsrc[kGranMax];                // plane offset (in floats) of every granule of the footprint
+    __shared__ int rlo[kRowsMax], rhi[kRowsMax], goff[kRowsMax + 1];
+    __shared__ int ylim[2];                       // first / last image row of the footprint
+    __shared__ RoiXform sX;
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int tiles_w = (p.PW + 31) / 32;
+    const int ph0 = (tile / tiles_w) * 8, pw0 = (tile % tiles_w) * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+
+    if (threadIdx.x < kRowsMax) { rlo[threadIdx.x] = INT_MAX; rhi[threadIdx.x] = INT_MIN; }
+    if (threadIdx.x == 0) { ylim[0] = INT_MAX; ylim[1] = INT_MIN; }
+    cta_xform_prologue(p, n, &sX);                // includes the grid-dependency wait and a __syncthreads()
+    const RoiXform X = sX;
+    const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+
+    // ---- 1. geometry: thread = bin (warp = one ph row of the block, lanes = 32 consecutive pw)
+    const int ph = ph0 + warp, pw = pw0 + lane;
+    const bool live = ph < p.PH && pw < p.PW;
+    uint32_t code = 0;
+    float wlt = 0.f, wrt = 0.f, wrb = 0.f, wlb = 0.f, ccx = 0.f, ccy = 0.f;
+    int gl = 0, gt = 0;
+    bool two_c = false, two_r = false;
+    if (live) {
+        const BinTaps g = bin_taps(X, ph, pw, p.H, p.W, (float)(p.W - 1), (float)(p.H - 1), batch_ok);
+        const bool in = g.flags & BIN_IN;
+        two_c = g.flags & TWO_COLS; two_r = g.flags & TWO_ROWS;
+        code = C_LIVE;
+        gl = g.l; gt = g.t;
+        if (in) {
+            const bool nanw = !(fabsf(g.cx) < INFINITY) || !(fabsf(g.cy) < INFINITY);
+            const bool l_lt = g.flags & TAP_LT;
+            const bool l_rt = (g.flags & TAP_RT) && two_c;
+            const bool l_lb = (g.flags & TAP_LB) && two_r;
+            const bool l_rb = (g.flags & TAP_RB) && two_c && two_r;
+            code |= (l_lt ? C_LT : 0u) | (l_rt ? C_RT : 0u) | (l_lb ? C_LB : 0u) | (l_rb ? C_RB : 0u);
+            wlt = (l_lt || nanw) ? g.wlt : 0.0f;
+            wrt = (l_rt || nanw) ? g.wrt : 0.0f;
+            wrb = (l_rb || nanw) ? g.wrb : 0.0f;
+            wlb = (l_lb || nanw) ? g.wlb : 0.0f;
+            ccx = g.cx; ccy = g.cy;
+        }
+        if (p.idx_mode == IDX_COMPACT) {
+            p.idx_x[(size_t)n * bins + ph * p.PW + pw] = ccx;
+            p.idx_y[(size_t)n * bins + ph * p.PW + pw] = ccy;
+        }
+    }
+    const bool top_used = code & (C_LT | C_RT), bot_used = code & (C_LB | C_RB);
+    // loaded taps lie inside the image (0 < x < W, 0 < y < H), so rows / columns below are valid indices
+    {
+        int ya = INT_MAX, yb = INT_MIN;
+        if (top_used) { ya = gt; yb = gt; }
+        if (bot_used) { ya = min(ya, gt + 1); yb = max(yb, gt + 1); }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            ya = min(ya, __shfl_xor_sync(0xffffffffu, ya, m));
+            yb = max(yb, __shfl_xor_sync(0xffffffffu, yb, m));
+        }
+        if (lane == 0 && yb >= ya) { atomicMin(&ylim[0], ya); atomicMax(&ylim[1], yb); }
+    }
+    __syncthreads();
+    const int y0 = ylim[0], nrows = ylim[1] >= ylim[0] ? ylim[1] - ylim[0] + 1 : 0;
+    const bool aligned = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.feat) & 15) == 0);
+    bool staged = aligned && nrows > 0 && nrows <= kRowsMax;                      // CTA-uniform
+    if (staged) {
+        // ---- 2. per-row spans of the loaded taps
+        if (top_used) {
+            const int xa = (code & C_LT) ? gl : gl + 1, xb = (code & C_RT) ? gl + 1 : gl;
+            atomicMin(&rlo[gt - y0], xa); atomicMax(&rhi[gt - y0], xb);
+        }
+        if (bot_used) {
+            const int xa = (code & C_LB) ? gl : gl + 1, xb = (code & C_RB) ? gl + 1 : gl;
+            atomicMin(&rlo[gt + 1 - y0], xa); atomicMax(&rhi[gt + 1 - y0], xb);
+        }
+    }
+    __syncthreads();
+    if (staged && warp == 0) {                    // exclusive scan of the rows' granule counts (<= 96 rows: 3 per lane)
+        int len[3], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int r = lane * 3 + k;
+            len[k] = (r < nrows && rhi[r] >= rlo[r]) ? ((rhi[r] | 3) - (rlo[r] & ~3) + 1) >> 2 : 0;
+            sum += len[k];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int r = lane * 3 + k;
+            if (r < kRowsMax) goff[r] = run;
+            run += len[k];
+        }
+        if (lane == 31) goff[kRowsMax] = incl;    // total granules of one channel
+    }
+    __syncthreads();
+    const int gtot = staged ? goff[kRowsMax] : 0;
+    staged = staged && gtot > 0 && gtot < kGranMax;        // + one zero granule per channel
+    if (staged) {
+        // table: plane offset of every granule (row r owns granules goff[r] .. goff[r+1])
+        for (int r = threadIdx.x; r < nrows; r += 256) {
+            if (rhi[r] < rlo[r]) continue;
+            const int a = rlo[r] & ~3, cnt = ((rhi[r] | 3) - a + 1) >> 2, base = (y0 + r) * p.W + a;
+            for (int k = 0; k < cnt; ++k) gsrc[goff[r] + k] = base + 4 * k;
+        }
+    }
+    __syncthreads();
+
+    const size_t HW = (size_t)p.H * p.W;
+    const size_t obin = (size_t)ph * p.PW + pw;
+    float* dst = p.out + (size_t)n * p.C * bins + obin;
+    const bool full_idx = p.idx_mode == IDX_FULL;
+    const float* plane0 = p.feat + (size_t)(batch_ok ? X.batch : 0) * p.C * HW;
+
+    if (staged) {
+        // Every staged channel is followed by one granule of zeros; a tap that is not loaded (border test, coinciding tap,
+        // bin outside the RoI) reads that zero, so the blend loop is branch-free: 4 LDS + 4 FFMA + 1 STG per channel.
+        const int chf = gtot * 4 + 4;                                             // floats per staged channel incl. the zero granule
+        const int cgs = min(8, kStageFloats / chf);                               // channels per stage (>= 1: gtot < kGranMax)
+        const int nst = (p.C + cgs - 1) / cgs;
+        for (int i = threadIdx.x; i < 2 * cgs * 4; i += 256) {
+            const int buf = i / (cgs * 4), rem = i - buf * cgs * 4;
+            stage[buf][(rem >> 2) * chf + gtot * 4 + (rem & 3)] = 0.0f;
+        }
+        const int zero = gtot * 4;
+        int o_lt = zero, o_rt = zero, o_lb = zero, o_rb = zero;
+        if (top_used) {
+            const int o = goff[gt - y0] * 4 + (gl - (rlo[gt - y0] & ~3));
+            if (code & C_LT) o_lt = o;
+            if (code & C_RT) o_rt = o + 1;
+        }
+        if (bot_used) {
+            const int o = goff[gt + 1 - y0] * 4 + (gl - (rlo[gt + 1 - y0] & ~3));
+            if (code & C_LB) o_lb = o;
+            if (code & C_RB) o_rb = o + 1;
+        }
+        // The stage's (channel, granule) pairs are dealt to the threads 256 apart (consecutive threads copy consecutive
+        // granules of one plane: coalesced).  A stage holds at most kStageFloats / 4 = 1280 granules, i.e. at most 5 pairs
+        // per thread, and the pairs are the same for every stage -- so their shared-memory offset and their plane offset
+        // are computed once and kept in registers; issuing a stage is then <= 5 x (add, add, LDGSTS).
+        constexpr int kPairs = kStageFloats / 4 / 256;                            // 5
+        uint32_t pair_dst[kPairs];
+        long long pair_src[kPairs];
+        int pair_ci[kPairs];
+        {
+            int gi = threadIdx.x, ci = 0;
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k) {
+                while (gi >= gtot && ci < cgs) { gi -= gtot; ++ci; }
+                pair_ci[k] = ci < cgs ? ci : 0x7fffffff;                           // past the stage: never issued
+                pair_dst[k] = (uint32_t)((ci * chf + gi * 4) * 4);
+                pair_src[k] = ci < cgs ? (long long)ci * (long long)HW + gsrc[gi] : 0;
+                gi += 256;
+            }
+        }
+        auto issue = [&](int st) {
+            const int c0 = st * cgs, cn = min(cgs, p.C - c0);
+            const uint32_t sb = smem_addr(stage[st & 1]);
+            const float* pl0 = plane0 + (size_t)c0 * HW;
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k)
+                if (pair_ci[k] < cn) cp_async_16(sb + pair_dst[k], pl0 + pair_src[k]);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        __syncthreads();                                                           // zero granules written before anybody blends
+        issue(0);
+        float* d = dst;
+        for (int st = 0; st < nst; ++st) {
+            if (st + 1 < nst) { issue(st + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                                       // everybody's copies of this stage have landed
+            const int cn = min(cgs, p.C - st * cgs);
+            if (live) {
+                const float* sc = stage[st & 1];
+#pragma unroll 2
+                for (int ci = 0; ci < cn; ++ci, sc += chf, d += bins) {
+                    float v = __fmaf_rn(sc[o_lt], wlt, 0.0f);
+                    v = __fmaf_rn(sc[o_rt], wrt, v);
+                    v = __fmaf_rn(wrb, sc[o_rb], v);
+                    v = __fmaf_rn(sc[o_lb], wlb, v);
+                    *d = v;
+                }
+            }
+            __syncthreads();                                                       // the buffer may be refilled (stage st + 2)
+        }
+        if (full_idx && live) {                                                    // legacy [N,C,PH,PW] centre tensors
+            for (int c = 0; c < p.C; ++c) {
+                p.idx_x[((size_t)n * p.C + c) * bins + obin] = ccx;
+                p.idx_y[((size_t)n * p.C + c) * bins + obin] = ccy;
+            }
+        }
+        return;
+    }
+
+    // ---- fallback: nothing to load, footprint too large, or unaligned rows ----
+    if (!live) return;
+    if (nrows == 0) {
+        // no bin of this block loads anything (the zero tail pw > roi_pooled_width, or a RoI off the image): the reference's
+        // sum of four 0-weight products, i.e. weights * 0 -- NaN weights (non-finite centre) still give NaN
+        const float v = __fmaf_rn(0.0f, wlb, __fmaf_rn(wrb, 0.0f, __fmaf_rn(0.0f, wrt, __fmaf_rn(0.0f, wlt, 0.0f))));
+        float* d = dst;
+        for (int c = 0; c < p.C; ++c, d += bins) *d = v;
+        if (full_idx)
+            for (int c = 0; c < p.C; ++c) {
+                p.idx_x[((size_t)n * p.C + c) * bins + obin] = ccx;
+                p.idx_y[((size_t)n * p.C + c) * bins + obin] = ccy;
+            }
+        return;
+    }
+    const float* top = plane0 + (unsigned)gt * (unsigned)p.W + (unsigned)gl;
+    const float* bot = top + p.W;
+#pragma unroll 1
+    for (int c = 0; c < p.C; ++c) {
+        const size_t po = (size_t)c * HW;
+        const float lt = ldg_pred_f32<0>(top + po, code & C_LT), rt = ldg_pred_f32<4>(top + po, code & C_RT);
+        const float lb = ldg_pred_f32<0>(bot + po, code & C_LB), rb = ldg_pred_f32<4>(bot + po, code & C_RB);
+        float v = __fmaf_rn(lt, wlt, 0.0f);
+        v = __fmaf_rn(rt, wrt, v);
+        v = __fmaf_rn(wrb, rb, v);
+        v = __fmaf_rn(lb, wlb, v);
+        dst[(size_t)c * bins] = v;
+        if (full_idx) {
+            p.idx_x[((size_t)n * p.C + c) * bins + obin] = ccx;
+            p.idx_y[((size_t)n * p.C + c) * bins + obin] = ccy;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -485,6 +743,19 @@ cudaError_t launch_fwd_nchw(const FwdParams& p0, const Opts& o, cudaStream_t s) 
             cfg.attrs = at;
             cfg.numAttrs = pdl ? 1 : 0;
             return cudaLaunchKernelEx(&cfg, rroi_fwd_nchw_tma_kernel, p, maps.m[0], maps.m[1], maps.m[2], maps.m[3]);
+        }
+    }
+    // Row-segment staging (rroi_fwd_nchw_rows_kernel) vs the gather kernel, measured on B200 (profiles/r02_sweep_nchw.txt):
+    // cfg4's per-GPU batch 130.6 vs 180.5 us, cfg1 on 8 streams 3.91 vs 5.58 us per launch -- but one cfg1 launch ALONE
+    // 20.2 vs 9.7 us (128 CTAs, each a chain of 8 dependent stage loads).  So: staged when the launch, together with the
+    // launches the caller overlaps with it, fills the machine; gather otherwise.  variant 1 / 2 force gather / staged.
+    {
+        const long long rtiles = (long long)p.N * ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
+        const bool staged = o.variant == 2 || (o.variant == 0 && o.nchw_cg == 0 && p.idx_mode != IDX_FULL &&
+                                               rtiles * (o.concurrency > 1 ? o.concurrency : 1) >= 148 * 4);
+        if (staged) {
+            p.tiles = ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
+            return launch_1d(rroi_fwd_nchw_rows_kernel, rtiles, 256, p, s, pdl);
         }
     }
     switch (o.nchw_cg) {     // channels in flight per lane

@@ -375,6 +375,38 @@ def test_nchw_tma_staged_forward_equals_gather_kernel_and_oracle(oracle, cuda, C
         Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")
 
 
+@pytest.mark.parametrize("C,H,W,scale,ph,pw,rois", [
+    (64, 180, 320, 0.25, 8, 64, None),                                         # cfg1
+    (7, 90, 160, 0.25, 8, 64, None),                                           # fewer channels than one stage holds
+    (3, 276, 500, 1.0, 44, 349, "test2"),                                      # the reference's test2.py scenario: PH = 44, ragged blocks
+    (16, 64, 64, 1.0, 8, 64, [[0, 32, 32, 60, 200, 33], [0, 10, 50, 40, 64, -70], [0, 30, 30, 62, 500, 90]]),  # footprints > 96 rows: gather fallback
+    (5, 33, 50, 0.5, 5, 13, None),                                             # W % 4 != 0: gather fallback; ragged block
+    (40, 45, 80, 0.25, 8, 64, "stress"),
+])
+def test_nchw_row_segment_staged_forward_equals_oracle(oracle, cuda, C, H, W, scale, ph, pw, rois):
+    """The NCHW forward that stages exactly the row segments a tile touches (rroi_fwd_nchw_rows_kernel, opts.variant = 2)
+    agrees bit for bit with the oracle and the gather kernel, centres included, also through the legacy [N,C,PH,PW] centres."""
+    from fots.pytorch_b200 import _cabi
+    B = 2
+    feats = WL.features(C + H, B, C, H, W)
+    if rois is None:
+        r = np.concatenate([WL.random_rois(3 + i, 24, i, img_w=int(W / scale), img_h=int(H / scale)) for i in range(B)], 0)
+        r[0, 1:3] = (2.0, 3.0)
+    elif rois == "test2":
+        r, _, _ = WL.test2_rois()
+    elif rois == "stress":
+        r = WL.stress_rois(91, 150, B, int(W / scale), int(H / scale))
+    else:
+        r = np.array(rois, np.float32)
+    want, wx, wy = oracle.forward(feats, r, ph, pw, scale, threads=0)
+    got, ix, iy = Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(variant=2))
+    Hh.assert_bit_equal(got, want, "row-staged NCHW forward")
+    Hh.assert_bit_equal(ix, wx[:, 0], "idx_x")
+    Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")
+    got2, _, _ = Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(variant=2, rois_ready=True, pdl=True))
+    Hh.assert_bit_equal(got2, want, "row-staged NCHW forward, RoIs ready")
+
+
 @pytest.mark.parametrize("layout", ["nhwc", "nchw"])
 @pytest.mark.parametrize("order", ["grouped", "grouped_with_empty_images", "shuffled", "crowded_image"])
 def test_backward_chunked_zero_fill_and_scatter(oracle, cuda, order, layout):

@@ -100,6 +100,7 @@ def sweep_nchw():
         for cg in (2, 4, 8):
             point(layout="nchw", images=images, streams=S, nchw_cg=cg, rois_ready=True)
         point(layout="nchw", images=images, streams=S, nchw_tma=1)
+        point(layout="nchw", images=images, streams=S, variant=2, rois_ready=True)
 
 
 if __name__ == "__main__":
