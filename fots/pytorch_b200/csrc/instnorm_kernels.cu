@@ -153,6 +153,184 @@ __global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __rest
     }
 }
 
+// ---- single-pass InstanceNorm for instances that fit in a cluster's shared memory --------------------------------
+// The two-pass form above costs three launches (memset, statistics, apply) and reads x twice.  Most InstanceNorms of the
+// step act on small instances (stages 2-4 of the feeder: <= 3.7 MB per image; the recogniser: 131 KB per RoI), where the
+// launches' ramp and tail cost as much as the data.  Here ONE launch does it: a cluster of CS CTAs owns one (image, slice
+// of the channels); every CTA loads its share of the pixels ONCE into shared memory while accumulating per-channel
+// sums, the per-CTA partial sums are exchanged through distributed shared memory (each CTA adds the CS partials in rank
+// order: deterministic, no atomics, no workspace), and the normalised / residual-added / activated tensor is written
+// from the shared-memory copy.  x is read from HBM exactly once.
+__device__ __forceinline__ uint32_t in_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void in_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
+    return v;
+}
+
+// grid (CS * slices, B), cluster (CS, 1, 1).  Cs = channels per slice (multiple of 8, Cs / 8 divides 256).
+template <bool kResidual>
+__global__ void __launch_bounds__(kThreads) in_fused_cluster_kernel(const Bf16x8* __restrict__ x, Bf16x8* __restrict__ y,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const Bf16x8* __restrict__ res, int HW, int C, int Cs, int CS,
+                                                                     int rows_per_cta, float eps, float slope) {
+    extern __shared__ __align__(16) uint8_t in_smem[];
+    const int G = Cs / 8, Gall = C / 8;
+    Bf16x8* const slab = reinterpret_cast<Bf16x8*>(in_smem);                                   // [rows_per_cta * G]
+    float* const red = reinterpret_cast<float*>(in_smem + (size_t)rows_per_cta * G * 16);      // [256][17] block reduction
+    float* const part = red + kThreads * 17;                                                   // [2 * Cs] this CTA's partial sums
+    float* const coef = part + 2 * Cs;                                                         // [2 * Cs] scale, shift
+    const uint32_t rank = in_cluster_rank();
+    const int slice = blockIdx.x / CS, b = blockIdx.y;
+    const int r0 = (int)rank * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+    const int g = threadIdx.x % G;                                  // this thread's channel group (G divides 256)
+    const size_t base = ((size_t)b * HW + r0) * Gall + (size_t)slice * G;
+
+    // ---- phase 1: load the slab once, keep it in shared memory, accumulate the sums
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0f;
+    constexpr int U = 4;
+    const int nrows = max(r1 - r0, 0), nph = kThreads / G, phase = threadIdx.x / G;   // thread -> rows phase, phase + nph, ...
+    // every 16-byte vector of the slab goes straight to shared memory with cp.async: no registers are held, so the WHOLE
+    // slab (up to 160 KB) is in flight at once -- with one resident CTA per SM that is what hides the HBM latency
+    // (register-staged loads, 4 per thread, kept only 16 KB in flight per SM and ran at a third of the bandwidth)
+    {
+        const uint32_t slab_s = (uint32_t)__cvta_generic_to_shared(slab);
+        for (int row = phase; row < nrows; row += nph)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slab_s + (uint32_t)((row * G + g) * 16)),
+                         "l"(x + base + (size_t)row * Gall + g) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    for (int row = phase; row < nrows; row += nph) {            // this thread sums exactly the vectors it copied
+        float f[8];
+        unpack8(slab[row * G + g], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[threadIdx.x * 17 + k] = s[k]; red[threadIdx.x * 17 + 8 + k] = q[k]; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * 16; idx += kThreads) {
+        const int gg = idx / 16, k = idx % 16;
+        float acc = 0.0f;
+        for (int ph = 0; ph < nph; ++ph) acc += red[(ph * G + gg) * 17 + k];
+        part[(k >> 3) * Cs + gg * 8 + (k & 7)] = acc;               // [sum | sumsq][channel of the slice]
+    }
+    in_cluster_sync();                                              // every CTA's partials are visible cluster-wide
+
+    // ---- statistics of the whole instance: add the CS partials in rank order (every CTA gets the same bits)
+    for (int c = threadIdx.x; c < Cs; c += kThreads) {
+        double sum = 0.0, sq = 0.0;
+        for (int rk = 0; rk < CS; ++rk) {
+            sum += (double)ld_dsmem_f32(part + c, (uint32_t)rk);
+            sq += (double)ld_dsmem_f32(part + Cs + c, (uint32_t)rk);
+        }
+        const double m = sum / HW;
+        double var = sq / HW - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = rsqrtf((float)var + eps), mean = (float)m;
+        const int cg = slice * Cs + c;
+        const float g0 = gamma ? gamma[cg] : 1.0f, b0 = beta ? beta[cg] : 0.0f;
+        coef[c] = rstd * g0;
+        coef[Cs + c] = b0 - mean * rstd * g0;
+    }
+    in_cluster_sync();                                              // peers are done reading this CTA's partials; coef visible to the CTA
+
+    // ---- phase 2: normalise from shared memory
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = coef[g * 8 + k]; sh[k] = coef[Cs + g * 8 + k]; }
+    for (int row = phase; row < nrows; row += U * nph) {
+        Bf16x8 rv[U];
+        if (kResidual) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int rr = row + u * nph;
+                if (rr < nrows) rv[u] = ld8(res + base + (size_t)rr * Gall + g);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = row + u * nph;
+            if (rr >= nrows) break;
+            float f[8], o[8];
+            unpack8(slab[rr * G + g], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(f[k], sc[k], sh[k]);
+            if (kResidual) {
+                float rr8[8];
+                unpack8(rv[u], rr8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] += rr8[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = o[k] > 0.0f ? o[k] : o[k] * slope;
+            y[base + (size_t)rr * Gall + g] = pack8(o);
+        }
+    }
+}
+
+// Shape of the single-pass launch, or false when the instance does not fit: cluster size CS (<= 8, portable), channel
+// slices, rows per CTA, dynamic shared memory.
+struct FusedPlan { int CS, slices, Cs, rows; size_t smem; };
+// MEASURED on B200 (tools/in_bench.py, profiles/r02_instnorm_single_pass.txt): with slabs of 115-160 KB only one CTA is
+// resident per SM and the load -> sums -> exchange -> apply phases of a cluster do not overlap with anything: 42 vs 23 us
+// (stage 2), 22 vs 17 (stage 3), 13 vs 12 (stage 4), 45 vs 42 (recogniser, 131 KB per RoI) against the two-pass kernels,
+// which run at full occupancy.  It wins where several instances share an SM: 12.2 vs 16.0 us on batch10_s (32 KB per
+// RoI).  Hence the automatic limit of 40 KB per CTA; `force` (tests, sweeps) allows the full 160 KB.
+static bool plan_fused(int HW, int C, FusedPlan* out, bool force) {
+    const size_t kSlabMax = (force ? 160 : 40) * 1024;
+    for (int slices = 1; slices <= 8; slices <<= 1) {
+        if (C % slices) break;
+        const int Cs = C / slices;
+        if (Cs < 32 || Cs % 8 != 0 || (kThreads % (Cs / 8)) != 0) break;        // >= 64-byte pixel segments; fixed channel group per thread
+        for (int CS = 1; CS <= 8; CS <<= 1) {
+            const int rows = (HW + CS - 1) / CS;
+            const size_t slab = (size_t)rows * Cs * 2;
+            if (slab <= kSlabMax) {
+                out->CS = CS; out->slices = slices; out->Cs = Cs; out->rows = rows;
+                out->smem = slab + (size_t)kThreads * 17 * 4 + (size_t)4 * Cs * 4;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <bool kResidual>
+static cudaError_t launch_fused(const FusedPlan& pl, const void* x, void* y, const float* gamma, const float* beta, const void* residual,
+                                int B, int HW, int C, float eps, float slope, cudaStream_t stream) {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        e = cudaFuncSetAttribute(in_fused_cluster_kernel<kResidual>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pl.CS * pl.slices), (unsigned)B);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, in_fused_cluster_kernel<kResidual>, static_cast<const Bf16x8*>(x), static_cast<Bf16x8*>(y), gamma, beta,
+                              static_cast<const Bf16x8*>(residual), HW, C, pl.Cs, pl.CS, pl.rows, eps, slope);
+}
+
 // ---- fused top-down merge: y = (up(a_lo) | c_hi) + b_hi * (up(sigmoid(g_lo)) | 1) --------------------------------
 // thread = one output pixel x 8 channels; consecutive threads on consecutive channel groups (16-byte accesses).
 struct Lerp { int i0, i1; float l0, l1; };
@@ -262,12 +440,28 @@ extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi,
     return RROI_B200_OK;
 }
 
+// A/B switch for sweeps and tests (fots_b200_instnorm_set_single_pass): the single-pass kernel is the default
+static int g_in_single_pass = 1;          // 0 = never, 1 = automatic (small instances), 2 = whenever the instance fits
+extern "C" int fots_b200_instnorm_set_single_pass(int mode) {
+    if (mode < 0 || mode > 2) return RROI_B200_ERR_INVALID_ARG;
+    g_in_single_pass = mode;
+    return RROI_B200_OK;
+}
+
 static int instnorm_impl(const void* x, void* y, const float* gamma, const float* beta, const void* residual,
                          double* workspace, int B, int HW, int C, float eps, float slope, int crelu, bool have_stats,
                          cudaStream_t stream) {
     if (!x || !y || !workspace || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || C > 1024 || (C / 8) > kThreads ||
         ((gamma == nullptr) != (beta == nullptr)) || (crelu && residual))
         return RROI_B200_ERR_INVALID_ARG;
+    // small instances: one launch, x read once (single-pass cluster kernel); B >= 65536 exceeds gridDim.y
+    FusedPlan pl;
+    if (!have_stats && !crelu && B < 65536 && g_in_single_pass && plan_fused(HW, C, &pl, g_in_single_pass == 2)) {
+        const cudaError_t ef = residual ? launch_fused<true>(pl, x, y, gamma, beta, residual, B, HW, C, eps, slope, stream)
+                                        : launch_fused<false>(pl, x, y, gamma, beta, nullptr, B, HW, C, eps, slope, stream);
+        if (ef != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+        return RROI_B200_OK;
+    }
     const int G = C / 8;
     const int nphase = kThreads / G;
     // enough CTAs for a few waves, at least a handful of rows per thread

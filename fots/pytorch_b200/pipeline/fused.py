@@ -18,6 +18,8 @@ def _lib():
         L.fots_b200_instnorm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
         L.fots_b200_instnorm_apply_nhwc_bf16.restype = i
         L.fots_b200_instnorm_apply_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, f, i, vp]
+        L.fots_b200_instnorm_set_single_pass.restype = i
+        L.fots_b200_instnorm_set_single_pass.argtypes = [i]
         L.fots_b200_maxpool_h2_nhwc_bf16.restype = i
         L.fots_b200_maxpool_h2_nhwc_bf16.argtypes = [vp, vp, i, i, i, i, vp]
         L.fots_b200_fpn_merge_nhwc_bf16.restype = i
@@ -39,6 +41,12 @@ def eligible(x, residual=None, weight=None, bias=None):
         ok = (residual.dtype == torch.bfloat16 and residual.shape == x.shape
               and residual.is_contiguous(memory_format=torch.channels_last))
     return ok
+
+
+def set_single_pass(mode):
+    """A/B switch (sweeps, tests): 0 / False = the three-launch two-pass InstanceNorm everywhere; 1 / True = automatic (the
+    default: single-pass cluster kernel for instances of <= 40 KB per CTA); 2 = single-pass whenever the instance fits."""
+    _cabi.check(_lib().fots_b200_instnorm_set_single_pass(int(mode)), "fots_b200_instnorm_set_single_pass")
 
 
 def workspace(device, numel):

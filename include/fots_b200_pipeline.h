@@ -152,6 +152,10 @@ int fots_b200_conv2d_strided_nhwc_bf16(const void* x, const void* w, const float
 int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
                                        const void* residual, const double* stats, int B, int HW, int C,
                                        float eps, float slope, int crelu, cudaStream_t stream);
+/* fots_b200_instnorm_nhwc_bf16 takes ONE launch (a cluster per instance keeps it in shared memory, x read once) for small
+ * instances (<= 40 KB per CTA: several instances per SM; measured slower than the two-pass form above that).
+ * mode 0 = never (A/B timing), 1 = automatic (default), 2 = whenever the instance fits 160 KB per CTA (tests, sweeps). */
+int fots_b200_instnorm_set_single_pass(int mode);
 /*
  * The feature extractor's first layer (tools/models.py:250-251: Conv2d(3, 16, 3, stride 1, pad 1, bias=False)) fused
  * with the statistics pass of the CReLU_IN that follows it (tools/models.py:41-48); csrc/stem_conv.cu.

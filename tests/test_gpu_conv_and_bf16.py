@@ -246,3 +246,39 @@ def test_recogniser_on_tensor_cores_matches_library_path(cuda):
     assert a.shape == b.shape == (6, 89, 64)
     assert float((a - b).abs().max()) < 0.15 and float((a - b).abs().mean()) < 0.02      # log-probabilities
     assert float((a.argmax(1) == b.argmax(1)).float().mean()) > 0.9
+
+
+@pytest.mark.parametrize("B,C,H,W,residual", [
+    (8, 128, 90, 160, True),      # stage 2 at 720p: 4 channel slices x 8-CTA clusters
+    (2, 256, 45, 80, True),       # stage 3
+    (2, 512, 23, 40, False),      # stage 4: 64 channel groups per pixel
+    (40, 128, 8, 64, False),      # recogniser batch5: one CTA per RoI
+    (40, 256, 1, 64, False),      # batch10_s
+    (3, 64, 37, 53, True),        # ragged rows per CTA
+    (1, 32, 5, 7, False),         # tiny
+    (2, 64, 180, 320, False),     # does not fit: two-pass form
+])
+def test_single_pass_cluster_instancenorm_equals_two_pass_and_torch(cuda, B, C, H, W, residual):
+    """in_fused_cluster_kernel (one launch, instance kept in a cluster's shared memory, partial sums exchanged through
+    distributed shared memory) against the two-pass kernels and against torch's InstanceNorm in fp32."""
+    from fots.pytorch_b200.pipeline import fused
+    g = torch.Generator().manual_seed(B * 100 + C + H)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.7 + 0.3).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(B, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if residual else None
+    gamma, beta = torch.randn(C, generator=g).to(cuda), torch.randn(C, generator=g).to(cuda)
+    fused.set_single_pass(2)                       # whenever the instance fits (automatic: only small instances)
+    try:
+        one = fused.instnorm_act(x, gamma, beta, 1e-5, 0.01, r)
+        again = fused.instnorm_act(x, gamma, beta, 1e-5, 0.01, r)
+        fused.set_single_pass(0)
+        two = fused.instnorm_act(x, gamma, beta, 1e-5, 0.01, r)
+    finally:
+        fused.set_single_pass(1)
+    ref = F.instance_norm(x.float(), weight=gamma, bias=beta, eps=1e-5)
+    if residual:
+        ref = ref + r.float()
+    ref = F.leaky_relu(ref, 0.01)
+    scale = float(ref.abs().max())
+    assert float((one.float() - ref).abs().max()) <= 2.0 ** -7 * scale + 1e-3
+    assert float((one.float() - two.float()).abs().max()) <= 2.0 ** -7 * scale      # same statistics up to summation order
+    assert torch.equal(one, again)                                                  # deterministic: no atomics
