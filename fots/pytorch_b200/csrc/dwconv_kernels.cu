@@ -1,0 +1,135 @@
+// dwconv_kernels.cu -- depthwise 3x3 convolution (groups == channels, pad 1, stride 1 or 2, no bias) of channels-last
+// bf16 activations: the first halves of the depthwise-separable residual blocks of stages 3-4 and of the two
+// up-convolutions of the top-down merge (/root/reference/tools/models.py:59-111 BasicBlockSepIn, :300-301 upconv1/2).
+//
+// 9 MACs per output value: pure bandwidth (read x once, write y once).  cuDNN's channels-last depthwise kernel
+// (conv2d_c1_k1_nhwc_specialized) reaches about a quarter of the copy roofline on these shapes (18 us for a 14.7 MB map,
+// 140 us for the 236 MB one); a first hand-written attempt in round 1 read its nine taps straight from global memory and
+// was L1-bound.  Here a CTA stages its input tile (+ halo) for 64 channels in shared memory with cp.async (every pixel
+// is 128 contiguous bytes; the whole tile is in flight at once, out-of-image vectors are zero-filled by the copy), and
+// every thread produces a strip of 4 horizontally adjacent outputs for 8 channels, so each staged vector is read from
+// shared memory once per (row, strip) instead of once per tap: 18 LDS.128 per 4 outputs at stride 1, 27 at stride 2.
+// fp32 accumulation in the order (r, s) = (0,0) .. (2,2), one rounding to bf16.
+#include "../../../include/fots_b200_pipeline.h"
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int kTW = 16;            // output pixels per tile row: 4 strips of 4
+constexpr int kCB = 64;            // channels per CTA: 8 vectors of 8 bf16
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// grid (tiles_w * tiles_h, C / 64, N); block TH * 4 strips * 8 vectors.
+template <int STRIDE, int TH>
+__global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
+                                                            uint4* __restrict__ y, int H, int W, int C, int Ho, int Wo, int tiles_w) {
+    constexpr int IH = (TH - 1) * STRIDE + 3, IW = (kTW - 1) * STRIDE + 3;      // input tile incl. halo
+    constexpr int NT = TH * 32;
+    __shared__ __align__(16) uint4 tile[IH * IW * 8];
+    const int tile_id = blockIdx.x, ty = tile_id / tiles_w, tx = tile_id - ty * tiles_w;
+    const int c0 = blockIdx.y * kCB, n = blockIdx.z;
+    const int oy0 = ty * TH, ox0 = tx * kTW;
+    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+    const int CV = C / 8;                                                          // 16-byte vectors per pixel
+    const uint4* img = x + (size_t)n * H * W * CV + c0 / 8;
+
+    // ---- stage the input tile: thread -> (pixel, vector); consecutive threads = the 8 vectors (128 B) of one pixel
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    for (int i = threadIdx.x; i < IH * IW * 8; i += NT) {
+        const int v = i & 7, p = i >> 3, r = p / IW, c = p - r * IW;
+        const int iy = iy0 + r, ix = ix0 + c;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const uint4* src = ok ? img + ((size_t)iy * W + ix) * CV + v : img;       // a valid address even when nothing is read
+        const uint32_t nbytes = ok ? 16u : 0u;                                    // 0: the 16 bytes are zero-filled (the padding)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + (uint32_t)i * 16u), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- this thread's 8 channels x 9 taps of weights (fp32 registers); w is [C][3][3]
+    const int v = threadIdx.x & 7, strip = threadIdx.x >> 3;                       // strip = row * 4 + quarter
+    const int row = strip >> 2, q4 = strip & 3;
+    float wr[9][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[t][k] = __bfloat162float(wgt[(size_t)(c0 + v * 8 + k) * 9 + t]);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    float acc[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[o][k] = 0.0f;
+    constexpr int NCOL = 3 * STRIDE + 3;                                           // input columns a strip of 4 outputs touches
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint4* trow = tile + ((row * STRIDE + r) * IW + q4 * 4 * STRIDE) * 8 + v;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            float f[8];
+            unpack8(trow[j * 8], f);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int s = j - o * STRIDE;                                       // tap column of output o fed by input column j
+                if (s >= 0 && s < 3) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[o][k] = fmaf(f[k], wr[r * 3 + s][k], acc[o][k]);
+                }
+            }
+        }
+    }
+    const int oy = oy0 + row;
+    if (oy < Ho) {
+        uint4* out = y + (((size_t)n * Ho + oy) * Wo) * CV + c0 / 8 + v;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int ox = ox0 + q4 * 4 + o;
+            if (ox < Wo) {
+                uint4 pk;
+                pk.x = pack2(acc[o][0], acc[o][1]); pk.y = pack2(acc[o][2], acc[o][3]);
+                pk.z = pack2(acc[o][4], acc[o][5]); pk.w = pack2(acc[o][6], acc[o][7]);
+                out[(size_t)ox * CV] = pk;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int fots_b200_dwconv3x3_nhwc_bf16(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride,
+                                             cudaStream_t stream) {
+    if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % kCB != 0 || (stride != 1 && stride != 2) || N > 65535 ||
+        C / kCB > 65535)
+        return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    const int tiles_w = (Wo + kTW - 1) / kTW;
+    const uint4* xp = static_cast<const uint4*>(x);
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
+    uint4* yp = static_cast<uint4*>(y);
+    if (stride == 1) {
+        constexpr int TH = 8;
+        const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
+        dwconv3x3_kernel<1, TH><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w);
+    } else {
+        constexpr int TH = 4;
+        const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
+        dwconv3x3_kernel<2, TH><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}

@@ -1,0 +1,106 @@
+// heads_kernels.cu -- the three EAST-style detection heads of the feeder in ONE pass over the shared feature map
+// (/root/reference/tools/models.py:440-456: act = Conv2d(256, 1, 1), rbox = Conv2d(256, 4, 1), angle = Conv2d(256, 2, 1);
+// seg = sigmoid(act), rbox = sigmoid(.) * 128, angle = sigmoid(.) * 2 - 1 normalised to unit length).
+//
+// The library path is three cuBLAS GEMMs with 1, 4 and 2 output columns -- each reads the whole 256-channel map -- plus
+// about fifteen element-wise launches.  Seven output columns are exactly one N = 8 tensor-core tile: a warp takes 16
+// pixels, loads their 256 channels once (16-byte vectors, 64 contiguous bytes per pixel and instruction), multiplies them
+// by the 8 x 256 weight block held in registers with mma.sync.m16n8k16 (fp32 accumulation), and finishes sigmoid,
+// scaling and the (sin, cos) normalisation in the accumulator registers.  HBM-bound: the map is read once, 28 bytes per
+// pixel are written.  mma.sync, not tcgen05: N = 8 is below a UMMA tile and the kernel is bound by the read of x.
+#include "../../../include/fots_b200_pipeline.h"
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Logical k of the MMA <-> physical channel.  Lane (g = lane / 4, t = lane % 4) loads, for load m, the 8 channels
+// 32 m + 8 t .. + 7 of pixel rows g and g + 8 (the four t-lanes of a pixel read 64 contiguous bytes); k-step 2m consumes
+// the first four of them (k = 2t, 2t+1 | 2t+8, 2t+9), k-step 2m+1 the last four.  The B fragment of lane (g, t) is head g at
+// the same channels, so the permutation cancels in the dot product.
+// wq: [8 heads][C] bf16, column order {act, 0, rbox0..3, angle0, angle1};  bias: [8] fp32 in the same order.
+template <int C>
+__global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wq,
+                                                    const float* __restrict__ bias, float* __restrict__ seg, float* __restrict__ rbox,
+                                                    float* __restrict__ angle, long long npix, int HW) {
+    constexpr int NL = C / 32;                        // 16-byte loads per pixel row and lane
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // this lane's weights: head g, channels 32 m + 8 t .. + 7 -> four 32-bit registers per m
+    uint32_t wb[NL][4];
+#pragma unroll
+    for (int m = 0; m < NL; ++m) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(wq + (size_t)g * C + m * 32 + t * 8));
+        wb[m][0] = v.x; wb[m][1] = v.y; wb[m][2] = v.z; wb[m][3] = v.w;
+    }
+    const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long ntiles = (npix + 15) / 16;
+    constexpr int CV = C / 8;
+    for (long long tile = warp0; tile < ntiles; tile += nwarps) {
+        const long long p0 = tile * 16 + g, p1 = p0 + 8;
+        const bool ok0 = p0 < npix, ok1 = p1 < npix;
+        uint4 xa[NL], xb[NL];
+#pragma unroll
+        for (int m = 0; m < NL; ++m) {
+            xa[m] = ok0 ? __ldg(x + p0 * CV + m * 4 + t) : make_uint4(0, 0, 0, 0);
+            xb[m] = ok1 ? __ldg(x + p1 * CV + m * 4 + t) : make_uint4(0, 0, 0, 0);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < NL; ++m) {
+            mma_16816(acc, xa[m].x, xb[m].x, xa[m].y, xb[m].y, wb[m][0], wb[m][1]);
+            mma_16816(acc, xa[m].z, xb[m].z, xa[m].w, xb[m].w, wb[m][2], wb[m][3]);
+        }
+        // acc[0], acc[1] = (pixel p0, columns 2t, 2t+1); acc[2], acc[3] = (pixel p1, same columns)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const long long p = half ? p1 : p0;
+            if (!(half ? ok1 : ok0)) continue;
+            const float v0 = acc[2 * half] + b0, v1 = acc[2 * half + 1] + b1;
+            const long long b = p / HW, hw = p - b * HW;
+            if (t == 0) {
+                seg[p] = sigmoid_f(v0);
+            } else if (t < 3) {
+                float* r = rbox + (b * 4 + (t - 1) * 2) * HW + hw;
+                r[0] = sigmoid_f(v0) * 128.0f;
+                r[HW] = sigmoid_f(v1) * 128.0f;
+            } else {
+                const float s = sigmoid_f(v0) * 2.0f - 1.0f, c = sigmoid_f(v1) * 2.0f - 1.0f;
+                const float nrm = sqrtf(s * s + c * c);
+                float* a = angle + (b * 2) * HW + hw;
+                a[0] = s / nrm;
+                a[HW] = c / nrm;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const float* bias, float* seg, float* rbox, float* angle,
+                                         int B, int H, int W, int C, cudaStream_t stream) {
+    if (!x || !wq || !bias || !seg || !rbox || !angle || B <= 0 || H <= 0 || W <= 0) return RROI_B200_ERR_INVALID_ARG;
+    if (C != 128 && C != 256 && C != 512) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    const long long npix = (long long)B * H * W;
+    const long long tiles = (npix + 15) / 16;
+    long long ctas = (tiles + 7) / 8;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    const uint4* xp = static_cast<const uint4*>(x);
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(wq);
+    if (C == 128) heads_kernel<128><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    else if (C == 256) heads_kernel<256><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    else heads_kernel<512><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}

@@ -288,11 +288,12 @@ struct FusedPlan { int CS, slices, Cs, rows; size_t smem; };
 // RoI).  Hence the automatic limit of 40 KB per CTA; `force` (tests, sweeps) allows the full 160 KB.
 static bool plan_fused(int HW, int C, FusedPlan* out, bool force) {
     const size_t kSlabMax = (force ? 160 : 40) * 1024;
-    for (int slices = 1; slices <= 8; slices <<= 1) {
+    const int max_split = force ? 8 : 1;              // automatic: whole instance in ONE CTA (no channel slices, no cluster)
+    for (int slices = 1; slices <= max_split; slices <<= 1) {
         if (C % slices) break;
         const int Cs = C / slices;
         if (Cs < 32 || Cs % 8 != 0 || (kThreads % (Cs / 8)) != 0) break;        // >= 64-byte pixel segments; fixed channel group per thread
-        for (int CS = 1; CS <= 8; CS <<= 1) {
+        for (int CS = 1; CS <= max_split; CS <<= 1) {
             const int rows = (HW + CS - 1) / CS;
             const size_t slab = (size_t)rows * Cs * 2;
             if (slab <= kSlabMax) {

@@ -420,7 +420,7 @@ rroi_fwd_nchw_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap 
 //   4. the blend reads its four taps from shared memory (predicated: an unloaded tap is 0, as in the gather kernel),
 //      same 4-FFMA chain, and stores 32 consecutive pw per warp (128-byte coalesced).
 // Tiles whose footprint does not fit (more than 96 rows or 20 KB per channel) or planes whose rows are not 16-byte
-// aligned take the gather loop inside the same kernel.  Bit-identical to the gather kernel and the oracle.
+// aligned take the gather loop inside the same kernel.  Bit-identical to the gather kernel (and to the reference kernel, see tests/).
 constexpr int kRowsMax = 96;                      // image rows a tile's footprint may span
 constexpr int kStageFloats = 5120;                // floats per stage (20 KB); two stages
 constexpr int kGranMax = kStageFloats / 4;        // granules of one channel

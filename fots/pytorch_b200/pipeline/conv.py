@@ -19,9 +19,10 @@ FUSE_STATS = os.environ.get("FOTS_B200_TC_STATS", "0") != "0"
 #   0 = only the convolutions whose activation it fuses (conv6/8/9, layer0_1[0]);
 #   1 = + every other convolution of the recogniser (conv5/7/10_s in front of an InstanceNorm, conv11 with its 89 classes
 #       padded to 128 output channels): forward_ocr then contains no library call;
-#   2 = + the stride-1 3x3 convolutions of stages 1-2 and every 1x1 convolution of the feeder (FPN laterals, separable
-#       blocks' pointwise halves, up-convolutions).
-LEVEL = int(os.environ.get("FOTS_B200_TC_LEVEL", "1"))
+#   2 = + the 3x3 convolutions of stages 1-2 (stride 1 and 2), every 1x1 convolution of the feeder (FPN laterals, separable
+#       blocks' pointwise halves, up-convolutions, down-sampling branches with their BatchNorm folded) and the depthwise
+#       3x3 convolutions (csrc/dwconv_kernels.cu).  Default: measured 4.79 ms per 8-image step against 4.77 ms at level 1.
+LEVEL = int(os.environ.get("FOTS_B200_TC_LEVEL", "2"))
 
 
 def _lib():
@@ -38,6 +39,10 @@ def _lib():
         L.fots_b200_stem_conv3x3_c3_c16.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.fots_b200_stem_conv3x3_c3_c16_u8.restype = i
         L.fots_b200_stem_conv3x3_c3_c16_u8.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+        L.fots_b200_dwconv3x3_nhwc_bf16.restype = i
+        L.fots_b200_dwconv3x3_nhwc_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
+        L.fots_b200_heads_nhwc_bf16.restype = i
+        L.fots_b200_heads_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
         L.fots_b200_conv_set_tile.restype = i
         L.fots_b200_conv_set_tile.argtypes = [i]
         L._conv_bound = True
@@ -113,6 +118,63 @@ def apply(conv, x, slope=1.0, level=0):
     if slope == 1.0:
         return y
     return torch.relu(y) if slope == 0.0 else torch.nn.functional.leaky_relu(y, slope)
+
+
+def dw_eligible(x, conv):
+    """Depthwise 3x3, pad 1, stride 1 or 2, no bias, C % 64 == 0, on bf16 channels-last activations outside autograd."""
+    w = conv.weight
+    C = conv.in_channels
+    return (LEVEL >= 2 and input_ok(x) and w.dtype == torch.bfloat16 and conv.groups == C == conv.out_channels and C % 64 == 0
+            and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride in ((1, 1), (2, 2))
+            and conv.dilation == (1, 1) and conv.bias is None and conv.padding_mode == "zeros"
+            and not (torch.is_grad_enabled() and w.requires_grad))
+
+
+def dwconv(conv, x):
+    """conv(x) for a depthwise 3x3 nn.Conv2d through fots_b200_dwconv3x3_nhwc_bf16 when eligible, else the module."""
+    if not dw_eligible(x, conv):
+        return conv(x)
+    N, C, H, W = x.shape
+    st = conv.stride[0]
+    y = torch.empty((N, C, (H - 1) // st + 1, (W - 1) // st + 1), dtype=torch.bfloat16, device=x.device,
+                    memory_format=torch.channels_last)
+    w = conv.weight.reshape(C, 9)
+    if not w.is_contiguous():
+        w = w.contiguous()
+    with torch.cuda.device(x.device):
+        rc = _lib().fots_b200_dwconv3x3_nhwc_bf16(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, C, st,
+                                                  torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_dwconv3x3_nhwc_bf16")
+    return y
+
+
+def pack_heads(act, rbox, angle):
+    """The three head convolutions (Conv2d(C, 1, 1), Conv2d(C, 4, 1), Conv2d(C, 2, 1), all with bias) as the [8, C] bf16
+    block + [8] fp32 bias fots_b200_heads_nhwc_bf16 wants: rows {act, zeros, rbox0..3, angle0, angle1}."""
+    C = act.in_channels
+    w = torch.zeros((8, C), dtype=torch.bfloat16, device=act.weight.device)
+    b = torch.zeros((8,), dtype=torch.float32, device=act.weight.device)
+    w[0] = act.weight.detach()[0, :, 0, 0]
+    w[2:6] = rbox.weight.detach()[:, :, 0, 0]
+    w[6:8] = angle.weight.detach()[:, :, 0, 0]
+    b[0] = act.bias.detach().float()[0]
+    b[2:6] = rbox.bias.detach().float()
+    b[6:8] = angle.bias.detach().float()
+    return w.contiguous(), b.contiguous()
+
+
+def heads(x, packed):
+    """x bf16 channels-last [B, C, H, W] -> (seg [B,1,H,W], rbox [B,4,H,W], angle [B,2,H,W]) fp32 in one pass over x."""
+    B, C, H, W = x.shape
+    seg = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    rb = torch.empty((B, 4, H, W), dtype=torch.float32, device=x.device)
+    an = torch.empty((B, 2, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib().fots_b200_heads_nhwc_bf16(x.data_ptr(), packed[0].data_ptr(), packed[1].data_ptr(), seg.data_ptr(),
+                                              rb.data_ptr(), an.data_ptr(), B, H, W, C,
+                                              torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_heads_nhwc_bf16")
+    return seg, rb, an
 
 
 def stem_eligible(x, conv):

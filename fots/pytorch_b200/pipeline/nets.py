@@ -79,7 +79,7 @@ class _ResIN(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        res = x if self.downsample is None else self.downsample(x)
+        res = x if self.downsample is None else _downsample(self, x)
         y = _conv_in_act(self.conv1, self.bn1, x, 0.0, level=2)
         return _conv_in_act(self.conv2, self.bn2, y, 0.0, res, level=2)
 
@@ -99,11 +99,22 @@ class _ResSepIN(nn.Module):
         self.relu = nn.LeakyReLU(0.01, inplace=True)
 
     def forward(self, x):
-        res = x if self.downsample is None else self.downsample(x)
+        res = x if self.downsample is None else _downsample(self, x)
         s1, s2 = self.conv_sep1, self.conv2
-        y = _in_act(s1[2], tc.apply(s1[1], s1[0](x), 1.0, level=2), 0.01)      # pointwise halves: 1x1 GEMMs on the tcgen05 kernel
-        y = _in_act(s2[1], s2[0](y), 0.01)
+        # depthwise halves: csrc/dwconv_kernels.cu; pointwise halves: 1x1 GEMMs on the tcgen05 kernel
+        y = _in_act(s1[2], tc.apply(s1[1], tc.dwconv(s1[0], x), 1.0, level=2), 0.01)
+        y = _in_act(s2[1], tc.dwconv(s2[0], y), 0.01)
         return _in_act(s2[4], tc.apply(s2[3], y, 1.0, level=2), 0.01, res)
+
+
+def _downsample(block, x):
+    """The residual branch of a stage's first block: Conv2d(1x1, stride 2) + eval-mode BatchNorm2d (tools/models.py:319-324).
+    On the B200 inference path the BatchNorm is folded into the convolution's weights and bias (FOTSNet.to_b200) and the
+    strided 1x1 convolution runs on the tcgen05 kernel; otherwise the module itself."""
+    pack = getattr(block, "_ds_pack", None)
+    if pack is not None and tc.LEVEL >= 2 and not block.training and tc.input_ok(x) and x.size(1) % 64 == 0:
+        return tc.conv2d(x, pack[0], pack[1], (0, 0), 1.0, stride=pack[2])
+    return block.downsample(x)
 
 
 def _up(x, like):
@@ -178,6 +189,9 @@ class FOTSNet(nn.Module):
     def _heads(self, x):
         # the 1x1 convolutions may run in bf16 under autocast; the squashing and the (sin, cos) normalisation are
         # done in fp32 (in bf16 both angle components can round to exactly 0 -> 0/0)
+        packed = getattr(self, "_heads_pack", None)
+        if packed is not None and tc.LEVEL >= 2 and not self.training and tc.input_ok(x) and x.size(1) in (128, 256, 512):
+            return tc.heads(x, packed)                   # all three heads + squashing in one pass over x (csrc/heads_kernels.cu)
         seg = torch.sigmoid(self.act(x).float())
         rbox = torch.sigmoid(self.rbox(x).float()) * 128
         ang = torch.sigmoid(self.angle(x).float()) * 2 - 1
@@ -196,7 +210,7 @@ class FOTSNet(nn.Module):
             # inference fast path: each merge step is one fused kernel (upsample + attention gate + add)
             att = self.conv_attenton if self.attention else (lambda t: None)
             x = fused.fpn_merge(a_lo=f4, b_hi=f3, gate_logits_lo=att(f4))
-            up = lambda seq, t: pw(seq[1], seq[0](t))                   # depthwise 3x3 (library) + pointwise 1x1
+            up = lambda seq, t: pw(seq[1], tc.dwconv(seq[0], t))        # depthwise 3x3 + pointwise 1x1
             f2 = fused.fpn_merge(c_hi=up(self.upconv1, fused.fpn_merge(a_lo=x, size=f2.shape[2:])), b_hi=f2,
                                  gate_logits_lo=att(x))
             x = fused.fpn_merge(c_hi=up(self.upconv2, fused.fpn_merge(a_lo=f2, size=f1.shape[2:])), b_hi=f1,
@@ -248,7 +262,7 @@ class FOTSNet(nn.Module):
         re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
         batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
         self.to(device=device, memory_format=torch.channels_last)
-        self._conv11_pad = None
+        self._conv11_pad = self._heads_pack = None
         if inference:
             for m in self.modules():
                 if isinstance(m, nn.Conv2d):
@@ -262,6 +276,20 @@ class FOTSNet(nn.Module):
             bias = torch.zeros((cpad,), dtype=torch.float32, device=w.device)
             bias[:c11.out_channels] = c11.bias.detach().float()
             self._conv11_pad = (w.contiguous(memory_format=torch.channels_last), bias)
+            self._heads_pack = tc.pack_heads(self.act, self.rbox, self.angle)
+            # down-sampling branches: eval-mode BatchNorm folded into the 1x1 stride-2 convolution (bf16 weights, fp32 bias)
+            for m in self.modules():
+                ds = getattr(m, "downsample", None)
+                if isinstance(ds, nn.Sequential) and len(ds) == 2 and isinstance(ds[1], nn.BatchNorm2d) and ds[0].bias is None:
+                    conv, bn = ds
+                    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+                    w = (conv.weight.detach().float() * scale.view(-1, 1, 1, 1)).to(torch.bfloat16)
+                    b = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+                    m._ds_pack = (w.contiguous(memory_format=torch.channels_last), b, conv.stride[0])
+        else:
+            for m in self.modules():
+                if hasattr(m, "_ds_pack"):
+                    m._ds_pack = None
         return self
 
 

@@ -191,6 +191,23 @@ int fots_b200_stem_conv3x3_c3_c16_u8(const unsigned char* x, const void* w, void
 int fots_b200_gemm_bf16w(const void* A, int a_is_f32, const void* W, const float* bias, float* C, int M, int N, int K,
                          cudaStream_t stream);
 int fots_b200_bilstm_recurrent(const float* G, const void* Whh, float* Y, int T, int N, int H, cudaStream_t stream);
+/*
+ * Depthwise 3x3 convolution, pad 1, stride 1 or 2, no bias (the first halves of BasicBlockSepIn and of upconv1/2,
+ * tools/models.py:59-111, :300-301): x bf16 [N, H, W, C], w bf16 [C, 3, 3] (the storage of a [C, 1, 3, 3] weight),
+ * y bf16 [N, (H - 1) / stride + 1, (W - 1) / stride + 1, C]; C % 64 == 0.  HBM-bound; csrc/dwconv_kernels.cu.
+ */
+int fots_b200_dwconv3x3_nhwc_bf16(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride,
+                                  cudaStream_t stream);
+/*
+ * The detection heads in one pass (tools/models.py:440-456): seg = sigmoid(act(x)), rbox = sigmoid(rbox(x)) * 128,
+ * angle = normalise(sigmoid(angle(x)) * 2 - 1), three 1x1 convolutions with 1 + 4 + 2 output channels.
+ *   x     bf16 [B, H, W, C], C in {128, 256, 512}
+ *   wq    bf16 [8, C]: rows {act, zeros, rbox0, rbox1, rbox2, rbox3, angle0, angle1}   bias fp32 [8], same order
+ *   seg fp32 [B, 1, H, W]   rbox fp32 [B, 4, H, W]   angle fp32 [B, 2, H, W]   (NCHW, as the reference returns them)
+ * HBM-bound: x is read once (the library path reads it three times and launches ~15 element-wise kernels).
+ */
+int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const float* bias, float* seg, float* rbox, float* angle,
+                              int B, int H, int W, int C, cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 

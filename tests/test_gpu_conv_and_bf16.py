@@ -242,7 +242,9 @@ def test_recogniser_on_tensor_cores_matches_library_path(cuda):
             TC.ENABLED = True
     for ta, tb in zip(fa[0] + fa[3], fb[0] + fb[3]):
         assert ta.shape == tb.shape
-        assert float((ta.float() - tb.float()).abs().mean()) < 0.03 * float(tb.float().abs().mean()) + 1e-3
+        # ~60 layers each rounded to bf16 once, by different kernels on the two sides (every convolution, depthwise
+        # convolution, head and folded BatchNorm now runs hand-written): the paths drift apart by bf16 noise only
+        assert float((ta.float() - tb.float()).abs().mean()) < 0.05 * float(tb.float().abs().mean()) + 1e-3
     assert a.shape == b.shape == (6, 89, 64)
     assert float((a - b).abs().max()) < 0.15 and float((a - b).abs().mean()) < 0.02      # log-probabilities
     assert float((a.argmax(1) == b.argmax(1)).float().mean()) > 0.9
@@ -282,3 +284,81 @@ def test_single_pass_cluster_instancenorm_equals_two_pass_and_torch(cuda, B, C, 
     assert float((one.float() - ref).abs().max()) <= 2.0 ** -7 * scale + 1e-3
     assert float((one.float() - two.float()).abs().max()) <= 2.0 ** -7 * scale      # same statistics up to summation order
     assert torch.equal(one, again)                                                  # deterministic: no atomics
+
+
+@pytest.mark.parametrize("N,C,H,W,stride", [(2, 256, 45, 80, 1), (1, 128, 90, 160, 2), (3, 512, 23, 40, 1), (2, 256, 45, 80, 2),
+                                             (1, 64, 7, 5, 1), (1, 64, 7, 5, 2), (2, 256, 180, 320, 1), (1, 192, 33, 47, 2)])
+def test_depthwise_3x3_matches_torch_fp32(cuda, N, C, H, W, stride):
+    """fots_b200_dwconv3x3_nhwc_bf16 (shared-memory tile + halo, 4-output strips) vs torch's grouped convolution in fp32
+    on the same bf16 operands: one bf16 rounding of an fp32 sum of nine products."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(N + C + H + stride)
+    conv = torch.nn.Conv2d(C, C, 3, stride, 1, groups=C, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(C, 1, 3, 3, generator=g) / 3.0)
+    conv = conv.to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.randn(N, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        assert TC.dw_eligible(x, conv)
+        y = TC.dwconv(conv, x)
+        ref = F.conv2d(x.float(), conv.weight.float(), None, stride, 1, groups=C)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    err = (y.float() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-5
+    assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 256, 45, 80), (1, 256, 180, 320), (3, 128, 7, 9), (1, 512, 5, 3)])
+def test_fused_detection_heads_match_torch_fp32(cuda, B, C, H, W):
+    """fots_b200_heads_nhwc_bf16: act / rbox / angle 1x1 convolutions + sigmoid, x128, (sin, cos) normalisation in one pass
+    over the feature map, against the three nn.Conv2d + torch ops of FOTSNet._heads evaluated in fp32 on the same bf16
+    operands."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(B + C + H)
+    mk = lambda co: torch.nn.Conv2d(C, co, 1, bias=True)
+    act, rbox, angle = mk(1), mk(4), mk(2)
+    with torch.no_grad():
+        for m in (act, rbox, angle):
+            m.weight.copy_(torch.randn(m.weight.shape, generator=g) / C ** 0.5)
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g))
+    act, rbox, angle = (m.to(cuda).to(torch.bfloat16) for m in (act, rbox, angle))
+    x = torch.randn(B, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        seg, rb, an = TC.heads(x, TC.pack_heads(act, rbox, angle))
+        f = lambda m: F.conv2d(x.float(), m.weight.float(), m.bias.float())
+        want_seg = torch.sigmoid(f(act))
+        want_rb = torch.sigmoid(f(rbox)) * 128
+        a = torch.sigmoid(f(angle)) * 2 - 1
+        want_an = a / torch.sqrt((a * a).sum(1, keepdim=True))
+    assert seg.shape == want_seg.shape and rb.shape == want_rb.shape and an.shape == want_an.shape
+    assert float((seg - want_seg).abs().max()) <= 1e-4
+    assert float((rb - want_rb).abs().max()) <= 1e-2            # values up to 128
+    assert float((an - want_an).abs().max()) <= 2e-3            # the normalisation amplifies near |a| ~ 0
+
+
+def test_folded_batchnorm_downsample_branch_matches_module(cuda):
+    """FOTSNet.to_b200(inference=True) folds the eval-mode BatchNorm of every stage's 1x1 stride-2 down-sampling branch
+    (tools/models.py:319-324) into the convolution (bf16 weights, fp32 bias) and runs it on the strided tcgen05 kernel:
+    equal to conv -> BatchNorm of the module with non-trivial running statistics."""
+    from fots.pytorch_b200.pipeline import FOTSNet
+    from fots.pytorch_b200.pipeline import conv as TC
+    from fots.pytorch_b200.pipeline.nets import _downsample
+    torch.manual_seed(3)
+    net = FOTSNet(attention=True, nclass=89)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.4, 1.6); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.3)
+    net.to_b200(cuda, inference=True)
+    checked = 0
+    with torch.no_grad():
+        for stage, cin, hw in ((net.layer2, 64, (45, 80)), (net.layer3, 128, (23, 41)), (net.layer4, 256, (12, 20))):
+            block = stage[0]
+            assert block._ds_pack is not None
+            x = torch.randn(2, cin, *hw, device=cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            got = _downsample(block, x)
+            want = block.downsample[1](block.downsample[0](x).float())            # library conv, BatchNorm in fp32
+            assert got.shape == want.shape
+            assert float((got.float() - want).abs().max()) <= 2.0 ** -6 * float(want.abs().max()) + 1e-3
+            checked += 1
+    assert checked == 3 and TC.LEVEL >= 2
