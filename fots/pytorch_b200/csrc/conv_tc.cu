@@ -116,6 +116,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Same, for an operand whose 8-row groups are `sbo` bytes apart and whose first row is NOT on a 1024-byte boundary of the
+// swizzle pattern (single-box halo mode: the start is a whole number of 128-byte rows into the box the TMA wrote).
+// MEASURED on B200 (tools/halo_box_check.py): the tensor core applies the 128-byte swizzle to the absolute shared-memory
+// address bits, exactly as the TMA did when it wrote the box, so the descriptor needs NO base_offset (bits 49-51 = 0);
+// setting base_offset to the start's row phase gives wrong results.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -189,13 +204,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // each CTA stages its own 128 pixels of A and HALF of the weight tile (BN/2 rows), the even CTA issues M = 256 MMAs that
 // read both shared memories and write both TMEMs, and both CTAs run their own epilogue.  A third fewer operand bytes
 // per MMA cycle and per stage -> six stages instead of four in the same shared memory.
-template <int MT, int BN, int STAGES, bool PAIR = false>
+// HALO (3x3, stride 1, pad 1 on large maps): a pipeline stage is not one filter tap but one COLUMN of taps (s fixed,
+// r = 0..2) of a 64-channel chunk.  The CTA tile is 8 pixels wide and MT x 16 pixels tall; ONE TMA box of 8 x (MT*16 + 2)
+// pixels -- the tile plus one halo row above and below, shifted by s - 1 pixels -- lands in shared memory as
+// [row][8 pixels][128 B], i.e. every image row is exactly one 1024-byte swizzle atom, so the A operand of tap (r, s) for
+// sub-tile j is the SAME buffer at byte offset (16 j + r) * 1024: three taps are fed from one load.  Operand bytes per
+// MMA cycle drop 2.0x (64-wide) / 1.7x (128-wide cout tiles), which is what bounds these shapes: with 64 output
+// channels the per-tap form needs 160 B/clk/SM from L2 against ~42 available (26 % tensor utilisation, as measured).
+// WRES (with HALO, Cin == 64, Cout == BN): the whole 3 x 3 x 64 x BN weight block (72 KB at BN = 64) is loaded ONCE per
+// CTA and stays in shared memory for every tile the persistent CTA walks; the ring then carries only the A halos.
+template <int MT, int BN, int STAGES, bool PAIR = false, bool HALO = false, bool WRES = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const ConvParams P) {
     static_assert(!PAIR || MT == 1, "pair mode: one 128-pixel sub-tile per CTA");
+    static_assert(!(PAIR && HALO), "halo reuse is a single-CTA mode");
     constexpr uint32_t kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
-    constexpr uint32_t kStageBytes = MT * kABytes + kBBytes;     // MT pixel sub-tiles share one weight tile
+    constexpr uint32_t kAHalo = (MT * 16 + 2) * 1024;            // HALO: (MT*16 + 2) image rows of 8 pixels x 128 B
+    static_assert(!WRES || HALO, "resident weights are a halo-mode option");
+    constexpr uint32_t kWRes = WRES ? 9 * kBBytes : 0;           // resident weight block in front of the ring
+    constexpr uint32_t kABox = (((MT * 16 + 2) * 10 * 128) + 1023) / 1024 * 1024;   // single-box halo: (MT*16 + 2) rows of 10 pixels
+    constexpr uint32_t kStageBytes = WRES ? (STAGES == 2 ? kABox : kAHalo) : HALO ? kAHalo + 3 * kBBytes : MT * kABytes + kBBytes;   // MT pixel sub-tiles share one weight tile
+    constexpr bool kBox = WRES && STAGES == 2;                   // the 2-stage WRES instantiation is the single-box form
     constexpr uint32_t kOutBlk = BM * 128;                       // staging block: 128 pixels x 64 channels of bf16
     constexpr uint32_t kAccCols = MT * BN;                       // one accumulator set: MT sub-tiles x BN columns
     constexpr uint32_t kTmemCols = 2 * kAccCols;                 // two sets: epilogue of tile i overlaps MMA of i+1
@@ -206,7 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
+    const uint32_t wres = (raw + 1023u) & ~1023u;                 // swizzle-128B tiles need 1024-byte alignment
+    const uint32_t base = wres + kWRes;                           // ring of pipeline stages
     uint8_t* const base_ptr = smem_raw + (base - raw);
     const uint32_t out_stage = base + STAGES * kStageBytes;       // 2 staging blocks for the TMA stores
     uint8_t* const out_ptr = base_ptr + STAGES * kStageBytes;
@@ -215,11 +246,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t wres_bar = bars + 8u * (2 * STAGES + 4);
     volatile uint32_t* const tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * kStageBytes + 2 * kOutBlk + 8 * (2 * STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * kStageBytes + 2 * kOutBlk + 8 * (2 * STAGES + 5));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = P.taps * P.cin_chunks;
+    const int num_kb = kBox ? 1 : HALO ? 3 * P.cin_chunks : P.taps * P.cin_chunks;      // HALO: k-block = (64-channel chunk, tap column s)
     const int num_mtiles = P.n_tiles_w * P.n_tiles_h * P.n_tiles_n;
     const int num_tiles = P.cout_tiles * (PAIR ? (num_mtiles + 1) / 2 : num_mtiles);
     // This CTA's tiles: runs of P.chunk consecutive tiles, the runs dealt round-robin to the CTAs.  chunk = 1 keeps all
@@ -251,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // both CTAs' loads; its tempty barrier collects the epilogue threads of both CTAs
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), PAIR ? 2 : 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 2 * kEpiThreads : kEpiThreads); }
+        mbar_init(wres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -273,12 +306,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0) {
             // ---- TMA producer: runs ahead of the MMA by up to STAGES k-blocks, across tile boundaries ----
             uint32_t it = 0;                                     // global k-block counter -> stage / phase
+            if (WRES) {                                          // the nine weight tiles, once (Cin == 64: K index = tap * 64)
+                mbar_expect_tx(wres_bar, kWRes);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * kBBytes, &map_w, wres_bar, tap * BK, 0);
+            }
             for (int ti = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++ti)) {
                 const Tile T = decode(tile);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t phase = (it / STAGES) & 1u;
                     mbar_wait(empty_bar(s), phase ^ 1u);
+                    if (kBox) {                                  // one box: tile + halo in both directions
+                        mbar_expect_tx(full_bar(s), (MT * 16 + 2) * 10 * 128);
+                        tma_load_4d(base + s * kStageBytes, &map_x, full_bar(s), 0, T.w0 - 1, T.h0 - 1, T.n0);
+                        continue;
+                    }
+                    if (HALO) {
+                        const int cc = kb / 3, sx = kb - cc * 3;
+                        const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + kAHalo;
+                        mbar_expect_tx(full_bar(s), kStageBytes);
+                        tma_load_4d(a_dst, &map_x, full_bar(s), cc * BK, T.w0 + sx - 1, T.h0 - 1, T.n0);
+                        if (!WRES) {
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+                                tma_load_2d(b_dst + r * kBBytes, &map_w, full_bar(s), ((r * 3 + sx) * P.cin_chunks + cc) * BK, T.c_out0);
+                        }
+                        continue;
+                    }
                     const int tap = kb / P.cin_chunks, cc = kb - tap * P.cin_chunks;
                     const int r = tap / P.S, sx = tap - r * P.S;
                     const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + MT * kABytes;
@@ -302,6 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0 && rank == 0) {
             // ---- MMA issuer (PAIR: the even CTA only) ----
             uint32_t it = 0, local = 0;
+            if (WRES) mbar_wait(wres_bar, 0);
             for (int ti = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++ti), ++local) {
                 const int as = local & 1;
                 mbar_wait(tempty_bar(as), ((local >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
@@ -313,6 +369,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     mbar_wait(full_bar(s), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = base + s * kStageBytes;
+                    if (kBox) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int r = tap / 3, sx = tap - r * 3;
+                            const uint64_t bdesc = umma_desc_sw128(wres + (uint32_t)tap * kBBytes);
+#pragma unroll
+                            for (int k = 0; k < BK / UK; ++k)
+#pragma unroll
+                                for (int j = 0; j < MT; ++j) {
+                                    const uint32_t a0 = a_addr + (uint32_t)((j * 16 + r) * 10 + sx) * 128u;
+                                    const uint64_t adesc = umma_desc_sw128_sbo(a0, 1280u);          // image rows are 10 pixels = 1280 B apart
+                                    umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(k * UK * 2 / 16), bdesc + (uint64_t)(k * UK * 2 / 16),
+                                              kIdesc, (uint32_t)((tap | k) != 0));
+                                }
+                        }
+                        umma_commit(empty_bar(s));
+                        continue;
+                    }
+                    if (HALO) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const uint64_t bdesc = WRES ? umma_desc_sw128(wres + (uint32_t)(r * 3 + (kb % 3)) * kBBytes)
+                                                        : umma_desc_sw128(a_addr + kAHalo + r * kBBytes);
+#pragma unroll
+                            for (int k = 0; k < BK / UK; ++k)
+#pragma unroll
+                                for (int j = 0; j < MT; ++j)
+                                    umma_bf16(d_tmem + (uint32_t)(j * BN), umma_desc_sw128(a_addr + (uint32_t)(j * 16 + r) * 1024u) + (uint64_t)(k * UK * 2 / 16),
+                                              bdesc + (uint64_t)(k * UK * 2 / 16), kIdesc, (uint32_t)((kb | r | k) != 0));
+                        }
+                        umma_commit(empty_bar(s));
+                        continue;
+                    }
                     const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + MT * kABytes);
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k)
@@ -525,10 +614,13 @@ bool make_map_weights(CUtensorMap* m, const void* ptr, int cout, int k, int bn) 
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MT, int BN, int STAGES, bool PAIR = false>
+template <int MT, int BN, int STAGES, bool PAIR = false, bool HALO = false, bool WRES = false>
 cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& P,
                    long long ctas, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)STAGES * (MT * kABytes + (PAIR ? BN / 2 : BN) * BK * 2) + 2 * BM * 128 + 8 * (2 * STAGES + 5) + 1024;
+    constexpr size_t stage = (WRES && STAGES == 2) ? (size_t)((((MT * 16 + 2) * 10 * 128) + 1023) / 1024 * 1024)
+                           : WRES ? (size_t)(MT * 16 + 2) * 1024
+                           : HALO ? (size_t)(MT * 16 + 2) * 1024 + 3 * (size_t)BN * BK * 2 : (size_t)(MT * kABytes + (PAIR ? BN / 2 : BN) * BK * 2);
+    constexpr size_t smem = (WRES ? 9 * (size_t)BN * BK * 2 : 0) + (size_t)STAGES * stage + 2 * BM * 128 + 8 * (2 * STAGES + 6) + 1024;
     static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
     // The shared-memory opt-in and the SM count are PER DEVICE: cache them per device ordinal (per instantiation; the
     // attribute call is idempotent, so a race between host threads only repeats it).
@@ -538,7 +630,7 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
     if (cudaGetDevice(&dev) != cudaSuccess) return cudaErrorInvalidDevice;
     const bool cached = dev >= 0 && dev < 64;
     if (!cached || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MT, BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (cached) attr_set[dev] = true;
     }
@@ -564,16 +656,24 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MT, BN, STAGES, PAIR>, mx, mw, my, P);
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES>, mx, mw, my, P);
     }
     const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
-    conv_tc_kernel<MT, BN, STAGES, PAIR><<<grid, kThreads, smem, stream>>>(mx, mw, my, P);
+    conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES><<<grid, kThreads, smem, stream>>>(mx, mw, my, P);
     return cudaGetLastError();
 }
 
 int g_force_bn = 0;        // 0 = automatic; set through fots_b200_conv_set_tile for sweeps
+int g_halo = -1;           // -1 = automatic, 0 = never, 1 = whenever the shape allows, 2 = same but always the three-copy form
+                           // (fots_b200_conv_set_halo; sweeps / tests)
 
 }  // namespace
+
+extern "C" int fots_b200_conv_set_halo(int mode) {
+    if (mode < -1 || mode > 2) return RROI_B200_ERR_INVALID_ARG;
+    g_halo = mode;
+    return RROI_B200_OK;
+}
 
 extern "C" int fots_b200_conv_set_tile(int bn) {
     if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return RROI_B200_ERR_INVALID_ARG;   // 512 = 256 on a CTA pair
@@ -604,6 +704,14 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     // MMAs per k-block to hide the single-thread issue path)
     const int mt = bn == 256 ? 1 : 2;
 
+    // Halo reuse (three taps per A load; see the kernel): 3x3, stride 1, pad 1, 64- or 128-wide cout tiles.  Automatic for
+    // maps of at least 32 x 16 pixels (the 8 x 32 CTA tile is then mostly inside the image): the backbone's stages, not
+    // the recogniser's 8- and 4-row RoI tensors.
+    const bool halo_ok = R == 3 && S == 3 && pad_h == 1 && pad_w == 1 && stride == 1 && stats == nullptr && !pair && (bn == 64 || bn == 128);
+    const bool halo = halo_ok && (g_halo >= 1 || (g_halo == -1 && Ho >= 32 && Wo >= 16));
+    // 64 -> 64 channels: the weights stay resident and ONE 10-pixel-wide box per tile carries all nine taps
+    const bool halo_box = halo && g_halo != 2 && bn == 64 && Cin == 64 && Cout == 64;
+
     // sub-tile box: tw*th*tn = 128 pixels; the CTA stacks mt of them along h (tn == 1) or n.  Fewest CTA tiles wins,
     // wider boxes on ties (longer contiguous runs per TMA row).
     int best_tw = 0, best_th = 0, best_tn = 0;
@@ -617,6 +725,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
             if (best < 0 || tiles < best) { best = tiles; best_tw = tw; best_th = th; best_tn = tn; }
         }
 
+    if (halo) { best_tw = 8; best_th = 16; best_tn = 1; }
     ConvParams P;
     P.tw = best_tw; P.th = best_th; P.tn = best_tn;
     const bool stack_n = best_tn > 1;
@@ -639,12 +748,18 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     }
 
     CUtensorMap mx, mw, my;
-    if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw, stride)) return RROI_B200_ERR_INVALID_ARG;
+    if (halo) {
+        if (!make_map_nhwc(&mx, x, N, H, W, Cin, 1, mt * 16 + 2, halo_box ? 10 : 8, 1)) return RROI_B200_ERR_INVALID_ARG;      // tile + halo rows
+    } else if (!make_map_nhwc(&mx, x, N, H, W, Cin, P.tn, P.th, P.tw, stride)) return RROI_B200_ERR_INVALID_ARG;
     if (!make_map_weights(&mw, w, Cout, R * S * Cin, pair ? bn / 2 : bn)) return RROI_B200_ERR_INVALID_ARG;
     if (!make_map_nhwc(&my, y, N, Ho, Wo, Cout, P.tn, P.th, P.tw)) return RROI_B200_ERR_INVALID_ARG;
 
     cudaError_t e;
-    if (bn == 64) e = launch<2, 64, 4>(mx, mw, my, P, ctas, stream);
+    if (halo_box) e = launch<2, 64, 2, false, true, true>(mx, mw, my, P, ctas, stream);                   // one halo box, weights resident
+    else if (halo && bn == 64 && Cin == 64 && Cout == 64) e = launch<2, 64, 3, false, true, true>(mx, mw, my, P, ctas, stream);   // weights resident
+    else if (halo && bn == 64) e = launch<2, 64, 3, false, true>(mx, mw, my, P, ctas, stream);
+    else if (halo) e = launch<2, 128, 2, false, true>(mx, mw, my, P, ctas, stream);
+    else if (bn == 64) e = launch<2, 64, 4>(mx, mw, my, P, ctas, stream);
     else if (bn == 128) e = launch<2, 128, 4>(mx, mw, my, P, ctas, stream);
     else if (pair) e = launch<1, 256, 6, true>(mx, mw, my, P, ctas, stream);
     else e = launch<1, 256, 4>(mx, mw, my, P, ctas, stream);

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -172,13 +173,16 @@ __device__ __forceinline__ float4 ld_cluster_v4(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tanh(x) = 2 sigmoid(2x) - 1 on the fast exponential (abs. error ~1e-6): libm's tanhf is ~5x the instructions, and the gate
+// phase sits on the critical path of all 65 steps
+__device__ __forceinline__ float tanh_f(float x) { return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f; }
 
 // G    fp32 [T, N, 2, 4H]   input projections + both biases, gate order i, f, g, o (nn.LSTM), direction-major
 // Whh  bf16 [2, 4H, H]      weight_hh_l0, weight_hh_l0_reverse
 // Y    fp32 [T, N, 2H]      h_t of the forward direction in [:, :, :H], of the reverse direction in [:, :, H:]
 // grid = (2 * LCL, ceil(N / 64)), clusters of LCL along x: cluster = (direction, block of 64 sequences).
 __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* __restrict__ G, const __nv_bfloat16* __restrict__ Whh,
-                                                                   float* __restrict__ Y, int T, int N) {
+                                                                   float* __restrict__ Y, int T, int N, int dbg) {
     extern __shared__ __align__(16) uint8_t smem[];
     __nv_bfloat16* const Wsm = reinterpret_cast<__nv_bfloat16*>(smem);                    // [LG][LP]
     __nv_bfloat16* const Hhi = Wsm + LG * LP;                                             // [LNB][LP]
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* _
 #pragma unroll
             for (int i = 0; i < kPull; ++i) {
                 const int idx = i * 256 + threadIdx.x;
-                const int src = idx / (LNB * LU / 4), rem = idx - src * (LNB * LU / 4);
+                const int src = (dbg & 2) ? (int)r : idx / (LNB * LU / 4), rem = idx - (idx / (LNB * LU / 4)) * (LNB * LU / 4);
                 v[i] = ld_cluster_v4(map_to_rank(outbox_s + (uint32_t)((par * LNB * LU + rem * 4) * 4), (uint32_t)src));
             }
 #pragma unroll
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* _
             __syncthreads();
             // ---- gates += h_{t-1} * W_hh^T  (hi and lo parts)
 #pragma unroll 4
-            for (int kk = 0; kk < LH; kk += 16) {
+            for (int kk = 0; kk < ((dbg & 1) ? 0 : LH); kk += 16) {
                 uint32_t ah[4], al[4];
                 const __nv_bfloat16* ap = Hhi + (wm + g) * LP + kk + 2 * t4;
                 ah[0] = *reinterpret_cast<const uint32_t*>(ap);           ah[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * LP);
@@ -274,10 +278,10 @@ __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* _
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float ig = sigmoid_f(acc[4 * u + 0][e]), fg = sigmoid_f(acc[4 * u + 1][e]);
-                const float gg = tanhf(acc[4 * u + 2][e]), og = sigmoid_f(acc[4 * u + 3][e]);
+                const float gg = tanh_f(acc[4 * u + 2][e]), og = sigmoid_f(acc[4 * u + 3][e]);
                 const float c = fg * cst[u][e] + ig * gg;
                 cst[u][e] = c;
-                const float h = og * tanhf(c);
+                const float h = og * tanh_f(c);
                 const int row = wm + g + (e >> 1) * 8;
                 const int unit = ((wn >> 5) + u) * 8 + 2 * t4 + (e & 1);               // local hidden unit 0..31
                 outbox[(par * LNB + row) * LU + unit] = h;
@@ -330,5 +334,6 @@ extern "C" int fots_b200_bilstm_recurrent(const float* G, const void* Whh, float
     at[0].val.clusterDim.x = LCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return status_of(cudaLaunchKernelEx(&cfg, bilstm_recurrent_kernel, G, static_cast<const __nv_bfloat16*>(Whh), Y, T, N));
+    static const int dbg = getenv("FOTS_B200_LSTM_DBG") ? atoi(getenv("FOTS_B200_LSTM_DBG")) : 0;   // timing experiments only
+    return status_of(cudaLaunchKernelEx(&cfg, bilstm_recurrent_kernel, G, static_cast<const __nv_bfloat16*>(Whh), Y, T, N, dbg));
 }

@@ -49,6 +49,14 @@ def _lib():
     return L
 
 
+def set_halo(mode):
+    """-1 automatic, 0 never, 1 whenever the shape allows: halo reuse of the A operand (sweeps, tests)."""
+    L = _lib()
+    L.fots_b200_conv_set_halo.restype = ctypes.c_int
+    L.fots_b200_conv_set_halo.argtypes = [ctypes.c_int]
+    _cabi.check(L.fots_b200_conv_set_halo(int(mode)), "fots_b200_conv_set_halo")
+
+
 def set_tile(bn):
     _cabi.check(_lib().fots_b200_conv_set_tile(int(bn)), "fots_b200_conv_set_tile")
 

@@ -210,6 +210,10 @@ int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const float* bias, 
                               int B, int H, int W, int C, cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
+/* Halo reuse of the A operand (3x3 stride-1 convolutions, 64- / 128-wide cout tiles: one TMA load of the tile + halo rows
+ * feeds three filter taps; 64 -> 64 channels: one box feeds all nine, weights resident): -1 = automatic (maps of at least
+ * 32 x 16 pixels), 0 = never, 1 = whenever the shape allows, 2 = same but always the three-copy form. */
+int fots_b200_conv_set_halo(int mode);
 
 #ifdef __cplusplus
 }

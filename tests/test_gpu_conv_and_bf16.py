@@ -362,3 +362,39 @@ def test_folded_batchnorm_downsample_branch_matches_module(cuda):
             assert float((got.float() - want).abs().max()) <= 2.0 ** -6 * float(want.abs().max()) + 1e-3
             checked += 1
     assert checked == 3 and TC.LEVEL >= 2
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,bias,slope", [
+    (1, 45, 80, 64, 64, False, 0.0),          # layer1 at reduced size: ragged in h (45 = 32 + 13)
+    (2, 90, 160, 128, 128, True, 1.0),        # layer2 block
+    (2, 23, 37, 128, 192, True, 0.0),         # odd sizes: ragged in w (37 = 4 x 8 + 5), three 64-wide cout tiles
+    (1, 180, 320, 64, 64, False, 1.0),        # layer1 at 720p
+    (3, 8, 64, 64, 128, False, 0.01),         # the recogniser's conv5 shape (forced: tiles mostly outside the image)
+    (1, 33, 9, 256, 128, True, 1.0),          # four 64-channel chunks, two tile columns
+    (2, 37, 21, 64, 64, True, 0.01),          # 64 -> 64 ragged in both directions, bias + leaky
+])
+def test_tcgen05_conv_halo_reuse_matches_torch_fp32(cuda, N, H, W, Cin, Cout, bias, slope):
+    """Halo reuse (one TMA load of the tile + halo rows feeds the three taps of a filter column; the A descriptor of tap
+    (r, s) is the same buffer at +r image rows) against torch's fp32 convolution and against the per-tap kernel."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(N * 31 + H + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(cuda).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g).to(cuda) if bias else None
+    TC.set_halo(1)                 # 64 -> 64: one 10-pixel-wide box + resident weights; otherwise three x-shifted copies
+    try:
+        y = TC.conv2d(x, w, b, (1, 1), slope)
+        TC.set_halo(2)             # always the three-copy form
+        y2 = TC.conv2d(x, w, b, (1, 1), slope)
+        TC.set_halo(0)
+        y0 = TC.conv2d(x, w, b, (1, 1), slope)
+    finally:
+        TC.set_halo(-1)
+    ref = F.conv2d(x.float(), w.float(), b, 1, (1, 1))
+    if slope != 1.0:
+        ref = F.leaky_relu(ref, slope)
+    err = (y.float() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3 * float(ref.abs().max())
+    assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
+    assert float((y.float() - y0.float()).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())     # fp32 sum order differs
+    assert float((y2.float() - y0.float()).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())
