@@ -31,10 +31,25 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return r;
 }
 
+// NORM: the input is the RAW output z of the preceding convolution and the kernel computes dw(act(IN(z))) -- the
+// InstanceNorm + leaky-ReLU that sits between the pointwise and the depthwise half of a separable block
+// (tools/models.py:59-111) is applied to the staged tile in shared memory (once per staged vector, padding stays zero),
+// from the per-image statistics of z (fots_b200_instnorm_stats_nhwc_bf16).  The normalised tensor never exists in HBM:
+// one read + one write of the activation map less per block.
+struct DwNorm {
+    const double* stats;      // [N, C, 2] sum / sum of squares of z per image and channel
+    const float* gamma;       // [C] or nullptr (affine = False)
+    const float* beta;
+    float eps, slope;
+    double* stats_out;        // optional [N, C, 2]: sums of the bf16 outputs of THIS kernel (cleared by the host wrapper) --
+                              // the statistics pass of the InstanceNorm that follows, for free in the epilogue
+};
+
 // grid (tiles_w * tiles_h, C / 64, N); block TH * 4 strips * 8 vectors.
-template <int STRIDE, int TH>
+template <int STRIDE, int TH, bool NORM>
 __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
-                                                            uint4* __restrict__ y, int H, int W, int C, int Ho, int Wo, int tiles_w) {
+                                                            uint4* __restrict__ y, int H, int W, int C, int Ho, int Wo, int tiles_w,
+                                                            const DwNorm nrm) {
     constexpr int IH = (TH - 1) * STRIDE + 3, IW = (kTW - 1) * STRIDE + 3;      // input tile incl. halo
     constexpr int NT = TH * 32;
     __shared__ __align__(16) uint4 tile[IH * IW * 8];
@@ -67,6 +82,38 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
         for (int t = 0; t < 9; ++t) wr[t][k] = __bfloat162float(wgt[(size_t)(c0 + v * 8 + k) * 9 + t]);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (NORM) {
+        // scale / shift of this CTA's 64 channels for image n, then normalise + activate the staged tile in place
+        __shared__ float coef[2 * kCB];
+        if (threadIdx.x < kCB) {
+            const int c = c0 + threadIdx.x;
+            const double hw = (double)H * (double)W;
+            const double m = nrm.stats[((size_t)n * C + c) * 2] / hw;
+            double var = nrm.stats[((size_t)n * C + c) * 2 + 1] / hw - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            const float rstd = rsqrtf((float)var + nrm.eps), mean = (float)m;
+            const float g0 = nrm.gamma ? nrm.gamma[c] : 1.0f, b0 = nrm.beta ? nrm.beta[c] : 0.0f;
+            coef[threadIdx.x] = rstd * g0;
+            coef[kCB + threadIdx.x] = b0 - mean * rstd * g0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < IH * IW * 8; i += NT) {
+            const int vv = i & 7, p = i >> 3, r = p / IW, c = p - r * IW;
+            const int iy = iy0 + r, ix = ix0 + c;
+            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;                 // padding: stays exactly zero
+            float f[8];
+            unpack8(tile[i], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float t = fmaf(f[k], coef[vv * 8 + k], coef[kCB + vv * 8 + k]);
+                f[k] = t > 0.0f ? t : t * nrm.slope;
+            }
+            uint4 pk;                                                              // one bf16 rounding, as the separate apply pass stores it
+            pk.x = pack2(f[0], f[1]); pk.y = pack2(f[2], f[3]); pk.z = pack2(f[4], f[5]); pk.w = pack2(f[6], f[7]);
+            tile[i] = pk;
+        }
+        __syncthreads();
+    }
 
     float acc[4][8];
 #pragma unroll
@@ -92,6 +139,9 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
         }
     }
     const int oy = oy0 + row;
+    float ssum[8], ssq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.0f;
     if (oy < Ho) {
         uint4* out = y + (((size_t)n * Ho + oy) * Wo) * CV + c0 / 8 + v;
 #pragma unroll
@@ -102,15 +152,33 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
                 pk.x = pack2(acc[o][0], acc[o][1]); pk.y = pack2(acc[o][2], acc[o][3]);
                 pk.z = pack2(acc[o][4], acc[o][5]); pk.w = pack2(acc[o][6], acc[o][7]);
                 out[(size_t)ox * CV] = pk;
+                if (nrm.stats_out) {                                     // of the ROUNDED values, as a separate pass would see them
+                    float f[8];
+                    unpack8(pk, f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { ssum[k] += f[k]; ssq[k] = fmaf(f[k], f[k], ssq[k]); }
+                }
             }
+        }
+    }
+    if (nrm.stats_out) {                                                 // CTA-uniform
+        __syncthreads();                                                 // everybody is done reading the tile: reuse it
+        float* red = reinterpret_cast<float*>(tile);                    // [NT][17]
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { red[threadIdx.x * 17 + k] = ssum[k]; red[threadIdx.x * 17 + 8 + k] = ssq[k]; }
+        __syncthreads();
+        if (threadIdx.x < 128) {                                         // 8 vectors x 16 values
+            const int vv = threadIdx.x >> 4, k = threadIdx.x & 15;
+            float a = 0.0f;
+            for (int st = 0; st < NT / 8; ++st) a += red[(st * 8 + vv) * 17 + k];
+            atomicAdd(nrm.stats_out + ((size_t)n * C + c0 + vv * 8 + (k & 7)) * 2 + (k >> 3), (double)a);
         }
     }
 }
 
 }  // namespace
 
-extern "C" int fots_b200_dwconv3x3_nhwc_bf16(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride,
-                                             cudaStream_t stream) {
+static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride, const DwNorm* nrm, cudaStream_t stream) {
     if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % kCB != 0 || (stride != 1 && stride != 2) || N > 65535 ||
         C / kCB > 65535)
         return RROI_B200_ERR_INVALID_ARG;
@@ -120,16 +188,38 @@ extern "C" int fots_b200_dwconv3x3_nhwc_bf16(const void* x, const void* w, void*
     const uint4* xp = static_cast<const uint4*>(x);
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
     uint4* yp = static_cast<uint4*>(y);
+    DwNorm none = {nullptr, nullptr, nullptr, 0.f, 1.f, nullptr};
+    if (nrm) none = *nrm;
+    if (none.stats_out) {
+        const cudaError_t em = cudaMemsetAsync(none.stats_out, 0, (size_t)N * C * 2 * sizeof(double), stream);
+        if (em != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    }
+    const bool norm_on = nrm != nullptr && nrm->stats != nullptr;
     if (stride == 1) {
         constexpr int TH = 8;
         const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
-        dwconv3x3_kernel<1, TH><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w);
+        if (norm_on) dwconv3x3_kernel<1, TH, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
+        else dwconv3x3_kernel<1, TH, false><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
     } else {
         constexpr int TH = 4;
         const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
-        dwconv3x3_kernel<2, TH><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w);
+        if (norm_on) dwconv3x3_kernel<2, TH, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
+        else dwconv3x3_kernel<2, TH, false><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
+}
+
+extern "C" int fots_b200_dwconv3x3_nhwc_bf16(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride,
+                                             cudaStream_t stream) {
+    return dw_launch(x, w, y, N, H, W, C, stride, nullptr, stream);
+}
+
+extern "C" int fots_b200_dwconv3x3_norm_nhwc_bf16(const void* x, const void* w, void* y, const double* stats, const float* gamma,
+                                                  const float* beta, float eps, float slope, double* stats_out, int N, int H, int W,
+                                                  int C, int stride, cudaStream_t stream) {
+    if ((gamma == nullptr) != (beta == nullptr) || (!stats && (gamma || beta))) return RROI_B200_ERR_INVALID_ARG;
+    const DwNorm nrm = {stats, gamma, beta, eps, slope, stats_out};
+    return dw_launch(x, w, y, N, H, W, C, stride, &nrm, stream);
 }

@@ -493,6 +493,24 @@ static int instnorm_impl(const void* x, void* y, const float* gamma, const float
     return RROI_B200_OK;
 }
 
+// statistics pass only: ws [B, C, 2] (cleared here) <- per-image per-channel sum / sum of squares of x
+extern "C" int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspace, int B, int HW, int C, cudaStream_t stream) {
+    if (!x || !workspace || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || C > 1024 || (C / 8) > kThreads || B > 65535)
+        return RROI_B200_ERR_INVALID_ARG;
+    const int G = C / 8, nphase = kThreads / G;
+    long long want_ctas = 148LL * 8 / B + 1;
+    int rows = (int)((HW + want_ctas - 1) / want_ctas);
+    rows = ((rows + nphase - 1) / nphase) * nphase;
+    if (rows < nphase * 4) rows = nphase * 4;
+    const int chunks = (HW + rows - 1) / rows;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    in_stats_kernel<<<dim3(chunks, B), kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
+
 extern "C" int fots_b200_instnorm_nhwc_bf16(const void* x, void* y, const float* gamma, const float* beta,
                                             const void* residual, double* workspace, int B, int HW, int C,
                                             float eps, float slope, int crelu, cudaStream_t stream) {

@@ -41,6 +41,8 @@ def _lib():
         L.fots_b200_stem_conv3x3_c3_c16_u8.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.fots_b200_dwconv3x3_nhwc_bf16.restype = i
         L.fots_b200_dwconv3x3_nhwc_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
+        L.fots_b200_dwconv3x3_norm_nhwc_bf16.restype = i
+        L.fots_b200_dwconv3x3_norm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, f, f, vp, i, i, i, i, i, vp]
         L.fots_b200_heads_nhwc_bf16.restype = i
         L.fots_b200_heads_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
         L.fots_b200_conv_set_tile.restype = i
@@ -154,6 +156,64 @@ def dwconv(conv, x):
                                                   torch.cuda.current_stream(x.device).cuda_stream)
     _cabi.check(rc, "fots_b200_dwconv3x3_nhwc_bf16")
     return y
+
+
+def dwconv_norm(conv, x, stats=None, norm=None, slope=1.0, stats_out=False):
+    """Depthwise 3x3 `conv` with the InstanceNorms either side of it fused (fots_b200_dwconv3x3_norm_nhwc_bf16):
+    stats / norm / slope: computes conv(act(norm(x))) WITHOUT materialising the normalised tensor -- x is the raw bf16
+      channels-last input, `stats` = fused.instnorm_stats(x), the normalisation is applied to the staged tile;
+    stats_out=True: also returns the fp64 [N, C, 2] sums of the output (for fused.instnorm_act(y, ..., stats=ws)).
+    Caller checks dw_eligible(x, conv)."""
+    from . import fused
+    N, C, H, W = x.shape
+    st = conv.stride[0]
+    y = torch.empty((N, C, (H - 1) // st + 1, (W - 1) // st + 1), dtype=torch.bfloat16, device=x.device,
+                    memory_format=torch.channels_last)
+    w = conv.weight.reshape(C, 9)
+    if not w.is_contiguous():
+        w = w.contiguous()
+    g = norm.weight.float().contiguous() if (norm is not None and norm.weight is not None) else None
+    b = norm.bias.float().contiguous() if (norm is not None and norm.bias is not None) else None
+    ws = fused.workspace(x.device, N * C * 2) if stats_out else None
+    with torch.cuda.device(x.device):
+        rc = _lib().fots_b200_dwconv3x3_norm_nhwc_bf16(x.data_ptr(), w.data_ptr(), y.data_ptr(),
+                                                       stats.data_ptr() if stats is not None else None,
+                                                       g.data_ptr() if g is not None else None,
+                                                       b.data_ptr() if b is not None else None,
+                                                       float(norm.eps) if norm is not None else 0.0, float(slope),
+                                                       ws.data_ptr() if ws is not None else None,
+                                                       N, H, W, C, st, torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_dwconv3x3_norm_nhwc_bf16")
+    return (y, ws) if stats_out else y
+
+
+def pack_pixel_pairs_s2(weight):
+    """Weights of a 3x3 stride-2 pad-1 convolution with FEWER than 64 input channels (layer0's 32 -> 32, tools/models.py:252)
+    re-expressed for the 64-channel kernel: two horizontally adjacent pixels are viewed as one pixel with 2*Cin channels
+    (a free reinterpretation of a channels-last tensor), on the input AND on the output side.  Output pair xo' (pixels
+    2xo', 2xo'+1) reads input pairs 2xo'-1 .. 2xo'+1, i.e. the result is again a 3x3 stride-2 pad-1 convolution,
+    [2*Cout, 2*Cin, 3, 3], with W'[(e,o), (p,c), r, s'] = W[o, c, r, 2s' + p - 2e - 1] where that tap exists, else 0."""
+    Cout, Cin, R, S = weight.shape
+    assert R == 3 and S == 3
+    w2 = torch.zeros((2 * Cout, 2 * Cin, 3, 3), dtype=weight.dtype, device=weight.device)
+    for e in range(2):
+        for p_ in range(2):
+            for s2 in range(3):
+                s1 = 2 * s2 + p_ - 2 * e - 1
+                if 0 <= s1 <= 2:
+                    w2[e * Cout:(e + 1) * Cout, p_ * Cin:(p_ + 1) * Cin, :, s2] = weight[:, :, :, s1]
+    return w2.contiguous(memory_format=torch.channels_last)
+
+
+def conv3x3_s2_pixel_pairs(x, w2):
+    """x bf16 channels-last [B, Cin, H, W] (W % 4 == 0), w2 = pack_pixel_pairs_s2(weight) -> conv2d(x, weight, stride 2, pad 1)
+    as bf16 channels-last [B, Cout, H', W / 2], computed on the 64-channel tcgen05 kernel through pixel-pair views."""
+    B, Cin, H, W = x.shape
+    Cout = w2.size(0) // 2
+    xp = x.permute(0, 2, 3, 1).reshape(B, H, W // 2, 2 * Cin).permute(0, 3, 1, 2)          # view, channels-last
+    yp = conv2d(xp, w2, None, (1, 1), 1.0, stride=2)                                          # [B, 2*Cout, H', W/4]
+    Ho, Wo2 = yp.shape[2], yp.shape[3]
+    return yp.permute(0, 2, 3, 1).reshape(B, Ho, 2 * Wo2, Cout).permute(0, 3, 1, 2)          # view [B, Cout, H', W/2]
 
 
 def pack_heads(act, rbox, angle):

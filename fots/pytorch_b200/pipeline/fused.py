@@ -76,6 +76,20 @@ def instnorm_act(x, weight, bias, eps, slope, residual=None, crelu=False, stats=
     return y
 
 
+def instnorm_stats(x):
+    """The statistics pass alone: fp64 [B, C, 2] per-image per-channel sum / sum of squares of x (bf16 channels-last), for a
+    consumer that normalises on load (conv.dwconv_norm)."""
+    B, C, H, W = x.shape
+    ws = workspace(x.device, B * C * 2)
+    L = _lib()
+    L.fots_b200_instnorm_stats_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_instnorm_stats_nhwc_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    with torch.cuda.device(x.device):
+        st = L.fots_b200_instnorm_stats_nhwc_bf16(x.data_ptr(), ws.data_ptr(), B, H * W, C, torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(st, "fots_b200_instnorm_stats_nhwc_bf16")
+    return ws
+
+
 def _cl_bf16(t):
     return (t is None) or (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4
                            and t.is_contiguous(memory_format=torch.channels_last)

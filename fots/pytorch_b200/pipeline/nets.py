@@ -102,8 +102,15 @@ class _ResSepIN(nn.Module):
         res = x if self.downsample is None else _downsample(self, x)
         s1, s2 = self.conv_sep1, self.conv2
         # depthwise halves: csrc/dwconv_kernels.cu; pointwise halves: 1x1 GEMMs on the tcgen05 kernel
-        y = _in_act(s1[2], tc.apply(s1[1], tc.dwconv(s1[0], x), 1.0, level=2), 0.01)
-        y = _in_act(s2[1], tc.dwconv(s2[0], y), 0.01)
+        z = tc.apply(s1[1], tc.dwconv(s1[0], x), 1.0, level=2)
+        if tc.dw_eligible(z, s2[0]) and fused.eligible(z, None, s1[2].weight, s1[2].bias):
+            # IN + leaky between the two halves is applied on load inside the depthwise kernel: statistics pass only,
+            # the normalised tensor is never written
+            # ... and the statistics of the InstanceNorm that follows come out of the depthwise kernel's epilogue
+            y, ws = tc.dwconv_norm(s2[0], z, fused.instnorm_stats(z), s1[2], 0.01, stats_out=True)
+            y = fused.instnorm_act(y, s2[1].weight, s2[1].bias, s2[1].eps, 0.01, stats=ws)
+        else:
+            y = _in_act(s2[1], tc.dwconv(s2[0], _in_act(s1[2], z, 0.01)), 0.01)
         return _in_act(s2[4], tc.apply(s2[3], y, 1.0, level=2), 0.01, res)
 
 
@@ -174,7 +181,12 @@ class FOTSNet(nn.Module):
             y, ws = tc.stem_conv_stats(x, conv0.weight)
             bn = crelu0.bn
             y = fused.instnorm_act(y, bn.weight, bn.bias, bn.eps, 0.01, crelu=True, stats=ws)
-            y = crelu1(conv1(y))
+            pairs = getattr(self, "_l0c1_pairs", None)
+            if pairs is not None and tc.LEVEL >= 2 and tc.input_ok(y) and y.size(3) % 4 == 0:
+                # 32 -> 32 stride 2: too few channels for a 64-wide k-block -- pixel pairs as 64 channels (conv.pack_pixel_pairs_s2)
+                y = crelu1(tc.conv3x3_s2_pixel_pairs(y, pairs))
+            else:
+                y = crelu1(conv1(y))
         else:
             if x.dtype == torch.uint8:                   # raw image: the reference's host-side preprocessing (test.py:80-83)
                 x = x.float() / 128 - 1
@@ -262,7 +274,7 @@ class FOTSNet(nn.Module):
         re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
         batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
         self.to(device=device, memory_format=torch.channels_last)
-        self._conv11_pad = self._heads_pack = None
+        self._conv11_pad = self._heads_pack = self._l0c1_pairs = None
         if inference:
             for m in self.modules():
                 if isinstance(m, nn.Conv2d):
@@ -277,6 +289,9 @@ class FOTSNet(nn.Module):
             bias[:c11.out_channels] = c11.bias.detach().float()
             self._conv11_pad = (w.contiguous(memory_format=torch.channels_last), bias)
             self._heads_pack = tc.pack_heads(self.act, self.rbox, self.angle)
+            c01 = self.layer0[2]
+            if c01.in_channels == 32 and c01.out_channels == 32 and c01.bias is None:
+                self._l0c1_pairs = tc.pack_pixel_pairs_s2(c01.weight.detach())
             # down-sampling branches: eval-mode BatchNorm folded into the 1x1 stride-2 convolution (bf16 weights, fp32 bias)
             for m in self.modules():
                 ds = getattr(m, "downsample", None)

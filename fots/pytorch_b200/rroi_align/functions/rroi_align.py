@@ -97,10 +97,10 @@ def backward_raw(grad_output, rois, idx_x, idx_y, feature_size, spatial_scale, l
 
 class _RRoiAlignOp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, features, rois, pooled_height, pooled_width, spatial_scale, holder):
+    def forward(ctx, features, rois, pooled_height, pooled_width, spatial_scale, holder, opts=None):
         want_idx = ctx.needs_input_grad[0] or holder is not None
         pooled, idx_x, idx_y, layout = forward_raw(features, rois, pooled_height, pooled_width,
-                                                   spatial_scale, want_idx=want_idx)
+                                                   spatial_scale, want_idx=want_idx, opts=opts)
         ctx.feature_size = tuple(features.shape)
         ctx.spatial_scale = float(spatial_scale)
         ctx.layout = layout
@@ -119,12 +119,14 @@ class _RRoiAlignOp(torch.autograd.Function):
         idx_x, idx_y = (saved[1], saved[2]) if len(saved) == 3 else (None, None)
         grad_input = backward_raw(grad_output, rois, idx_x, idx_y, ctx.feature_size,
                                   ctx.spatial_scale, ctx.layout)
-        return grad_input, None, None, None, None, None   # reference: (grad_input, None)
+        return grad_input, None, None, None, None, None, None   # reference: (grad_input, None)
 
 
-def rroi_align(features, rois, pooled_height, pooled_width, spatial_scale):
-    """Functional form: RoIRotate of `rois` over `features` -> [N, C, PH, PW] (differentiable in features)."""
-    return _RRoiAlignOp.apply(features, rois, int(pooled_height), int(pooled_width), float(spatial_scale), None)
+def rroi_align(features, rois, pooled_height, pooled_width, spatial_scale, concurrency=0, rois_ready=False):
+    """Functional form: RoIRotate of `rois` over `features` -> [N, C, PH, PW] (differentiable in features).
+    concurrency / rois_ready: per-call launch hints (rroi_b200_opts); results never depend on them."""
+    opts = _cabi.opts(concurrency=concurrency, rois_ready=rois_ready) if (concurrency or rois_ready) else None
+    return _RRoiAlignOp.apply(features, rois, int(pooled_height), int(pooled_width), float(spatial_scale), None, opts)
 
 
 def rroi_align_bf16(features, rois, pooled_height, pooled_width, spatial_scale, opts=None):
@@ -177,7 +179,7 @@ class RRoiAlignFunction(object):
 
     def __call__(self, features, rois):
         return _RRoiAlignOp.apply(features, rois, int(self.pooled_height), int(self.pooled_width),
-                                  float(self.spatial_scale), self)
+                                  float(self.spatial_scale), self, None)
 
     # -- legacy direct methods (reference: forward(ctx, features, rois) / backward(ctx, grad_output)) --
     def forward(self, features, rois):

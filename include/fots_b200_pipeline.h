@@ -208,6 +208,17 @@ int fots_b200_dwconv3x3_nhwc_bf16(const void* x, const void* w, void* y, int N, 
  */
 int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const float* bias, float* seg, float* rbox, float* angle,
                               int B, int H, int W, int C, cudaStream_t stream);
+/* Same with the InstanceNorms either side of it fused:
+ *   stats != NULL: computes dw(act(IN(x))) -- the InstanceNorm (+ affine gamma / beta, or both NULL) + leaky-ReLU(slope)
+ *     between the pointwise and the depthwise half of a separable block is applied to the staged tile in shared memory, from
+ *     `stats` [N, C, 2] (the sums of x, fots_b200_instnorm_stats_nhwc_bf16).  The normalised tensor never exists in HBM.
+ *   stats_out != NULL: [N, C, 2] (cleared by the call) receives the sums of the bf16 outputs -- the statistics pass of the
+ *     InstanceNorm that FOLLOWS, accumulated in the epilogue (feeds fots_b200_instnorm_apply_nhwc_bf16). */
+int fots_b200_dwconv3x3_norm_nhwc_bf16(const void* x, const void* w, void* y, const double* stats, const float* gamma,
+                                       const float* beta, float eps, float slope, double* stats_out, int N, int H, int W,
+                                       int C, int stride, cudaStream_t stream);
+/* The statistics pass of fots_b200_instnorm_nhwc_bf16 on its own: workspace [B, C, 2] fp64 (cleared by the call). */
+int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspace, int B, int HW, int C, cudaStream_t stream);
 /* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 /* Halo reuse of the A operand (3x3 stride-1 convolutions, 64- / 128-wide cout tiles: one TMA load of the tile + halo rows

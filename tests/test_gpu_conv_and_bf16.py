@@ -398,3 +398,58 @@ def test_tcgen05_conv_halo_reuse_matches_torch_fp32(cuda, N, H, W, Cin, Cout, bi
     assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
     assert float((y.float() - y0.float()).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())     # fp32 sum order differs
     assert float((y2.float() - y0.float()).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 45, 84), (1, 720, 1280)])
+def test_stride2_conv_with_32_channels_through_pixel_pairs(cuda, B, H, W):
+    """layer0's second convolution (32 -> 32, 3x3, stride 2, tools/models.py:252) has too few channels for a 64-wide
+    k-block: two adjacent pixels are viewed as one 64-channel pixel on both sides (conv.pack_pixel_pairs_s2) and the
+    result is again a 3x3 stride-2 convolution on the tcgen05 kernel.  Against torch's fp32 convolution."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(B + H)
+    w = (torch.randn(32, 32, 3, 3, generator=g) / 17.0).to(cuda).to(torch.bfloat16)
+    x = torch.randn(B, 32, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y = TC.conv3x3_s2_pixel_pairs(x, TC.pack_pixel_pairs_s2(w))
+        ref = F.conv2d(x.float(), w.float(), None, 2, 1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    err = (y.float() - ref).abs()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3 * float(ref.abs().max())
+    assert bool((err <= tol).all()), "max excess %.4g" % float((err - tol).max())
+
+
+@pytest.mark.parametrize("N,C,H,W,stride,affine", [(2, 256, 45, 80, 1, False), (1, 128, 33, 47, 2, True), (3, 512, 23, 40, 1, False), (1, 64, 7, 5, 1, True)])
+def test_depthwise_with_instancenorm_on_load_equals_two_kernels(cuda, N, C, H, W, stride, affine):
+    """fots_b200_dwconv3x3_norm_nhwc_bf16 = depthwise(leaky(InstanceNorm(x))) with the normalisation applied to the staged
+    tile: bit-identical to the InstanceNorm kernels followed by the plain depthwise kernel (same coefficients, same bf16
+    rounding of the normalised values, zero padding untouched), and within bf16 noise of torch in fp32."""
+    from fots.pytorch_b200.pipeline import conv as TC, fused
+    g = torch.Generator().manual_seed(N + C + H)
+    conv = torch.nn.Conv2d(C, C, 3, stride, 1, groups=C, bias=False)
+    norm = torch.nn.InstanceNorm2d(C, eps=1e-5, affine=affine)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(C, 1, 3, 3, generator=g) / 3.0)
+        if affine:
+            norm.weight.copy_(torch.rand(C, generator=g) + 0.5); norm.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    conv = conv.to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    norm = norm.to(cuda)
+    x = (torch.randn(N, C, H, W, generator=g) * 2 + 0.5).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = TC.dwconv_norm(conv, x, fused.instnorm_stats(x), norm, 0.01)
+        fused.set_single_pass(0)
+        try:
+            two = TC.dwconv(conv, fused.instnorm_act(x, norm.weight, norm.bias, norm.eps, 0.01))
+        finally:
+            fused.set_single_pass(1)
+        ref = F.conv2d(F.leaky_relu(norm(x.float()), 0.01), conv.weight.float(), None, stride, 1, groups=C)
+    assert torch.equal(got, two)
+    assert float((got.float() - ref).abs().max()) <= 2.0 ** -6 * float(ref.abs().max()) + 1e-3
+    # epilogue statistics: the sums of exactly the tensor it stored, with and without the normalisation on load
+    with torch.no_grad():
+        y2, ws = TC.dwconv_norm(conv, x, fused.instnorm_stats(x), norm, 0.01, stats_out=True)
+        y3, ws3 = TC.dwconv_norm(conv, x, stats_out=True)
+    assert torch.equal(y2, got) and torch.equal(y3, TC.dwconv(conv, x))
+    for yy, w_ in ((y2, ws), (y3, ws3)):
+        yd = yy.double()
+        want = torch.stack([yd.sum((2, 3)), (yd * yd).sum((2, 3))], 2)
+        assert torch.allclose(w_[:N * C * 2].view(N, C, 2), want, rtol=1e-5, atol=1e-3)

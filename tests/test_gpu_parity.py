@@ -327,6 +327,29 @@ def test_module_api_and_function_attributes(oracle, cuda):
     y0.sum().backward()
 
 
+def test_module_launch_hints_do_not_change_results(oracle, cuda):
+    """_RRoiAlign(ph, pw, scale, concurrency=, rois_ready=): the optional launch hints pick kernels, never values (forward
+    bit-exact, backward to 1e-4), in both layouts."""
+    import torch
+    from fots.pytorch_b200 import _RRoiAlign
+    feats, rois, ph, pw, scale = WL.cfg1(64)
+    want, _, _ = oracle.forward(feats, rois, ph, pw, scale, threads=0)
+    r = Hh.to_cuda(rois, cuda)
+    for cl in (False, True):
+        f = Hh.to_cuda(feats, cuda, cl).requires_grad_(True)
+        base = None
+        for kw in (dict(), dict(concurrency=8), dict(rois_ready=True), dict(concurrency=8, rois_ready=True)):
+            f.grad = None
+            y = _RRoiAlign(ph, pw, scale, **kw)(f, r)
+            Hh.assert_bit_equal(y.detach().cpu().numpy(), want, "module forward %r cl=%s" % (kw, cl))
+            y.backward(torch.ones_like(y))
+            g = f.grad.detach().cpu().numpy()
+            if base is None:
+                base = g
+            else:
+                Hh.assert_close_rel(g, base, REL_BWD, "module backward %r" % (kw,))
+
+
 def test_error_behaviour(cuda):
     import torch
     from fots.pytorch_b200 import _RRoiAlign, _cabi

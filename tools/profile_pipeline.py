@@ -17,7 +17,7 @@ if __name__ == "__main__":
     net = FOTSNet(attention=True, nclass=89).to_b200(dev, inference=True)
     pipe = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=torch.bfloat16)
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    images = torch.randn(B, 3, 720, 1280, device=dev)
+    images = torch.randint(0, 256, (B, 720, 1280, 3), device=dev, dtype=torch.uint8).permute(0, 3, 1, 2)   # raw uint8, as bench.py feeds it
     quads = torch.from_numpy(planted_quads(B, 64)).to(dev)
     for _ in range(3):
         pipe.step_local(images, quads)
