@@ -57,7 +57,7 @@ def parse():
                     help="rroi_b200_opts.variant: 0 = automatic (from grid size and the concurrency hint)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / variants legs")
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--e2e-streams", type=int, default=2, help="host-buffer sets / streams of the e2e leg")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="host-buffer sets / streams of the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
     ap.add_argument("--pipeline-steps", type=int, default=4)

@@ -43,10 +43,24 @@ struct DwNorm {
     float eps, slope;
     double* stats_out;        // optional [N, C, 2]: sums of the bf16 outputs of THIS kernel (cleared by the host wrapper) --
                               // the statistics pass of the InstanceNorm that follows, for free in the epilogue
+    int lh, lw;               // UP: x is a LOW-resolution map [N, lh, lw, C]; the tile is its bilinear (align_corners) upsampling
+    float sy, sx;             //     to H x W, computed while staging (tools/models.py:418-436: upconv(F.interpolate(...)))
 };
 
+// torch's area_pixel_compute_source_index for align_corners = True (the same helper fots_b200_fpn_merge_nhwc_bf16 uses)
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {
+    Lerp r;
+    const float s = scale * (float)dst;
+    r.i0 = (int)s;
+    r.i1 = r.i0 + ((r.i0 < in - 1) ? 1 : 0);
+    r.l1 = s - (float)r.i0;
+    r.l0 = 1.0f - r.l1;
+    return r;
+}
+
 // grid (tiles_w * tiles_h, C / 64, N); block TH * 4 strips * 8 vectors.
-template <int STRIDE, int TH, bool NORM>
+template <int STRIDE, int TH, bool NORM, bool UP = false>
 __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
                                                             uint4* __restrict__ y, int H, int W, int C, int Ho, int Wo, int tiles_w,
                                                             const DwNorm nrm) {
@@ -62,7 +76,28 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
 
     // ---- stage the input tile: thread -> (pixel, vector); consecutive threads = the 8 vectors (128 B) of one pixel
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-    for (int i = threadIdx.x; i < IH * IW * 8; i += NT) {
+    if (UP) {
+        // the tile is the bilinear 2x upsampling of the low-resolution map, computed here instead of being written to and
+        // read back from HBM by a separate kernel; same arithmetic and the same single bf16 rounding as that kernel
+        const uint4* lo = x + (size_t)n * nrm.lh * nrm.lw * CV + c0 / 8;
+        for (int i = threadIdx.x; i < IH * IW * 8; i += NT) {
+            const int v = i & 7, p = i >> 3, r = p / IW, c = p - r * IW;
+            const int iy = iy0 + r, ix = ix0 + c;
+            uint4 pk = make_uint4(0, 0, 0, 0);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                const Lerp ly = lerp_coord(iy, nrm.lh, nrm.sy), lx = lerp_coord(ix, nrm.lw, nrm.sx);
+                float v00[8], v01[8], v10[8], v11[8], o[8];
+                unpack8(__ldg(lo + ((size_t)ly.i0 * nrm.lw + lx.i0) * CV + v), v00); unpack8(__ldg(lo + ((size_t)ly.i0 * nrm.lw + lx.i1) * CV + v), v01);
+                unpack8(__ldg(lo + ((size_t)ly.i1 * nrm.lw + lx.i0) * CV + v), v10); unpack8(__ldg(lo + ((size_t)ly.i1 * nrm.lw + lx.i1) * CV + v), v11);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    o[k] = ly.l0 * (lx.l0 * v00[k] + lx.l1 * v01[k]) + ly.l1 * (lx.l0 * v10[k] + lx.l1 * v11[k]);
+                pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
+            }
+            tile[i] = pk;
+        }
+    }
+    for (int i = threadIdx.x; i < (UP ? 0 : IH * IW * 8); i += NT) {
         const int v = i & 7, p = i >> 3, r = p / IW, c = p - r * IW;
         const int iy = iy0 + r, ix = ix0 + c;
         const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
@@ -188,13 +223,22 @@ static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W,
     const uint4* xp = static_cast<const uint4*>(x);
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
     uint4* yp = static_cast<uint4*>(y);
-    DwNorm none = {nullptr, nullptr, nullptr, 0.f, 1.f, nullptr};
+    DwNorm none = {nullptr, nullptr, nullptr, 0.f, 1.f, nullptr, 0, 0, 0.f, 0.f};
     if (nrm) none = *nrm;
     if (none.stats_out) {
         const cudaError_t em = cudaMemsetAsync(none.stats_out, 0, (size_t)N * C * 2 * sizeof(double), stream);
         if (em != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     }
     const bool norm_on = nrm != nullptr && nrm->stats != nullptr;
+    if (none.lh > 0) {                                        // upsample-on-load: stride 1, no normalisation
+        if (stride != 1 || norm_on) return RROI_B200_ERR_INVALID_ARG;
+        constexpr int TH = 8;
+        const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
+        dwconv3x3_kernel<1, TH, false, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
+        const cudaError_t eu = cudaGetLastError();
+        if (eu != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+        return RROI_B200_OK;
+    }
     if (stride == 1) {
         constexpr int TH = 8;
         const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
@@ -220,6 +264,18 @@ extern "C" int fots_b200_dwconv3x3_norm_nhwc_bf16(const void* x, const void* w, 
                                                   const float* beta, float eps, float slope, double* stats_out, int N, int H, int W,
                                                   int C, int stride, cudaStream_t stream) {
     if ((gamma == nullptr) != (beta == nullptr) || (!stats && (gamma || beta))) return RROI_B200_ERR_INVALID_ARG;
-    const DwNorm nrm = {stats, gamma, beta, eps, slope, stats_out};
+    const DwNorm nrm = {stats, gamma, beta, eps, slope, stats_out, 0, 0, 0.f, 0.f};
     return dw_launch(x, w, y, N, H, W, C, stride, &nrm, stream);
+}
+
+// dw(upsample(x_lo)): x_lo bf16 [N, h, w, C] -> bilinear (align_corners = True) upsampling to H x W computed while the tile
+// is staged -> depthwise 3x3 stride 1 -> y bf16 [N, H, W, C].  The upsampled map (the largest tensor of the top-down merge:
+// 236 MB per 8 images at 1/4 scale) is never written.
+extern "C" int fots_b200_dwconv3x3_up_nhwc_bf16(const void* x_lo, const void* w, void* y, int N, int h, int wlo, int H, int W, int C,
+                                                cudaStream_t stream) {
+    if (h <= 0 || wlo <= 0) return RROI_B200_ERR_INVALID_ARG;
+    DwNorm nrm = {nullptr, nullptr, nullptr, 0.f, 1.f, nullptr, h, wlo, 0.f, 0.f};
+    nrm.sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
+    nrm.sx = W > 1 ? (float)(wlo - 1) / (float)(W - 1) : 0.0f;
+    return dw_launch(x_lo, w, y, N, H, W, C, 1, &nrm, stream);
 }

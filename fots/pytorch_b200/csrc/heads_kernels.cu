@@ -27,7 +27,10 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __ex
 // the first four of them (k = 2t, 2t+1 | 2t+8, 2t+9), k-step 2m+1 the last four.  The B fragment of lane (g, t) is head g at
 // the same channels, so the permutation cancels in the dot product.
 // wq: [8 heads][C] bf16, column order {act, 0, rbox0..3, angle0, angle1};  bias: [8] fp32 in the same order.
-template <int C>
+// RAW: a 1x1 convolution to ONE output channel (the attention gate of the top-down merge, tools/models.py:405-438:
+// conv_attenton = Conv2d(256, 1, 1)): column 0 + bias, no squashing, written as bf16 [npix] -- the logits
+// fots_b200_fpn_merge_nhwc_bf16 consumes.  Same loads and MMAs; `seg` then points at the bf16 output.
+template <int C, bool RAW>
 __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wq,
                                                     const float* __restrict__ bias, float* __restrict__ seg, float* __restrict__ rbox,
                                                     float* __restrict__ angle, long long npix, int HW) {
@@ -66,6 +69,10 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x,
             const long long p = half ? p1 : p0;
             if (!(half ? ok1 : ok0)) continue;
             const float v0 = acc[2 * half] + b0, v1 = acc[2 * half + 1] + b1;
+            if (RAW) {
+                if (t == 0) reinterpret_cast<__nv_bfloat16*>(seg)[p] = __float2bfloat16_rn(v0);
+                continue;
+            }
             const long long b = p / HW, hw = p - b * HW;
             if (t == 0) {
                 seg[p] = sigmoid_f(v0);
@@ -97,9 +104,31 @@ extern "C" int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const fl
     if (ctas > 148 * 8) ctas = 148 * 8;
     const uint4* xp = static_cast<const uint4*>(x);
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(wq);
-    if (C == 128) heads_kernel<128><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
-    else if (C == 256) heads_kernel<256><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
-    else heads_kernel<512><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    if (C == 128) heads_kernel<128, false><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    else if (C == 256) heads_kernel<256, false><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    else heads_kernel<512, false><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
+
+// One-output-channel 1x1 convolution (+ bias) -> bf16 logits [B, 1, H, W]; wq / bias in the 8-row layout above with the
+// filter in row 0 and zeros elsewhere.
+extern "C" int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, const float* bias, void* out, int B, int H, int W, int C,
+                                               cudaStream_t stream) {
+    if (!x || !wq || !bias || !out || B <= 0 || H <= 0 || W <= 0) return RROI_B200_ERR_INVALID_ARG;
+    if (C != 128 && C != 256 && C != 512) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    const long long npix = (long long)B * H * W;
+    const long long tiles = (npix + 15) / 16;
+    long long ctas = (tiles + 7) / 8;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    const uint4* xp = static_cast<const uint4*>(x);
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(wq);
+    float* o = static_cast<float*>(out);
+    if (C == 128) heads_kernel<128, true><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, o, nullptr, nullptr, npix, H * W);
+    else if (C == 256) heads_kernel<256, true><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, o, nullptr, nullptr, npix, H * W);
+    else heads_kernel<512, true><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, o, nullptr, nullptr, npix, H * W);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;

@@ -22,7 +22,6 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 namespace {
 
@@ -182,7 +181,7 @@ __device__ __forceinline__ float tanh_f(float x) { return 2.0f / (1.0f + __expf(
 // Y    fp32 [T, N, 2H]      h_t of the forward direction in [:, :, :H], of the reverse direction in [:, :, H:]
 // grid = (2 * LCL, ceil(N / 64)), clusters of LCL along x: cluster = (direction, block of 64 sequences).
 __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* __restrict__ G, const __nv_bfloat16* __restrict__ Whh,
-                                                                   float* __restrict__ Y, int T, int N, int dbg) {
+                                                                   float* __restrict__ Y, int T, int N) {
     extern __shared__ __align__(16) uint8_t smem[];
     __nv_bfloat16* const Wsm = reinterpret_cast<__nv_bfloat16*>(smem);                    // [LG][LP]
     __nv_bfloat16* const Hhi = Wsm + LG * LP;                                             // [LNB][LP]
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* _
 #pragma unroll
             for (int i = 0; i < kPull; ++i) {
                 const int idx = i * 256 + threadIdx.x;
-                const int src = (dbg & 2) ? (int)r : idx / (LNB * LU / 4), rem = idx - (idx / (LNB * LU / 4)) * (LNB * LU / 4);
+                const int src = idx / (LNB * LU / 4), rem = idx - src * (LNB * LU / 4);
                 v[i] = ld_cluster_v4(map_to_rank(outbox_s + (uint32_t)((par * LNB * LU + rem * 4) * 4), (uint32_t)src));
             }
 #pragma unroll
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(256, 1) bilstm_recurrent_kernel(const float* _
             __syncthreads();
             // ---- gates += h_{t-1} * W_hh^T  (hi and lo parts)
 #pragma unroll 4
-            for (int kk = 0; kk < ((dbg & 1) ? 0 : LH); kk += 16) {
+            for (int kk = 0; kk < LH; kk += 16) {
                 uint32_t ah[4], al[4];
                 const __nv_bfloat16* ap = Hhi + (wm + g) * LP + kk + 2 * t4;
                 ah[0] = *reinterpret_cast<const uint32_t*>(ap);           ah[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * LP);
@@ -334,6 +333,5 @@ extern "C" int fots_b200_bilstm_recurrent(const float* G, const void* Whh, float
     at[0].val.clusterDim.x = LCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    static const int dbg = getenv("FOTS_B200_LSTM_DBG") ? atoi(getenv("FOTS_B200_LSTM_DBG")) : 0;   // timing experiments only
-    return status_of(cudaLaunchKernelEx(&cfg, bilstm_recurrent_kernel, G, static_cast<const __nv_bfloat16*>(Whh), Y, T, N, dbg));
+    return status_of(cudaLaunchKernelEx(&cfg, bilstm_recurrent_kernel, G, static_cast<const __nv_bfloat16*>(Whh), Y, T, N));
 }

@@ -187,6 +187,25 @@ def dwconv_norm(conv, x, stats=None, norm=None, slope=1.0, stats_out=False):
     return (y, ws) if stats_out else y
 
 
+def dwconv_up(conv, x_lo, size):
+    """conv(bilinear_upsample(x_lo, size, align_corners=True)) for a depthwise 3x3 stride-1 `conv` without materialising the
+    upsampled map (fots_b200_dwconv3x3_up_nhwc_bf16).  Caller checks dw_eligible(x_lo, conv) and conv.stride == (1, 1)."""
+    N, C, h, w = x_lo.shape
+    H, W = int(size[0]), int(size[1])
+    y = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=x_lo.device, memory_format=torch.channels_last)
+    wt = conv.weight.reshape(C, 9)
+    if not wt.is_contiguous():
+        wt = wt.contiguous()
+    L = _lib()
+    L.fots_b200_dwconv3x3_up_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_dwconv3x3_up_nhwc_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    with torch.cuda.device(x_lo.device):
+        rc = L.fots_b200_dwconv3x3_up_nhwc_bf16(x_lo.data_ptr(), wt.data_ptr(), y.data_ptr(), N, h, w, H, W, C,
+                                                torch.cuda.current_stream(x_lo.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_dwconv3x3_up_nhwc_bf16")
+    return y
+
+
 def pack_pixel_pairs_s2(weight):
     """Weights of a 3x3 stride-2 pad-1 convolution with FEWER than 64 input channels (layer0's 32 -> 32, tools/models.py:252)
     re-expressed for the 64-channel kernel: two horizontally adjacent pixels are viewed as one pixel with 2*Cin channels
@@ -229,6 +248,30 @@ def pack_heads(act, rbox, angle):
     b[2:6] = rbox.bias.detach().float()
     b[6:8] = angle.bias.detach().float()
     return w.contiguous(), b.contiguous()
+
+
+def pack_to1(conv):
+    """Conv2d(C, 1, 1, bias=True) in the 8-row block of fots_b200_conv1x1_to1_nhwc_bf16 (filter in row 0)."""
+    C = conv.in_channels
+    w = torch.zeros((8, C), dtype=torch.bfloat16, device=conv.weight.device)
+    b = torch.zeros((8,), dtype=torch.float32, device=conv.weight.device)
+    w[0] = conv.weight.detach()[0, :, 0, 0]
+    b[0] = conv.bias.detach().float()[0]
+    return w.contiguous(), b.contiguous()
+
+
+def conv1x1_to1(x, packed):
+    """x bf16 channels-last [B, C, H, W] -> bf16 logits [B, 1, H, W] (one pass over x, bias added, no activation)."""
+    B, C, H, W = x.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.bfloat16, device=x.device)
+    L = _lib()
+    L.fots_b200_conv1x1_to1_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_conv1x1_to1_nhwc_bf16.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    with torch.cuda.device(x.device):
+        rc = L.fots_b200_conv1x1_to1_nhwc_bf16(x.data_ptr(), packed[0].data_ptr(), packed[1].data_ptr(), out.data_ptr(), B, H, W, C,
+                                               torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_conv1x1_to1_nhwc_bf16")
+    return out
 
 
 def heads(x, packed):

@@ -221,12 +221,18 @@ class FOTSNet(nn.Module):
         if fused.merge_eligible(f1, f2, f3, f4):
             # inference fast path: each merge step is one fused kernel (upsample + attention gate + add)
             att = self.conv_attenton if self.attention else (lambda t: None)
+            apack = getattr(self, "_att_pack", None)
+            if self.attention and apack is not None and tc.LEVEL >= 2 and f4.size(1) in (128, 256, 512):
+                att = lambda t: tc.conv1x1_to1(t, apack)                  # one pass over t, bf16 logits for the merge kernel
             x = fused.fpn_merge(a_lo=f4, b_hi=f3, gate_logits_lo=att(f4))
-            up = lambda seq, t: pw(seq[1], tc.dwconv(seq[0], t))        # depthwise 3x3 + pointwise 1x1
-            f2 = fused.fpn_merge(c_hi=up(self.upconv1, fused.fpn_merge(a_lo=x, size=f2.shape[2:])), b_hi=f2,
-                                 gate_logits_lo=att(x))
-            x = fused.fpn_merge(c_hi=up(self.upconv2, fused.fpn_merge(a_lo=f2, size=f1.shape[2:])), b_hi=f1,
-                                gate_logits_lo=att(f2))
+            def up(seq, lo, size):
+                # upconv(F.interpolate(lo)): depthwise 3x3 + pointwise 1x1 on the 2x bilinear upsampling of `lo`.  The upsampling
+                # is computed while the depthwise kernel stages its tile, so the upsampled map is never written.
+                if tc.dw_eligible(lo, seq[0]) and seq[0].stride == (1, 1):
+                    return pw(seq[1], tc.dwconv_up(seq[0], lo, size))
+                return pw(seq[1], tc.dwconv(seq[0], fused.fpn_merge(a_lo=lo, size=size)))
+            f2 = fused.fpn_merge(c_hi=up(self.upconv1, x, f2.shape[2:]), b_hi=f2, gate_logits_lo=att(x))
+            x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, gate_logits_lo=att(f2))
         elif self.attention:
             x = _up(f4, f3) + f3 * _up(torch.sigmoid(self.conv_attenton(f4)).expand_as(f4), f3)
             gate = self._gate(x, f2)
@@ -274,7 +280,7 @@ class FOTSNet(nn.Module):
         re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
         batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
         self.to(device=device, memory_format=torch.channels_last)
-        self._conv11_pad = self._heads_pack = self._l0c1_pairs = None
+        self._conv11_pad = self._heads_pack = self._l0c1_pairs = self._att_pack = None
         if inference:
             for m in self.modules():
                 if isinstance(m, nn.Conv2d):
@@ -289,6 +295,8 @@ class FOTSNet(nn.Module):
             bias[:c11.out_channels] = c11.bias.detach().float()
             self._conv11_pad = (w.contiguous(memory_format=torch.channels_last), bias)
             self._heads_pack = tc.pack_heads(self.act, self.rbox, self.angle)
+            if self.attention:
+                self._att_pack = tc.pack_to1(self.conv_attenton)
             c01 = self.layer0[2]
             if c01.in_channels == 32 and c01.out_channels == 32 and c01.bias is None:
                 self._l0c1_pairs = tc.pack_pixel_pairs_s2(c01.weight.detach())

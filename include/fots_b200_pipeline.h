@@ -217,9 +217,20 @@ int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const float* bias, 
 int fots_b200_dwconv3x3_norm_nhwc_bf16(const void* x, const void* w, void* y, const double* stats, const float* gamma,
                                        const float* beta, float eps, float slope, double* stats_out, int N, int H, int W,
                                        int C, int stride, cudaStream_t stream);
+/* dw(upsample(x_lo)): bilinear (align_corners = True) upsampling of x_lo [N, h, w, C] to H x W computed while the depthwise
+ * kernel stages its tile (tools/models.py:418-436: upconv(F.interpolate(x))): the upsampled map is never written. */
+int fots_b200_dwconv3x3_up_nhwc_bf16(const void* x_lo, const void* w, void* y, int N, int h, int wlo, int H, int W, int C,
+                                     cudaStream_t stream);
 /* The statistics pass of fots_b200_instnorm_nhwc_bf16 on its own: workspace [B, C, 2] fp64 (cleared by the call). */
 int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspace, int B, int HW, int C, cudaStream_t stream);
-/* Output-channel tile of the kernel above: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
+/* A 1x1 convolution to ONE output channel + bias (the attention gate conv_attenton of the top-down merge,
+ * tools/models.py:405-438) -> bf16 logits [B, 1, H, W] (what fots_b200_fpn_merge_nhwc_bf16 takes as gate_logits):
+ * x bf16 [B, H, W, C], wq bf16 [8, C] with the filter in row 0 and zeros elsewhere, bias fp32 [8].  Same kernel as the heads. */
+int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, const float* bias, void* out, int B, int H, int W, int C,
+                                    cudaStream_t stream);
+/* The three fots_b200_*_set_* switches below are process-wide A/B switches for sweeps and parity tests (not thread-safe,
+ * never needed for correct results); everything a production caller selects travels with the call.
+ * Output-channel tile of fots_b200_conv2d_nhwc_bf16: 0 = automatic, or 64 / 128 / 256 (for sweeps). */
 int fots_b200_conv_set_tile(int bn);
 /* Halo reuse of the A operand (3x3 stride-1 convolutions, 64- / 128-wide cout tiles: one TMA load of the tile + halo rows
  * feeds three filter taps; 64 -> 64 channels: one box feeds all nine, weights resident): -1 = automatic (maps of at least

@@ -334,6 +334,11 @@ def test_fused_detection_heads_match_torch_fp32(cuda, B, C, H, W):
     assert float((seg - want_seg).abs().max()) <= 1e-4
     assert float((rb - want_rb).abs().max()) <= 1e-2            # values up to 128
     assert float((an - want_an).abs().max()) <= 2e-3            # the normalisation amplifies near |a| ~ 0
+    # the one-channel variant (attention gate logits, bf16 out)
+    with torch.no_grad():
+        got = TC.conv1x1_to1(x, TC.pack_to1(act))
+    assert got.shape == (B, 1, H, W) and got.dtype == torch.bfloat16
+    assert float((got.float() - f(act)).abs().max()) <= 2.0 ** -8 * float(f(act).abs().max()) + 1e-3
 
 
 def test_folded_batchnorm_downsample_branch_matches_module(cuda):
@@ -453,3 +458,24 @@ def test_depthwise_with_instancenorm_on_load_equals_two_kernels(cuda, N, C, H, W
         yd = yy.double()
         want = torch.stack([yd.sum((2, 3)), (yd * yd).sum((2, 3))], 2)
         assert torch.allclose(w_[:N * C * 2].view(N, C, 2), want, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("N,C,h,w,H,W", [(2, 256, 45, 80, 90, 160), (1, 256, 23, 40, 45, 80), (1, 64, 5, 7, 9, 13), (1, 128, 8, 8, 8, 8)])
+def test_depthwise_with_upsample_on_load_equals_two_kernels(cuda, N, C, h, w, H, W):
+    """fots_b200_dwconv3x3_up_nhwc_bf16 = depthwise(bilinear_upsample(x_lo)) with the upsampling computed while the tile is
+    staged: bit-identical to fots_b200_fpn_merge_nhwc_bf16 (upsample only) followed by the plain depthwise kernel, and within
+    bf16 noise of torch's F.interpolate(align_corners=True) + grouped convolution in fp32."""
+    from fots.pytorch_b200.pipeline import conv as TC, fused
+    g = torch.Generator().manual_seed(N + C + h)
+    conv = torch.nn.Conv2d(C, C, 3, 1, 1, groups=C, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(C, 1, 3, 3, generator=g) / 3.0)
+    conv = conv.to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    lo = torch.randn(N, C, h, w, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = TC.dwconv_up(conv, lo, (H, W))
+        two = TC.dwconv(conv, fused.fpn_merge(a_lo=lo, size=(H, W)))
+        up = F.interpolate(lo.float(), size=(H, W), mode="bilinear", align_corners=True)
+        ref = F.conv2d(up, conv.weight.float(), None, 1, 1, groups=C)
+    assert got.shape == (N, C, H, W) and torch.equal(got, two)
+    assert float((got.float() - ref).abs().max()) <= 2.0 ** -6 * float(ref.abs().max()) + 1e-3
