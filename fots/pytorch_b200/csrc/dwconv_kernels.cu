@@ -59,8 +59,9 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {
     return r;
 }
 
+// One tile per CTA (stride 2; the stride-1 shapes take the persistent pipelined kernel below).
 // grid (tiles_w * tiles_h, C / 64, N); block TH * 4 strips * 8 vectors.
-template <int STRIDE, int TH, bool NORM, bool UP = false>
+template <int STRIDE, int TH, bool NORM>
 __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
                                                             uint4* __restrict__ y, int H, int W, int C, int Ho, int Wo, int tiles_w,
                                                             const DwNorm nrm) {
@@ -76,28 +77,7 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
 
     // ---- stage the input tile: thread -> (pixel, vector); consecutive threads = the 8 vectors (128 B) of one pixel
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-    if (UP) {
-        // the tile is the bilinear 2x upsampling of the low-resolution map, computed here instead of being written to and
-        // read back from HBM by a separate kernel; same arithmetic and the same single bf16 rounding as that kernel
-        const uint4* lo = x + (size_t)n * nrm.lh * nrm.lw * CV + c0 / 8;
-        for (int i = threadIdx.x; i < IH * IW * 8; i += NT) {
-            const int v = i & 7, p = i >> 3, r = p / IW, c = p - r * IW;
-            const int iy = iy0 + r, ix = ix0 + c;
-            uint4 pk = make_uint4(0, 0, 0, 0);
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-                const Lerp ly = lerp_coord(iy, nrm.lh, nrm.sy), lx = lerp_coord(ix, nrm.lw, nrm.sx);
-                float v00[8], v01[8], v10[8], v11[8], o[8];
-                unpack8(__ldg(lo + ((size_t)ly.i0 * nrm.lw + lx.i0) * CV + v), v00); unpack8(__ldg(lo + ((size_t)ly.i0 * nrm.lw + lx.i1) * CV + v), v01);
-                unpack8(__ldg(lo + ((size_t)ly.i1 * nrm.lw + lx.i0) * CV + v), v10); unpack8(__ldg(lo + ((size_t)ly.i1 * nrm.lw + lx.i1) * CV + v), v11);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    o[k] = ly.l0 * (lx.l0 * v00[k] + lx.l1 * v01[k]) + ly.l1 * (lx.l0 * v10[k] + lx.l1 * v11[k]);
-                pk.x = pack2(o[0], o[1]); pk.y = pack2(o[2], o[3]); pk.z = pack2(o[4], o[5]); pk.w = pack2(o[6], o[7]);
-            }
-            tile[i] = pk;
-        }
-    }
-    for (int i = threadIdx.x; i < (UP ? 0 : IH * IW * 8); i += NT) {
+    for (int i = threadIdx.x; i < IH * IW * 8; i += NT) {
         const int v = i & 7, p = i >> 3, r = p / IW, c = p - r * IW;
         const int iy = iy0 + r, ix = ix0 + c;
         const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
@@ -211,7 +191,311 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
     }
 }
 
+// ---- stride 1: persistent, software-pipelined ---------------------------------------------------------------------
+// The one-tile-per-CTA form above loads, waits, computes, stores: with three CTAs per SM about a third of the SM's tiles
+// are in flight at any time and the kernel sits at 0.4 of the copy roofline.  Here a CTA owns ONE 64-channel block (its
+// 72 weights per thread stay in registers) and walks over that block's tiles; the cp.async of tile i+1 is issued before
+// tile i is computed (two shared-memory buffers), so loads are always in flight.  The 3x3 accumulation uses packed fp32
+// FMAs (fma.rn.f32x2: each half an ordinary IEEE fp32 FMA in the same (r, s) order -> bit-identical to the scalar chain).
+constexpr int kTH = 8, kIH = kTH + 2, kIW = kTW + 2;                 // 16 x 8 outputs from an 18 x 10 input tile
+constexpr int kTileVec = kIH * kIW * 8;                              // 1 440 uint4 = 23 040 B
+constexpr int kLoH = 8, kLoW = 12, kLoVec = kLoH * kLoW * 8;          // UP: low-resolution footprint of a tile (2x: 7 x 11), 12 288 B
+constexpr int kNT = 256;
+enum { kPlain = 0, kNorm = 1, kUp = 2 };
+
+__device__ __forceinline__ uint64_t pair_f32(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t widen2(uint32_t w) { return pair_f32(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ void split2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+struct TilePos { int n, oy0, ox0; };
+__device__ __forceinline__ TilePos tile_pos(int t, int tiles_w, int tiles_h) {
+    TilePos p;
+    const int tx = t % tiles_w;
+    t /= tiles_w;
+    p.n = t / tiles_h;
+    p.oy0 = (t - p.n * tiles_h) * kTH;
+    p.ox0 = tx * kTW;
+    return p;
+}
+
+// Low-resolution footprint of a tile for the UP mode: rows [y0, y0 + nh), columns [x0, x0 + nw); fits = it can be staged.
+struct LoBox { int y0, x0, nh, nw; bool fits; };
+__device__ __forceinline__ LoBox lo_box(const TilePos& tp, int H, int W, const DwNorm& nrm) {
+    LoBox b;
+    const int ya = max(tp.oy0 - 1, 0), yb = min(tp.oy0 + kTH, H - 1), xa = max(tp.ox0 - 1, 0), xb = min(tp.ox0 + kTW, W - 1);
+    b.y0 = lerp_coord(ya, nrm.lh, nrm.sy).i0;
+    b.x0 = lerp_coord(xa, nrm.lw, nrm.sx).i0;
+    b.nh = lerp_coord(yb, nrm.lh, nrm.sy).i1 - b.y0 + 1;
+    b.nw = lerp_coord(xb, nrm.lw, nrm.sx).i1 - b.x0 + 1;
+    b.fits = b.nh <= kLoH && b.nw <= kLoW;
+    return b;
+}
+
+// grid (CTAs per channel block, C / 64); block 256 = 8 rows x 4 strips x 8 vectors.  Dynamic shared memory:
+//   plain / NORM: two input tiles (+ NORM: 128 coefficients, + stats_out: the [256][17] reduction scratch)
+//   UP:           two low-resolution footprints + one (upsampled) input tile
+template <int MODE>
+__global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
+                                                                                        uint4* __restrict__ y, int H, int W, int C, int tiles_w,
+                                                                                        int tiles_h, int ntiles, const DwNorm nrm) {
+    extern __shared__ __align__(16) uint4 dsm[];
+    uint4* const stage0 = dsm;                                                    // [2][kTileVec] or (UP) [2][kLoVec]
+    uint4* const hi_tile = dsm + 2 * kLoVec;                                      // UP only
+    float* const coef = reinterpret_cast<float*>(dsm + 2 * kTileVec);            // NORM only: scale[64], shift[64]
+    float* const red = coef + 2 * kCB;                                            // NORM + stats_out only: [256][17]
+    const int c0 = blockIdx.y * kCB;
+    const int CV = C / 8;
+    const int tid = threadIdx.x;
+    const int v = tid & 7, strip = tid >> 3, row = strip >> 2, q4 = strip & 3;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage0);
+
+    // ---- prefetch of one tile (plain / NORM: the 18 x 10 input tile, zero-filled outside the image = the padding;
+    //      UP: the low-resolution footprint, when it fits)
+    auto prefetch = [&](int t, int buf) {
+        const TilePos tp = tile_pos(t, tiles_w, tiles_h);
+        if (MODE == kUp) {
+            const LoBox lb = lo_box(tp, H, W, nrm);
+            if (lb.fits) {
+                const uint4* lo = x + (size_t)tp.n * nrm.lh * nrm.lw * CV + c0 / 8;
+                for (int i = tid; i < kLoVec; i += kNT) {
+                    const int vv = i & 7, p = i >> 3, r = p / kLoW, c = p - r * kLoW;
+                    if (r < lb.nh && c < lb.nw) {
+                        const uint4* src = lo + ((size_t)(lb.y0 + r) * nrm.lw + lb.x0 + c) * CV + vv;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_s + (uint32_t)(buf * kLoVec + i) * 16u), "l"(src) : "memory");
+                    }
+                }
+            }
+        } else {
+            const uint4* img = x + (size_t)tp.n * H * W * CV + c0 / 8;
+            const int iy0 = tp.oy0 - 1, ix0 = tp.ox0 - 1;
+            for (int i = tid; i < kTileVec; i += kNT) {
+                const int vv = i & 7, p = i >> 3, r = p / kIW, c = p - r * kIW;
+                const int iy = iy0 + r, ix = ix0 + c;
+                const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+                const uint4* src = ok ? img + ((size_t)iy * W + ix) * CV + vv : img;
+                const uint32_t nbytes = ok ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(stage_s + (uint32_t)(buf * kTileVec + i) * 16u), "l"(src), "r"(nbytes) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int t = blockIdx.x;
+    if (t < ntiles) prefetch(t, 0);
+
+    // ---- this thread's 8 channels x 9 taps of weights as fp32 pairs; w is [C][3][3]
+    uint64_t wr[9][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+            wr[tp][k] = pair_f32(__bfloat162float(wgt[(size_t)(c0 + v * 8 + 2 * k) * 9 + tp]), __bfloat162float(wgt[(size_t)(c0 + v * 8 + 2 * k + 1) * 9 + tp]));
+
+    // stats_out: every thread keeps running sums of its outputs in ITS row of `red` (shared memory, not registers: the
+    // weights and accumulators already fill the register file), flushed to the fp64 workspace when the image changes
+    const bool want_sums = MODE == kNorm && nrm.stats_out != nullptr;
+    if (want_sums) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) red[tid * 17 + k] = 0.0f;
+    }
+    int sums_n = -1;
+    auto flush_sums = [&](int n) {                            // CTA-uniform call
+        __syncthreads();
+        float a = 0.0f;
+        const int vv = tid >> 4, k = tid & 15;                // tid < 128: 8 vectors x 16 values
+        if (tid < 128) {
+            for (int st = 0; st < kNT / 8; ++st) a += red[(st * 8 + vv) * 17 + k];
+            atomicAdd(nrm.stats_out + ((size_t)n * C + c0 + vv * 8 + (k & 7)) * 2 + (k >> 3), (double)a);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) red[tid * 17 + kk] = 0.0f;
+    };
+
+    for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) {
+            prefetch(tn, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const TilePos tp = tile_pos(t, tiles_w, tiles_h);
+        const int iy0 = tp.oy0 - 1, ix0 = tp.ox0 - 1;
+        uint4* tile = MODE == kUp ? hi_tile : stage0 + cur * kTileVec;
+
+        if (MODE == kUp) {
+            // ---- expand: the staged tile is the bilinear upsampling of the low-resolution map, four taps per staged vector read
+            // from the staged footprint.  o = fma(ly.l1, t1, ly.l0 * t0), t = fma(lx.l1, v1, lx.l0 * v0) in fp32 pairs: the
+            // arithmetic of fots_b200_fpn_merge_nhwc_bf16 (instnorm_kernels.cu), one rounding to bf16.
+            {
+                const LoBox lb = lo_box(tp, H, W, nrm);
+                const uint4* src;                            // generic pointer: the staged footprint or (it did not fit) the map itself
+                int pitch_r, pitch_c, yorg, xorg;
+                if (lb.fits) { src = stage0 + cur * kLoVec; pitch_r = kLoW * 8; pitch_c = 8; yorg = lb.y0; xorg = lb.x0; }
+                else { src = x + (size_t)tp.n * nrm.lh * nrm.lw * CV + c0 / 8; pitch_r = nrm.lw * CV; pitch_c = CV; yorg = 0; xorg = 0; }
+                for (int i = tid; i < kTileVec; i += kNT) {
+                    const int vv = i & 7, p = i >> 3, r = p / kIW, c = p - r * kIW;
+                    const int iy = iy0 + r, ix = ix0 + c;
+                    uint4 pk = make_uint4(0, 0, 0, 0);
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                        const Lerp ly = lerp_coord(iy, nrm.lh, nrm.sy), lx = lerp_coord(ix, nrm.lw, nrm.sx);
+                        const uint4* r0 = src + (size_t)(ly.i0 - yorg) * pitch_r + vv;
+                        const uint4* r1 = src + (size_t)(ly.i1 - yorg) * pitch_r + vv;
+                        const int o0 = (lx.i0 - xorg) * pitch_c, o1 = (lx.i1 - xorg) * pitch_c;
+                        const uint4 q00 = r0[o0], q01 = r0[o1], q10 = r1[o0], q11 = r1[o1];
+                        const uint32_t w00[4] = {q00.x, q00.y, q00.z, q00.w}, w01[4] = {q01.x, q01.y, q01.z, q01.w};
+                        const uint32_t w10[4] = {q10.x, q10.y, q10.z, q10.w}, w11[4] = {q11.x, q11.y, q11.z, q11.w};
+                        const uint64_t lx0 = pair_f32(lx.l0, lx.l0), lx1 = pair_f32(lx.l1, lx.l1);
+                        const uint64_t ly0 = pair_f32(ly.l0, ly.l0), ly1 = pair_f32(ly.l1, ly.l1);
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t t0 = fma2(lx1, widen2(w01[k]), mul2(lx0, widen2(w00[k])));
+                            const uint64_t t1 = fma2(lx1, widen2(w11[k]), mul2(lx0, widen2(w10[k])));
+                            float lo_, hi_;
+                            split2(fma2(ly1, t1, mul2(ly0, t0)), lo_, hi_);
+                            ow[k] = pack2(lo_, hi_);
+                        }
+                        pk = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                    tile[i] = pk;
+                }
+            }
+            __syncthreads();
+        }
+        if (MODE == kNorm) {
+            // scale / shift of this CTA's 64 channels for image n, then normalise + activate the staged tile in place
+            if (want_sums && sums_n != tp.n) {
+                if (sums_n >= 0) flush_sums(sums_n);
+                sums_n = tp.n;
+            }
+            if (nrm.stats == nullptr) goto conv;              // CTA-uniform: output statistics only, nothing to normalise
+            if (tid < kCB) {
+                const int c = c0 + tid;
+                const double hw = (double)H * (double)W;
+                const double m = nrm.stats[((size_t)tp.n * C + c) * 2] / hw;
+                double var = nrm.stats[((size_t)tp.n * C + c) * 2 + 1] / hw - m * m;
+                var = var < 0.0 ? 0.0 : var;
+                const float rstd = rsqrtf((float)var + nrm.eps), mean = (float)m;
+                const float g0 = nrm.gamma ? nrm.gamma[c] : 1.0f, b0 = nrm.beta ? nrm.beta[c] : 0.0f;
+                coef[tid] = rstd * g0;
+                coef[kCB + tid] = b0 - mean * rstd * g0;
+            }
+            __syncthreads();
+            for (int i = tid; i < kTileVec; i += kNT) {
+                const int vv = i & 7, p = i >> 3, r = p / kIW, c = p - r * kIW;
+                const int iy = iy0 + r, ix = ix0 + c;
+                if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;                 // padding: stays exactly zero
+                float f[8];
+                unpack8(tile[i], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float tt = fmaf(f[k], coef[vv * 8 + k], coef[kCB + vv * 8 + k]);
+                    f[k] = tt > 0.0f ? tt : tt * nrm.slope;
+                }
+                uint4 pk;                                                              // one bf16 rounding, as the separate apply pass stores it
+                pk.x = pack2(f[0], f[1]); pk.y = pack2(f[2], f[3]); pk.z = pack2(f[4], f[5]); pk.w = pack2(f[6], f[7]);
+                tile[i] = pk;
+            }
+            __syncthreads();
+        }
+
+    conv:
+        // ---- 3x3 accumulation: 4 outputs x 8 channels per thread, fp32 pairs, order (r, s) = (0,0) .. (2,2)
+        uint64_t acc[4][4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[o][k] = 0ull;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint4* trow = tile + ((row + r) * kIW + q4 * 4) * 8 + v;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const uint4 raw = trow[j * 8];
+                const uint64_t f[4] = {widen2(raw.x), widen2(raw.y), widen2(raw.z), widen2(raw.w)};
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int sx = j - o;                                              // tap column of output o fed by input column j
+                    if (sx >= 0 && sx < 3) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[o][k] = fma2(f[k], wr[r * 3 + sx][k], acc[o][k]);
+                    }
+                }
+            }
+        }
+        const int oy = tp.oy0 + row;
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.0f;
+        if (oy < H) {
+            uint4* out = y + (((size_t)tp.n * H + oy) * W) * CV + c0 / 8 + v;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int ox = tp.ox0 + q4 * 4 + o;
+                if (ox < W) {
+                    float a[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) split2(acc[o][k], a[2 * k], a[2 * k + 1]);
+                    uint4 pk;
+                    pk.x = pack2(a[0], a[1]); pk.y = pack2(a[2], a[3]); pk.z = pack2(a[4], a[5]); pk.w = pack2(a[6], a[7]);
+                    out[(size_t)ox * CV] = pk;
+                    if (want_sums) {                                     // of the ROUNDED values, as a separate pass would see them
+                        float f[8];
+                        unpack8(pk, f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { ssum[k] += f[k]; ssq[k] = fmaf(f[k], f[k], ssq[k]); }
+                    }
+                }
+            }
+        }
+        if (want_sums) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { red[tid * 17 + k] += ssum[k]; red[tid * 17 + 8 + k] += ssq[k]; }
+        }
+        __syncthreads();                                      // the tile buffer is free: the next iteration prefetches into it
+    }
+    if (want_sums && sums_n >= 0) flush_sums(sums_n);
+}
+
 }  // namespace
+
+// Persistent launch: as many CTAs per channel block as the device holds at once (whole waves; see resident sizing in
+// instnorm_kernels.cu), never more than there are tiles.  The dynamic shared-memory opt-in is set on every launch (it is
+// per device, and cheap).
+template <int MODE>
+static cudaError_t dw_pipe_launch(size_t smem, const uint4* xp, const __nv_bfloat16* wp, uint4* yp, int H, int W, int C, int tiles_w,
+                                  int tiles_h, int ntiles, int cblocks, const DwNorm& nrm, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_s1_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, occ = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwconv3x3_s1_pipe_kernel<MODE>, kNT, smem)) != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    int gx = sms * occ / cblocks;
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    dwconv3x3_s1_pipe_kernel<MODE><<<dim3((unsigned)gx, (unsigned)cblocks), kNT, smem, stream>>>(xp, wp, yp, H, W, C, tiles_w, tiles_h, ntiles, nrm);
+    return cudaGetLastError();
+}
 
 static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride, const DwNorm* nrm, cudaStream_t stream) {
     if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % kCB != 0 || (stride != 1 && stride != 2) || N > 65535 ||
@@ -230,21 +514,21 @@ static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W,
         if (em != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     }
     const bool norm_on = nrm != nullptr && nrm->stats != nullptr;
-    if (none.lh > 0) {                                        // upsample-on-load: stride 1, no normalisation
-        if (stride != 1 || norm_on) return RROI_B200_ERR_INVALID_ARG;
-        constexpr int TH = 8;
-        const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
-        dwconv3x3_kernel<1, TH, false, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
-        const cudaError_t eu = cudaGetLastError();
-        if (eu != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    const bool up = none.lh > 0;
+    if (up && (stride != 1 || norm_on)) return RROI_B200_ERR_INVALID_ARG;     // upsample-on-load: stride 1, no normalisation
+    if (stride == 1) {
+        const int tiles_h = (Ho + kTH - 1) / kTH;
+        const long long ntiles = (long long)tiles_w * tiles_h * N;
+        if (ntiles > (1LL << 30)) return RROI_B200_ERR_INVALID_ARG;
+        const int cblocks = C / kCB;
+        cudaError_t e1 = cudaSuccess;
+        if (up) e1 = dw_pipe_launch<kUp>((size_t)(2 * kLoVec + kTileVec) * 16, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
+        else if (norm_on || none.stats_out) e1 = dw_pipe_launch<kNorm>((size_t)2 * kTileVec * 16 + 2 * kCB * 4 + (none.stats_out ? kNT * 17 * 4 : 0), xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
+        else e1 = dw_pipe_launch<kPlain>((size_t)2 * kTileVec * 16, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
+        if (e1 != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
         return RROI_B200_OK;
     }
-    if (stride == 1) {
-        constexpr int TH = 8;
-        const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
-        if (norm_on) dwconv3x3_kernel<1, TH, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
-        else dwconv3x3_kernel<1, TH, false><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
-    } else {
+    {
         constexpr int TH = 4;
         const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
         if (norm_on) dwconv3x3_kernel<2, TH, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);

@@ -31,7 +31,7 @@ __device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
 }
 
 // grid (chunks, B).  Thread -> channel group g = tid % G (8 channels), row phase tid / G.
-__global__ void __launch_bounds__(kThreads) in_stats_kernel(const Bf16x8* __restrict__ x, double* __restrict__ ws,
+__global__ void __launch_bounds__(kThreads, 4) in_stats_kernel(const Bf16x8* __restrict__ x, double* __restrict__ ws,
                                                              int HW, int C, int rows_per_cta) {
     const int G = C / 8;
     const int b = blockIdx.y;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) in_stats_kernel(const Bf16x8* __rest
 
 // grid (chunks, B).  y = act(((+-)(x - mean) * rstd) * gamma + beta [+ residual])
 template <bool kCRelu, bool kResidual>
-__global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __restrict__ x, Bf16x8* __restrict__ y,
+__global__ void __launch_bounds__(kThreads, kResidual ? 3 : 4) in_apply_kernel(const Bf16x8* __restrict__ x, Bf16x8* __restrict__ y,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const Bf16x8* __restrict__ res, const double* __restrict__ ws,
                                                              int HW, int C, int rows_per_cta, float eps, float slope) {
@@ -101,18 +101,20 @@ __global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __rest
         }
     }
     __syncthreads();
-    const int g = threadIdx.x % G, phase = threadIdx.x / G, nphase = kThreads / G;
+    // Thread -> one OUTPUT channel group g (8 channels) and a row phase.  CReLU: output groups [0, G) are IN(x), [G, 2G) are
+    // IN(-x) of input group g - G (the sign lives in the coefficients), so consecutive lanes still store consecutive 16-byte
+    // vectors (whole lines per warp) and the two lanes that share an input vector load the same address (one transaction).
+    const int Gout = Cout / 8;
+    const int g = threadIdx.x % Gout, phase = threadIdx.x / Gout, nphase = kThreads / Gout;
     if (phase >= nphase) return;
+    const int gin = kCRelu ? (g >= G ? g - G : g) : g;
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(HW, r0 + rows_per_cta);
     const size_t plane = (size_t)b * HW;
-    const int Gout = Cout / 8;
     // this thread's 8 channels: coefficients in registers, U rows in flight (memory-level parallelism)
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = scale[g * 8 + i]; sh[i] = shift[g * 8 + i]; }
-    const float* sc2 = scale + C + g * 8;                 // CReLU's second half: read from shared memory (saves 16 registers)
-    const float* sh2 = shift + C + g * 8;
     constexpr int U = 4;
     for (int r = r0 + phase; r < r1; r += U * nphase) {
         Bf16x8 xv[U], rv[U];
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __rest
         for (int u = 0; u < U; ++u) {
             const int rr_ = r + u * nphase;
             if (rr_ < r1) {
-                xv[u] = ld8(x + (plane + rr_) * G + g);
+                xv[u] = ld8(x + (plane + rr_) * G + gin);
                 if (kResidual) rv[u] = ld8(res + (plane + rr_) * G + g);
             }
         }
@@ -141,14 +143,6 @@ __global__ void __launch_bounds__(kThreads) in_apply_kernel(const Bf16x8* __rest
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.0f ? o[i] : o[i] * slope;
             y[(plane + rr_) * Gout + g] = pack8(o);
-            if (kCRelu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float v = fmaf(f[i], sc2[i], sh2[i]);
-                    o[i] = v > 0.0f ? v : v * slope;
-                }
-                y[(plane + rr_) * Gout + G + g] = pack8(o);
-            }
         }
     }
 }
@@ -345,48 +339,82 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {   // 
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads) fpn_merge_kernel(const Bf16x8* __restrict__ a_lo, const Bf16x8* __restrict__ c_hi,
-                                                              const Bf16x8* __restrict__ b_hi, const __nv_bfloat16* __restrict__ g_lo,
-                                                              Bf16x8* __restrict__ y, int B, int h, int w, int H, int W, int C) {
+// Work item = kMergeU * kThreads consecutive 16-byte vectors of ONE output row (b, Y): the row's vertical coordinates are
+// CTA-uniform, everything per thread is 32-bit, and a thread has kMergeU independent vectors (all their loads) in flight.
+// kUp: the first operand is the low-resolution a_lo (four taps per vector, kU = 2); else the full-resolution c_hi (kU = 4).
+template <bool kUp, int kMergeU>
+__global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __restrict__ a_lo, const Bf16x8* __restrict__ c_hi,
+                                                                 const Bf16x8* __restrict__ b_hi, const __nv_bfloat16* __restrict__ g_lo,
+                                                                 Bf16x8* __restrict__ y, int B, int h, int w, int H, int W, int C,
+                                                                 int segs, long long items) {
     const int G = C / 8;
-    const long long total = (long long)B * H * W * G;
+    const int rowv = W * G;                                   // vectors per output row
     const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
     const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        const int g = (int)(i % G);
-        long long p = i / G;
-        const int X = (int)(p % W); p /= W;
-        const int Y = (int)(p % H);
-        const int b = (int)(p / H);
-        const Lerp ly = lerp_coord(Y, h, sy), lx = lerp_coord(X, w, sx);
-        const long long lo00 = ((long long)b * h + ly.i0) * w + lx.i0, lo01 = ((long long)b * h + ly.i0) * w + lx.i1;
-        const long long lo10 = ((long long)b * h + ly.i1) * w + lx.i0, lo11 = ((long long)b * h + ly.i1) * w + lx.i1;
-        float o[8];
-        if (a_lo) {
-            float v00[8], v01[8], v10[8], v11[8];
-            unpack8(ld8(a_lo + lo00 * G + g), v00); unpack8(ld8(a_lo + lo01 * G + g), v01);
-            unpack8(ld8(a_lo + lo10 * G + g), v10); unpack8(ld8(a_lo + lo11 * G + g), v11);
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const int seg = (int)(item % segs);
+        const long long row = item / segs;                    // b * H + Y
+        const int Y = (int)(row % H);
+        const int b = (int)(row / H);
+        const Lerp ly = lerp_coord(Y, h, sy);
+        const size_t lo_r0 = ((size_t)b * h + ly.i0) * w, lo_r1 = ((size_t)b * h + ly.i1) * w;
+        const Bf16x8* crow = kUp ? nullptr : c_hi + (size_t)row * rowv;
+        const Bf16x8* brow = b_hi ? b_hi + (size_t)row * rowv : nullptr;
+        Bf16x8* yrow = y + (size_t)row * rowv;
+        const int i0 = seg * (kMergeU * kThreads) + threadIdx.x;
+        Bf16x8 va[kMergeU][kUp ? 4 : 1], vb[kMergeU];
+        float gl[kMergeU][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                o[k] = ly.l0 * (lx.l0 * v00[k] + lx.l1 * v01[k]) + ly.l1 * (lx.l0 * v10[k] + lx.l1 * v11[k]);
-        } else {
-            unpack8(ld8(c_hi + i), o);
-        }
-        if (b_hi) {
-            float gate = 1.0f;
-            if (g_lo) {
-                const float s00 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo00])));
-                const float s01 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo01])));
-                const float s10 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo10])));
-                const float s11 = 1.0f / (1.0f + __expf(-__bfloat162float(g_lo[lo11])));
-                gate = ly.l0 * (lx.l0 * s00 + lx.l1 * s01) + ly.l1 * (lx.l0 * s10 + lx.l1 * s11);
+        for (int u = 0; u < kMergeU; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i >= rowv) break;
+            const int X = i / G, g = i - X * G;
+            const Lerp lxu = lerp_coord(X, w, sx);
+            if (kUp) {
+                va[u][0] = ld8(a_lo + (lo_r0 + lxu.i0) * G + g); va[u][1] = ld8(a_lo + (lo_r0 + lxu.i1) * G + g);
+                va[u][2] = ld8(a_lo + (lo_r1 + lxu.i0) * G + g); va[u][3] = ld8(a_lo + (lo_r1 + lxu.i1) * G + g);
+            } else {
+                va[u][0] = ld8(crow + i);
             }
-            float bb[8];
-            unpack8(ld8(b_hi + i), bb);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fmaf(bb[k], gate, o[k]);
+            if (b_hi) {
+                vb[u] = ld8(brow + i);
+                if (g_lo) {
+                    gl[u][0] = __bfloat162float(g_lo[lo_r0 + lxu.i0]); gl[u][1] = __bfloat162float(g_lo[lo_r0 + lxu.i1]);
+                    gl[u][2] = __bfloat162float(g_lo[lo_r1 + lxu.i0]); gl[u][3] = __bfloat162float(g_lo[lo_r1 + lxu.i1]);
+                }
+            }
         }
-        y[i] = pack8(o);
+#pragma unroll
+        for (int u = 0; u < kMergeU; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i >= rowv) break;
+            float o[8];
+            const Lerp lxu = lerp_coord(i / G, w, sx);          // recomputed: cheaper than 16 registers held across the loads
+            if (kUp) {
+                float v00[8], v01[8], v10[8], v11[8];
+                unpack8(va[u][0], v00); unpack8(va[u][1], v01); unpack8(va[u][2], v10); unpack8(va[u][3], v11);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                 // explicit contraction: the depthwise kernel's upsample-on-load repeats it bit for bit
+                    const float t0 = fmaf(lxu.l1, v01[k], __fmul_rn(lxu.l0, v00[k])), t1 = fmaf(lxu.l1, v11[k], __fmul_rn(lxu.l0, v10[k]));
+                    o[k] = fmaf(ly.l1, t1, __fmul_rn(ly.l0, t0));
+                }
+            } else {
+                unpack8(va[u][0], o);
+            }
+            if (b_hi) {
+                float gate = 1.0f;
+                if (g_lo) {
+                    const float s00 = 1.0f / (1.0f + __expf(-gl[u][0])), s01 = 1.0f / (1.0f + __expf(-gl[u][1]));
+                    const float s10 = 1.0f / (1.0f + __expf(-gl[u][2])), s11 = 1.0f / (1.0f + __expf(-gl[u][3]));
+                    gate = ly.l0 * (lxu.l0 * s00 + lxu.l1 * s01) + ly.l1 * (lxu.l0 * s10 + lxu.l1 * s11);
+                }
+                float bb[8];
+                unpack8(vb[u], bb);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = fmaf(bb[k], gate, o[k]);
+            }
+            yrow[i] = pack8(o);
+        }
     }
 }
 
@@ -407,6 +435,40 @@ __global__ void __launch_bounds__(kThreads) maxpool_h2_kernel(const uint4* __res
         for (int k = 0; k < 4; ++k) po[k] = __hmax2_nan(pa[k], pb[k]);
         y[i] = o;
     }
+}
+
+
+// CTAs of `kernel` the device holds at once (kThreads threads, `smem` dynamic bytes).  The grids below are sized in whole
+// waves of this number: a grid of 1 192 CTAs on 592 slots runs as THREE waves, the last one 1 % full.
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || sms <= 0 || occ <= 0) {
+        (void)cudaGetLastError();
+        return 148 * 4;
+    }
+    return sms * occ;
+}
+
+// Chunks per image so that B * chunks CTAs fill whole waves of `slots`: the best wave efficiency among the splits that keep
+// at least `min_rows` rows per CTA and at most two waves (more CTAs only repeat the per-CTA prologue); ties -> finer split.
+static int wave_chunks(int B, int HW, int slots, int min_rows, int nphase, int* rows_out) {
+    int max_chunks = HW / (min_rows > 0 ? min_rows : 1);
+    if (max_chunks < 1) max_chunks = 1;
+    int best = 1;
+    double best_eff = -1.0;
+    for (int c = 1; c <= max_chunks; ++c) {
+        const long long total = (long long)B * c;
+        if (c > 1 && total > 2LL * slots) break;
+        const long long waves = (total + slots - 1) / slots;
+        const double eff = (double)total / (double)(waves * slots);
+        if (eff >= best_eff) { best_eff = eff; best = c; }
+    }
+    int rows = (HW + best - 1) / best;
+    rows = ((rows + nphase - 1) / nphase) * nphase;
+    *rows_out = rows;
+    return (HW + rows - 1) / rows;
 }
 
 }  // namespace
@@ -430,12 +492,21 @@ extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi,
     if (!y || ((a_lo == nullptr) == (c_hi == nullptr)) || (g_lo && !b_hi) || B <= 0 || h <= 0 || w <= 0 || H <= 0 ||
         W <= 0 || C <= 0 || C % 8 != 0)
         return RROI_B200_ERR_INVALID_ARG;
-    const long long total = (long long)B * H * W * (C / 8);
-    long long grid = (total + kThreads - 1) / kThreads;
-    if (grid > 148LL * 32) grid = 148LL * 32;
-    fpn_merge_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(static_cast<const Bf16x8*>(a_lo), static_cast<const Bf16x8*>(c_hi),
-                                                              static_cast<const Bf16x8*>(b_hi), static_cast<const __nv_bfloat16*>(g_lo),
-                                                              static_cast<Bf16x8*>(y), B, h, w, H, W, C);
+    if ((long long)W * (C / 8) > (1LL << 30)) return RROI_B200_ERR_INVALID_ARG;
+    const int rowv = W * (C / 8);
+    const int U = a_lo ? 2 : 4;
+    const int segs = (rowv + U * kThreads - 1) / (U * kThreads);
+    const long long items = (long long)B * H * segs;
+    const long long slots = a_lo ? resident_ctas(fpn_merge_kernel<true, 2>, 0) : resident_ctas(fpn_merge_kernel<false, 4>, 0);
+    long long grid = items;
+    if (grid > slots) {                                       // equal shares of the items, at most two waves of CTAs
+        const long long per = (items + 2 * slots - 1) / (2 * slots);
+        grid = (items + per - 1) / per;
+    }
+    const Bf16x8 *ap = static_cast<const Bf16x8*>(a_lo), *cp = static_cast<const Bf16x8*>(c_hi), *bp = static_cast<const Bf16x8*>(b_hi);
+    const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(g_lo);
+    if (a_lo) fpn_merge_kernel<true, 2><<<(unsigned)grid, kThreads, 0, stream>>>(ap, cp, bp, gp, static_cast<Bf16x8*>(y), B, h, w, H, W, C, segs, items);
+    else fpn_merge_kernel<false, 4><<<(unsigned)grid, kThreads, 0, stream>>>(ap, cp, bp, gp, static_cast<Bf16x8*>(y), B, h, w, H, W, C, segs, items);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
@@ -465,20 +536,21 @@ static int instnorm_impl(const void* x, void* y, const float* gamma, const float
     }
     const int G = C / 8;
     const int nphase = kThreads / G;
-    // enough CTAs for a few waves, at least a handful of rows per thread
-    long long want_ctas = 148LL * 8 / B + 1;
-    int rows = (int)((HW + want_ctas - 1) / want_ctas);
-    rows = ((rows + nphase - 1) / nphase) * nphase;
-    if (rows < nphase * 4) rows = nphase * 4;
-    const int chunks = (HW + rows - 1) / rows;
+    // whole waves of resident CTAs, at least a handful of rows per thread; the apply kernel is the longer of the two launches
+    const size_t smem = (size_t)(crelu ? 4 : 2) * C * sizeof(float);
+    const int slots = crelu ? resident_ctas(in_apply_kernel<true, false>, smem)
+                            : residual ? resident_ctas(in_apply_kernel<false, true>, smem) : resident_ctas(in_apply_kernel<false, false>, smem);
+    int rows = 0;
+    const int chunks = wave_chunks(B, HW, slots, nphase * 4, nphase, &rows);
     cudaError_t e = cudaSuccess;
     const dim3 grid(chunks, B);
     if (!have_stats) {
         e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
-        in_stats_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
+        int srows = 0;
+        const int schunks = wave_chunks(B, HW, resident_ctas(in_stats_kernel, 0), nphase * 4, nphase, &srows);
+        in_stats_kernel<<<dim3(schunks, B), kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, srows);
     }
-    const size_t smem = (size_t)(crelu ? 4 : 2) * C * sizeof(float);
     const Bf16x8* xr = static_cast<const Bf16x8*>(x);
     Bf16x8* yr = static_cast<Bf16x8*>(y);
     const Bf16x8* rr = static_cast<const Bf16x8*>(residual);
@@ -498,11 +570,8 @@ extern "C" int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspa
     if (!x || !workspace || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || C > 1024 || (C / 8) > kThreads || B > 65535)
         return RROI_B200_ERR_INVALID_ARG;
     const int G = C / 8, nphase = kThreads / G;
-    long long want_ctas = 148LL * 8 / B + 1;
-    int rows = (int)((HW + want_ctas - 1) / want_ctas);
-    rows = ((rows + nphase - 1) / nphase) * nphase;
-    if (rows < nphase * 4) rows = nphase * 4;
-    const int chunks = (HW + rows - 1) / rows;
+    int rows = 0;
+    const int chunks = wave_chunks(B, HW, resident_ctas(in_stats_kernel, 0), nphase * 4, nphase, &rows);
     cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     in_stats_kernel<<<dim3(chunks, B), kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
