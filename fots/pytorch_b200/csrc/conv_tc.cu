@@ -21,6 +21,7 @@
 // sum of squares of the stored values (the statistics pass of the InstanceNorm that follows).
 // Also used by CRNN.to_b200 (tools/models.py:853-909) with the BatchNorms folded into weights and bias.
 #include "../../../include/fots_b200_pipeline.h"
+#include "pdl.cuh"
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -217,6 +218,7 @@ template <int MT, int BN, int STAGES, bool PAIR = false, bool HALO = false, bool
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const ConvParams P) {
+    pdl::trigger();          // programmatic dependent launch (pdl.cuh): barrier / TMEM set-up below overlaps the previous kernel's tail
     static_assert(!PAIR || MT == 1, "pair mode: one 128-pixel sub-tile per CTA");
     static_assert(!(PAIR && HALO), "halo reuse is a single-CTA mode");
     constexpr uint32_t kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
@@ -301,6 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (PAIR) cluster_sync_all(); else __syncthreads();        // barriers of both CTAs exist before anybody signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl::wait();             // from here on: activations in, outputs and statistics out
 
     if (warp == 0) {
         if (lane == 0) {
@@ -433,9 +436,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < BN / 64; ++i) st_acc[i][0] = st_acc[i][1] = st_acc[i][2] = st_acc[i][3] = 0.f;
         int st_key = -1;                                         // image * cout_tiles + cout tile the sums belong to
+        // Flushing the running sums.  Every epilogue thread holds partial sums of the SAME BN channels (8 warps = 8 row groups),
+        // and up to ~30 CTAs work on the same image: flushed thread by thread that was 4 096 fp64 atomics per CTA and flush on
+        // 2 * BN addresses -- on small maps (a tile or two per CTA) slower than the statistics pass it replaces.  When a tile
+        // never spans images (P.tn == 1: the key is CTA-uniform) the eight partials are first added in shared memory (fp32
+        // atomics, 128 channels = 1 KB at a time), then ONE fp64 atomic per channel and statistic leaves the CTA.
+        const bool st_uni = P.tn == 1;
+        float* const st_red = reinterpret_cast<float*>(base_ptr + STAGES * kStageBytes + 2 * kOutBlk + 8 * (2 * STAGES + 6));   // [128][2]
+        const int et = (int)threadIdx.x - 64;                    // 0 .. 255 among the epilogue threads
         auto stats_flush = [&]() {
             if (st_key >= 0) {
                 const int n = st_key / P.cout_tiles, ct = st_key - n * P.cout_tiles;
+                if (st_uni) {
+#pragma unroll
+                    for (int i0 = 0; i0 < BN / 64; i0 += 2) {
+                        st_red[et] = 0.f;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                        for (int i = i0; i < i0 + 2 && i < BN / 64; ++i) {
+                            float* d = st_red + ((i - i0) * 64 + 2 * lane) * 2;
+                            atomicAdd(d, st_acc[i][0]); atomicAdd(d + 1, st_acc[i][1]); atomicAdd(d + 2, st_acc[i][2]); atomicAdd(d + 3, st_acc[i][3]);
+                            st_acc[i][0] = st_acc[i][1] = st_acc[i][2] = st_acc[i][3] = 0.f;
+                        }
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        const int nch = (BN / 64 - i0 >= 2 ? 2 : 1) * 64;
+                        if (et < 2 * nch && n < P.N) atomicAdd(P.stats + ((size_t)n * P.Cout + ct * BN + i0 * 64) * 2 + et, (double)st_red[et]);
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int i = 0; i < BN / 64; ++i) {
                     double* dst = P.stats + ((size_t)n * P.Cout + ct * BN + i * 64 + 2 * lane) * 2;
@@ -454,6 +483,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll 1
             for (int cb = 0; cb < MT * BN / 64; ++cb, ++blk) {         // cb walks sub-tile j = cb / (BN/64), then channels
                 const int j = cb / (BN / 64), cblk = cb - j * (BN / 64);
+                if (P.stats != nullptr && st_uni) {              // CTA-uniform: every epilogue thread takes part in the flush
+                    const int key = (T.n0 + j * P.sub_n) * P.cout_tiles + (T.c_out0 / BN);
+                    if (key != st_key) { stats_flush(); st_key = key; }
+                }
                 // the TMA store issued two blocks ago has finished reading this staging buffer
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -520,8 +553,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int chunk = lane >> 2;
                     if (valid == 0xffffu && P.tn == 1) {
                         // common case: the whole 32-row group lies inside one image -> 32 independent loads, then sums
-                        const int key = (T.n0 + j * P.sub_n) * P.cout_tiles + (T.c_out0 / BN);
-                        if (key != st_key) { stats_flush(); st_key = key; }
                         uint32_t wv[16];
 #pragma unroll
                         for (int rr = 0; rr < 16; ++rr)
@@ -546,9 +577,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll 1
                         for (int rr = 0; rr < 16; ++rr) {
                             if (!((valid >> rr) & 1u)) continue;                       // warp-uniform
-                            const int n = __shfl_sync(0xffffffffu, n_mine, eh * 16 + rr);
-                            const int key = n * P.cout_tiles + (T.c_out0 / BN);
-                            if (key != st_key) { stats_flush(); st_key = key; }
+                            if (!st_uni) {
+                                const int n = __shfl_sync(0xffffffffu, n_mine, eh * 16 + rr);
+                                const int key = n * P.cout_tiles + (T.c_out0 / BN);
+                                if (key != st_key) { stats_flush(); st_key = key; }
+                            }
                             const uint32_t word = *reinterpret_cast<const uint32_t*>(grp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
                             const float a = __uint_as_float(word << 16), b = __uint_as_float(word & 0xffff0000u);
 #pragma unroll
@@ -620,7 +653,7 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
     constexpr size_t stage = (WRES && STAGES == 2) ? (size_t)((((MT * 16 + 2) * 10 * 128) + 1023) / 1024 * 1024)
                            : WRES ? (size_t)(MT * 16 + 2) * 1024
                            : HALO ? (size_t)(MT * 16 + 2) * 1024 + 3 * (size_t)BN * BK * 2 : (size_t)(MT * kABytes + (PAIR ? BN / 2 : BN) * BK * 2);
-    constexpr size_t smem = (WRES ? 9 * (size_t)BN * BK * 2 : 0) + (size_t)STAGES * stage + 2 * BM * 128 + 8 * (2 * STAGES + 6) + 1024;
+    constexpr size_t smem = (WRES ? 9 * (size_t)BN * BK * 2 : 0) + (size_t)STAGES * stage + 2 * BM * 128 + 8 * (2 * STAGES + 6) + 1024 /* statistics flush scratch */ + 1024;
     static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
     // The shared-memory opt-in and the SM count are PER DEVICE: cache them per device ordinal (per instantiation; the
     // attribute call is idempotent, so a race between host threads only repeats it).
@@ -646,21 +679,11 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
         // clusters of two CTAs (one per SM of a TPC); `ctas` counts pixel tiles x cout tiles, a cluster takes two pixel tiles
         const long long items = (long long)P.cout_tiles * (((long long)P.n_tiles_w * P.n_tiles_h * P.n_tiles_n + 1) / 2);
         const long long clusters = items < sms / 2 ? items : sms / 2;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(2 * clusters));
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES>, mx, mw, my, P);
+        return pdl::launch_cluster(conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES>, dim3((unsigned)(2 * clusters)), dim3(kThreads), smem, stream,
+                                   2u, mx, mw, my, P);
     }
     const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
-    conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES><<<grid, kThreads, smem, stream>>>(mx, mw, my, P);
-    return cudaGetLastError();
+    return pdl::launch(conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES>, dim3(grid), dim3(kThreads), smem, stream, mx, mw, my, P);
 }
 
 int g_force_bn = 0;        // 0 = automatic; set through fots_b200_conv_set_tile for sweeps
@@ -737,7 +760,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     P.stats = stats; P.N = N; P.Ho = Ho; P.Wo = Wo; P.Cout = Cout;
     P.chunk = 1;
     if (stats) {
-        const cudaError_t em = cudaMemsetAsync(stats, 0, (size_t)N * Cout * 2 * sizeof(double), stream);
+        const cudaError_t em = pdl::zero_f64(stats, (size_t)N * Cout * 2, stream);
         if (em != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     }
     const long long ctas = (long long)P.n_tiles_w * P.n_tiles_h * P.n_tiles_n * P.cout_tiles;

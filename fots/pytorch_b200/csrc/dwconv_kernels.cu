@@ -11,6 +11,7 @@
 // shared memory once per (row, strip) instead of once per tap: 18 LDS.128 per 4 outputs at stride 1, 27 at stride 2.
 // fp32 accumulation in the order (r, s) = (0,0) .. (2,2), one rounding to bf16.
 #include "../../../include/fots_b200_pipeline.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
     constexpr int IH = (TH - 1) * STRIDE + 3, IW = (kTW - 1) * STRIDE + 3;      // input tile incl. halo
     constexpr int NT = TH * 32;
     __shared__ __align__(16) uint4 tile[IH * IW * 8];
+    pdl::trigger();
+    pdl::wait();
     const int tile_id = blockIdx.x, ty = tile_id / tiles_w, tx = tile_id - ty * tiles_w;
     const int c0 = blockIdx.y * kCB, n = blockIdx.z;
     const int oy0 = ty * TH, ox0 = tx * kTW;
@@ -221,6 +224,7 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ void split2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
+struct __align__(16) Tap { int o0, o1; float l0, l1; };
 struct TilePos { int n, oy0, ox0; };
 __device__ __forceinline__ TilePos tile_pos(int t, int tiles_w, int tiles_h) {
     TilePos p;
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
                 for (int i = tid; i < kLoVec; i += kNT) {
                     const int vv = i & 7, p = i >> 3, r = p / kLoW, c = p - r * kLoW;
                     if (r < lb.nh && c < lb.nw) {
-                        const uint4* src = lo + ((size_t)(lb.y0 + r) * nrm.lw + lb.x0 + c) * CV + vv;
+                        const uint4* src = lo + (((lb.y0 + r) * nrm.lw + lb.x0 + c) * CV + vv);      // 32-bit: a plane is < 2^31 vectors
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_s + (uint32_t)(buf * kLoVec + i) * 16u), "l"(src) : "memory");
                     }
                 }
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
                 const int vv = i & 7, p = i >> 3, r = p / kIW, c = p - r * kIW;
                 const int iy = iy0 + r, ix = ix0 + c;
                 const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-                const uint4* src = ok ? img + ((size_t)iy * W + ix) * CV + vv : img;
+                const uint4* src = img + (ok ? (iy * W + ix) * CV + vv : 0);              // 32-bit: a plane is < 2^31 vectors
                 const uint32_t nbytes = ok ? 16u : 0u;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(stage_s + (uint32_t)(buf * kTileVec + i) * 16u), "l"(src), "r"(nbytes) : "memory");
             }
@@ -294,9 +298,7 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    int t = blockIdx.x;
-    if (t < ntiles) prefetch(t, 0);
-
+    pdl::trigger();
     // ---- this thread's 8 channels x 9 taps of weights as fp32 pairs; w is [C][3][3]
     uint64_t wr[9][4];
 #pragma unroll
@@ -304,6 +306,10 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
 #pragma unroll
         for (int tp = 0; tp < 9; ++tp)
             wr[tp][k] = pair_f32(__bfloat162float(wgt[(size_t)(c0 + v * 8 + 2 * k) * 9 + tp]), __bfloat162float(wgt[(size_t)(c0 + v * 8 + 2 * k + 1) * 9 + tp]));
+
+    pdl::wait();                                              // the weights above are constants; everything below depends on the stream
+    int t = blockIdx.x;
+    if (t < ntiles) prefetch(t, 0);
 
     // stats_out: every thread keeps running sums of its outputs in ITS row of `red` (shared memory, not registers: the
     // weights and accumulators already fill the register file), flushed to the fp64 workspace when the image changes
@@ -345,25 +351,46 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
             // from the staged footprint.  o = fma(ly.l1, t1, ly.l0 * t0), t = fma(lx.l1, v1, lx.l0 * v0) in fp32 pairs: the
             // arithmetic of fots_b200_fpn_merge_nhwc_bf16 (instnorm_kernels.cu), one rounding to bf16.
             {
+                // per-tile tables: for every tile row / column the two source offsets (uint4 units from `src`) and weights
+                __shared__ Tap rowtab[kIH], coltab[kIW];
                 const LoBox lb = lo_box(tp, H, W, nrm);
                 const uint4* src;                            // generic pointer: the staged footprint or (it did not fit) the map itself
                 int pitch_r, pitch_c, yorg, xorg;
                 if (lb.fits) { src = stage0 + cur * kLoVec; pitch_r = kLoW * 8; pitch_c = 8; yorg = lb.y0; xorg = lb.x0; }
                 else { src = x + (size_t)tp.n * nrm.lh * nrm.lw * CV + c0 / 8; pitch_r = nrm.lw * CV; pitch_c = CV; yorg = 0; xorg = 0; }
-                for (int i = tid; i < kTileVec; i += kNT) {
+                if (tid < kIH) {
+                    const int iy = iy0 + tid;
+                    Tap tq = {-1, -1, 0.f, 0.f};
+                    if (iy >= 0 && iy < H) {
+                        const Lerp l = lerp_coord(iy, nrm.lh, nrm.sy);
+                        tq.o0 = (l.i0 - yorg) * pitch_r; tq.o1 = (l.i1 - yorg) * pitch_r; tq.l0 = l.l0; tq.l1 = l.l1;
+                    }
+                    rowtab[tid] = tq;
+                } else if (tid >= 32 && tid < 32 + kIW) {
+                    const int c = tid - 32, ix = ix0 + c;
+                    Tap tq = {-1, -1, 0.f, 0.f};
+                    if (ix >= 0 && ix < W) {
+                        const Lerp l = lerp_coord(ix, nrm.lw, nrm.sx);
+                        tq.o0 = (l.i0 - xorg) * pitch_c; tq.o1 = (l.i1 - xorg) * pitch_c; tq.l0 = l.l0; tq.l1 = l.l1;
+                    }
+                    coltab[c] = tq;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < (kTileVec + kNT - 1) / kNT; ++kk) {
+                    const int i = tid + kk * kNT;
+                    if (i >= kTileVec) break;
                     const int vv = i & 7, p = i >> 3, r = p / kIW, c = p - r * kIW;
-                    const int iy = iy0 + r, ix = ix0 + c;
+                    const Tap tr = rowtab[r], tc = coltab[c];
                     uint4 pk = make_uint4(0, 0, 0, 0);
-                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-                        const Lerp ly = lerp_coord(iy, nrm.lh, nrm.sy), lx = lerp_coord(ix, nrm.lw, nrm.sx);
-                        const uint4* r0 = src + (size_t)(ly.i0 - yorg) * pitch_r + vv;
-                        const uint4* r1 = src + (size_t)(ly.i1 - yorg) * pitch_r + vv;
-                        const int o0 = (lx.i0 - xorg) * pitch_c, o1 = (lx.i1 - xorg) * pitch_c;
-                        const uint4 q00 = r0[o0], q01 = r0[o1], q10 = r1[o0], q11 = r1[o1];
+                    if (tr.o0 >= 0 && tc.o0 >= 0) {
+                        const uint4* r0 = src + (tr.o0 + vv);
+                        const uint4* r1 = src + (tr.o1 + vv);
+                        const uint4 q00 = r0[tc.o0], q01 = r0[tc.o1], q10 = r1[tc.o0], q11 = r1[tc.o1];
                         const uint32_t w00[4] = {q00.x, q00.y, q00.z, q00.w}, w01[4] = {q01.x, q01.y, q01.z, q01.w};
                         const uint32_t w10[4] = {q10.x, q10.y, q10.z, q10.w}, w11[4] = {q11.x, q11.y, q11.z, q11.w};
-                        const uint64_t lx0 = pair_f32(lx.l0, lx.l0), lx1 = pair_f32(lx.l1, lx.l1);
-                        const uint64_t ly0 = pair_f32(ly.l0, ly.l0), ly1 = pair_f32(ly.l1, ly.l1);
+                        const uint64_t lx0 = pair_f32(tc.l0, tc.l0), lx1 = pair_f32(tc.l1, tc.l1);
+                        const uint64_t ly0 = pair_f32(tr.l0, tr.l0), ly1 = pair_f32(tr.l1, tr.l1);
                         uint32_t ow[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -493,8 +520,8 @@ static cudaError_t dw_pipe_launch(size_t smem, const uint4* xp, const __nv_bfloa
     int gx = sms * occ / cblocks;
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
-    dwconv3x3_s1_pipe_kernel<MODE><<<dim3((unsigned)gx, (unsigned)cblocks), kNT, smem, stream>>>(xp, wp, yp, H, W, C, tiles_w, tiles_h, ntiles, nrm);
-    return cudaGetLastError();
+    return pdl::launch(dwconv3x3_s1_pipe_kernel<MODE>, dim3((unsigned)gx, (unsigned)cblocks), dim3(kNT), smem, stream, xp, wp, yp, H, W, C, tiles_w,
+                       tiles_h, ntiles, nrm);
 }
 
 static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride, const DwNorm* nrm, cudaStream_t stream) {
@@ -510,7 +537,7 @@ static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W,
     DwNorm none = {nullptr, nullptr, nullptr, 0.f, 1.f, nullptr, 0, 0, 0.f, 0.f};
     if (nrm) none = *nrm;
     if (none.stats_out) {
-        const cudaError_t em = cudaMemsetAsync(none.stats_out, 0, (size_t)N * C * 2 * sizeof(double), stream);
+        const cudaError_t em = pdl::zero_f64(none.stats_out, (size_t)N * C * 2, stream);
         if (em != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     }
     const bool norm_on = nrm != nullptr && nrm->stats != nullptr;
@@ -519,7 +546,7 @@ static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W,
     if (stride == 1) {
         const int tiles_h = (Ho + kTH - 1) / kTH;
         const long long ntiles = (long long)tiles_w * tiles_h * N;
-        if (ntiles > (1LL << 30)) return RROI_B200_ERR_INVALID_ARG;
+        if (ntiles > (1LL << 30) || (long long)H * W * (C / 8) >= (1LL << 31)) return RROI_B200_ERR_INVALID_ARG;   // 32-bit offsets inside a plane
         const int cblocks = C / kCB;
         cudaError_t e1 = cudaSuccess;
         if (up) e1 = dw_pipe_launch<kUp>((size_t)(2 * kLoVec + kTileVec) * 16, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
@@ -531,8 +558,8 @@ static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W,
     {
         constexpr int TH = 4;
         const dim3 grid((unsigned)(tiles_w * ((Ho + TH - 1) / TH)), (unsigned)(C / kCB), (unsigned)N);
-        if (norm_on) dwconv3x3_kernel<2, TH, true><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
-        else dwconv3x3_kernel<2, TH, false><<<grid, TH * 32, 0, stream>>>(xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
+        if (norm_on) (void)pdl::launch(dwconv3x3_kernel<2, TH, true>, dim3(grid), dim3(TH * 32), 0, stream, xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
+        else (void)pdl::launch(dwconv3x3_kernel<2, TH, false>, dim3(grid), dim3(TH * 32), 0, stream, xp, wp, yp, H, W, C, Ho, Wo, tiles_w, none);
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }

@@ -9,6 +9,7 @@
 // scaling and the (sin, cos) normalisation in the accumulator registers.  HBM-bound: the map is read once, 28 bytes per
 // pixel are written.  mma.sync, not tcgen05: N = 8 is below a UMMA tile and the kernel is bound by the read of x.
 #include "../../../include/fots_b200_pipeline.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,11 +31,12 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __ex
 // RAW: a 1x1 convolution to ONE output channel (the attention gate of the top-down merge, tools/models.py:405-438:
 // conv_attenton = Conv2d(256, 1, 1)): column 0 + bias, no squashing, written as bf16 [npix] -- the logits
 // fots_b200_fpn_merge_nhwc_bf16 consumes.  Same loads and MMAs; `seg` then points at the bf16 output.
-template <int C, bool RAW>
+template <int C, int RAW>
 __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wq,
                                                     const float* __restrict__ bias, float* __restrict__ seg, float* __restrict__ rbox,
                                                     float* __restrict__ angle, long long npix, int HW) {
     constexpr int NL = C / 32;                        // 16-byte loads per pixel row and lane
+    pdl::trigger();                                   // the weights / bias below are constants: loaded before pdl::wait()
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     // this lane's weights: head g, channels 32 m + 8 t .. + 7 -> four 32-bit registers per m
     uint32_t wb[NL][4];
@@ -44,6 +46,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x,
         wb[m][0] = v.x; wb[m][1] = v.y; wb[m][2] = v.z; wb[m][3] = v.w;
     }
     const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
+    pdl::wait();
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long ntiles = (npix + 15) / 16;
@@ -69,8 +72,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x,
             const long long p = half ? p1 : p0;
             if (!(half ? ok1 : ok0)) continue;
             const float v0 = acc[2 * half] + b0, v1 = acc[2 * half + 1] + b1;
-            if (RAW) {
-                if (t == 0) reinterpret_cast<__nv_bfloat16*>(seg)[p] = __float2bfloat16_rn(v0);
+            if (RAW) {                                       // 1: logits, 2: sigmoid(logit)
+                if (t == 0) reinterpret_cast<__nv_bfloat16*>(seg)[p] = __float2bfloat16_rn(RAW == 2 ? sigmoid_f(v0) : v0);
                 continue;
             }
             const long long b = p / HW, hw = p - b * HW;
@@ -104,9 +107,9 @@ extern "C" int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const fl
     if (ctas > 148 * 8) ctas = 148 * 8;
     const uint4* xp = static_cast<const uint4*>(x);
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(wq);
-    if (C == 128) heads_kernel<128, false><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
-    else if (C == 256) heads_kernel<256, false><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
-    else heads_kernel<512, false><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, seg, rbox, angle, npix, H * W);
+    if (C == 128) (void)pdl::launch(heads_kernel<128, 0>, dim3((unsigned)ctas), dim3(256), 0, stream, xp, wp, bias, seg, rbox, angle, npix, H * W);
+    else if (C == 256) (void)pdl::launch(heads_kernel<256, 0>, dim3((unsigned)ctas), dim3(256), 0, stream, xp, wp, bias, seg, rbox, angle, npix, H * W);
+    else (void)pdl::launch(heads_kernel<512, 0>, dim3((unsigned)ctas), dim3(256), 0, stream, xp, wp, bias, seg, rbox, angle, npix, H * W);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
@@ -115,7 +118,7 @@ extern "C" int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const fl
 // One-output-channel 1x1 convolution (+ bias) -> bf16 logits [B, 1, H, W]; wq / bias in the 8-row layout above with the
 // filter in row 0 and zeros elsewhere.
 extern "C" int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, const float* bias, void* out, int B, int H, int W, int C,
-                                               cudaStream_t stream) {
+                                               int sigmoid, cudaStream_t stream) {
     if (!x || !wq || !bias || !out || B <= 0 || H <= 0 || W <= 0) return RROI_B200_ERR_INVALID_ARG;
     if (C != 128 && C != 256 && C != 512) return RROI_B200_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return RROI_B200_ERR_INVALID_ARG;
@@ -126,9 +129,16 @@ extern "C" int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, co
     const uint4* xp = static_cast<const uint4*>(x);
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(wq);
     float* o = static_cast<float*>(out);
-    if (C == 128) heads_kernel<128, true><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, o, nullptr, nullptr, npix, H * W);
-    else if (C == 256) heads_kernel<256, true><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, o, nullptr, nullptr, npix, H * W);
-    else heads_kernel<512, true><<<(unsigned)ctas, 256, 0, stream>>>(xp, wp, bias, o, nullptr, nullptr, npix, H * W);
+    const unsigned g = (unsigned)ctas;
+    if (sigmoid) {
+        if (C == 128) (void)pdl::launch(heads_kernel<128, 2>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
+        else if (C == 256) (void)pdl::launch(heads_kernel<256, 2>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
+        else (void)pdl::launch(heads_kernel<512, 2>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
+    } else {
+        if (C == 128) (void)pdl::launch(heads_kernel<128, 1>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
+        else if (C == 256) (void)pdl::launch(heads_kernel<256, 1>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
+        else (void)pdl::launch(heads_kernel<512, 1>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;

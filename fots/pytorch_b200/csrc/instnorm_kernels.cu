@@ -2,6 +2,7 @@
 // statistics) for the feeder/consumer networks.  See include/fots_b200_pipeline.h.  HBM-bound: the tensor is read
 // twice and written once; every access is a 16-byte vector, consecutive threads on consecutive channel groups.
 #include "../../../include/fots_b200_pipeline.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,6 +34,8 @@ __device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
 // grid (chunks, B).  Thread -> channel group g = tid % G (8 channels), row phase tid / G.
 __global__ void __launch_bounds__(kThreads, 4) in_stats_kernel(const Bf16x8* __restrict__ x, double* __restrict__ ws,
                                                              int HW, int C, int rows_per_cta) {
+    pdl::trigger();
+    pdl::wait();
     const int G = C / 8;
     const int b = blockIdx.y;
     const int g = threadIdx.x % G, phase = threadIdx.x / G, nphase = kThreads / G;
@@ -80,6 +83,8 @@ __global__ void __launch_bounds__(kThreads, kResidual ? 3 : 4) in_apply_kernel(c
                                                              const Bf16x8* __restrict__ res, const double* __restrict__ ws,
                                                              int HW, int C, int rows_per_cta, float eps, float slope) {
     extern __shared__ float coef[];          // scale[Cout], shift[Cout]
+    pdl::trigger();
+    pdl::wait();
     const int G = C / 8;
     const int Cout = kCRelu ? 2 * C : C;
     const int b = blockIdx.y;
@@ -175,6 +180,8 @@ __global__ void __launch_bounds__(kThreads) in_fused_cluster_kernel(const Bf16x8
                                                                      const Bf16x8* __restrict__ res, int HW, int C, int Cs, int CS,
                                                                      int rows_per_cta, float eps, float slope) {
     extern __shared__ __align__(16) uint8_t in_smem[];
+    pdl::trigger();
+    pdl::wait();
     const int G = Cs / 8, Gall = C / 8;
     Bf16x8* const slab = reinterpret_cast<Bf16x8*>(in_smem);                                   // [rows_per_cta * G]
     float* const red = reinterpret_cast<float*>(in_smem + (size_t)rows_per_cta * G * 16);      // [256][17] block reduction
@@ -312,18 +319,9 @@ static cudaError_t launch_fused(const FusedPlan& pl, const void* x, void* y, con
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(pl.CS * pl.slices), (unsigned)B);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = pl.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)pl.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, in_fused_cluster_kernel<kResidual>, static_cast<const Bf16x8*>(x), static_cast<Bf16x8*>(y), gamma, beta,
-                              static_cast<const Bf16x8*>(residual), HW, C, pl.Cs, pl.CS, pl.rows, eps, slope);
+    return pdl::launch_cluster(in_fused_cluster_kernel<kResidual>, dim3((unsigned)(pl.CS * pl.slices), (unsigned)B), dim3(kThreads), pl.smem,
+                               stream, (unsigned)pl.CS, static_cast<const Bf16x8*>(x), static_cast<Bf16x8*>(y), gamma, beta,
+                               static_cast<const Bf16x8*>(residual), HW, C, pl.Cs, pl.CS, pl.rows, eps, slope);
 }
 
 // ---- fused top-down merge: y = (up(a_lo) | c_hi) + b_hi * (up(sigmoid(g_lo)) | 1) --------------------------------
@@ -341,12 +339,18 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {   // 
 
 // Work item = kMergeU * kThreads consecutive 16-byte vectors of ONE output row (b, Y): the row's vertical coordinates are
 // CTA-uniform, everything per thread is 32-bit, and a thread has kMergeU independent vectors (all their loads) in flight.
-// kUp: the first operand is the low-resolution a_lo (four taps per vector, kU = 2); else the full-resolution c_hi (kU = 4).
+// These kernels are ISSUE-bound, not HBM-bound (ncu: 390 warp-level instructions per output vector in the first version,
+// 70 % issue utilisation at 0.36 of the copy roofline), hence: row-relative 32-bit offsets, a shift instead of a division
+// when C / 8 is a power of two, and gate_is_prob -- the gate map may already hold sigmoid(logit) (what the one-channel
+// convolution kernel can emit), so the four expf + divisions per vector, repeated by all C / 8 lanes of a pixel, disappear.
+// kUp: the first operand is the low-resolution a_lo (four taps per vector, kMergeU = 2); else the full-resolution c_hi (4).
 template <bool kUp, int kMergeU>
 __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __restrict__ a_lo, const Bf16x8* __restrict__ c_hi,
                                                                  const Bf16x8* __restrict__ b_hi, const __nv_bfloat16* __restrict__ g_lo,
                                                                  Bf16x8* __restrict__ y, int B, int h, int w, int H, int W, int C,
-                                                                 int segs, long long items) {
+                                                                 int segs, long long items, int gshift, int gate_is_prob) {
+    pdl::trigger();
+    pdl::wait();
     const int G = C / 8;
     const int rowv = W * G;                                   // vectors per output row
     const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
@@ -357,7 +361,11 @@ __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __
         const int Y = (int)(row % H);
         const int b = (int)(row / H);
         const Lerp ly = lerp_coord(Y, h, sy);
-        const size_t lo_r0 = ((size_t)b * h + ly.i0) * w, lo_r1 = ((size_t)b * h + ly.i1) * w;
+        // row bases: everything below is a 32-bit offset from one of these
+        const Bf16x8* a0 = kUp ? a_lo + ((size_t)b * h + ly.i0) * w * G : nullptr;
+        const Bf16x8* a1 = kUp ? a_lo + ((size_t)b * h + ly.i1) * w * G : nullptr;
+        const __nv_bfloat16* g0 = g_lo ? g_lo + ((size_t)b * h + ly.i0) * w : nullptr;
+        const __nv_bfloat16* g1 = g_lo ? g_lo + ((size_t)b * h + ly.i1) * w : nullptr;
         const Bf16x8* crow = kUp ? nullptr : c_hi + (size_t)row * rowv;
         const Bf16x8* brow = b_hi ? b_hi + (size_t)row * rowv : nullptr;
         Bf16x8* yrow = y + (size_t)row * rowv;
@@ -368,19 +376,20 @@ __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __
         for (int u = 0; u < kMergeU; ++u) {
             const int i = i0 + u * kThreads;
             if (i >= rowv) break;
-            const int X = i / G, g = i - X * G;
+            const int X = gshift >= 0 ? (i >> gshift) : i / G;
+            const int g = i - X * G;
             const Lerp lxu = lerp_coord(X, w, sx);
             if (kUp) {
-                va[u][0] = ld8(a_lo + (lo_r0 + lxu.i0) * G + g); va[u][1] = ld8(a_lo + (lo_r0 + lxu.i1) * G + g);
-                va[u][2] = ld8(a_lo + (lo_r1 + lxu.i0) * G + g); va[u][3] = ld8(a_lo + (lo_r1 + lxu.i1) * G + g);
+                va[u][0] = ld8(a0 + lxu.i0 * G + g); va[u][1] = ld8(a0 + lxu.i1 * G + g);
+                va[u][2] = ld8(a1 + lxu.i0 * G + g); va[u][3] = ld8(a1 + lxu.i1 * G + g);
             } else {
                 va[u][0] = ld8(crow + i);
             }
             if (b_hi) {
                 vb[u] = ld8(brow + i);
                 if (g_lo) {
-                    gl[u][0] = __bfloat162float(g_lo[lo_r0 + lxu.i0]); gl[u][1] = __bfloat162float(g_lo[lo_r0 + lxu.i1]);
-                    gl[u][2] = __bfloat162float(g_lo[lo_r1 + lxu.i0]); gl[u][3] = __bfloat162float(g_lo[lo_r1 + lxu.i1]);
+                    gl[u][0] = __bfloat162float(g0[lxu.i0]); gl[u][1] = __bfloat162float(g0[lxu.i1]);
+                    gl[u][2] = __bfloat162float(g1[lxu.i0]); gl[u][3] = __bfloat162float(g1[lxu.i1]);
                 }
             }
         }
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __
             const int i = i0 + u * kThreads;
             if (i >= rowv) break;
             float o[8];
-            const Lerp lxu = lerp_coord(i / G, w, sx);          // recomputed: cheaper than 16 registers held across the loads
+            const Lerp lxu = lerp_coord(gshift >= 0 ? (i >> gshift) : i / G, w, sx);   // recomputed: cheaper than registers held across the loads
             if (kUp) {
                 float v00[8], v01[8], v10[8], v11[8];
                 unpack8(va[u][0], v00); unpack8(va[u][1], v01); unpack8(va[u][2], v10); unpack8(va[u][3], v11);
@@ -404,8 +413,11 @@ __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __
             if (b_hi) {
                 float gate = 1.0f;
                 if (g_lo) {
-                    const float s00 = 1.0f / (1.0f + __expf(-gl[u][0])), s01 = 1.0f / (1.0f + __expf(-gl[u][1]));
-                    const float s10 = 1.0f / (1.0f + __expf(-gl[u][2])), s11 = 1.0f / (1.0f + __expf(-gl[u][3]));
+                    float s00 = gl[u][0], s01 = gl[u][1], s10 = gl[u][2], s11 = gl[u][3];
+                    if (!gate_is_prob) {
+                        s00 = 1.0f / (1.0f + __expf(-s00)); s01 = 1.0f / (1.0f + __expf(-s01));
+                        s10 = 1.0f / (1.0f + __expf(-s10)); s11 = 1.0f / (1.0f + __expf(-s11));
+                    }
                     gate = ly.l0 * (lxu.l0 * s00 + lxu.l1 * s01) + ly.l1 * (lxu.l0 * s10 + lxu.l1 * s11);
                 }
                 float bb[8];
@@ -422,6 +434,8 @@ __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __
 // thread = 8 channels of one output pixel; the two input rows are W*C elements apart.  NaNs propagate like torch's.
 __global__ void __launch_bounds__(kThreads) maxpool_h2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                                long long total, int Ho, long long rowv, int H) {
+    pdl::trigger();
+    pdl::wait();
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         const long long r = i / rowv, e = i - r * rowv;        // r = n * Ho + ho
         const long long n = r / Ho, ho = r - n * Ho;
@@ -481,19 +495,22 @@ extern "C" int fots_b200_maxpool_h2_nhwc_bf16(const void* x, void* y, int N, int
     const long long total = (long long)N * Ho * rowv;
     long long grid = (total + kThreads - 1) / kThreads;
     if (grid > 148LL * 16) grid = 148LL * 16;
-    maxpool_h2_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), total, Ho, rowv, H);
+    (void)pdl::launch(maxpool_h2_kernel, dim3((unsigned)grid), dim3(kThreads), 0, stream, static_cast<const uint4*>(x), static_cast<uint4*>(y), total, Ho, rowv, H);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
 }
 
-extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo,
-                                             void* y, int B, int h, int w, int H, int W, int C, cudaStream_t stream) {
+static int fpn_merge_impl(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo, void* y, int B, int h, int w, int H,
+                          int W, int C, int gate_is_prob, cudaStream_t stream) {
     if (!y || ((a_lo == nullptr) == (c_hi == nullptr)) || (g_lo && !b_hi) || B <= 0 || h <= 0 || w <= 0 || H <= 0 ||
         W <= 0 || C <= 0 || C % 8 != 0)
         return RROI_B200_ERR_INVALID_ARG;
-    if ((long long)W * (C / 8) > (1LL << 30)) return RROI_B200_ERR_INVALID_ARG;
-    const int rowv = W * (C / 8);
+    if ((long long)W * (C / 8) > (1LL << 30) || (long long)w * (C / 8) > (1LL << 30)) return RROI_B200_ERR_INVALID_ARG;
+    const int G = C / 8;
+    const int rowv = W * G;
+    int gshift = -1;
+    if ((G & (G - 1)) == 0) { gshift = 0; while ((1 << gshift) < G) ++gshift; }
     const int U = a_lo ? 2 : 4;
     const int segs = (rowv + U * kThreads - 1) / (U * kThreads);
     const long long items = (long long)B * H * segs;
@@ -505,11 +522,23 @@ extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi,
     }
     const Bf16x8 *ap = static_cast<const Bf16x8*>(a_lo), *cp = static_cast<const Bf16x8*>(c_hi), *bp = static_cast<const Bf16x8*>(b_hi);
     const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(g_lo);
-    if (a_lo) fpn_merge_kernel<true, 2><<<(unsigned)grid, kThreads, 0, stream>>>(ap, cp, bp, gp, static_cast<Bf16x8*>(y), B, h, w, H, W, C, segs, items);
-    else fpn_merge_kernel<false, 4><<<(unsigned)grid, kThreads, 0, stream>>>(ap, cp, bp, gp, static_cast<Bf16x8*>(y), B, h, w, H, W, C, segs, items);
+    Bf16x8* yp = static_cast<Bf16x8*>(y);
+    if (a_lo) (void)pdl::launch(fpn_merge_kernel<true, 2>, dim3((unsigned)grid), dim3(kThreads), 0, stream, ap, cp, bp, gp, yp, B, h, w, H, W, C, segs, items, gshift, gate_is_prob);
+    else (void)pdl::launch(fpn_merge_kernel<false, 4>, dim3((unsigned)grid), dim3(kThreads), 0, stream, ap, cp, bp, gp, yp, B, h, w, H, W, C, segs, items, gshift, gate_is_prob);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
+}
+
+extern "C" int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo,
+                                             void* y, int B, int h, int w, int H, int W, int C, cudaStream_t stream) {
+    return fpn_merge_impl(a_lo, c_hi, b_hi, g_lo, y, B, h, w, H, W, C, 0, stream);
+}
+
+// The same with the gate map already holding sigmoid(logit) (fots_b200_conv1x1_to1_nhwc_bf16 with sigmoid = 1).
+extern "C" int fots_b200_fpn_merge_prob_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_prob_lo,
+                                                  void* y, int B, int h, int w, int H, int W, int C, cudaStream_t stream) {
+    return fpn_merge_impl(a_lo, c_hi, b_hi, g_prob_lo, y, B, h, w, H, W, C, 1, stream);
 }
 
 // A/B switch for sweeps and tests (fots_b200_instnorm_set_single_pass): the single-pass kernel is the default
@@ -545,21 +574,21 @@ static int instnorm_impl(const void* x, void* y, const float* gamma, const float
     cudaError_t e = cudaSuccess;
     const dim3 grid(chunks, B);
     if (!have_stats) {
-        e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
+        e = pdl::zero_f64(workspace, (size_t)B * C * 2, stream);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
         int srows = 0;
         const int schunks = wave_chunks(B, HW, resident_ctas(in_stats_kernel, 0), nphase * 4, nphase, &srows);
-        in_stats_kernel<<<dim3(schunks, B), kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, srows);
+        (void)pdl::launch(in_stats_kernel, dim3(schunks, B), dim3(kThreads), 0, stream, static_cast<const Bf16x8*>(x), workspace, HW, C, srows);
     }
     const Bf16x8* xr = static_cast<const Bf16x8*>(x);
     Bf16x8* yr = static_cast<Bf16x8*>(y);
     const Bf16x8* rr = static_cast<const Bf16x8*>(residual);
     if (crelu)
-        in_apply_kernel<true, false><<<grid, kThreads, smem, stream>>>(xr, yr, gamma, beta, nullptr, workspace, HW, C, rows, eps, slope);
+        (void)pdl::launch(in_apply_kernel<true, false>, dim3(grid), dim3(kThreads), smem, stream, xr, yr, gamma, beta, (const Bf16x8*)nullptr, workspace, HW, C, rows, eps, slope);
     else if (residual)
-        in_apply_kernel<false, true><<<grid, kThreads, smem, stream>>>(xr, yr, gamma, beta, rr, workspace, HW, C, rows, eps, slope);
+        (void)pdl::launch(in_apply_kernel<false, true>, dim3(grid), dim3(kThreads), smem, stream, xr, yr, gamma, beta, rr, workspace, HW, C, rows, eps, slope);
     else
-        in_apply_kernel<false, false><<<grid, kThreads, smem, stream>>>(xr, yr, gamma, beta, nullptr, workspace, HW, C, rows, eps, slope);
+        (void)pdl::launch(in_apply_kernel<false, false>, dim3(grid), dim3(kThreads), smem, stream, xr, yr, gamma, beta, (const Bf16x8*)nullptr, workspace, HW, C, rows, eps, slope);
     e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
@@ -572,9 +601,9 @@ extern "C" int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspa
     const int G = C / 8, nphase = kThreads / G;
     int rows = 0;
     const int chunks = wave_chunks(B, HW, resident_ctas(in_stats_kernel, 0), nphase * 4, nphase, &rows);
-    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)B * C * 2 * sizeof(double), stream);
+    cudaError_t e = pdl::zero_f64(workspace, (size_t)B * C * 2, stream);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
-    in_stats_kernel<<<dim3(chunks, B), kThreads, 0, stream>>>(static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
+    (void)pdl::launch(in_stats_kernel, dim3(chunks, B), dim3(kThreads), 0, stream, static_cast<const Bf16x8*>(x), workspace, HW, C, rows);
     e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;

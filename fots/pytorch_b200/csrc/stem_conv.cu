@@ -13,6 +13,7 @@
 // accumulated in registers across the CTA's tiles and flushed once per image.
 // tcgen05 is not used on purpose: K = 27 cannot fill a UMMA tile and the tensor pipe is idle either way.
 #include "../../../include/fots_b200_pipeline.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -53,6 +54,7 @@ stem_conv_kernel(const In* __restrict__ x, const __nv_bfloat16* __restrict__ wgt
                  double* __restrict__ stats, int B, int H, int W, int tiles_x, int tiles_y, int tiles_per_cta) {
     __shared__ __align__(16) __nv_bfloat16 tile[HALO_H * PITCH];
     __shared__ float red[32];                   // [16 channels][sum, sumsq] of one flush
+    pdl::trigger();                             // weights are constants: fragments are built before pdl::wait()
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
@@ -77,6 +79,7 @@ stem_conv_kernel(const In* __restrict__ x, const __nv_bfloat16* __restrict__ wgt
             }
     for (int i = threadIdx.x; i < HALO_H * PITCH; i += kThreads) tile[i] = __float2bfloat16(0.0f);   // channel 3 stays 0
     if (threadIdx.x < 32) red[threadIdx.x] = 0.0f;
+    pdl::wait();
 
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};   // this thread's 4 output channels
     int cur_b = -1;
@@ -254,14 +257,14 @@ static int stem_launch(const In* x, const void* w, void* y, double* stats, int B
     const long long total = (long long)tiles_x * tiles_y * B;
     if (total > 0x7fffffffLL) return RROI_B200_ERR_TOO_LARGE;
     if (stats) {
-        const cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * 32 * sizeof(double), stream);
+        const cudaError_t e = pdl::zero_f64(stats, (size_t)B * 32, stream);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     }
     // persistent: contiguous tile ranges, so a CTA stays inside one image and flushes its sums once or twice
     const long long ctas_wanted = 148LL * 6;
     const int per = (int)((total + ctas_wanted - 1) / ctas_wanted);
     const int grid = (int)((total + per - 1) / per);
-    stem_conv_kernel<In><<<grid, kThreads, 0, stream>>>(x, static_cast<const __nv_bfloat16*>(w), static_cast<uint32_t*>(y), stats,
+    (void)pdl::launch(stem_conv_kernel<In>, dim3(grid), dim3(kThreads), 0, stream, x, static_cast<const __nv_bfloat16*>(w), static_cast<uint32_t*>(y), stats,
                                                         B, H, W, tiles_x, tiles_y, per);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }

@@ -15,6 +15,9 @@ ENABLED = os.environ.get("FOTS_B200_TC_CONV", "1") != "0"   # A/B switch against
 # on B200 (profiles/r01_conv_tc_bench.txt) the bare library convolution + a separate statistics pass is still a
 # little faster for these shapes (the statistics make the 4-warp epilogue the bottleneck), so the default is off.
 FUSE_STATS = os.environ.get("FOTS_B200_TC_STATS", "0") != "0"
+# Epilogue statistics only for SMALL outputs (MB of bf16 output; 0 = off): there the separate statistics pass is two
+# launch-bound launches (memset + kernel, ~8 us for a few MB), which costs more than the longer epilogue.
+STATS_MAX_MB = float(os.environ.get("FOTS_B200_TC_STATS_MAX_MB", "0"))
 # How much of the networks runs on this kernel (A/B switch for the step-time sweeps, tools/profile_pipeline.py):
 #   0 = only the convolutions whose activation it fuses (conv6/8/9, layer0_1[0]);
 #   1 = + every other convolution of the recogniser (conv5/7/10_s in front of an InstanceNorm, conv11 with its 89 classes
@@ -23,6 +26,8 @@ FUSE_STATS = os.environ.get("FOTS_B200_TC_STATS", "0") != "0"
 #       blocks' pointwise halves, up-convolutions, down-sampling branches with their BatchNorm folded) and the depthwise
 #       3x3 convolutions (csrc/dwconv_kernels.cu).  Default: measured 4.79 ms per 8-image step against 4.77 ms at level 1.
 LEVEL = int(os.environ.get("FOTS_B200_TC_LEVEL", "2"))
+# A/B switch: compute the 2x upsampling of the top-down merge inside the depthwise kernel (1) or as its own kernel (0)
+DW_UP = os.environ.get("FOTS_B200_DW_UP", "1") != "0"
 
 
 def _lib():
@@ -118,6 +123,18 @@ def conv2d(x, weight, bias=None, padding=(0, 0), slope=1.0, stats=False, stride=
                 N, H, W, Cin, Cout, R, S, ph, pw, float(slope), stream)
     _cabi.check(st, "fots_b200_conv2d_nhwc_bf16")
     return (y, ws) if stats else y
+
+
+def conv_stats_small(conv, x, level=2):
+    """conv(x) for a stride-1 convolution that is followed by an InstanceNorm -> (y, ws or None): ws = the epilogue's fp64
+    statistics when the output is small enough for that to pay (STATS_MAX_MB), else None (caller runs the statistics pass)."""
+    if LEVEL >= level and eligible(x, conv):
+        N, _, H, W = x.shape
+        small = N * conv.out_channels * H * W * 2 <= STATS_MAX_MB * 1e6
+        if small and conv.stride == (1, 1) and 128 <= conv.out_channels <= 1024:
+            return conv2d(x, conv.weight, conv.bias, conv.padding, 1.0, stats=True)
+        return conv2d(x, conv.weight, conv.bias, conv.padding, 1.0, stride=conv.stride), None
+    return conv(x), None
 
 
 def apply(conv, x, slope=1.0, level=0):
@@ -260,16 +277,16 @@ def pack_to1(conv):
     return w.contiguous(), b.contiguous()
 
 
-def conv1x1_to1(x, packed):
-    """x bf16 channels-last [B, C, H, W] -> bf16 logits [B, 1, H, W] (one pass over x, bias added, no activation)."""
+def conv1x1_to1(x, packed, sigmoid=False):
+    """x bf16 channels-last [B, C, H, W] -> bf16 logits [B, 1, H, W] (one pass over x, bias added); sigmoid=True: sigmoid(logits)."""
     B, C, H, W = x.shape
     out = torch.empty((B, 1, H, W), dtype=torch.bfloat16, device=x.device)
     L = _lib()
     L.fots_b200_conv1x1_to1_nhwc_bf16.restype = ctypes.c_int
-    L.fots_b200_conv1x1_to1_nhwc_bf16.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    L.fots_b200_conv1x1_to1_nhwc_bf16.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
     with torch.cuda.device(x.device):
         rc = L.fots_b200_conv1x1_to1_nhwc_bf16(x.data_ptr(), packed[0].data_ptr(), packed[1].data_ptr(), out.data_ptr(), B, H, W, C,
-                                               torch.cuda.current_stream(x.device).cuda_stream)
+                                               1 if sigmoid else 0, torch.cuda.current_stream(x.device).cuda_stream)
     _cabi.check(rc, "fots_b200_conv1x1_to1_nhwc_bf16")
     return out
 
@@ -286,6 +303,41 @@ def heads(x, packed):
                                               torch.cuda.current_stream(x.device).cuda_stream)
     _cabi.check(rc, "fots_b200_heads_nhwc_bf16")
     return seg, rb, an
+
+
+def conv3x3_c3_pool(x, weight, bias, pool2x2):
+    """Consumer B's first layer in one kernel (fots_b200_conv3x3_c3_pool_nhwc_bf16): x fp32 NCHW [N, 3, H, W] ->
+    [maxpool2x2](relu(conv3x3_pad1(x, weight) + bias)) as bf16 channels-last.  weight bf16 [Cout, 3, 3, 3], bias fp32 [Cout]."""
+    N, _, H, W = x.shape
+    Cout = weight.size(0)
+    P = 2 if pool2x2 else 1
+    x = x.float().contiguous()
+    wt = weight.contiguous()                                  # plain NCHW-contiguous [Cout, 3, 3, 3]
+    y = torch.empty((N, Cout, H // P, W // P), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    L = _lib()
+    L.fots_b200_conv3x3_c3_pool_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_conv3x3_c3_pool_nhwc_bf16.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    with torch.cuda.device(x.device):
+        rc = L.fots_b200_conv3x3_c3_pool_nhwc_bf16(x.data_ptr(), wt.data_ptr(), bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                                   N, H, W, Cout, 1 if pool2x2 else 0, torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_conv3x3_c3_pool_nhwc_bf16")
+    return y
+
+
+def maxpool(x, kernel, stride, padding):
+    """MaxPool2d(kernel, stride, padding) (floor mode) of a bf16 channels-last tensor on fots_b200_maxpool_nhwc_bf16."""
+    N, C, H, W = x.shape
+    (kh, kw), (sh, sw), (ph, pw) = kernel, stride, padding
+    Ho, Wo = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    y = torch.empty((N, C, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    L = _lib()
+    L.fots_b200_maxpool_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_maxpool_nhwc_bf16.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 10 + [ctypes.c_void_p]
+    with torch.cuda.device(x.device):
+        rc = L.fots_b200_maxpool_nhwc_bf16(x.data_ptr(), y.data_ptr(), N, H, W, C, kh, kw, sh, sw, ph, pw,
+                                           torch.cuda.current_stream(x.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_maxpool_nhwc_bf16")
+    return y
 
 
 def stem_eligible(x, conv):

@@ -24,6 +24,8 @@ def _lib():
         L.fots_b200_maxpool_h2_nhwc_bf16.argtypes = [vp, vp, i, i, i, i, vp]
         L.fots_b200_fpn_merge_nhwc_bf16.restype = i
         L.fots_b200_fpn_merge_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+        L.fots_b200_fpn_merge_prob_nhwc_bf16.restype = i
+        L.fots_b200_fpn_merge_prob_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
         L._instnorm_bound = True
     return L
 
@@ -101,9 +103,15 @@ def merge_eligible(*tensors):
     return len(ts) > 0 and all(_cl_bf16(t) for t in ts) and ts[0].size(1) % 8 == 0
 
 
-def fpn_merge(a_lo=None, c_hi=None, b_hi=None, gate_logits_lo=None, size=None):
+def fpn_merge(a_lo=None, c_hi=None, b_hi=None, gate_logits_lo=None, size=None, gate_prob_lo=None):
     """y = (upsample(a_lo) | c_hi) + b_hi * (upsample(sigmoid(gate_logits_lo)) | 1); bilinear, align_corners=True.
-    a_lo [B,C,h,w] / c_hi, b_hi [B,C,H,W] / gate_logits_lo [B,1,h,w]; size=(H, W) when only low-res inputs are given."""
+    a_lo [B,C,h,w] / c_hi, b_hi [B,C,H,W] / gate_logits_lo [B,1,h,w]; size=(H, W) when only low-res inputs are given.
+    gate_prob_lo: the gate as sigmoid(logits) already (bf16 [B,1,h,w], conv.conv1x1_to1(..., sigmoid=True)) instead of logits."""
+    if gate_prob_lo is not None and gate_logits_lo is not None:
+        raise ValueError("fpn_merge: pass the gate either as logits or as probabilities")
+    prob = gate_prob_lo is not None
+    if prob:
+        gate_logits_lo = gate_prob_lo
     hi = c_hi if c_hi is not None else b_hi
     lo = a_lo if a_lo is not None else gate_logits_lo
     H, W = (hi.shape[2], hi.shape[3]) if hi is not None else size
@@ -113,8 +121,9 @@ def fpn_merge(a_lo=None, c_hi=None, b_hi=None, gate_logits_lo=None, size=None):
     y = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=ref.device, memory_format=torch.channels_last)
     ptr = lambda t: t.data_ptr() if t is not None else None
     with torch.cuda.device(ref.device):
-        st = _lib().fots_b200_fpn_merge_nhwc_bf16(ptr(a_lo), ptr(c_hi), ptr(b_hi), ptr(gate_logits_lo), y.data_ptr(),
-                                                  B, h, w, H, W, C, torch.cuda.current_stream(ref.device).cuda_stream)
+        fn = _lib().fots_b200_fpn_merge_prob_nhwc_bf16 if prob else _lib().fots_b200_fpn_merge_nhwc_bf16
+        st = fn(ptr(a_lo), ptr(c_hi), ptr(b_hi), ptr(gate_logits_lo), y.data_ptr(),
+                B, h, w, H, W, C, torch.cuda.current_stream(ref.device).cuda_stream)
     _cabi.check(st, "fots_b200_fpn_merge_nhwc_bf16")
     return y
 

@@ -102,16 +102,19 @@ class _ResSepIN(nn.Module):
         res = x if self.downsample is None else _downsample(self, x)
         s1, s2 = self.conv_sep1, self.conv2
         # depthwise halves: csrc/dwconv_kernels.cu; pointwise halves: 1x1 GEMMs on the tcgen05 kernel
-        z = tc.apply(s1[1], tc.dwconv(s1[0], x), 1.0, level=2)
+        z, zs = tc.conv_stats_small(s1[1], tc.dwconv(s1[0], x))
         if tc.dw_eligible(z, s2[0]) and fused.eligible(z, None, s1[2].weight, s1[2].bias):
-            # IN + leaky between the two halves is applied on load inside the depthwise kernel: statistics pass only,
-            # the normalised tensor is never written
-            # ... and the statistics of the InstanceNorm that follows come out of the depthwise kernel's epilogue
-            y, ws = tc.dwconv_norm(s2[0], z, fused.instnorm_stats(z), s1[2], 0.01, stats_out=True)
+            # IN + leaky between the two halves is applied on load inside the depthwise kernel: statistics only (from the
+            # pointwise convolution's epilogue when the map is small, else their own pass), the normalised tensor is never
+            # written ... and the statistics of the InstanceNorm that follows come out of the depthwise kernel's epilogue
+            y, ws = tc.dwconv_norm(s2[0], z, zs if zs is not None else fused.instnorm_stats(z), s1[2], 0.01, stats_out=True)
             y = fused.instnorm_act(y, s2[1].weight, s2[1].bias, s2[1].eps, 0.01, stats=ws)
         else:
             y = _in_act(s2[1], tc.dwconv(s2[0], _in_act(s1[2], z, 0.01)), 0.01)
-        return _in_act(s2[4], tc.apply(s2[3], y, 1.0, level=2), 0.01, res)
+        u, us = tc.conv_stats_small(s2[3], y)
+        if us is not None and fused.eligible(u, res, s2[4].weight, s2[4].bias):
+            return fused.instnorm_act(u, s2[4].weight, s2[4].bias, s2[4].eps, 0.01, res, stats=us)
+        return _in_act(s2[4], u, 0.01, res)
 
 
 def _downsample(block, x):
@@ -220,19 +223,24 @@ class FOTSNet(nn.Module):
         f4 = pw(self.feature4, self.drop1(self.layer4(s1)))
         if fused.merge_eligible(f1, f2, f3, f4):
             # inference fast path: each merge step is one fused kernel (upsample + attention gate + add)
-            att = self.conv_attenton if self.attention else (lambda t: None)
             apack = getattr(self, "_att_pack", None)
             if self.attention and apack is not None and tc.LEVEL >= 2 and f4.size(1) in (128, 256, 512):
-                att = lambda t: tc.conv1x1_to1(t, apack)                  # one pass over t, bf16 logits for the merge kernel
-            x = fused.fpn_merge(a_lo=f4, b_hi=f3, gate_logits_lo=att(f4))
+                # one pass over t -> sigmoid(logits) in bf16 (what torch's autocast path interpolates); the merge kernel then
+                # only interpolates the gate
+                gate = lambda t: dict(gate_prob_lo=tc.conv1x1_to1(t, apack, sigmoid=True))
+            elif self.attention:
+                gate = lambda t: dict(gate_logits_lo=self.conv_attenton(t))
+            else:
+                gate = lambda t: {}
+            x = fused.fpn_merge(a_lo=f4, b_hi=f3, **gate(f4))
             def up(seq, lo, size):
                 # upconv(F.interpolate(lo)): depthwise 3x3 + pointwise 1x1 on the 2x bilinear upsampling of `lo`.  The upsampling
                 # is computed while the depthwise kernel stages its tile, so the upsampled map is never written.
-                if tc.dw_eligible(lo, seq[0]) and seq[0].stride == (1, 1):
+                if tc.DW_UP and tc.dw_eligible(lo, seq[0]) and seq[0].stride == (1, 1):
                     return pw(seq[1], tc.dwconv_up(seq[0], lo, size))
                 return pw(seq[1], tc.dwconv(seq[0], fused.fpn_merge(a_lo=lo, size=size)))
-            f2 = fused.fpn_merge(c_hi=up(self.upconv1, x, f2.shape[2:]), b_hi=f2, gate_logits_lo=att(x))
-            x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, gate_logits_lo=att(f2))
+            f2 = fused.fpn_merge(c_hi=up(self.upconv1, x, f2.shape[2:]), b_hi=f2, **gate(x))
+            x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, **gate(f2))
         elif self.attention:
             x = _up(f4, f3) + f3 * _up(torch.sigmoid(self.conv_attenton(f4)).expand_as(f4), f3)
             gate = self._gate(x, f2)
@@ -394,6 +402,7 @@ class CRNN(nn.Module):
                 b = (b - m.running_mean.detach().float()) * scale + m.bias.detach().float()
             packs.append((w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), b.contiguous(), pad, pool))
         self._b200 = packs
+        self._w0_plain = packs[0][0].contiguous()             # first layer's [Cout, 3, 3, 3] in plain layout for the 3-channel kernel
         self._rnn_b200 = None
         if os.environ.get("FOTS_B200_LSTM", "1") != "0":
             from .lstm import BiLSTMPack
@@ -402,13 +411,24 @@ class CRNN(nn.Module):
 
     @torch.no_grad()
     def _cnn_b200(self, x):
-        y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        for w, b, pad, pool in self._b200:
-            if tc.ENABLED and w.size(1) % 64 == 0:
-                y = tc.conv2d(y, w, b, (pad, pad), 0.0)                      # conv + folded BN + bias + ReLU, one kernel
+        y = x
+        for i, (w, b, pad, pool) in enumerate(self._b200):
+            pooled = False
+            if tc.ENABLED and i == 0 and w.size(1) == 3 and w.shape[2:] == (3, 3) and pad == 1 and w.size(0) % 8 == 0 and w.size(0) <= 256:
+                # first layer: conv + bias + ReLU + (2,2)/(2,2) pooling in one kernel straight from the fp32 NCHW crops
+                pooled = pool == (2, 2, 2, 2, 0, 0) and y.size(2) % 2 == 0 and y.size(3) % 2 == 0
+                y = tc.conv3x3_c3_pool(y, self._w0_plain, b, pooled)
             else:
-                y = torch.relu(F.conv2d(y, w, b.to(torch.bfloat16), 1, pad))
-            if pool is not None:
+                if y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=torch.channels_last):
+                    y = y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                if tc.ENABLED and w.size(1) % 64 == 0:
+                    y = tc.conv2d(y, w, b, (pad, pad), 0.0)                  # conv + folded BN + bias + ReLU, one kernel
+                else:
+                    y = torch.relu(F.conv2d(y, w, b.to(torch.bfloat16), 1, pad))
+            if pool is not None and not pooled:
                 kh, kw, sh, sw, ph, pw = pool
-                y = F.max_pool2d(y, (kh, kw), (sh, sw), (ph, pw))
+                if tc.ENABLED and y.size(1) % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
+                    y = tc.maxpool(y, (kh, kw), (sh, sw), (ph, pw))
+                else:
+                    y = F.max_pool2d(y, (kh, kw), (sh, sw), (ph, pw))
         return y

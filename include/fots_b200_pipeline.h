@@ -118,6 +118,10 @@ int fots_b200_maxpool_h2_nhwc_bf16(const void* x, void* y, int N, int H, int W, 
  */
 int fots_b200_fpn_merge_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_lo, void* y,
                                   int B, int h, int w, int H, int W, int C, cudaStream_t stream);
+/* The same with the gate map already holding sigmoid(logit) as bf16 (what torch's bf16 autocast path interpolates; emitted by
+ * fots_b200_conv1x1_to1_nhwc_bf16 with sigmoid = 1): saves four expf + divisions per 16-byte output vector. */
+int fots_b200_fpn_merge_prob_nhwc_bf16(const void* a_lo, const void* c_hi, const void* b_hi, const void* g_prob_lo, void* y,
+                                       int B, int h, int w, int H, int W, int C, cudaStream_t stream);
 
 /*
  * Stride-1 convolution of channels-last bf16 activations on the sm_100a tensor cores (tcgen05.mma with TMEM
@@ -224,10 +228,21 @@ int fots_b200_dwconv3x3_up_nhwc_bf16(const void* x_lo, const void* w, void* y, i
 /* The statistics pass of fots_b200_instnorm_nhwc_bf16 on its own: workspace [B, C, 2] fp64 (cleared by the call). */
 int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspace, int B, int HW, int C, cudaStream_t stream);
 /* A 1x1 convolution to ONE output channel + bias (the attention gate conv_attenton of the top-down merge,
- * tools/models.py:405-438) -> bf16 logits [B, 1, H, W] (what fots_b200_fpn_merge_nhwc_bf16 takes as gate_logits):
+ * tools/models.py:405-438) -> bf16 logits [B, 1, H, W] (what fots_b200_fpn_merge_nhwc_bf16 takes as gate_logits), or with
+ * sigmoid != 0 sigmoid(logit) (what fots_b200_fpn_merge_prob_nhwc_bf16 takes):
  * x bf16 [B, H, W, C], wq bf16 [8, C] with the filter in row 0 and zeros elsewhere, bias fp32 [8].  Same kernel as the heads. */
 int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, const float* bias, void* out, int B, int H, int W, int C,
-                                    cudaStream_t stream);
+                                    int sigmoid, cudaStream_t stream);
+/* Consumer B's first layer (tools/models.py:853-897, CRNN.cnn conv0 + relu0 + pooling0): 3 input channels cannot fill a
+ * k-block of the tcgen05 kernel.  x fp32 NCHW [N, 3, H, W] (RoIRotate of the raw image, src/utils.py:430-436), w bf16
+ * [Cout, 3, 3, 3] contiguous, bias fp32 [Cout] or NULL -> y bf16 NHWC = maxpool2x2(relu(conv3x3_pad1(x) + bias)) when
+ * pool2x2 != 0 ([N, H/2, W/2, Cout]), else relu(conv + bias) ([N, H, W, Cout]).  Cout % 8 == 0, Cout <= 256. */
+int fots_b200_conv3x3_c3_pool_nhwc_bf16(const float* x, const void* w, const float* bias, void* y, int N, int H, int W, int Cout,
+                                        int pool2x2, cudaStream_t stream);
+/* MaxPool2d((kh, kw), stride (sh, sw), padding (ph, pw)), floor mode, of a channels-last bf16 tensor (CRNN.cnn pooling0-3):
+ * x [N, H, W, C] -> y [N, (H + 2 ph - kh) / sh + 1, (W + 2 pw - kw) / sw + 1, C]; padding counts as -inf, NaNs propagate. */
+int fots_b200_maxpool_nhwc_bf16(const void* x, void* y, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int ph, int pw,
+                                cudaStream_t stream);
 /* The three fots_b200_*_set_* switches below are process-wide A/B switches for sweeps and parity tests (not thread-safe,
  * never needed for correct results); everything a production caller selects travels with the call.
  * Output-channel tile of fots_b200_conv2d_nhwc_bf16: 0 = automatic, or 64 / 128 / 256 (for sweeps). */

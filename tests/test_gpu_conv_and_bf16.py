@@ -339,6 +339,9 @@ def test_fused_detection_heads_match_torch_fp32(cuda, B, C, H, W):
         got = TC.conv1x1_to1(x, TC.pack_to1(act))
     assert got.shape == (B, 1, H, W) and got.dtype == torch.bfloat16
     assert float((got.float() - f(act)).abs().max()) <= 2.0 ** -8 * float(f(act).abs().max()) + 1e-3
+    with torch.no_grad():
+        gs = TC.conv1x1_to1(x, TC.pack_to1(act), sigmoid=True)
+    assert float((gs.float() - want_seg).abs().max()) <= 2.0 ** -8
 
 
 def test_folded_batchnorm_downsample_branch_matches_module(cuda):

@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import helpers as Hh
 import workloads as WL
@@ -207,6 +208,11 @@ def test_fused_fpn_merge_matches_torch(cuda, B, C, h, w, H, W):
         (dict(a_lo=a_lo, size=(H, W)), up(a_lo)),
         (dict(c_hi=c_hi, b_hi=b_hi, gate_logits_lo=gl), c_hi.float() + b_hi.float() * up(torch.sigmoid(gl.float()))),
         (dict(c_hi=c_hi, b_hi=b_hi), c_hi.float() + b_hi.float()),
+        # the gate handed over as bf16 probabilities (fots_b200_fpn_merge_prob_nhwc_bf16)
+        (dict(c_hi=c_hi, b_hi=b_hi, gate_prob_lo=torch.sigmoid(gl.float()).to(torch.bfloat16)),
+         c_hi.float() + b_hi.float() * up(torch.sigmoid(gl.float()).to(torch.bfloat16))),
+        (dict(a_lo=a_lo, b_hi=b_hi, gate_prob_lo=torch.sigmoid(gl.float()).to(torch.bfloat16)),
+         up(a_lo) + b_hi.float() * up(torch.sigmoid(gl.float()).to(torch.bfloat16))),
     ]
     assert fused.merge_eligible(a_lo, c_hi, b_hi)
     for kw, want in cases:
@@ -311,6 +317,39 @@ def test_crnn_on_tensor_cores_matches_fp32(cuda):
     assert got.shape == want.shape == (128 // 4 + 1, 5, 89)
     err = (got - want).abs()
     assert float(err.mean()) < 0.03 * float(want.abs().mean()) + 2e-3 and float(err.max()) < 0.25 * float(want.abs().max()) + 2e-2
+
+
+@pytest.mark.parametrize("N,H,W,Cout,pool", [(5, 32, 128, 64, True), (2, 32, 100, 64, True), (1, 7, 9, 8, False), (3, 6, 10, 256, True)])
+def test_crnn_first_layer_kernel_matches_torch(cuda, N, H, W, Cout, pool):
+    """fots_b200_conv3x3_c3_pool_nhwc_bf16 (CRNN.cnn conv0 + relu0 + pooling0, tools/models.py:853-897): fp32 NCHW crops in,
+    bf16 channels-last out, against torch's conv2d -> relu -> max_pool2d in fp32 on the same bf16-representable weights
+    (tolerance: the one bf16 rounding of the output)."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(N * 100 + W)
+    w = (torch.randn(Cout, 3, 3, 3, generator=g) / 5.0).to(cuda).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    x = torch.randn(N, 3, H, W, generator=g).to(cuda)
+    got = TC.conv3x3_c3_pool(x, w, b, pool)
+    ref = F.relu(F.conv2d(x, w.float(), b, 1, 1))
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    assert got.shape == ref.shape and got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    assert float((got.float() - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max()) + 1e-5
+
+
+@pytest.mark.parametrize("N,C,H,W,k,s,p", [(3, 128, 16, 64, (2, 2), (2, 2), (0, 0)), (2, 256, 8, 33, (2, 2), (2, 1), (0, 1)),
+                                            (2, 512, 4, 17, (2, 2), (2, 1), (0, 1)), (1, 8, 5, 7, (3, 2), (1, 2), (1, 1))])
+def test_general_maxpool_kernel_equals_torch(cuda, N, C, H, W, k, s, p):
+    """fots_b200_maxpool_nhwc_bf16 (CRNN.cnn pooling0-3: (2,2)/(2,2) and (2,2)/(2,1) pad (0,1)) is exact: a max of bf16 values."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator().manual_seed(C + H + W)
+    x = torch.randn(N, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x[0, 0, 0, 0] = float("nan")
+    x[0, 1, H - 1, W - 1] = float("-inf")
+    got = TC.maxpool(x, k, s, p)
+    ref = F.max_pool2d(x.float(), k, s, p)
+    assert got.shape == ref.shape
+    assert torch.equal(torch.nan_to_num(got.float(), nan=12345.0), torch.nan_to_num(ref, nan=12345.0))
 
 
 def test_step_with_detector_postprocessing_in_the_loop(cuda):
