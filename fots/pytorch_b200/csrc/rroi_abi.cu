@@ -33,7 +33,7 @@ bool parse_opts(const rroi_b200_opts* in, rroi::Opts* out) {
     if (o.flags & ~(RROI_B200_FLAG_NO_PDL | RROI_B200_FLAG_ROIS_READY)) return false;
     if (o.concurrency < 0 || o.variant < 0 || o.variant > 32) return false;
     if (o.nchw_cg != 0 && o.nchw_cg != 1 && o.nchw_cg != 2 && o.nchw_cg != 4 && o.nchw_cg != 8 && o.nchw_cg != 16) return false;
-    if (o.bwd_mode < 0 || o.bwd_mode > 3 || o.nchw_tma < 0 || o.nchw_tma > 5 || o.zero_chunk_images < -1) return false;
+    if (o.bwd_mode < 0 || o.bwd_mode > 4 || o.nchw_tma < 0 || o.nchw_tma > 5 || o.zero_chunk_images < -1) return false;
     out->pdl = !(o.flags & RROI_B200_FLAG_NO_PDL);
     out->rois_ready = (o.flags & RROI_B200_FLAG_ROIS_READY) != 0 && out->pdl;
     out->concurrency = o.concurrency; out->variant = o.variant; out->nchw_cg = o.nchw_cg;

@@ -15,6 +15,7 @@
 // fp32 accumulation order is unspecified exactly as in the reference, so parity is to 1e-4 rel.
 #include "rroi_geom.cuh"
 #include "rroi_kernels.cuh"
+#include <limits.h>
 
 namespace rroi {
 
@@ -156,6 +157,247 @@ __global__ void __launch_bounds__(kBlock) rroi_bwd_nchw_kernel(const BwdParams p
     }
 }
 
+// ------------------------------------------------------------------------------- NCHW, row segments + gather
+// The kernel above issues one 4-byte RED per tap, channel and run of bins: ~190 M reductions for cfg4's per-GPU batch, and
+// the L2 retires ~0.5 reductions per ns whatever their width (the channels-last kernel moves 16 bytes with each) -- 390 us.
+// Here a CTA (one RoI x 8 x 32 bins, as in rroi_fwd_nchw_rows_kernel) first TRANSPOSES its scatter: it builds the list of
+// 16-byte granules (4 consecutive pixels of an image row) its taps touch -- per-row spans, a warp scan -- and, with native
+// integer shared-memory atomics, a CSR table pixel slot -> (bin, weight) of the taps that land on it.  Then, per group of 8
+// channels: the tile's 256 gradients per channel are staged in shared memory (coalesced along pw), and every GRANULE owner
+// thread sums its four pixels' contributions in registers (no floating-point atomics in shared memory -- those compile to
+// a compare-and-swap loop on sm_100) and issues ONE red.global.add.v4.f32 per channel plane: taps that coincide are merged
+// before they leave the SM and a reduction carries up to four pixels.  ~5x fewer L2 reductions.
+constexpr int kBRows = 96;                         // image rows a tile's footprint may span
+constexpr int kBGran = 512;                        // granules of one channel plane per tile
+constexpr int kBSlots = kBGran * 4;                // pixel slots
+constexpr int kBCh = 8;                            // channels per stage
+
+__global__ void __launch_bounds__(256, 4) rroi_bwd_nchw_rows_kernel(const BwdParams p) {
+    __shared__ int rlo[kBRows], rhi[kBRows], goff[kBRows + 1];
+    __shared__ int gsrc[kBGran];                   // plane offset (floats) of every granule
+    __shared__ int start[kBSlots];                 // counts -> exclusive starts -> (after the fill) ends of the slots' entry lists
+    __shared__ int2 ent[1024];                     // {weight bits, local bin} of every tap, grouped by pixel slot
+    // staged gradients [channel][bin]: a warp's gather loads hit random bins of ONE channel row (few bank conflicts); the
+    // [bin][channel] form with two LDS.128 per tap was measured slower (320 vs 264 us: conflicts + 82 registers)
+    __shared__ __align__(16) float gs[2][kBCh][256];
+    __shared__ int ylim[2], wsum[8];
+    __shared__ RoiXform sX;
+    const int n = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x - n * p.tiles;
+    const int tiles_w = (p.PW + 31) / 32;
+    const int ph0 = (tile / tiles_w) * 8, pw0 = (tile % tiles_w) * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bins = p.PH * p.PW;
+
+    if (threadIdx.x < kBRows) { rlo[threadIdx.x] = INT_MAX; rhi[threadIdx.x] = INT_MIN; }
+    if (threadIdx.x == 0) { ylim[0] = INT_MAX; ylim[1] = INT_MIN; }
+    pdl_wait();
+    pdl_launch_dependents();
+    if (!in_image_window(p, n)) return;
+    if (threadIdx.x < 32) {
+        RoiXform X;
+        if (p.idx_mode == IDX_NONE) {
+            X = roi_xform(p.rois + (size_t)n * 6, p.scale, p.PH);
+        } else {  // centres are loaded: only the batch index and the width mask are needed
+            const float* roi = p.rois + (size_t)n * 6;
+            X.batch = __float2int_rz(__ldg(roi));
+            X.rpw = __fdiv_rn(__fmul_rn(__ldg(roi + 4), (float)p.PH), __ldg(roi + 3));
+        }
+        if (threadIdx.x == 0) sX = X;
+    }
+    __syncthreads();
+    const RoiXform X = sX;
+    const bool batch_ok = (X.batch >= 0) & (X.batch < p.B);
+
+    // ---- 1. geometry: thread = bin (warp = one ph row of the tile, lanes = 32 consecutive pw)
+    const int ph = ph0 + warp, pw = pw0 + lane;
+    const bool live = ph < p.PH && pw < p.PW;
+    const int bin = ph * p.PW + pw;
+    float cx = 0.f, cy = 0.f;
+    if (live) {
+        if (p.idx_mode == IDX_NONE) bin_center(X, ph, pw, (float)(p.W - 1), (float)(p.H - 1), cx, cy);
+        else { cx = __ldg(p.idx_x + (size_t)n * bins + bin); cy = __ldg(p.idx_y + (size_t)n * bins + bin); }
+    }
+    const bool in = live & batch_ok & !(X.rpw < (float)pw);
+    const ScatterGeom g = scatter_geom<false>(cx, cy, in, p.H, p.W);
+    const bool s_lt = g.p_lt & (g.wlt != 0.0f), s_rt = g.p_rt & (g.wrt != 0.0f);
+    const bool s_rb = g.p_rb & (g.wrb != 0.0f), s_lb = g.p_lb & (g.wlb != 0.0f);
+    const bool top_used = s_lt | s_rt, bot_used = s_rb | s_lb;
+    {
+        int ya = INT_MAX, yb = INT_MIN;
+        if (top_used) { ya = g.t; yb = g.t; }
+        if (bot_used) { ya = min(ya, g.b); yb = max(yb, g.b); }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            ya = min(ya, __shfl_xor_sync(0xffffffffu, ya, m));
+            yb = max(yb, __shfl_xor_sync(0xffffffffu, yb, m));
+        }
+        if (lane == 0 && yb >= ya) { atomicMin(&ylim[0], ya); atomicMax(&ylim[1], yb); }
+    }
+    __syncthreads();
+    const int y0 = ylim[0], nrows = ylim[1] >= ylim[0] ? ylim[1] - ylim[0] + 1 : 0;
+    if (nrows == 0) return;                                                        // nothing to scatter (CTA-uniform)
+    const bool aligned = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.bottom_diff) & 15) == 0);
+    bool staged = aligned && nrows <= kBRows;                                      // CTA-uniform
+    if (staged) {
+        // ---- 2. per-row spans of the scattered taps (scattered taps satisfy 0 < x < W-1, 0 < y < H-1: valid indices)
+        if (top_used) {
+            atomicMin(&rlo[g.t - y0], s_lt ? g.l : g.r); atomicMax(&rhi[g.t - y0], s_rt ? g.r : g.l);
+        }
+        if (bot_used) {
+            atomicMin(&rlo[g.b - y0], s_lb ? g.l : g.r); atomicMax(&rhi[g.b - y0], s_rb ? g.r : g.l);
+        }
+    }
+    __syncthreads();
+    if (staged && warp == 0) {                    // exclusive scan of the rows' granule counts (<= 96 rows: 3 per lane)
+        int len[3], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int r = lane * 3 + k;
+            len[k] = (r < nrows && rhi[r] >= rlo[r]) ? ((rhi[r] | 3) - (rlo[r] & ~3) + 1) >> 2 : 0;
+            sum += len[k];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int r = lane * 3 + k;
+            if (r < kBRows) goff[r] = run;
+            run += len[k];
+        }
+        if (lane == 31) goff[kBRows] = incl;      // total granules of one channel plane
+    }
+    __syncthreads();
+    const int gtot = staged ? goff[kBRows] : 0;
+    staged = staged && gtot > 0 && gtot <= kBGran;
+
+    const size_t HW = (size_t)p.H * p.W;
+    const float* gsrc_bin = p.top_diff + (size_t)n * p.C * bins + bin;             // + c * bins
+    float* plane0 = p.bottom_diff + (size_t)(batch_ok ? X.batch : 0) * p.C * HW;
+
+    if (!staged) {
+        // ---- fallback (footprint too large or unaligned rows): one reduction per tap and channel
+        if (!in) return;
+        const unsigned o_lt = (unsigned)g.t * (unsigned)p.W + (unsigned)g.l, o_rt = (unsigned)g.t * (unsigned)p.W + (unsigned)g.r;
+        const unsigned o_rb = (unsigned)g.b * (unsigned)p.W + (unsigned)g.r, o_lb = (unsigned)g.b * (unsigned)p.W + (unsigned)g.l;
+#pragma unroll 1
+        for (int c = 0; c < p.C; ++c) {
+            const float gv = __ldg(gsrc_bin + (size_t)c * bins);
+            float* d = plane0 + (size_t)c * HW;
+            if (s_lt) red_add(d + o_lt, __fmul_rn(g.wlt, gv));
+            if (s_rt) red_add(d + o_rt, __fmul_rn(g.wrt, gv));
+            if (s_rb) red_add(d + o_rb, __fmul_rn(g.wrb, gv));
+            if (s_lb) red_add(d + o_lb, __fmul_rn(g.wlb, gv));
+        }
+        return;
+    }
+
+    // ---- 3. granule table and the CSR table slot -> taps
+    const int nslots = gtot * 4;
+    for (int r = threadIdx.x; r < nrows; r += 256) {
+        if (rhi[r] < rlo[r]) continue;
+        const int a = rlo[r] & ~3, cnt = ((rhi[r] | 3) - a + 1) >> 2, base = (y0 + r) * p.W + a;
+        for (int k = 0; k < cnt; ++k) gsrc[goff[r] + k] = base + 4 * k;
+    }
+    for (int i = threadIdx.x; i < nslots; i += 256) start[i] = 0;
+    __syncthreads();
+    int sl_lt = 0, sl_rt = 0, sl_rb = 0, sl_lb = 0;
+    if (top_used) {
+        const int o = goff[g.t - y0] * 4 - (rlo[g.t - y0] & ~3);
+        sl_lt = o + g.l; sl_rt = o + g.r;
+    }
+    if (bot_used) {
+        const int o = goff[g.b - y0] * 4 - (rlo[g.b - y0] & ~3);
+        sl_lb = o + g.l; sl_rb = o + g.r;
+    }
+    if (s_lt) atomicAdd(&start[sl_lt], 1);
+    if (s_rt) atomicAdd(&start[sl_rt], 1);
+    if (s_rb) atomicAdd(&start[sl_rb], 1);
+    if (s_lb) atomicAdd(&start[sl_lb], 1);
+    __syncthreads();
+    {   // block-wide exclusive scan of start[0 .. nslots): 8 consecutive slots per thread
+        int v[8], sum = 0;
+        const int i0 = threadIdx.x * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = (i0 + k) < nslots ? start[i0 + k] : 0; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int base = incl - sum;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((i0 + k) < nslots) start[i0 + k] = base;
+            base += v[k];
+        }
+    }
+    __syncthreads();
+    const int tl = threadIdx.x;                                                    // local bin index of this thread
+    if (s_lt) ent[atomicAdd(&start[sl_lt], 1)] = make_int2(__float_as_int(g.wlt), tl);
+    if (s_rt) ent[atomicAdd(&start[sl_rt], 1)] = make_int2(__float_as_int(g.wrt), tl);
+    if (s_rb) ent[atomicAdd(&start[sl_rb], 1)] = make_int2(__float_as_int(g.wrb), tl);
+    if (s_lb) ent[atomicAdd(&start[sl_lb], 1)] = make_int2(__float_as_int(g.wlb), tl);
+    // start[s] is now the END of slot s; its entries begin at start[s - 1] (0 for s = 0)
+
+    // ---- 4. channel stages: gradients of the tile -> shared memory -> per-granule sums -> one vector reduction per plane
+    const int nst = (p.C + kBCh - 1) / kBCh;
+    float gv[kBCh];
+    auto load_stage = [&](int st) {
+        const int c0 = st * kBCh;
+#pragma unroll
+        for (int ci = 0; ci < kBCh; ++ci) gv[ci] = (in && (c0 + ci) < p.C) ? __ldg(gsrc_bin + (size_t)(c0 + ci) * bins) : 0.0f;
+    };
+    auto store_stage = [&](int buf) {
+#pragma unroll
+        for (int ci = 0; ci < kBCh; ++ci) gs[buf][ci][tl] = gv[ci];
+    };
+    load_stage(0);
+    store_stage(0);
+    for (int st = 0; st < nst; ++st) {
+        __syncthreads();                          // gs[st & 1] is complete (and, first time round, so is the CSR table)
+        if (st + 1 < nst) load_stage(st + 1);     // in flight during the gather below
+        const int c0 = st * kBCh, cn = min(kBCh, p.C - c0);
+        const float (*gb)[256] = gs[st & 1];
+        for (int gi = threadIdx.x; gi < gtot; gi += 256) {
+            float acc[kBCh][4];
+#pragma unroll
+            for (int ci = 0; ci < kBCh; ++ci) acc[ci][0] = acc[ci][1] = acc[ci][2] = acc[ci][3] = 0.0f;
+            int e = gi > 0 ? start[gi * 4 - 1] : 0;
+            bool any = false;
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                const int e1 = start[gi * 4 + px];
+                any |= e1 > e;
+                for (; e < e1; ++e) {
+                    const int2 en = ent[e];
+                    const float w = __int_as_float(en.x);
+#pragma unroll
+                    for (int ci = 0; ci < kBCh; ++ci) acc[ci][px] = __fmaf_rn(w, gb[ci][en.y], acc[ci][px]);
+                }
+            }
+            if (any) {
+                float* d = plane0 + (size_t)c0 * HW + gsrc[gi];
+#pragma unroll
+                for (int ci = 0; ci < kBCh; ++ci)
+                    if (ci < cn)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + (size_t)ci * HW), "f"(acc[ci][0]), "f"(acc[ci][1]),
+                                     "f"(acc[ci][2]), "f"(acc[ci][3]) : "memory");
+            }
+        }
+        if (st + 1 < nst) store_stage((st + 1) & 1);
+    }
+}
+
 template <bool kDedupe>
 static cudaError_t launch_bwd_nchw_cg(const BwdParams& p, int cg, long long grid, cudaStream_t s, bool pdl) {
     switch (cg) {
@@ -181,6 +423,16 @@ cudaError_t launch_bwd_nchw(const BwdParams& p0, const Opts& o, cudaStream_t s) 
     p.cgroups = (p.C + cg - 1) / cg;
     const long long grid = (long long)p.N * p.cgroups * p.tiles;
     const bool pdl = o.pdl;
+    // Automatic: row segments + gather (per-tile fallback when rows are unaligned) once its 256-bin CTAs fill the machine a few
+    // times over -- measured (profiles/r02_sweep_bwd_nchw.txt) 264 vs 468 us at 2 048 RoIs, 90 vs 120 us at 512, but 41 vs 21 us
+    // for 64 RoIs alone, where 128 CTAs each walk a chain of set-up phases and 8 channel stages.
+    const long long rows_ctas = (long long)p.N * ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
+    if (o.bwd_mode == 4 || (o.bwd_mode == 0 && rows_ctas >= 4 * 148)) {
+        p.tiles = ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
+        if ((long long)p.H * p.W * 4 < (1LL << 31))                               // granule offsets are 32-bit
+            return launch_1d(rroi_bwd_nchw_rows_kernel, (long long)p.N * p.tiles, 256, p, s, pdl);
+        p.tiles = (bins + kBlock - 1) / kBlock;
+    }
     return o.bwd_mode != 3 ? launch_bwd_nchw_cg<true>(p, cg, grid, s, pdl)
                            : launch_bwd_nchw_cg<false>(p, cg, grid, s, pdl);
 }

@@ -49,7 +49,7 @@ struct Opts {
     int concurrency = 0;     // independent launches the caller keeps in flight (0/1 = alone)
     int variant = 0;         // 0 = automatic; > 0 forces a forward kernel variant
     int nchw_cg = 0;         // channels per lane / per CTA in the NCHW kernels: 1,2,4,8,16 (0 = default)
-    int bwd_mode = 0;        // 0 auto; 1 plain per-tap reductions; 2 generic channels-last kernel; 3 NCHW without the warp merge
+    int bwd_mode = 0;        // 0 auto; 1 per-tap reductions (NCHW: warp-merged runs); 2 generic channels-last kernel; 3 NCHW without the warp merge; 4 NCHW row segments + gather (= auto)
     int nchw_tma = 0;        // 0 = NCHW forward gathers through L1; 1 = TMA box staging; 2..5 = same, box index >= value - 2
     int zero_chunk_images = 0; // backward zero_fill: images per zero/scatter chunk (0 auto, -1 whole map)
 };

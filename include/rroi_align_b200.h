@@ -59,7 +59,8 @@ typedef struct rroi_b200_opts {
                                /* (sweeps and parity tests; see launch_fwd_nhwc / launch_fwd_nchw)                  */
     int nchw_cg;               /* NCHW kernels: channels in flight per lane / per CTA: 1,2,4,8,16 (0 = default)     */
     int bwd_mode;              /* backward: 0 = automatic; 2 = generic (non-packed) channels-last kernel;            */
-                               /* NCHW: 3 = no warp-level merge of equal centres (A/B measurements)                 */
+                               /* NCHW: 4 = row segments + per-granule gather (= automatic), 1 = one reduction per  */
+                               /* run of equal centres, 3 = one per tap (A/B measurements)                          */
     int nchw_tma;              /* NCHW forward: 0 gather through L1 (default); 1 = stage the patch footprint with    */
                                /* TMA box loads; 2..5 = same with a minimum box index (sweeps)                      */
     int zero_chunk_images;     /* backward with zero_fill: 0 (default) = one memset of the whole map, then one      */

@@ -217,17 +217,23 @@ def test_full_size_properties(oracle, cuda):
     assert torch.allclose(gt, gt2, rtol=1e-4, atol=1e-5)
 
 
-def test_backward_dedupe_on_off_agree(cuda):
-    import torch
+def test_backward_nchw_variants_agree(oracle, cuda):
+    """The three NCHW backward kernels -- row segments + per-granule gather (automatic, bwd_mode 4), one reduction per run of
+    equal centres (1) and per tap (3) -- against the CPU oracle and each other, on RoIs whose bin pitch is below one feature
+    pixel (many taps per pixel: the case the gather kernel merges in shared memory) and on an unaligned map (W % 4 != 0: the
+    gather kernel's per-tile fallback)."""
     from fots.pytorch_b200 import _cabi
-    feats = WL.features(3, 2, 16, 90, 160)
-    rois = WL.stress_rois(33, 200, 2, 640, 360)
-    rois[:, 3] = np.minimum(rois[:, 3], 6)          # bin pitch < 1 px -> long runs of equal centres
-    out, ix, iy = Hh.run_new_forward(feats, rois, 8, 64, 0.25, cuda)
-    g = np.random.default_rng(0).standard_normal(out.shape, dtype=np.float32)
-    a = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda)
-    b = Hh.run_new_backward(g, rois, (ix, iy), feats.shape, 0.25, cuda, opts=_cabi.opts(bwd_mode=3))
-    Hh.assert_close_rel(a, b, REL_BWD, "dedupe on vs off")
+    for (H, W) in ((90, 160), (45, 79)):
+        feats = WL.features(3, 2, 16, H, W)
+        rois = WL.stress_rois(33, 200, 2, W * 4, H * 4)
+        rois[:, 3] = np.minimum(rois[:, 3], 6)          # bin pitch < 1 px -> long runs of equal centres
+        out, ix, iy = Hh.run_new_forward(feats, rois, 8, 64, 0.25, cuda)
+        g = np.random.default_rng(0).standard_normal(out.shape, dtype=np.float32)
+        want = oracle.backward(g, rois, Hh.expand_idx(ix, 16), Hh.expand_idx(iy, 16), feats.shape, 0.25, threads=0)
+        for mode in (0, 4, 1, 3):
+            for idx in ((ix, iy), None):
+                got = Hh.run_new_backward(g, rois, idx, feats.shape, 0.25, cuda, opts=_cabi.opts(bwd_mode=mode))
+                Hh.assert_close_rel(got, want, REL_BWD, "NCHW backward mode %d, %dx%d, saved centres %s" % (mode, H, W, idx is not None))
 
 
 @pytest.mark.parametrize("cg", [1, 2, 4, 8, 16])

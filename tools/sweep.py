@@ -88,6 +88,14 @@ def sweep_bwd():
     point(images=1, layout="nchw", backward=True)
 
 
+def sweep_bwd_nchw():
+    for images in (32, 8, 1):
+        for mode in (4, 1, 3):
+            point(images=images, layout="nchw", backward=True, zero_chunk_images=-1, bwd_mode=mode)
+    point(images=32, layout="nchw", C=256, backward=True, zero_chunk_images=-1, bwd_mode=4)
+    point(images=32, layout="nchw", C=256, backward=True, zero_chunk_images=-1, bwd_mode=1)
+
+
 def sweep_bf16():
     for images, S in ((1, 8), (32, 1)):
         for C in (64, 256):
@@ -106,7 +114,7 @@ def sweep_nchw():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fwd"]
     for w in which:
-        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bf16": sweep_bf16, "nchw": sweep_nchw}[w]()
+        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw}[w]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "sweep_%s.json" % "_".join(which)), "w") as f:
         json.dump(RECS, f, indent=1)
