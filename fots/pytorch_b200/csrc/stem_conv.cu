@@ -261,9 +261,20 @@ static int stem_launch(const In* x, const void* w, void* y, double* stats, int B
         if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     }
     // persistent: contiguous tile ranges, so a CTA stays inside one image and flushes its sums once or twice
-    const long long ctas_wanted = 148LL * 6;
-    const int per = (int)((total + ctas_wanted - 1) / ctas_wanted);
-    const int grid = (int)((total + per - 1) / per);
+    // two whole waves of resident CTAs (the tile ranges are equal, so a ragged last wave is pure loss)
+    int dev = 0, sms = 148, occ = 3;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_conv_kernel<In>, kThreads, 0) != cudaSuccess || sms <= 0 || occ <= 0) {
+        (void)cudaGetLastError();
+        sms = 148; occ = 3;
+    }
+    const long long ctas_wanted = 2LL * sms * occ;
+    int per = (int)((total + ctas_wanted - 1) / ctas_wanted);
+    int grid = (int)((total + per - 1) / per);
+    if (grid > sms * occ && grid < ctas_wanted * 15 / 16) {    // second wave under ~88 % full: one tile more per CTA -> a single fuller wave pair
+        const int per1 = (int)((total + (long long)sms * occ - 1) / ((long long)sms * occ));
+        if ((long long)per1 * sms * occ - total < total / 16) { per = per1; grid = (int)((total + per - 1) / per); }
+    }
     (void)pdl::launch(stem_conv_kernel<In>, dim3(grid), dim3(kThreads), 0, stream, x, static_cast<const __nv_bfloat16*>(w), static_cast<uint32_t*>(y), stats,
                                                         B, H, W, tiles_x, tiles_y, per);
     const cudaError_t e = cudaGetLastError();
