@@ -616,9 +616,10 @@ def pipeline_leg(args, torch, device, dist, world, rank):
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
             "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
-            "dtype": "uint8 images in (normalised on load by the stem kernel); bf16 activations: hand-written tcgen05 convolutions and "
-                     "mma.sync stem conv, library calls for the remaining convolutions, fused InstanceNorm / FPN-merge / max-pool "
-                     "kernels, bf16-in/bf16-out RoIRotate (fp32 arithmetic, == bf16(reference(float(features))) bit for bit)",
+            "dtype": "uint8 images in (normalised on load by the stem kernel); bf16 activations, fp32 accumulation: every convolution on "
+                     "this repo's kernels (tcgen05 implicit GEMM, mma.sync stem / heads, depthwise), fused InstanceNorm / top-down "
+                     "merge / max-pool kernels, bf16-in/bf16-out RoIRotate (fp32 arithmetic, == bf16(reference(float(features))) "
+                     "bit for bit; NOT within 1e-4 of the fp32 pipeline by construction: one bf16 rounding per activation)",
             "collective": "one all_gather of int32 [images, 64, 74] records per step" if world > 1 else "none (1 rank)",
             "boxes": "planted (seeded) boxes are an INPUT of this number; `with_detection` has the decode + merge inside the step",
             "with_detection": det_info,
