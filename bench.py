@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
     ap.add_argument("--pipeline-steps", type=int, default=4)
+    ap.add_argument("--pipeline-lanes", type=int, default=4, help="parallel graph branches the step's micro-batches are dealt to")
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-images", type=int, default=32, help="batch of the cfg3 training step")
@@ -518,7 +519,9 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     images = torch.randint(0, 256, (per_gpu, 720, 1280, 3), device=device, generator=gen, dtype=torch.uint8).permute(0, 3, 1, 2)
     quads = torch.from_numpy(planted_quads(per_gpu, 64, seed0=rank * per_gpu)).to(device)
 
-    local = pipe.capture(images, quads, micro)      # one CUDA graph for the rank-local part of the step
+    # one CUDA graph for the rank-local part of the step; its four 8-image micro-batches are independent and run as
+    # `lanes` parallel branches of the graph (the latency-bound launches of one fill the bubbles of the other)
+    local = pipe.capture(images, quads, micro, lanes=args.pipeline_lanes)
 
     def step():
         return all_gather_records(local(), batch)
@@ -614,7 +617,8 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     cpu = pipeline_cpu_baseline(torch) if (rank == 0 and world == 1) else None      # N=1 only, like cpu_baseline
     return {"images_per_s": batch / (ms_host * 1e-3), "ms_per_step": ms_host, "cpu_baseline": cpu,
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
-            "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64,
+            "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64, "micro_batch": micro,
+            "graph_branches": args.pipeline_lanes,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
             "dtype": "uint8 images in (normalised on load by the stem kernel); bf16 activations, fp32 accumulation: every convolution on "
                      "this repo's kernels (tcgen05 implicit GEMM, mma.sync stem / heads, depthwise), fused InstanceNorm / top-down "

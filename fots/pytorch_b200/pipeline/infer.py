@@ -86,15 +86,33 @@ class FOTSPipeline:
         return merge_candidates(counts, cand, seg.size(3), seg.size(2))
 
     @torch.no_grad()
-    def capture(self, images, quads, micro=8):
+    def capture(self, images, quads, micro=8, lanes=1):
         """Capture this rank's whole local step (micro-batches of `micro` images, no host sync inside) into one
         CUDA graph bound to the given `images` / `quads` buffers.  Returns a callable `replay()` -> records
         [b, R, 9 + T + 1]; refill the two buffers in place between replays.  The step has ~600 launches per
-        micro-batch, so eager execution is CPU-launch-bound (8.4 ms of CPU for 9.2 ms of GPU at 8 images)."""
+        micro-batch, so eager execution is CPU-launch-bound (8.4 ms of CPU for 9.2 ms of GPU at 8 images).
+
+        lanes > 1: the micro-batches are dealt round-robin to `lanes` parallel branches of the graph (independent images,
+        no shared state).  A third of the step is launches on maps of a few MB (stages 3-4, the recogniser's normalisations)
+        that are latency-bound, not bandwidth-bound: two independent chains fill each other's bubbles."""
         b = images.size(0)
+        lanes = max(1, min(int(lanes), (b + micro - 1) // micro))
+        branch = [torch.cuda.Stream(images.device) for _ in range(lanes)] if lanes > 1 else []
 
         def local():
-            recs = [self.step_local(images[i:i + micro], quads[i:i + micro])[0] for i in range(0, b, micro)]
+            starts = list(range(0, b, micro))
+            if lanes <= 1:
+                recs = [self.step_local(images[i:i + micro], quads[i:i + micro])[0] for i in starts]
+            else:
+                cur = torch.cuda.current_stream(images.device)
+                recs = [None] * len(starts)
+                for st in branch:
+                    st.wait_stream(cur)                      # fork
+                for k, i in enumerate(starts):
+                    with torch.cuda.stream(branch[k % lanes]):
+                        recs[k] = self.step_local(images[i:i + micro], quads[i:i + micro])[0]
+                for st in branch:
+                    cur.wait_stream(st)                      # join
             return recs[0] if len(recs) == 1 else torch.cat(recs, 0)
 
         side = torch.cuda.Stream()

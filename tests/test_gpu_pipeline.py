@@ -102,6 +102,8 @@ def test_inference_step_end_to_end(oracle, cuda):
     assert torch.equal(graphed(), rec16)
     images.copy_(torch.randn_like(images))                       # buffers are refilled in place between replays
     assert torch.equal(graphed(), pipe16.step_local(images, quads)[0])
+    branched = pipe16.capture(images, quads, micro=1, lanes=2)   # micro-batches on parallel branches of the graph: same records
+    assert torch.equal(branched(), pipe16.step_local(images, quads)[0])
 
 
 def test_training_step_runs_and_reduces_loss(cuda):
