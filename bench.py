@@ -609,8 +609,9 @@ def pipeline_leg(args, torch, device, dist, world, rank):
         det_info = {"images_per_s": batch / (ms_det * 1e-3), "ms_per_step": ms_det, "host_threads_per_rank": threads,
                     "boxes_found_per_image_mean": float(np.mean(found["n"])),
                     "boxes": "head outputs overwritten by planted detection maps (64 boxes per image, SURVEY 8d), then "
-                             "fots_b200_decode_candidates (GPU) + fots_b200_merge_candidates_host_batch (host thread pool, "
-                             "overlapped with the backbone of the next 8-image micro-batch); images device-resident"}
+                             "fots_b200_decode_candidates (GPU) + fots_b200_merge_candidates_host_batch (one host worker per "
+                             "8-image micro-batch; all head graphs enqueued up front, the recogniser graphs on a second stream as "
+                             "their boxes arrive); images device-resident"}
         del det, maps
     except Exception as e:
         det_info = {"error": repr(e)}

@@ -11,6 +11,8 @@ therefore takes the boxes as an input -- `planted_quads()` builds the seeded 64-
 protocol -- while the backbone and the detection heads are still computed for real every step.
 """
 import numpy as np
+import os
+
 import torch
 
 from ..rroi_align.functions.rroi_align import rroi_align, rroi_align_bf16
@@ -211,38 +213,58 @@ class FOTSPipeline:
                        "fill_h": fill_quads[i * micro:i * micro + m].cpu(),
                        "evA": torch.cuda.Event(), "evQ": torch.cuda.Event()})
 
-        def step():
-            found = []
-            A[0].replay()
-            st[0]["evA"].record(main)
-            for i in range(nb):
-                if i + 1 < nb:                                 # the GPU works on the next micro-batch while the host merges this one
-                    A[i + 1].replay()
-                    st[i + 1]["evA"].record(main)
-                S = st[i]
-                with torch.cuda.stream(copy):
-                    copy.wait_event(S["evA"])
-                    S["counts_h"].copy_(S["counts"], non_blocking=True)
-                    copy.synchronize()
-                    cnt = S["counts_h"].numpy()
-                    for k in range(S["m"]):
-                        if cnt[k] > 0:
-                            S["rows_h"][k, :cnt[k]].copy_(S["cand"][k, :cnt[k]], non_blocking=True)
-                    copy.synchronize()
-                boxes, num = merge_rows_host(cnt, S["rows_h"].numpy(), w4, h4, max_boxes=R, threads=threads)
-                qh = S["quads_h"]
-                qh.copy_(S["fill_h"])
-                qn = qh.numpy()
+        # Scheduling of one step: ALL head graphs are enqueued up front on the main stream; every micro-batch has a host
+        # worker (its own copy stream) that waits for its head graph, brings the candidate rows over, runs the merge (the C
+        # call releases the GIL; `threads` workers inside it, so several micro-batches merge at once on a many-core host),
+        # sends the boxes back and signals; the recogniser graphs run on a second stream as soon as their boxes are there,
+        # next to the head graphs of later micro-batches.
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=nb)
+        tail_stream = torch.cuda.Stream(dev)
+        copies = [torch.cuda.Stream(dev) for _ in range(nb)]
+        per_job = max(1, min(micro, threads if threads > 0 else (os.cpu_count() or 1)))
+
+        def host_part(i):
+            torch.cuda.set_device(dev)
+            S, cs = st[i], copies[i]
+            with torch.cuda.stream(cs):
+                cs.wait_event(S["evA"])
+                S["counts_h"].copy_(S["counts"], non_blocking=True)
+                cs.synchronize()
+                cnt = S["counts_h"].numpy()
                 for k in range(S["m"]):
-                    n = min(int(num[k]), R)
-                    qn[k, :n] = boxes[k, :n]
-                    qn[k, :n, :8] /= 10000.0                   # nms/__init__.py:13-15
-                    found.append(int(num[k]))
-                with torch.cuda.stream(copy):
-                    S["quads"].copy_(qh, non_blocking=True)
-                    S["evQ"].record(copy)
-                main.wait_event(S["evQ"])
-                Bg[i].replay()
+                    if cnt[k] > 0:
+                        S["rows_h"][k, :cnt[k]].copy_(S["cand"][k, :cnt[k]], non_blocking=True)
+                cs.synchronize()
+            boxes, num = merge_rows_host(cnt, S["rows_h"].numpy(), w4, h4, max_boxes=R, threads=per_job)
+            qh = S["quads_h"]
+            qh.copy_(S["fill_h"])
+            qn = qh.numpy()
+            found = []
+            for k in range(S["m"]):
+                n = min(int(num[k]), R)
+                qn[k, :n] = boxes[k, :n]
+                qn[k, :n, :8] /= 10000.0                       # nms/__init__.py:13-15
+                found.append(int(num[k]))
+            with torch.cuda.stream(cs):
+                S["quads"].copy_(qh, non_blocking=True)
+                S["evQ"].record(cs)
+                cs.synchronize()                               # the event is recorded before the main thread waits on it
+            return found
+
+        def step():
+            for i in range(nb):
+                A[i].replay()
+                st[i]["evA"].record(main)
+            jobs = [pool.submit(host_part, i) for i in range(nb)]
+            found = []
+            for i in range(nb):
+                found.extend(jobs[i].result())
+                tail_stream.wait_event(st[i]["evA"])           # focr of this micro-batch
+                tail_stream.wait_event(st[i]["evQ"])           # its merged boxes
+                with torch.cuda.stream(tail_stream):
+                    Bg[i].replay()
+            main.wait_stream(tail_stream)
             recs = [S["rec"] for S in st]
             return (recs[0] if len(recs) == 1 else torch.cat(recs, 0)), found
 
