@@ -222,6 +222,13 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// {acc_lo, acc_hi} += {x.lo * w.lo, x.hi * w.hi}: two mixed-precision FMAs on the halves of packed bf16 pairs
+__device__ __forceinline__ void fma_bf16x2(float& acc_lo, float& acc_hi, uint32_t x, uint32_t w) {
+    asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\t"
+        "mov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, xl, wl, %0;\n\tfma.rn.f32.bf16 %1, xh, wh, %1;\n\t}"
+        : "+f"(acc_lo), "+f"(acc_hi) : "r"(x), "r"(w));
+}
 __device__ __forceinline__ void split2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
 struct __align__(16) Tap { int o0, o1; float l0, l1; };
@@ -299,14 +306,17 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
     };
 
     pdl::trigger();
-    // ---- this thread's 8 channels x 9 taps of weights as fp32 pairs; w is [C][3][3]
-    uint64_t wr[9][4];
+    // ---- this thread's 8 channels x 9 taps of weights, kept as the bf16 PAIRS they are stored as ({ch 2k, ch 2k+1} per
+    // register: 36 registers instead of 72 fp32 values); w is [C][3][3]
+    uint32_t wr[9][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int tp = 0; tp < 9; ++tp)
-            wr[tp][k] = pair_f32(__bfloat162float(wgt[(size_t)(c0 + v * 8 + 2 * k) * 9 + tp]), __bfloat162float(wgt[(size_t)(c0 + v * 8 + 2 * k + 1) * 9 + tp]));
-
+        for (int tp = 0; tp < 9; ++tp) {
+            const uint32_t lo = *reinterpret_cast<const unsigned short*>(wgt + (size_t)(c0 + v * 8 + 2 * k) * 9 + tp);
+            const uint32_t hi = *reinterpret_cast<const unsigned short*>(wgt + (size_t)(c0 + v * 8 + 2 * k + 1) * 9 + tp);
+            wr[tp][k] = lo | (hi << 16);
+        }
     pdl::wait();                                              // the weights above are constants; everything below depends on the stream
     int t = blockIdx.x;
     if (t < ntiles) prefetch(t, 0);
@@ -445,25 +455,28 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
         }
 
     conv:
-        // ---- 3x3 accumulation: 4 outputs x 8 channels per thread, fp32 pairs, order (r, s) = (0,0) .. (2,2)
-        uint64_t acc[4][4];
+        // ---- 3x3 accumulation: 4 outputs x 8 channels per thread, order (r, s) = (0,0) .. (2,2).  fma.rn.f32.bf16 (sm_100
+        // FHFMA.BF16) multiplies two bf16 operands -- selected as halves of the packed registers, nothing is widened -- into
+        // an fp32 accumulator: exact product, one rounding, i.e. bit-identical to fmaf(float(x), float(w), acc), without the
+        // shift / mask per element that kept the ALU pipe at 58 % (profiles/r02_dwconv_up_first_version.txt).
+        float acc[4][8];
 #pragma unroll
         for (int o = 0; o < 4; ++o)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[o][k] = 0ull;
+            for (int k = 0; k < 8; ++k) acc[o][k] = 0.0f;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const uint4* trow = tile + ((row + r) * kIW + q4 * 4) * 8 + v;
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 const uint4 raw = trow[j * 8];
-                const uint64_t f[4] = {widen2(raw.x), widen2(raw.y), widen2(raw.z), widen2(raw.w)};
+                const uint32_t xw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
                     const int sx = j - o;                                              // tap column of output o fed by input column j
                     if (sx >= 0 && sx < 3) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[o][k] = fma2(f[k], wr[r * 3 + sx][k], acc[o][k]);
+                        for (int k = 0; k < 4; ++k) fma_bf16x2(acc[o][2 * k], acc[o][2 * k + 1], xw[k], wr[r * 3 + sx][k]);
                     }
                 }
             }
@@ -478,9 +491,7 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
             for (int o = 0; o < 4; ++o) {
                 const int ox = tp.ox0 + q4 * 4 + o;
                 if (ox < W) {
-                    float a[8];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) split2(acc[o][k], a[2 * k], a[2 * k + 1]);
+                    const float* a = acc[o];
                     uint4 pk;
                     pk.x = pack2(a[0], a[1]); pk.y = pack2(a[2], a[3]); pk.z = pack2(a[4], a[5]); pk.w = pack2(a[6], a[7]);
                     out[(size_t)ox * CV] = pk;
