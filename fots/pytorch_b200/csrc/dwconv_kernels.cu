@@ -12,9 +12,11 @@
 // fp32 accumulation in the order (r, s) = (0,0) .. (2,2), one rounding to bf16.
 #include "../../../include/fots_b200_pipeline.h"
 #include "pdl.cuh"
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 
 namespace {
 
@@ -194,16 +196,55 @@ __global__ void __launch_bounds__(TH * 32) dwconv3x3_kernel(const uint4* __restr
     }
 }
 
+// ---- TMA staging (cp.async.bulk.tensor + mbarrier), used by the persistent stride-1 kernel -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on the phase parity; trap after ~2 s instead of hanging the device if a copy never completes.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spin & 0xfff) == 0xfff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---- stride 1: persistent, software-pipelined ---------------------------------------------------------------------
 // The one-tile-per-CTA form above loads, waits, computes, stores: with three CTAs per SM about a third of the SM's tiles
 // are in flight at any time and the kernel sits at 0.4 of the copy roofline.  Here a CTA owns ONE 64-channel block (its
-// 72 weights per thread stay in registers) and walks over that block's tiles; the cp.async of tile i+1 is issued before
-// tile i is computed (two shared-memory buffers), so loads are always in flight.  The 3x3 accumulation uses packed fp32
+// 72 weights per thread stay in registers) and walks over that block's tiles.  A tile (18 x 10 pixels x 64 channels incl. halo;
+// UP: the 12 x 8 low-resolution footprint) is ONE TMA box load: thread 0 issues cp.async.bulk.tensor for the tile kStages - 1
+// ahead into a ring of shared-memory buffers (mbarrier completion; out-of-image rows / columns are zero-filled by the copy
+// engine = the padding), so loads are always in flight and nobody spends issue slots on per-vector address arithmetic (the
+// cp.async form: ~90 of ~400 instructions per thread and tile).  The 3x3 accumulation uses packed fp32
 // FMAs (fma.rn.f32x2: each half an ordinary IEEE fp32 FMA in the same (r, s) order -> bit-identical to the scalar chain).
 constexpr int kTH = 8, kIH = kTH + 2, kIW = kTW + 2;                 // 16 x 8 outputs from an 18 x 10 input tile
 constexpr int kTileVec = kIH * kIW * 8;                              // 1 440 uint4 = 23 040 B
 constexpr int kLoH = 8, kLoW = 12, kLoVec = kLoH * kLoW * 8;          // UP: low-resolution footprint of a tile (2x: 7 x 11), 12 288 B
 constexpr int kNT = 256;
+constexpr int kStages = 3;                                           // ring depth of the TMA staging
 enum { kPlain = 0, kNorm = 1, kUp = 2 };
 
 __device__ __forceinline__ uint64_t pair_f32(float lo, float hi) {
@@ -260,49 +301,45 @@ __device__ __forceinline__ LoBox lo_box(const TilePos& tp, int H, int W, const D
 //   plain / NORM: two input tiles (+ NORM: 128 coefficients, + stats_out: the [256][17] reduction scratch)
 //   UP:           two low-resolution footprints + one (upsampled) input tile
 template <int MODE>
-__global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
-                                                                                        uint4* __restrict__ y, int H, int W, int C, int tiles_w,
-                                                                                        int tiles_h, int ntiles, const DwNorm nrm) {
-    extern __shared__ __align__(16) uint4 dsm[];
-    uint4* const stage0 = dsm;                                                    // [2][kTileVec] or (UP) [2][kLoVec]
-    uint4* const hi_tile = dsm + 2 * kLoVec;                                      // UP only
-    float* const coef = reinterpret_cast<float*>(dsm + 2 * kTileVec);            // NORM only: scale[64], shift[64]
+__global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const uint4* __restrict__ x,
+                                                                   const __nv_bfloat16* __restrict__ wgt, uint4* __restrict__ y, int H, int W,
+                                                                   int C, int tiles_w, int tiles_h, int ntiles, const DwNorm nrm) {
+    extern __shared__ __align__(128) uint4 dsm[];
+    __shared__ __align__(8) unsigned long long bars[kStages];
+    constexpr int kStageVec = MODE == kUp ? kLoVec : kTileVec;
+    uint4* const stage0 = dsm;                                                    // [kStages][kStageVec]
+    uint4* const hi_tile = dsm + kStages * kLoVec;                                // UP only
+    float* const coef = reinterpret_cast<float*>(dsm + kStages * kTileVec);      // NORM only: scale[64], shift[64]
     float* const red = coef + 2 * kCB;                                            // NORM + stats_out only: [256][17]
     const int c0 = blockIdx.y * kCB;
     const int CV = C / 8;
     const int tid = threadIdx.x;
     const int v = tid & 7, strip = tid >> 3, row = strip >> 2, q4 = strip & 3;
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage0);
+    const uint32_t stage_s = smem_u32(stage0);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kStages; ++k) mbar_init(smem_u32(&bars[k]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    // ---- prefetch of one tile (plain / NORM: the 18 x 10 input tile, zero-filled outside the image = the padding;
-    //      UP: the low-resolution footprint, when it fits)
-    auto prefetch = [&](int t, int buf) {
-        const TilePos tp = tile_pos(t, tiles_w, tiles_h);
+    // ---- issue of one tile's box load (thread 0; the slot was released by the __syncthreads() that ended its last use).
+    // UP: the footprint box always starts at the tile's first low-resolution row / column; when the footprint does not fit
+    // the box the expand phase reads the map itself, the (unused) copy still keeps the ring's phases in step.
+    auto issue = [&](int itq) {
+        const long long tq = (long long)blockIdx.x + (long long)itq * gridDim.x;
+        if (tid != 0 || tq >= ntiles) return;
+        const TilePos tp = tile_pos((int)tq, tiles_w, tiles_h);
+        const int slot = itq % kStages;
+        const uint32_t bar = smem_u32(&bars[slot]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                // generic-proxy accesses of the slot -> before the async copy
+        mbar_expect_tx(bar, (uint32_t)kStageVec * 16u);
         if (MODE == kUp) {
             const LoBox lb = lo_box(tp, H, W, nrm);
-            if (lb.fits) {
-                const uint4* lo = x + (size_t)tp.n * nrm.lh * nrm.lw * CV + c0 / 8;
-                for (int i = tid; i < kLoVec; i += kNT) {
-                    const int vv = i & 7, p = i >> 3, r = p / kLoW, c = p - r * kLoW;
-                    if (r < lb.nh && c < lb.nw) {
-                        const uint4* src = lo + (((lb.y0 + r) * nrm.lw + lb.x0 + c) * CV + vv);      // 32-bit: a plane is < 2^31 vectors
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_s + (uint32_t)(buf * kLoVec + i) * 16u), "l"(src) : "memory");
-                    }
-                }
-            }
+            tma_load_4d(stage_s + (uint32_t)(slot * kStageVec) * 16u, &map_x, bar, c0, lb.x0, lb.y0, tp.n);
         } else {
-            const uint4* img = x + (size_t)tp.n * H * W * CV + c0 / 8;
-            const int iy0 = tp.oy0 - 1, ix0 = tp.ox0 - 1;
-            for (int i = tid; i < kTileVec; i += kNT) {
-                const int vv = i & 7, p = i >> 3, r = p / kIW, c = p - r * kIW;
-                const int iy = iy0 + r, ix = ix0 + c;
-                const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-                const uint4* src = img + (ok ? (iy * W + ix) * CV + vv : 0);              // 32-bit: a plane is < 2^31 vectors
-                const uint32_t nbytes = ok ? 16u : 0u;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(stage_s + (uint32_t)(buf * kTileVec + i) * 16u), "l"(src), "r"(nbytes) : "memory");
-            }
+            tma_load_4d(stage_s + (uint32_t)(slot * kStageVec) * 16u, &map_x, bar, c0, tp.ox0 - 1, tp.oy0 - 1, tp.n);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     pdl::trigger();
@@ -319,7 +356,8 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
         }
     pdl::wait();                                              // the weights above are constants; everything below depends on the stream
     int t = blockIdx.x;
-    if (t < ntiles) prefetch(t, 0);
+#pragma unroll
+    for (int k = 0; k < kStages - 1; ++k) issue(k);
 
     // stats_out: every thread keeps running sums of its outputs in ITS row of `red` (shared memory, not registers: the
     // weights and accumulators already fill the register file), flushed to the fp64 workspace when the image changes
@@ -343,15 +381,9 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
     };
 
     for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
-        const int cur = it & 1;
-        const int tn = t + gridDim.x;
-        if (tn < ntiles) {
-            prefetch(tn, cur ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
+        const int cur = it % kStages;
+        issue(it + kStages - 1);                              // into the slot the previous iteration finished with
+        mbar_wait(smem_u32(&bars[cur]), (uint32_t)(it / kStages) & 1u);
         const TilePos tp = tile_pos(t, tiles_w, tiles_h);
         const int iy0 = tp.oy0 - 1, ix0 = tp.ox0 - 1;
         uint4* tile = MODE == kUp ? hi_tile : stage0 + cur * kTileVec;
@@ -366,7 +398,7 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
                 const LoBox lb = lo_box(tp, H, W, nrm);
                 const uint4* src;                            // generic pointer: the staged footprint or (it did not fit) the map itself
                 int pitch_r, pitch_c, yorg, xorg;
-                if (lb.fits) { src = stage0 + cur * kLoVec; pitch_r = kLoW * 8; pitch_c = 8; yorg = lb.y0; xorg = lb.x0; }
+                if (lb.fits) { src = stage0 + cur * kLoVec; pitch_r = kLoW * 8; pitch_c = 8; yorg = lb.y0; xorg = lb.x0; }   // the TMA box [kLoH][kLoW][64 ch]
                 else { src = x + (size_t)tp.n * nrm.lh * nrm.lw * CV + c0 / 8; pitch_r = nrm.lw * CV; pitch_c = CV; yorg = 0; xorg = 0; }
                 if (tid < kIH) {
                     const int iy = iy0 + tid;
@@ -515,12 +547,39 @@ __global__ void __launch_bounds__(kNT, 2) dwconv3x3_s1_pipe_kernel(const uint4* 
 
 }  // namespace
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn dw_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+// bf16 [N, H, W, C] with a box of 64 channels x bw x bh pixels of one image, dense in shared memory ([bh][bw][64]); rows /
+// columns outside the image arrive as zeros
+static bool dw_make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bw, int bh) {
+    if (!dw_encode_fn()) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kCB, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    return dw_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Persistent launch: as many CTAs per channel block as the device holds at once (whole waves; see resident sizing in
 // instnorm_kernels.cu), never more than there are tiles.  The dynamic shared-memory opt-in is set on every launch (it is
 // per device, and cheap).
 template <int MODE>
-static cudaError_t dw_pipe_launch(size_t smem, const uint4* xp, const __nv_bfloat16* wp, uint4* yp, int H, int W, int C, int tiles_w,
-                                  int tiles_h, int ntiles, int cblocks, const DwNorm& nrm, cudaStream_t stream) {
+static cudaError_t dw_pipe_launch(size_t smem, const CUtensorMap& map, const uint4* xp, const __nv_bfloat16* wp, uint4* yp, int H, int W, int C,
+                                  int tiles_w, int tiles_h, int ntiles, int cblocks, const DwNorm& nrm, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(dwconv3x3_s1_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, occ = 0;
@@ -531,8 +590,8 @@ static cudaError_t dw_pipe_launch(size_t smem, const uint4* xp, const __nv_bfloa
     int gx = sms * occ / cblocks;
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
-    return pdl::launch(dwconv3x3_s1_pipe_kernel<MODE>, dim3((unsigned)gx, (unsigned)cblocks), dim3(kNT), smem, stream, xp, wp, yp, H, W, C, tiles_w,
-                       tiles_h, ntiles, nrm);
+    return pdl::launch(dwconv3x3_s1_pipe_kernel<MODE>, dim3((unsigned)gx, (unsigned)cblocks), dim3(kNT), smem, stream, map, xp, wp, yp, H, W, C,
+                       tiles_w, tiles_h, ntiles, nrm);
 }
 
 static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W, int C, int stride, const DwNorm* nrm, cudaStream_t stream) {
@@ -560,9 +619,11 @@ static int dw_launch(const void* x, const void* w, void* y, int N, int H, int W,
         if (ntiles > (1LL << 30) || (long long)H * W * (C / 8) >= (1LL << 31)) return RROI_B200_ERR_INVALID_ARG;   // 32-bit offsets inside a plane
         const int cblocks = C / kCB;
         cudaError_t e1 = cudaSuccess;
-        if (up) e1 = dw_pipe_launch<kUp>((size_t)(2 * kLoVec + kTileVec) * 16, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
-        else if (norm_on || none.stats_out) e1 = dw_pipe_launch<kNorm>((size_t)2 * kTileVec * 16 + 2 * kCB * 4 + (none.stats_out ? kNT * 17 * 4 : 0), xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
-        else e1 = dw_pipe_launch<kPlain>((size_t)2 * kTileVec * 16, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
+        CUtensorMap map;
+        if (up ? !dw_make_map(&map, x, N, none.lh, none.lw, C, kLoW, kLoH) : !dw_make_map(&map, x, N, H, W, C, kIW, kIH)) return RROI_B200_ERR_CUDA;
+        if (up) e1 = dw_pipe_launch<kUp>((size_t)(kStages * kLoVec + kTileVec) * 16, map, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
+        else if (norm_on || none.stats_out) e1 = dw_pipe_launch<kNorm>((size_t)kStages * kTileVec * 16 + 2 * kCB * 4 + (none.stats_out ? kNT * 17 * 4 : 0), map, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
+        else e1 = dw_pipe_launch<kPlain>((size_t)kStages * kTileVec * 16, map, xp, wp, yp, H, W, C, tiles_w, tiles_h, (int)ntiles, cblocks, none, stream);
         if (e1 != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
         return RROI_B200_OK;
     }
