@@ -252,10 +252,15 @@ class FOTSPipeline:
                 cs.synchronize()                               # the event is recorded before the main thread waits on it
             return found
 
+        head_lanes = [main, torch.cuda.Stream(dev)]             # head graphs of consecutive micro-batches overlap (see capture(lanes=...))
+
         def step():
+            head_lanes[1].wait_stream(main)
             for i in range(nb):
-                A[i].replay()
-                st[i]["evA"].record(main)
+                ln = head_lanes[i % 2]
+                with torch.cuda.stream(ln):
+                    A[i].replay()
+                    st[i]["evA"].record(ln)
             jobs = [pool.submit(host_part, i) for i in range(nb)]
             found = []
             for i in range(nb):
@@ -265,6 +270,7 @@ class FOTSPipeline:
                 with torch.cuda.stream(tail_stream):
                     Bg[i].replay()
             main.wait_stream(tail_stream)
+            main.wait_stream(head_lanes[1])
             recs = [S["rec"] for S in st]
             return (recs[0] if len(recs) == 1 else torch.cat(recs, 0)), found
 
