@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Small launches of this round's new kernels for compute-sanitizer (memcheck / racecheck / synccheck):
+
+    compute-sanitizer --tool memcheck python tools/sanitize_target.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from fots.pytorch_b200 import _cabi  # noqa: E402
+from fots.pytorch_b200.pipeline import conv as TC, fused  # noqa: E402
+from fots.pytorch_b200.rroi_align.functions.rroi_align import backward_raw, forward_raw  # noqa: E402
+import workloads as WL  # noqa: E402
+
+dev = torch.device("cuda:0")
+cl = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+with torch.no_grad():
+    # depthwise: plain / norm (+ statistics) / upsample-on-load, ragged sizes
+    for (N, C, H, W) in ((2, 128, 21, 37), (1, 64, 7, 5), (1, 256, 45, 80)):
+        conv = torch.nn.Conv2d(C, C, 3, 1, 1, groups=C, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        norm = torch.nn.InstanceNorm2d(C, affine=True).to(dev)
+        x = cl(N, C, H, W)
+        TC.dwconv(conv, x)
+        TC.dwconv_norm(conv, x, fused.instnorm_stats(x), norm, 0.01, stats_out=True)
+        TC.dwconv_norm(conv, x, stats_out=True)
+        lo = cl(N, C, (H + 1) // 2, (W + 1) // 2)
+        TC.dwconv_up(conv, lo, (H, W))
+    # InstanceNorm variants, merge kernels, gate convolution
+    x = cl(2, 64, 33, 20)
+    g, b = torch.randn(64, device=dev), torch.randn(64, device=dev)
+    fused.set_single_pass(0)
+    fused.instnorm_act(x, g, b, 1e-5, 0.01, cl(2, 64, 33, 20))
+    fused.instnorm_act(cl(2, 16, 33, 20), torch.randn(32, device=dev), torch.randn(32, device=dev), 1e-5, 0.01, crelu=True)
+    fused.set_single_pass(1)
+    a_lo, c_hi, b_hi = cl(2, 256, 6, 10), cl(2, 256, 12, 20), cl(2, 256, 12, 20)
+    act = torch.nn.Conv2d(256, 1, 1).to(dev).to(torch.bfloat16)
+    gate = TC.conv1x1_to1(a_lo, TC.pack_to1(act), sigmoid=True)
+    fused.fpn_merge(a_lo=a_lo, b_hi=b_hi, gate_prob_lo=gate)
+    fused.fpn_merge(c_hi=c_hi, b_hi=b_hi, gate_prob_lo=gate)
+    fused.fpn_merge(c_hi=c_hi, b_hi=b_hi, gate_logits_lo=gate)
+    # CRNN front end
+    w = (torch.randn(64, 3, 3, 3, device=dev) / 5).to(torch.bfloat16)
+    y = TC.conv3x3_c3_pool(torch.randn(3, 3, 32, 100, device=dev), w, torch.randn(64, device=dev), True)
+    TC.maxpool(y, (2, 2), (2, 1), (0, 1))
+    # a small tcgen05 convolution with statistics (shared-memory reduced flush)
+    xs = cl(2, 64, 16, 24)
+    ws = (torch.randn(128, 64, 3, 3, device=dev) / 24).to(torch.bfloat16)
+    TC.conv2d(xs, ws, None, (1, 1), 1.0, stats=True)
+
+# NCHW backward: row segments + gather, aligned and unaligned maps
+for (H, W) in ((45, 80), (45, 79)):
+    feats = WL.features(3, 2, 16, H, W)
+    rois = WL.stress_rois(33, 40, 2, W * 4, H * 4)
+    f, r = torch.from_numpy(feats).to(dev), torch.from_numpy(rois).to(dev)
+    out, ix, iy, _ = forward_raw(f, r, 8, 64, 0.25, want_idx=True)
+    gt = torch.randn_like(out)
+    backward_raw(gt, r, ix, iy, feats.shape, 0.25, _cabi.LAYOUT_NCHW, opts=_cabi.opts(bwd_mode=4))
+    backward_raw(gt, r, None, None, feats.shape, 0.25, _cabi.LAYOUT_NCHW, opts=_cabi.opts(bwd_mode=4))
+torch.cuda.synchronize()
+print("sanitize target done")
