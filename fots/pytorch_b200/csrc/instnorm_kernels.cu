@@ -152,6 +152,137 @@ __global__ void __launch_bounds__(kThreads, kResidual ? 3 : 4) in_apply_kernel(c
     }
 }
 
+// ---- backward of y = act(IN(x) * gamma + beta [+ residual]) --------------------------------------------------------------
+// With xh = (x - mean) * rstd, g = dy * act'(.) (act' from the sign of the stored output y: 1 where y > 0, else slope):
+//     dx   = gamma * rstd * (g - mean_hw(g) - xh * mean_hw(g * xh))          (per image and channel)
+//     dres = g,   dgamma[c] = sum_n S2[n, c],   dbeta[c] = sum_n S1[n, c]     with S1 = sum_hw g, S2 = sum_hw g * xh
+// Two passes like the forward: in_bwd_stats accumulates S1 / S2 per (image, channel) into an fp64 workspace, in_bwd_apply
+// writes dx (and dres).  Same thread layout as in_stats_kernel / in_apply_kernel: thread = 8 channels x a row phase.
+__global__ void __launch_bounds__(kThreads, 3) in_bwd_stats_kernel(const Bf16x8* __restrict__ x, const Bf16x8* __restrict__ y,
+                                                                    const Bf16x8* __restrict__ dy, const double* __restrict__ ws,
+                                                                    double* __restrict__ wsb, int HW, int C, int rows_per_cta, float eps,
+                                                                    float slope) {
+    pdl::trigger();
+    pdl::wait();
+    const int G = C / 8;
+    const int b = blockIdx.y;
+    const int g = threadIdx.x % G, phase = threadIdx.x / G, nphase = kThreads / G;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(HW, r0 + rows_per_cta);
+    float s1[8], s2[8], mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s1[i] = s2[i] = 0.0f;
+        const int c = g * 8 + i;
+        const double m = ws[((size_t)b * C + c) * 2] / HW;
+        double var = ws[((size_t)b * C + c) * 2 + 1] / HW - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        mean[i] = (float)m;
+        rstd[i] = rsqrtf((float)var + eps);
+    }
+    if (phase < nphase) {
+        const size_t base = ((size_t)b * HW) * G + g;
+        constexpr int U = 2;
+        for (int r = r0 + phase; r < r1; r += U * nphase) {
+            Bf16x8 xv[U], yv[U], gv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u * nphase < r1) {
+                    const size_t o = base + (size_t)(r + u * nphase) * G;
+                    xv[u] = ld8(x + o); yv[u] = ld8(y + o); gv[u] = ld8(dy + o);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * nphase >= r1) break;
+                float fx[8], fy[8], fg[8];
+                unpack8(xv[u], fx); unpack8(yv[u], fy); unpack8(gv[u], fg);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float gg = fy[i] > 0.0f ? fg[i] : fg[i] * slope;
+                    s1[i] += gg;
+                    s2[i] = fmaf(gg, (fx[i] - mean[i]) * rstd[i], s2[i]);
+                }
+            }
+        }
+    }
+    __shared__ float sh[kThreads][17];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sh[threadIdx.x][i] = s1[i]; sh[threadIdx.x][8 + i] = s2[i]; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * 16; idx += kThreads) {
+        const int gg = idx / 16, k = idx % 16;
+        double acc = 0.0;
+        for (int ph = 0; ph < nphase; ++ph) acc += (double)sh[ph * G + gg][k];
+        const int c = gg * 8 + (k & 7);
+        atomicAdd(wsb + ((size_t)b * C + c) * 2 + (k >> 3), acc);
+    }
+}
+
+template <bool kResidual>
+__global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const Bf16x8* __restrict__ x, const Bf16x8* __restrict__ y,
+                                                                    const Bf16x8* __restrict__ dy, const float* __restrict__ gamma,
+                                                                    const double* __restrict__ ws, const double* __restrict__ wsb,
+                                                                    Bf16x8* __restrict__ dx, Bf16x8* __restrict__ dres, int HW, int C,
+                                                                    int rows_per_cta, float eps, float slope) {
+    extern __shared__ float coef[];          // a[C], m1[C], m2[C], mean[C], rstd[C]
+    pdl::trigger();
+    pdl::wait();
+    const int G = C / 8;
+    const int b = blockIdx.y;
+    float *ca = coef, *cm1 = coef + C, *cm2 = coef + 2 * C, *cmean = coef + 3 * C, *crstd = coef + 4 * C;
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+        const double m = ws[((size_t)b * C + c) * 2] / HW;
+        double var = ws[((size_t)b * C + c) * 2 + 1] / HW - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float rs = rsqrtf((float)var + eps);
+        ca[c] = (gamma ? gamma[c] : 1.0f) * rs;
+        cm1[c] = (float)(wsb[((size_t)b * C + c) * 2] / HW);
+        cm2[c] = (float)(wsb[((size_t)b * C + c) * 2 + 1] / HW);
+        cmean[c] = (float)m;
+        crstd[c] = rs;
+    }
+    __syncthreads();
+    const int g = threadIdx.x % G, phase = threadIdx.x / G, nphase = kThreads / G;
+    if (phase >= nphase) return;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(HW, r0 + rows_per_cta);
+    const size_t base = ((size_t)b * HW) * G + g;
+    // this thread's 8 channels: dx = A * g - (B0 + x * B1) with A = gamma * rstd, B1 = A * rstd * m2, B0 = A * (m1 - mean * rstd * m2)
+    float cA[8], cB0[8], cB1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        cA[i] = ca[c];
+        cB1[i] = ca[c] * crstd[c] * cm2[c];
+        cB0[i] = ca[c] * (cm1[c] - cmean[c] * crstd[c] * cm2[c]);
+    }
+    constexpr int U = 2;
+    for (int r = r0 + phase; r < r1; r += U * nphase) {
+        Bf16x8 xv[U], yv[U], gv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + u * nphase < r1) {
+                const size_t o = base + (size_t)(r + u * nphase) * G;
+                xv[u] = ld8(x + o); yv[u] = ld8(y + o); gv[u] = ld8(dy + o);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u * nphase >= r1) break;
+            const size_t o = base + (size_t)(r + u * nphase) * G;
+            float fx[8], fy[8], fg[8], od[8], orr[8];
+            unpack8(xv[u], fx); unpack8(yv[u], fy); unpack8(gv[u], fg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float gg = fy[i] > 0.0f ? fg[i] : fg[i] * slope;
+                od[i] = fmaf(cA[i], gg, -fmaf(fx[i], cB1[i], cB0[i]));
+                orr[i] = gg;
+            }
+            dx[o] = pack8(od);
+            if (kResidual) dres[o] = pack8(orr);
+        }
+    }
+}
+
 // ---- single-pass InstanceNorm for instances that fit in a cluster's shared memory --------------------------------
 // The two-pass form above costs three launches (memset, statistics, apply) and reads x twice.  Most InstanceNorms of the
 // step act on small instances (stages 2-4 of the feeder: <= 3.7 MB per image; the recogniser: 131 KB per RoI), where the
@@ -619,4 +750,39 @@ extern "C" int fots_b200_instnorm_apply_nhwc_bf16(const void* x, void* y, const 
                                                   const void* residual, const double* stats, int B, int HW, int C,
                                                   float eps, float slope, int crelu, cudaStream_t stream) {
     return instnorm_impl(x, y, gamma, beta, residual, const_cast<double*>(stats), B, HW, C, eps, slope, crelu, true, stream);
+}
+
+// Backward of fots_b200_instnorm_nhwc_bf16 (crelu == 0): see the kernels.  stats = the forward's fp64 [B, C, 2] sums of x;
+// stats_bwd fp64 [B, C, 2] is cleared and filled here (S1 = sum g, S2 = sum g * xhat per image and channel: the caller reduces
+// them over the images for dgamma = sum_n S2, dbeta = sum_n S1).  dres may be NULL.
+extern "C" int fots_b200_instnorm_bwd_nhwc_bf16(const void* x, const void* y, const void* dy, const float* gamma, const double* stats,
+                                                double* stats_bwd, void* dx, void* dres, int B, int HW, int C, float eps, float slope,
+                                                cudaStream_t stream) {
+    if (!x || !y || !dy || !stats || !stats_bwd || !dx || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || C > 1024 || (C / 8) > kThreads ||
+        B > 65535)
+        return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+         reinterpret_cast<uintptr_t>(dres)) & 15)
+        return RROI_B200_ERR_INVALID_ARG;
+    const int G = C / 8, nphase = kThreads / G;
+    cudaError_t e = pdl::zero_f64(stats_bwd, (size_t)B * C * 2, stream);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    const Bf16x8 *xp = static_cast<const Bf16x8*>(x), *yp = static_cast<const Bf16x8*>(y), *gp = static_cast<const Bf16x8*>(dy);
+    int rows = 0;
+    const int chunks = wave_chunks(B, HW, resident_ctas(in_bwd_stats_kernel, 0), nphase * 4, nphase, &rows);
+    e = pdl::launch(in_bwd_stats_kernel, dim3(chunks, B), dim3(kThreads), 0, stream, xp, yp, gp, stats, stats_bwd, HW, C, rows, eps, slope);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    const size_t smem = (size_t)5 * C * sizeof(float);
+    int arows = 0;
+    if (dres) {
+        const int ach = wave_chunks(B, HW, resident_ctas(in_bwd_apply_kernel<true>, smem), nphase * 4, nphase, &arows);
+        e = pdl::launch(in_bwd_apply_kernel<true>, dim3(ach, B), dim3(kThreads), smem, stream, xp, yp, gp, gamma, stats, (const double*)stats_bwd,
+                        static_cast<Bf16x8*>(dx), static_cast<Bf16x8*>(dres), HW, C, arows, eps, slope);
+    } else {
+        const int ach = wave_chunks(B, HW, resident_ctas(in_bwd_apply_kernel<false>, smem), nphase * 4, nphase, &arows);
+        e = pdl::launch(in_bwd_apply_kernel<false>, dim3(ach, B), dim3(kThreads), smem, stream, xp, yp, gp, gamma, stats, (const double*)stats_bwd,
+                        static_cast<Bf16x8*>(dx), (Bf16x8*)nullptr, HW, C, arows, eps, slope);
+    }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
 }

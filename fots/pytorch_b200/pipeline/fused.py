@@ -3,6 +3,7 @@
 channels-last inference path; everywhere else (CPU, fp32, training) the networks run torch's own ops, which
 are the definition the fused kernel is tested against."""
 import ctypes
+import os
 
 import torch
 
@@ -90,6 +91,64 @@ def instnorm_stats(x):
         st = L.fots_b200_instnorm_stats_nhwc_bf16(x.data_ptr(), ws.data_ptr(), B, H * W, C, torch.cuda.current_stream(x.device).cuda_stream)
     _cabi.check(st, "fots_b200_instnorm_stats_nhwc_bf16")
     return ws
+
+
+# ---- the same normalisation under autograd (training step) ------------------------------------------------------------
+TRAIN_KERNELS = os.environ.get("FOTS_B200_TRAIN_IN", "1") != "0"   # A/B switch: hand-written InstanceNorm forward + backward in training
+
+
+def train_eligible(x, residual=None):
+    """InstanceNorm (+ residual) + activation through this repo's forward AND backward kernels under autograd: bf16
+    channels-last CUDA activations (what the bf16-autocast training step hands over)."""
+    ok = (TRAIN_KERNELS and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.size(1) % 8 == 0 and x.size(1) <= 1024
+          and x.size(0) <= 65535 and x.is_contiguous(memory_format=torch.channels_last))
+    if ok and residual is not None:
+        ok = (residual.dtype == torch.bfloat16 and residual.shape == x.shape and residual.is_cuda
+              and residual.is_contiguous(memory_format=torch.channels_last))
+    return ok
+
+
+class _InstNormActFn(torch.autograd.Function):
+    """y = act(IN(x) * weight + bias [+ residual]) with fots_b200_instnorm_{stats,apply}_nhwc_bf16 forward and
+    fots_b200_instnorm_bwd_nhwc_bf16 backward (two HBM passes each way; torch's instance_norm copies a channels-last tensor to
+    NCHW and back around its batch-norm kernels in both directions)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, eps, slope):
+        ws = instnorm_stats(x)
+        y = instnorm_act(x, weight, bias, eps, slope, residual, stats=ws)
+        ctx.save_for_backward(x, y, weight, ws)
+        ctx.eps, ctx.slope, ctx.has_res, ctx.has_affine = float(eps), float(slope), residual is not None, weight is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, ws = ctx.saved_tensors
+        B, C, H, W = x.shape
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        wsb = workspace(x.device, B * C * 2)
+        w = weight.float().contiguous() if weight is not None else None
+        L = _lib()
+        L.fots_b200_instnorm_bwd_nhwc_bf16.restype = ctypes.c_int
+        L.fots_b200_instnorm_bwd_nhwc_bf16.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p]
+        with torch.cuda.device(x.device):
+            st = L.fots_b200_instnorm_bwd_nhwc_bf16(x.data_ptr(), y.data_ptr(), dy.data_ptr(), w.data_ptr() if w is not None else None,
+                                                    ws.data_ptr(), wsb.data_ptr(), dx.data_ptr(), dres.data_ptr() if dres is not None else None,
+                                                    B, H * W, C, ctx.eps, ctx.slope, torch.cuda.current_stream(x.device).cuda_stream)
+        _cabi.check(st, "fots_b200_instnorm_bwd_nhwc_bf16")
+        dgamma = dbeta = None
+        if ctx.has_affine:
+            sums = wsb[:B * C * 2].view(B, C, 2).sum(0)                   # [C, 2]: (sum g, sum g * xhat) over the batch
+            dbeta, dgamma = sums[:, 0].to(weight.dtype), sums[:, 1].to(weight.dtype)
+        return dx, dgamma, dbeta, dres, None, None
+
+
+def instnorm_act_train(x, weight, bias, eps, slope, residual=None):
+    """Differentiable act(IN(x) * weight + bias [+ residual]); caller checks train_eligible(x, residual)."""
+    return _InstNormActFn.apply(x, weight, bias, residual, eps, slope)
 
 
 def _cl_bf16(t):

@@ -29,6 +29,9 @@ def _in_act(norm, x, slope, residual=None):
     path this is ONE fused pair of kernels (statistics + apply); otherwise torch's ops."""
     if fused.eligible(x, residual, norm.weight, norm.bias):
         return fused.instnorm_act(x, norm.weight, norm.bias, norm.eps, slope, residual)
+    if torch.is_grad_enabled() and fused.train_eligible(x, residual):
+        # training step (bf16 autocast, channels-last): forward AND backward on this repo's kernels
+        return fused.instnorm_act_train(x, norm.weight, norm.bias, norm.eps, slope, residual)
     y = norm(x)
     if residual is not None:
         y = y + residual

@@ -233,6 +233,16 @@ int fots_b200_instnorm_stats_nhwc_bf16(const void* x, double* workspace, int B, 
  * x bf16 [B, H, W, C], wq bf16 [8, C] with the filter in row 0 and zeros elsewhere, bias fp32 [8].  Same kernel as the heads. */
 int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, const float* bias, void* out, int B, int H, int W, int C,
                                     int sigmoid, cudaStream_t stream);
+/* Backward of fots_b200_instnorm_nhwc_bf16 (crelu == 0) for the training step (train.py:79-123 runs the same InstanceNorm
+ * layers under autograd; torch's path copies channels-last tensors to NCHW and back around batch-norm kernels, forward and
+ * backward).  y = act(IN(x) * gamma + beta [+ residual]) as stored by the forward, dy its gradient (bf16 [B, HW, C]):
+ *     g = dy * act'(.)  (1 where y > 0, else slope),  xh = (x - mean) * rstd
+ *     dx = gamma * rstd * (g - mean_hw(g) - xh * mean_hw(g * xh)),   dres = g (optional, NULL to skip)
+ * stats = the forward's fp64 [B, C, 2] sums of x; stats_bwd fp64 [B, C, 2] is cleared and filled with (sum g, sum g * xh) per
+ * image and channel -- dbeta[c] = sum_b stats_bwd[b, c, 0], dgamma[c] = sum_b stats_bwd[b, c, 1].  Two HBM passes. */
+int fots_b200_instnorm_bwd_nhwc_bf16(const void* x, const void* y, const void* dy, const float* gamma, const double* stats,
+                                     double* stats_bwd, void* dx, void* dres, int B, int HW, int C, float eps, float slope,
+                                     cudaStream_t stream);
 /* Consumer B's first layer (tools/models.py:853-897, CRNN.cnn conv0 + relu0 + pooling0): 3 input channels cannot fill a
  * k-block of the tcgen05 kernel.  x fp32 NCHW [N, 3, H, W] (RoIRotate of the raw image, src/utils.py:430-436), w bf16
  * [Cout, 3, 3, 3] contiguous, bias fp32 [Cout] or NULL -> y bf16 NHWC = maxpool2x2(relu(conv3x3_pad1(x) + bias)) when

@@ -106,6 +106,46 @@ def test_inference_step_end_to_end(oracle, cuda):
     assert torch.equal(branched(), pipe16.step_local(images, quads)[0])
 
 
+@pytest.mark.parametrize("B,C,H,W,slope,res,affine", [(2, 64, 17, 23, 0.0, True, True), (3, 128, 9, 16, 0.01, False, True),
+                                                       (2, 256, 8, 64, 0.01, False, True), (1, 32, 5, 7, 1.0, True, False),
+                                                       (2, 512, 6, 10, 0.01, True, True)])
+def test_instancenorm_backward_kernels_match_torch_autograd(cuda, B, C, H, W, slope, res, affine):
+    """fots_b200_instnorm_bwd_nhwc_bf16 (through fused.instnorm_act_train, the autograd Function of the training step): output
+    and the gradients wrt the input, the residual and the affine parameters against torch's autograd of
+    leaky(instance_norm(x) [+ res]) evaluated in fp32 on the same bf16 operands."""
+    from fots.pytorch_b200.pipeline import fused
+    g = torch.Generator().manual_seed(B * 31 + C)
+    mk = lambda: (torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x, r, dy = mk(), (mk() if res else None), mk()
+    w = (torch.rand(C, generator=g) + 0.5).to(cuda) if affine else None
+    b = (torch.randn(C, generator=g) * 0.3).to(cuda) if affine else None
+    xs = [t.clone().requires_grad_(True) for t in (x, r, w, b) if t is not None]
+    it = iter(xs)
+    x1 = next(it); r1 = next(it) if res else None; w1 = next(it) if affine else None; b1 = next(it) if affine else None
+    assert fused.train_eligible(x1, r1)
+    y = fused.instnorm_act_train(x1, w1, b1, 1e-5, slope, r1)
+    y.backward(dy)
+    # reference in fp32
+    xf = x.float().requires_grad_(True)
+    rf = r.float().requires_grad_(True) if res else None
+    wf = w.clone().requires_grad_(True) if affine else None
+    bf = b.clone().requires_grad_(True) if affine else None
+    z = F.instance_norm(xf, weight=wf, bias=bf, eps=1e-5)
+    if res:
+        z = z + rf
+    yr = z if slope == 1.0 else F.leaky_relu(z, slope)
+    yr.backward(dy.float())
+    close = lambda a, ref, what: (float((a.float() - ref).abs().max()) <= 2.0 ** -6 * float(ref.abs().max()) + 1e-3, what)
+    checks = [close(y, yr, "y"), close(x1.grad, xf.grad, "dx")]
+    if res:
+        checks.append(close(r1.grad, rf.grad, "dres"))
+    if affine:
+        tol = lambda ref: 2.0 ** -6 * float(ref.abs().max()) + 0.05 * (B * H * W) ** 0.5 * 2.0 ** -8
+        checks.append((float((w1.grad - wf.grad).abs().max()) <= tol(wf.grad), "dgamma"))
+        checks.append((float((b1.grad - bf.grad).abs().max()) <= tol(bf.grad), "dbeta"))
+    assert all(ok for ok, _ in checks), [what for ok, what in checks if not ok]
+
+
 def test_training_step_runs_and_reduces_loss(cuda):
     """cfg3-shaped step at reduced size: finite losses, the detection loss falls, and the CTC gradient reaches the
     stem THROUGH the RoIRotate backward kernel (with the detection loss switched off it is the only path)."""
