@@ -283,6 +283,110 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const Bf16x8*
     }
 }
 
+// ---- backward of the CReLU form y = act(IN(concat(x, -x)) * gamma + beta)  (y has 2C channels) -----------------------------
+// IN(-x) = -xh with the same rstd, so with g1 / g2 the activation-masked gradients of the two halves and a1 = gamma[c],
+// a2 = gamma[C + c]:  G = a1 * g1 - a2 * g2,  dx = rstd * (G - mean(G) - xh * mean(G * xh)).
+// Workspace [B, 2C, 2]: (sum g1, sum g1 * xh) for channel c, (sum g2, -sum g2 * xh) for channel C + c, so that
+// dbeta[j] = sum_b ws[b, j, 0] and dgamma[j] = sum_b ws[b, j, 1] for all 2C output channels alike.
+__global__ void __launch_bounds__(kThreads, 2) in_bwd_crelu_stats_kernel(const Bf16x8* __restrict__ x, const Bf16x8* __restrict__ y,
+                                                                          const Bf16x8* __restrict__ dy, const double* __restrict__ ws,
+                                                                          double* __restrict__ wsb, int HW, int C, int rows_per_cta, float eps,
+                                                                          float slope) {
+    pdl::trigger();
+    pdl::wait();
+    const int G = C / 8;
+    const int b = blockIdx.y;
+    const int g = threadIdx.x % G, phase = threadIdx.x / G, nphase = kThreads / G;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(HW, r0 + rows_per_cta);
+    float s[4][8], mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s[0][i] = s[1][i] = s[2][i] = s[3][i] = 0.0f;
+        const int c = g * 8 + i;
+        const double m = ws[((size_t)b * C + c) * 2] / HW;
+        double var = ws[((size_t)b * C + c) * 2 + 1] / HW - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        mean[i] = (float)m;
+        rstd[i] = rsqrtf((float)var + eps);
+    }
+    if (phase < nphase) {
+        for (int r = r0 + phase; r < r1; r += nphase) {
+            const size_t oi = ((size_t)b * HW + r) * G + g, oo = ((size_t)b * HW + r) * 2 * G + g;
+            float fx[8], y1[8], y2[8], d1[8], d2[8];
+            unpack8(ld8(x + oi), fx);
+            unpack8(ld8(y + oo), y1); unpack8(ld8(y + oo + G), y2);
+            unpack8(ld8(dy + oo), d1); unpack8(ld8(dy + oo + G), d2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float g1 = y1[i] > 0.0f ? d1[i] : d1[i] * slope, g2 = y2[i] > 0.0f ? d2[i] : d2[i] * slope;
+                const float xh = (fx[i] - mean[i]) * rstd[i];
+                s[0][i] += g1; s[1][i] = fmaf(g1, xh, s[1][i]);
+                s[2][i] += g2; s[3][i] = fmaf(g2, -xh, s[3][i]);
+            }
+        }
+    }
+    __shared__ float sh[kThreads][33];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh[threadIdx.x][k * 8 + i] = s[k][i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * 32; idx += kThreads) {
+        const int gg = idx / 32, k = idx % 32;
+        double acc = 0.0;
+        for (int ph = 0; ph < nphase; ++ph) acc += (double)sh[ph * G + gg][k];
+        const int c = gg * 8 + (k & 7), which = k >> 3;                              // 0: S1 of c, 1: S2 of c, 2: S1 of C + c, 3: S2 of C + c
+        atomicAdd(wsb + ((size_t)b * 2 * C + (which >= 2 ? C : 0) + c) * 2 + (which & 1), acc);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) in_bwd_crelu_apply_kernel(const Bf16x8* __restrict__ x, const Bf16x8* __restrict__ y,
+                                                                          const Bf16x8* __restrict__ dy, const float* __restrict__ gamma,
+                                                                          const double* __restrict__ ws, const double* __restrict__ wsb,
+                                                                          Bf16x8* __restrict__ dx, int HW, int C, int rows_per_cta, float eps,
+                                                                          float slope) {
+    pdl::trigger();
+    pdl::wait();
+    const int G = C / 8;
+    const int b = blockIdx.y;
+    const int g = threadIdx.x % G, phase = threadIdx.x / G, nphase = kThreads / G;
+    if (phase >= nphase) return;
+    // dx = rstd * (a1 g1 - a2 g2 - mG - xh * mGx) = A1 g1 - A2 g2 - (B0 + x * B1)
+    float A1[8], A2[8], B0[8], B1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        const double m = ws[((size_t)b * C + c) * 2] / HW;
+        double var = ws[((size_t)b * C + c) * 2 + 1] / HW - m * m;
+        var = var < 0.0 ? 0.0 : var;
+        const float rs = rsqrtf((float)var + eps), mean = (float)m;
+        const float a1 = gamma ? gamma[c] : 1.0f, a2 = gamma ? gamma[C + c] : 1.0f;
+        const double* w1 = wsb + ((size_t)b * 2 * C + c) * 2;
+        const double* w2 = wsb + ((size_t)b * 2 * C + C + c) * 2;
+        const float mG = (float)((a1 * w1[0] - a2 * w2[0]) / HW);
+        const float mGx = (float)((a1 * w1[1] + a2 * w2[1]) / HW);                  // w2[1] already carries the minus sign
+        A1[i] = rs * a1; A2[i] = rs * a2;
+        B1[i] = rs * rs * mGx;
+        B0[i] = rs * (mG - mean * rs * mGx);
+    }
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(HW, r0 + rows_per_cta);
+    for (int r = r0 + phase; r < r1; r += nphase) {
+        const size_t oi = ((size_t)b * HW + r) * G + g, oo = ((size_t)b * HW + r) * 2 * G + g;
+        float fx[8], y1[8], y2[8], d1[8], d2[8], od[8];
+        unpack8(ld8(x + oi), fx);
+        unpack8(ld8(y + oo), y1); unpack8(ld8(y + oo + G), y2);
+        unpack8(ld8(dy + oo), d1); unpack8(ld8(dy + oo + G), d2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float g1 = y1[i] > 0.0f ? d1[i] : d1[i] * slope, g2 = y2[i] > 0.0f ? d2[i] : d2[i] * slope;
+            od[i] = fmaf(A1[i], g1, fmaf(-A2[i], g2, -fmaf(fx[i], B1[i], B0[i])));
+        }
+        dx[oi] = pack8(od);
+    }
+}
+
 // ---- single-pass InstanceNorm for instances that fit in a cluster's shared memory --------------------------------
 // The two-pass form above costs three launches (memset, statistics, apply) and reads x twice.  Most InstanceNorms of the
 // step act on small instances (stages 2-4 of the feeder: <= 3.7 MB per image; the recogniser: 131 KB per RoI), where the
@@ -783,6 +887,31 @@ extern "C" int fots_b200_instnorm_bwd_nhwc_bf16(const void* x, const void* y, co
         e = pdl::launch(in_bwd_apply_kernel<false>, dim3(ach, B), dim3(kThreads), smem, stream, xp, yp, gp, gamma, stats, (const double*)stats_bwd,
                         static_cast<Bf16x8*>(dx), (Bf16x8*)nullptr, HW, C, arows, eps, slope);
     }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
+
+// Backward of the CReLU form (crelu != 0): y / dy bf16 [B, HW, 2C], gamma fp32 [2C] or NULL, stats = the forward's sums of x
+// [B, C, 2], stats_bwd fp64 [B, 2C, 2] cleared and filled (dbeta[j] = sum_b [b, j, 0], dgamma[j] = sum_b [b, j, 1]).
+extern "C" int fots_b200_instnorm_crelu_bwd_nhwc_bf16(const void* x, const void* y, const void* dy, const float* gamma, const double* stats,
+                                                      double* stats_bwd, void* dx, int B, int HW, int C, float eps, float slope,
+                                                      cudaStream_t stream) {
+    if (!x || !y || !dy || !stats || !stats_bwd || !dx || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || C > 512 || B > 65535)
+        return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
+        return RROI_B200_ERR_INVALID_ARG;
+    const int G = C / 8, nphase = kThreads / G;
+    cudaError_t e = pdl::zero_f64(stats_bwd, (size_t)B * 2 * C * 2, stream);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    const Bf16x8 *xp = static_cast<const Bf16x8*>(x), *yp = static_cast<const Bf16x8*>(y), *gp = static_cast<const Bf16x8*>(dy);
+    int rows = 0;
+    const int chunks = wave_chunks(B, HW, resident_ctas(in_bwd_crelu_stats_kernel, 0), nphase * 4, nphase, &rows);
+    e = pdl::launch(in_bwd_crelu_stats_kernel, dim3(chunks, B), dim3(kThreads), 0, stream, xp, yp, gp, stats, stats_bwd, HW, C, rows, eps, slope);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    int arows = 0;
+    const int ach = wave_chunks(B, HW, resident_ctas(in_bwd_crelu_apply_kernel, 0), nphase * 4, nphase, &arows);
+    e = pdl::launch(in_bwd_crelu_apply_kernel, dim3(ach, B), dim3(kThreads), 0, stream, xp, yp, gp, gamma, stats, (const double*)stats_bwd,
+                    static_cast<Bf16x8*>(dx), HW, C, arows, eps, slope);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
 }

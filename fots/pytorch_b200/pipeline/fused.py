@@ -151,6 +151,47 @@ def instnorm_act_train(x, weight, bias, eps, slope, residual=None):
     return _InstNormActFn.apply(x, weight, bias, residual, eps, slope)
 
 
+class _CReLUNormFn(torch.autograd.Function):
+    """y = act(IN(concat(x, -x)) * weight + bias) (tools/models.py:41-48 CReLU_IN) with this repo's forward kernels and
+    fots_b200_instnorm_crelu_bwd_nhwc_bf16 backward; weight / bias have 2C entries."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, slope):
+        ws = instnorm_stats(x)
+        y = instnorm_act(x, weight, bias, eps, slope, crelu=True, stats=ws)
+        ctx.save_for_backward(x, y, weight, ws)
+        ctx.eps, ctx.slope, ctx.has_affine = float(eps), float(slope), weight is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, ws = ctx.saved_tensors
+        B, C, H, W = x.shape
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        wsb = workspace(x.device, B * 2 * C * 2)
+        w = weight.float().contiguous() if weight is not None else None
+        L = _lib()
+        L.fots_b200_instnorm_crelu_bwd_nhwc_bf16.restype = ctypes.c_int
+        L.fots_b200_instnorm_crelu_bwd_nhwc_bf16.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_int] * 3 + [ctypes.c_float] * 2 + [ctypes.c_void_p]
+        with torch.cuda.device(x.device):
+            st = L.fots_b200_instnorm_crelu_bwd_nhwc_bf16(x.data_ptr(), y.data_ptr(), dy.data_ptr(), w.data_ptr() if w is not None else None,
+                                                          ws.data_ptr(), wsb.data_ptr(), dx.data_ptr(), B, H * W, C, ctx.eps, ctx.slope,
+                                                          torch.cuda.current_stream(x.device).cuda_stream)
+        _cabi.check(st, "fots_b200_instnorm_crelu_bwd_nhwc_bf16")
+        dgamma = dbeta = None
+        if ctx.has_affine:
+            sums = wsb[:B * 2 * C * 2].view(B, 2 * C, 2).sum(0)
+            dbeta, dgamma = sums[:, 0].to(weight.dtype), sums[:, 1].to(weight.dtype)
+        return dx, dgamma, dbeta, None, None
+
+
+def crelu_norm_train(x, weight, bias, eps, slope):
+    """Differentiable act(IN(concat(x, -x)) * weight + bias); caller checks train_eligible(x) and C <= 512."""
+    return _CReLUNormFn.apply(x, weight, bias, eps, slope)
+
+
 def _cl_bf16(t):
     return (t is None) or (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4
                            and t.is_contiguous(memory_format=torch.channels_last)

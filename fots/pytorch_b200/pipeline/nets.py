@@ -62,6 +62,8 @@ class _CReLUNorm(nn.Module):
     def forward(self, x):
         if fused.eligible(x, None, self.bn.weight, self.bn.bias):
             return fused.instnorm_act(x, self.bn.weight, self.bn.bias, self.bn.eps, 0.01, crelu=True)
+        if torch.is_grad_enabled() and fused.train_eligible(x) and x.size(1) <= 512:
+            return fused.crelu_norm_train(x, self.bn.weight, self.bn.bias, self.bn.eps, 0.01)     # training: forward + backward kernels
         return F.leaky_relu(self.bn(torch.cat((x, -x), 1)), 0.01)
 
 

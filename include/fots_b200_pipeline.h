@@ -243,6 +243,12 @@ int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, const float* 
 int fots_b200_instnorm_bwd_nhwc_bf16(const void* x, const void* y, const void* dy, const float* gamma, const double* stats,
                                      double* stats_bwd, void* dx, void* dres, int B, int HW, int C, float eps, float slope,
                                      cudaStream_t stream);
+/* The same for the CReLU form (crelu != 0 in the forward: y = act(IN(concat(x, -x)) * gamma + beta), 2C output channels):
+ * y / dy bf16 [B, HW, 2C], gamma fp32 [2C] or NULL, stats_bwd fp64 [B, 2C, 2] (dbeta[j] = sum_b [b, j, 0], dgamma[j] = sum_b
+ * [b, j, 1] for all 2C channels). */
+int fots_b200_instnorm_crelu_bwd_nhwc_bf16(const void* x, const void* y, const void* dy, const float* gamma, const double* stats,
+                                           double* stats_bwd, void* dx, int B, int HW, int C, float eps, float slope,
+                                           cudaStream_t stream);
 /* Consumer B's first layer (tools/models.py:853-897, CRNN.cnn conv0 + relu0 + pooling0): 3 input channels cannot fill a
  * k-block of the tcgen05 kernel.  x fp32 NCHW [N, 3, H, W] (RoIRotate of the raw image, src/utils.py:430-436), w bf16
  * [Cout, 3, 3, 3] contiguous, bias fp32 [Cout] or NULL -> y bf16 NHWC = maxpool2x2(relu(conv3x3_pad1(x) + bias)) when

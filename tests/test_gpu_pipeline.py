@@ -146,6 +146,28 @@ def test_instancenorm_backward_kernels_match_torch_autograd(cuda, B, C, H, W, sl
     assert all(ok for ok, _ in checks), [what for ok, what in checks if not ok]
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 16, 24, 40), (3, 32, 9, 11), (1, 64, 7, 5)])
+def test_crelu_instancenorm_backward_kernels_match_torch_autograd(cuda, B, C, H, W):
+    """fots_b200_instnorm_crelu_bwd_nhwc_bf16 (fused.crelu_norm_train): leaky(IN(concat(x, -x)) * gamma + beta) and its gradients
+    against torch's autograd in fp32 on the same bf16 operands."""
+    from fots.pytorch_b200.pipeline import fused
+    g = torch.Generator().manual_seed(B * 13 + C)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(B, 2 * C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w, b = (torch.rand(2 * C, generator=g) + 0.5).to(cuda), (torch.randn(2 * C, generator=g) * 0.3).to(cuda)
+    x1, w1, b1 = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = fused.crelu_norm_train(x1, w1, b1, 1e-5, 0.01)
+    y.backward(dy)
+    xf, wf, bf = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.leaky_relu(F.instance_norm(torch.cat((xf, -xf), 1), weight=wf, bias=bf, eps=1e-5), 0.01)
+    yr.backward(dy.float())
+    tol = lambda ref: 2.0 ** -6 * float(ref.detach().abs().max()) + 1e-3
+    assert float((y.detach().float() - yr.detach()).abs().max()) <= tol(yr)
+    assert float((x1.grad.float() - xf.grad).abs().max()) <= tol(xf.grad)
+    ptol = lambda ref: 2.0 ** -6 * float(ref.abs().max()) + 0.05 * (B * H * W) ** 0.5 * 2.0 ** -8
+    assert float((w1.grad - wf.grad).abs().max()) <= ptol(wf.grad) and float((b1.grad - bf.grad).abs().max()) <= ptol(bf.grad)
+
+
 def test_training_step_runs_and_reduces_loss(cuda):
     """cfg3-shaped step at reduced size: finite losses, the detection loss falls, and the CTC gradient reaches the
     stem THROUGH the RoIRotate backward kernel (with the detection loss switched off it is the only path)."""
