@@ -5,11 +5,15 @@
 // 9 MACs per output value: pure bandwidth (read x once, write y once).  cuDNN's channels-last depthwise kernel
 // (conv2d_c1_k1_nhwc_specialized) reaches about a quarter of the copy roofline on these shapes (18 us for a 14.7 MB map,
 // 140 us for the 236 MB one); a first hand-written attempt in round 1 read its nine taps straight from global memory and
-// was L1-bound.  Here a CTA stages its input tile (+ halo) for 64 channels in shared memory with cp.async (every pixel
-// is 128 contiguous bytes; the whole tile is in flight at once, out-of-image vectors are zero-filled by the copy), and
-// every thread produces a strip of 4 horizontally adjacent outputs for 8 channels, so each staged vector is read from
-// shared memory once per (row, strip) instead of once per tap: 18 LDS.128 per 4 outputs at stride 1, 27 at stride 2.
-// fp32 accumulation in the order (r, s) = (0,0) .. (2,2), one rounding to bf16.
+// was L1-bound.  A CTA stages its input tile (+ halo) for 64 channels in shared memory (every pixel is 128 contiguous
+// bytes, out-of-image pixels arrive as zeros = the padding) and every thread produces a strip of 4 horizontally adjacent
+// outputs for 8 channels, so each staged vector is read from shared memory once per (row, strip) instead of once per tap:
+// 18 LDS.128 per 4 outputs at stride 1, 27 at stride 2.  fp32 accumulation in the order (r, s) = (0,0) .. (2,2), one
+// rounding to bf16.
+//   stride 2: one tile per CTA, staged with cp.async (dwconv3x3_kernel; two small launches per step);
+//   stride 1: persistent CTAs, tiles staged by TMA box loads into an mbarrier ring, mixed-precision FMAs on the packed bf16
+//             operands (dwconv3x3_s1_pipe_kernel: 0.91 of the copy roofline on the 236 MB map), with the InstanceNorm in
+//             front of it or the bilinear upsampling of the top-down merge applied to the staged tile (NORM / UP modes).
 #include "../../../include/fots_b200_pipeline.h"
 #include "pdl.cuh"
 #include <cuda.h>
