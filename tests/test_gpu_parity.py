@@ -122,10 +122,16 @@ def test_stress_forward_backward(oracle, cuda, seed, B, C, H, W, N, ph, pw, scal
     out, ix, iy = _check_forward_all_paths(oracle, feats, rois, ph, pw, scale, cuda)
     g = np.random.default_rng(seed).standard_normal(out.shape, dtype=np.float32)
     want = oracle.backward(g, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), feats.shape, scale, threads=0)
+    from fots.pytorch_b200 import _cabi
     for cl in (False, True):
         for idx in ((ix, iy), None):
             got = Hh.run_new_backward(g, rois, idx, feats.shape, scale, cuda, channels_last=cl)
             Hh.assert_close_rel(got, want, REL_BWD, "stress backward cl=%s saved_idx=%s" % (cl, idx is not None))
+    # the NCHW gather kernel is the automatic choice only for large launches: force it on these shapes too (odd channel
+    # counts, PH not a multiple of 8, PW not a multiple of 32, several bin tiles per RoI, unaligned rows -> per-tile fallback)
+    for idx in ((ix, iy), None):
+        got = Hh.run_new_backward(g, rois, idx, feats.shape, scale, cuda, opts=_cabi.opts(bwd_mode=4))
+        Hh.assert_close_rel(got, want, REL_BWD, "stress backward, NCHW gather kernel, saved_idx=%s" % (idx is not None))
     got = Hh.run_legacy_backward(g, rois, Hh.expand_idx(ix, C), Hh.expand_idx(iy, C), feats.shape, scale, cuda)
     Hh.assert_close_rel(got, want, REL_BWD, "stress legacy backward")
 
