@@ -665,6 +665,51 @@ __global__ void __launch_bounds__(kThreads, 3) fpn_merge_kernel(const Bf16x8* __
     }
 }
 
+// ---- backward of the bilinear (align_corners) upsampling of the top-down merge: dlo = U^T dhi --------------------------------
+// Gather form: thread = one LOW-resolution pixel x 8 channels; it visits the high-resolution rows / columns whose source
+// index pair (lerp_coord, the forward's own arithmetic) contains its row / column and accumulates weight * gradient in fp32.
+// No atomics, deterministic; every high-resolution vector is read by the <= 4 low-resolution pixels it was interpolated from.
+__global__ void __launch_bounds__(kThreads) upsample_bwd_kernel(const Bf16x8* __restrict__ dhi, Bf16x8* __restrict__ dlo, int B, int h, int w,
+                                                                int H, int W, int C) {
+    pdl::trigger();
+    pdl::wait();
+    const int G = C / 8;
+    const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
+    const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
+    const long long total = (long long)B * h * w * G;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int g = (int)(i % G);
+        long long p = i / G;
+        const int x = (int)(p % w); p /= w;
+        const int y = (int)(p % h);
+        const int b = (int)(p / h);
+        // candidate ranges: source index s * Y lies in (y - 1, y + 1); two extra on each side absorb the float rounding
+        int Ya = 0, Yb = H - 1, Xa = 0, Xb = W - 1;
+        if (sy > 0.0f) { Ya = max(0, (int)floorf((float)(y - 1) / sy) - 1); Yb = min(H - 1, (int)ceilf((float)(y + 1) / sy) + 1); }
+        if (sx > 0.0f) { Xa = max(0, (int)floorf((float)(x - 1) / sx) - 1); Xb = min(W - 1, (int)ceilf((float)(x + 1) / sx) + 1); }
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+        for (int Y = Ya; Y <= Yb; ++Y) {
+            const Lerp ly = lerp_coord(Y, h, sy);
+            const float wy = (ly.i0 == y ? ly.l0 : 0.0f) + (ly.i1 == y ? ly.l1 : 0.0f);
+            if (wy == 0.0f) continue;
+            const Bf16x8* rowp = dhi + (((size_t)b * H + Y) * W) * G + g;
+            for (int X = Xa; X <= Xb; ++X) {
+                const Lerp lx = lerp_coord(X, w, sx);
+                const float wx = (lx.i0 == x ? lx.l0 : 0.0f) + (lx.i1 == x ? lx.l1 : 0.0f);
+                if (wx == 0.0f) continue;
+                float f[8];
+                unpack8(ld8(rowp + (size_t)X * G), f);
+                const float wgt = wy * wx;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, f[k], acc[k]);
+            }
+        }
+        dlo[i] = pack8(acc);
+    }
+}
+
 // ---- max-pool (2,1)/(2,1) over H of a channels-last tensor (tools/models.py:344, :360 `max2`) --------------------
 // thread = 8 channels of one output pixel; the two input rows are W*C elements apart.  NaNs propagate like torch's.
 __global__ void __launch_bounds__(kThreads) maxpool_h2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
@@ -912,6 +957,22 @@ extern "C" int fots_b200_instnorm_crelu_bwd_nhwc_bf16(const void* x, const void*
     const int ach = wave_chunks(B, HW, resident_ctas(in_bwd_crelu_apply_kernel, 0), nphase * 4, nphase, &arows);
     e = pdl::launch(in_bwd_crelu_apply_kernel, dim3(ach, B), dim3(kThreads), 0, stream, xp, yp, gp, gamma, stats, (const double*)stats_bwd,
                     static_cast<Bf16x8*>(dx), HW, C, arows, eps, slope);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
+
+// dlo [B, h, w, C] = U^T dhi [B, H, W, C]: the backward of the align_corners bilinear upsampling fots_b200_fpn_merge_nhwc_bf16
+// computes for a_lo (training step; torch's channels-last upsample backward runs at ~0.55 TB/s).
+extern "C" int fots_b200_upsample_bilinear_bwd_nhwc_bf16(const void* dhi, void* dlo, int B, int h, int w, int H, int W, int C,
+                                                         cudaStream_t stream) {
+    if (!dhi || !dlo || B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(dhi) | reinterpret_cast<uintptr_t>(dlo)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    const long long total = (long long)B * h * w * (C / 8);
+    long long grid = (total + kThreads - 1) / kThreads;
+    const long long cap = 4LL * resident_ctas(upsample_bwd_kernel, 0);
+    if (grid > cap) grid = cap;
+    const cudaError_t e = pdl::launch(upsample_bwd_kernel, dim3((unsigned)grid), dim3(kThreads), 0, stream, static_cast<const Bf16x8*>(dhi),
+                                      static_cast<Bf16x8*>(dlo), B, h, w, H, W, C);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
 }

@@ -192,6 +192,37 @@ def crelu_norm_train(x, weight, bias, eps, slope):
     return _CReLUNormFn.apply(x, weight, bias, eps, slope)
 
 
+class _UpsampleFn(torch.autograd.Function):
+    """Bilinear (align_corners = True) upsampling of a bf16 channels-last map to `size` with this repo's kernels in both
+    directions (forward: the a_lo-only form of fots_b200_fpn_merge_nhwc_bf16; backward: fots_b200_upsample_bilinear_bwd_nhwc_bf16)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        ctx.lo_shape = tuple(x.shape)
+        return fpn_merge(a_lo=x, size=(H, W))
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, h, w = ctx.lo_shape
+        H, W = dy.shape[2], dy.shape[3]
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((B, C, h, w), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+        L = _lib()
+        L.fots_b200_upsample_bilinear_bwd_nhwc_bf16.restype = ctypes.c_int
+        L.fots_b200_upsample_bilinear_bwd_nhwc_bf16.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+        with torch.cuda.device(dy.device):
+            st = L.fots_b200_upsample_bilinear_bwd_nhwc_bf16(dy.data_ptr(), dx.data_ptr(), B, h, w, H, W, C,
+                                                             torch.cuda.current_stream(dy.device).cuda_stream)
+        _cabi.check(st, "fots_b200_upsample_bilinear_bwd_nhwc_bf16")
+        return dx, None, None
+
+
+def upsample_train(x, size):
+    """Differentiable bilinear (align_corners) upsampling; caller checks train_eligible(x)."""
+    return _UpsampleFn.apply(x, int(size[0]), int(size[1]))
+
+
 def _cl_bf16(t):
     return (t is None) or (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4
                            and t.is_contiguous(memory_format=torch.channels_last)

@@ -135,6 +135,8 @@ def _downsample(block, x):
 def _up(x, like):
     # CUDA autocast lists upsample_bilinear2d as an fp32 op: a 256-channel map at 1/4 scale would be blown up to
     # fp32 (and every add/mul after it promoted).  Interpolate in the tensor's own dtype instead.
+    if torch.is_grad_enabled() and fused.train_eligible(x):
+        return fused.upsample_train(x, like.shape[2:])          # training step: forward + backward on this repo's kernels
     with torch.autocast(device_type=x.device.type, enabled=False):
         return F.interpolate(x, size=like.shape[2:], mode="bilinear", align_corners=True)
 
@@ -247,7 +249,9 @@ class FOTSNet(nn.Module):
             f2 = fused.fpn_merge(c_hi=up(self.upconv1, x, f2.shape[2:]), b_hi=f2, **gate(x))
             x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, **gate(f2))
         elif self.attention:
-            x = _up(f4, f3) + f3 * _up(torch.sigmoid(self.conv_attenton(f4)).expand_as(f4), f3)
+            # (the reference upsamples the gate expanded to all channels; upsampling the one-channel gate and broadcasting is
+            # the same arithmetic per element)
+            x = _up(f4, f3) + f3 * self._gate(f4, f3)
             gate = self._gate(x, f2)
             f2 = self.upconv1(_up(x, f2)) + f2 * gate
             gate = self._gate(f2, f1)

@@ -249,6 +249,9 @@ int fots_b200_instnorm_bwd_nhwc_bf16(const void* x, const void* y, const void* d
 int fots_b200_instnorm_crelu_bwd_nhwc_bf16(const void* x, const void* y, const void* dy, const float* gamma, const double* stats,
                                            double* stats_bwd, void* dx, int B, int HW, int C, float eps, float slope,
                                            cudaStream_t stream);
+/* Backward of the align_corners bilinear upsampling of the top-down merge (the a_lo-only form of fots_b200_fpn_merge_nhwc_bf16;
+ * tools/models.py:411-438 F.interpolate under autograd): dlo bf16 [B, h, w, C] = U^T dhi bf16 [B, H, W, C].  Gather form, no atomics. */
+int fots_b200_upsample_bilinear_bwd_nhwc_bf16(const void* dhi, void* dlo, int B, int h, int w, int H, int W, int C, cudaStream_t stream);
 /* Consumer B's first layer (tools/models.py:853-897, CRNN.cnn conv0 + relu0 + pooling0): 3 input channels cannot fill a
  * k-block of the tcgen05 kernel.  x fp32 NCHW [N, 3, H, W] (RoIRotate of the raw image, src/utils.py:430-436), w bf16
  * [Cout, 3, 3, 3] contiguous, bias fp32 [Cout] or NULL -> y bf16 NHWC = maxpool2x2(relu(conv3x3_pad1(x) + bias)) when

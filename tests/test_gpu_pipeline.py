@@ -168,6 +168,24 @@ def test_crelu_instancenorm_backward_kernels_match_torch_autograd(cuda, B, C, H,
     assert float((w1.grad - wf.grad).abs().max()) <= ptol(wf.grad) and float((b1.grad - bf.grad).abs().max()) <= ptol(bf.grad)
 
 
+@pytest.mark.parametrize("B,C,h,w,H,W", [(2, 256, 23, 40, 45, 80), (1, 64, 5, 7, 9, 13), (2, 8, 1, 1, 4, 4), (1, 128, 6, 10, 12, 20), (1, 32, 4, 4, 4, 4)])
+def test_upsample_backward_kernel_matches_torch_autograd(cuda, B, C, h, w, H, W):
+    """fots_b200_upsample_bilinear_bwd_nhwc_bf16 (fused.upsample_train): forward and input gradient against torch's autograd of
+    F.interpolate(bilinear, align_corners=True) in fp32 on the same bf16 operands."""
+    from fots.pytorch_b200.pipeline import fused
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, h, w, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(B, C, H, W, generator=g).to(cuda).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x1 = x.clone().requires_grad_(True)
+    y = fused.upsample_train(x1, (H, W))
+    y.backward(dy)
+    xf = x.float().requires_grad_(True)
+    yr = F.interpolate(xf, size=(H, W), mode="bilinear", align_corners=True)
+    yr.backward(dy.float())
+    assert float((y.detach().float() - yr.detach()).abs().max()) <= 2.0 ** -7 * float(yr.detach().abs().max()) + 1e-3
+    assert float((x1.grad.float() - xf.grad).abs().max()) <= 2.0 ** -7 * float(xf.grad.abs().max()) + 1e-3
+
+
 def test_training_step_runs_and_reduces_loss(cuda):
     """cfg3-shaped step at reduced size: finite losses, the detection loss falls, and the CTC gradient reaches the
     stem THROUGH the RoIRotate backward kernel (with the detection loss switched off it is the only path)."""
