@@ -61,7 +61,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
     ap.add_argument("--pipeline-steps", type=int, default=4)
-    ap.add_argument("--pipeline-lanes", type=int, default=4, help="parallel graph branches the step's micro-batches are dealt to")
+    ap.add_argument("--pipeline-lanes", type=int, default=2, help="parallel graph branches the step's micro-batches are dealt to")
+    ap.add_argument("--pipeline-micro", type=int, default=16, help="images per micro-batch of the end-to-end step")
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-images", type=int, default=32, help="batch of the cfg3 training step")
@@ -503,7 +504,7 @@ def train_leg(args, torch, device):
 def pipeline_leg(args, torch, device, dist, world, rank):
     """End-to-end images/s (BASELINE.json configs[2]/[4]): random-init FOTSNet in bf16 channels-last, 1280x720
     synthetic images, 64 planted boxes per image, backbone + heads -> RoI rows -> RoIRotate (bf16 in/out) -> forward_ocr ->
-    greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 8, the rank-local part replayed
+    greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 16 on 2 graph branches, the rank-local part replayed
     from one CUDA graph) with ONE all_gather of the per-image records per step.  Images start on the device; timed with CUDA events, max over ranks."""
     from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
     from fots.pytorch_b200.pipeline.infer import planted_quads
@@ -511,7 +512,8 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     torch.manual_seed(0)
     net = FOTSNet(attention=True, nclass=89).to_b200(device, inference=True)
     pipe = FOTSPipeline(net, 8, 64, 0.25, amp_dtype=torch.bfloat16)
-    per_gpu, micro = args.pipeline_images, 8
+    per_gpu, micro = args.pipeline_images, 8                 # micro: the step with detection (host merge per 8-image micro-batch)
+    micro_plain = args.pipeline_micro if per_gpu % args.pipeline_micro == 0 else micro
     batch = per_gpu * world
     gen = torch.Generator(device=device).manual_seed(100 + rank)
     # raw uint8 images [b, 720, 1280, 3] as cv2.imread returns them (viewed as channels-last [b, 3, 720, 1280]); the
@@ -519,9 +521,10 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     images = torch.randint(0, 256, (per_gpu, 720, 1280, 3), device=device, generator=gen, dtype=torch.uint8).permute(0, 3, 1, 2)
     quads = torch.from_numpy(planted_quads(per_gpu, 64, seed0=rank * per_gpu)).to(device)
 
-    # one CUDA graph for the rank-local part of the step; its four 8-image micro-batches are independent and run as
-    # `lanes` parallel branches of the graph (the latency-bound launches of one fill the bubbles of the other)
-    local = pipe.capture(images, quads, micro, lanes=args.pipeline_lanes)
+    # one CUDA graph for the rank-local part of the step; its micro-batches are independent and run as `lanes` parallel
+    # branches of the graph (the latency-bound launches of one fill the bubbles of the other).  Measured on B200
+    # (tools/step_time.py, 32 images): 16 x 2 lanes 14.05 ms, 32 x 1 14.07, 8 x 4 14.35, 8 x 1 15.7, 4 x 8 15.36
+    local = pipe.capture(images, quads, micro_plain, lanes=args.pipeline_lanes)
 
     def step():
         return all_gather_records(local(), batch)
@@ -618,7 +621,7 @@ def pipeline_leg(args, torch, device, dist, world, rank):
     cpu = pipeline_cpu_baseline(torch) if (rank == 0 and world == 1) else None      # N=1 only, like cpu_baseline
     return {"images_per_s": batch / (ms_host * 1e-3), "ms_per_step": ms_host, "cpu_baseline": cpu,
             "images_per_s_device_resident": batch / (ms * 1e-3), "ms_per_step_device_resident": ms,
-            "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64, "micro_batch": micro,
+            "images_per_step": batch, "images_per_gpu": per_gpu, "rois_per_image": 64, "micro_batch": micro_plain,
             "graph_branches": args.pipeline_lanes,
             "h2d_bytes_per_step": images.numel() * images.element_size() * world, "d2h_bytes_per_step": out.numel() * 4,
             "dtype": "uint8 images in (normalised on load by the stem kernel); bf16 activations, fp32 accumulation: every convolution on "

@@ -20,7 +20,8 @@ if __name__ == "__main__":
     images = torch.randint(0, 256, (B, 720, 1280, 3), device=dev, dtype=torch.uint8).permute(0, 3, 1, 2)
     quads = torch.from_numpy(planted_quads(B, 64)).to(dev)
     lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-    g = pipe.capture(images, quads, micro=8, lanes=lanes)
+    micro = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    g = pipe.capture(images, quads, micro=micro, lanes=lanes)
     for _ in range(3):
         g()
     torch.cuda.synchronize()
@@ -30,5 +31,5 @@ if __name__ == "__main__":
         g()
     e1.record()
     torch.cuda.synchronize()
-    print("lanes=%d LEVEL=%d STATS=%d ENABLED=%d: %.3f ms per %d-image step (CUDA graph), %.0f images/s" % (
-        lanes, TC.LEVEL, int(TC.FUSE_STATS), int(TC.ENABLED), e0.elapsed_time(e1) / 20, B, B / (e0.elapsed_time(e1) / 20e3)), flush=True)
+    print("micro=%d lanes=%d LEVEL=%d STATS=%d ENABLED=%d: %.3f ms per %d-image step (CUDA graph), %.0f images/s" % (
+        micro, lanes, TC.LEVEL, int(TC.FUSE_STATS), int(TC.ENABLED), e0.elapsed_time(e1) / 20, B, B / (e0.elapsed_time(e1) / 20e3)), flush=True)
