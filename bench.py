@@ -61,8 +61,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline-images", type=int, default=32, help="images per GPU per end-to-end step (cfg4: 32)")
     ap.add_argument("--pipeline-steps", type=int, default=4)
-    ap.add_argument("--pipeline-lanes", type=int, default=2, help="parallel graph branches the step's micro-batches are dealt to")
-    ap.add_argument("--pipeline-micro", type=int, default=16, help="images per micro-batch of the end-to-end step")
+    ap.add_argument("--pipeline-lanes", type=int, default=1, help="parallel graph branches the step's micro-batches are dealt to")
+    ap.add_argument("--pipeline-micro", type=int, default=32, help="images per micro-batch of the end-to-end step")
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-images", type=int, default=32, help="batch of the cfg3 training step")
@@ -504,7 +504,7 @@ def train_leg(args, torch, device):
 def pipeline_leg(args, torch, device, dist, world, rank):
     """End-to-end images/s (BASELINE.json configs[2]/[4]): random-init FOTSNet in bf16 channels-last, 1280x720
     synthetic images, 64 planted boxes per image, backbone + heads -> RoI rows -> RoIRotate (bf16 in/out) -> forward_ocr ->
-    greedy CTC decode, image-sharded (32 images per GPU per step, micro-batches of 16 on 2 graph branches, the rank-local part replayed
+    greedy CTC decode, image-sharded (32 images per GPU per step, one 32-image micro-batch, the rank-local part replayed
     from one CUDA graph) with ONE all_gather of the per-image records per step.  Images start on the device; timed with CUDA events, max over ranks."""
     from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline
     from fots.pytorch_b200.pipeline.infer import planted_quads
@@ -523,7 +523,7 @@ def pipeline_leg(args, torch, device, dist, world, rank):
 
     # one CUDA graph for the rank-local part of the step; its micro-batches are independent and run as `lanes` parallel
     # branches of the graph (the latency-bound launches of one fill the bubbles of the other).  Measured on B200
-    # (tools/step_time.py, 32 images): 16 x 2 lanes 14.05 ms, 32 x 1 14.07, 8 x 4 14.35, 8 x 1 15.7, 4 x 8 15.36
+    # (tools/step_time.py, 32 images, micro-batch x lanes): 32 x 1 13.74 ms, 16 x 2 13.98, 8 x 4 14.35, 8 x 1 15.7, 4 x 8 15.36
     local = pipe.capture(images, quads, micro_plain, lanes=args.pipeline_lanes)
 
     def step():

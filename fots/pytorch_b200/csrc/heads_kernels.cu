@@ -23,6 +23,25 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// Squashing + store of one pixel's two columns (2t, 2t + 1) of the 8-column head block {act, 0, rbox0..3, angle0, angle1}.
+__device__ __forceinline__ void heads_store(int t, float v0, float v1, long long p, int HW, float* __restrict__ seg, float* __restrict__ rbox,
+                                            float* __restrict__ angle) {
+    const long long b = p / HW, hw = p - b * HW;
+    if (t == 0) {
+        seg[p] = sigmoid_f(v0);
+    } else if (t < 3) {
+        float* r = rbox + (b * 4 + (t - 1) * 2) * HW + hw;
+        r[0] = sigmoid_f(v0) * 128.0f;
+        r[HW] = sigmoid_f(v1) * 128.0f;
+    } else {
+        const float s = sigmoid_f(v0) * 2.0f - 1.0f, c = sigmoid_f(v1) * 2.0f - 1.0f;
+        const float nrm = sqrtf(s * s + c * c);
+        float* a = angle + (b * 2) * HW + hw;
+        a[0] = s / nrm;
+        a[HW] = c / nrm;
+    }
+}
+
 // Logical k of the MMA <-> physical channel.  Lane (g = lane / 4, t = lane % 4) loads, for load m, the 8 channels
 // 32 m + 8 t .. + 7 of pixel rows g and g + 8 (the four t-lanes of a pixel read 64 contiguous bytes); k-step 2m consumes
 // the first four of them (k = 2t, 2t+1 | 2t+8, 2t+9), k-step 2m+1 the last four.  The B fragment of lane (g, t) is head g at
@@ -76,21 +95,88 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x,
                 if (t == 0) reinterpret_cast<__nv_bfloat16*>(seg)[p] = __float2bfloat16_rn(RAW == 2 ? sigmoid_f(v0) : v0);
                 continue;
             }
-            const long long b = p / HW, hw = p - b * HW;
-            if (t == 0) {
-                seg[p] = sigmoid_f(v0);
-            } else if (t < 3) {
-                float* r = rbox + (b * 4 + (t - 1) * 2) * HW + hw;
-                r[0] = sigmoid_f(v0) * 128.0f;
-                r[HW] = sigmoid_f(v1) * 128.0f;
-            } else {
-                const float s = sigmoid_f(v0) * 2.0f - 1.0f, c = sigmoid_f(v1) * 2.0f - 1.0f;
-                const float nrm = sqrtf(s * s + c * c);
-                float* a = angle + (b * 2) * HW + hw;
-                a[0] = s / nrm;
-                a[HW] = c / nrm;
-            }
+            heads_store(t, v0, v1, p, HW, seg, rbox, angle);
         }
+    }
+}
+
+
+// ---- the last level of the top-down merge COLLAPSED into the heads (inference) --------------------------------------------
+// tools/models.py:430-456 computes, at 1/4 scale,  x = upconv2_pw(d) + feature1(s) * gate  and then the three 1x1 heads on x,
+// where d = upconv2_dw(upsample(f2)), s = the stage-1 output (64 channels) and gate = upsample(sigmoid(conv_attenton(f2))).
+// x feeds nothing else at inference time (the recogniser reads the stage-0 map), and everything between d / s and the head
+// logits is linear:   logits = (Wh Wpw) d + gate * (Wh Wf1) s + bh.   The two products are 8 x 256 and 8 x 64 matrices folded
+// once at placement time (FOTSNet.to_b200), so the 256 -> 256 pointwise convolution, the 64 -> 256 lateral convolution, the
+// merge kernel and the 236 MB map x itself (written once, read twice per 8 images) disappear: this kernel reads d and s once.
+// Same fragment scheme as heads_kernel; the gate is interpolated per pixel with the merge kernel's arithmetic.
+template <int C1, int C2>
+__global__ void __launch_bounds__(256) heads_dual_kernel(const uint4* __restrict__ x1, const __nv_bfloat16* __restrict__ w1,
+                                                         const uint4* __restrict__ x2, const __nv_bfloat16* __restrict__ w2,
+                                                         const __nv_bfloat16* __restrict__ gate, const float* __restrict__ bias,
+                                                         float* __restrict__ seg, float* __restrict__ rbox, float* __restrict__ angle,
+                                                         long long npix, int H, int W, int gh, int gw) {
+    constexpr int N1 = C1 / 32, N2 = C2 / 32;
+    pdl::trigger();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint32_t wa[N1][4], wb[N2][4];
+#pragma unroll
+    for (int m = 0; m < N1; ++m) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w1 + (size_t)g * C1 + m * 32 + t * 8));
+        wa[m][0] = v.x; wa[m][1] = v.y; wa[m][2] = v.z; wa[m][3] = v.w;
+    }
+#pragma unroll
+    for (int m = 0; m < N2; ++m) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w2 + (size_t)g * C2 + m * 32 + t * 8));
+        wb[m][0] = v.x; wb[m][1] = v.y; wb[m][2] = v.z; wb[m][3] = v.w;
+    }
+    const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
+    pdl::wait();
+    const int HW = H * W;
+    const float sy = H > 1 ? (float)(gh - 1) / (float)(H - 1) : 0.0f, sx = W > 1 ? (float)(gw - 1) / (float)(W - 1) : 0.0f;
+    auto gate_at = [&](long long p) {                                    // bilinear, align_corners (fpn_merge's arithmetic)
+        const long long b = p / HW;
+        const int hw = (int)(p - b * HW), Y = hw / W, X = hw - Y * W;
+        const float fy = sy * (float)Y, fx = sx * (float)X;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < gh - 1 ? 1 : 0), xx1 = x0 + (x0 < gw - 1 ? 1 : 0);
+        const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+        const __nv_bfloat16* gp = gate + b * (long long)gh * gw;
+        const float s00 = __bfloat162float(gp[y0 * gw + x0]), s01 = __bfloat162float(gp[y0 * gw + xx1]);
+        const float s10 = __bfloat162float(gp[y1 * gw + x0]), s11 = __bfloat162float(gp[y1 * gw + xx1]);
+        return ly0 * (lx0 * s00 + lx1 * s01) + ly1 * (lx0 * s10 + lx1 * s11);
+    };
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long ntiles = (npix + 15) / 16;
+    constexpr int CV1 = C1 / 8, CV2 = C2 / 8;
+    for (long long tile = warp0; tile < ntiles; tile += nwarps) {
+        const long long p0 = tile * 16 + g, p1 = p0 + 8;
+        const bool ok0 = p0 < npix, ok1 = p1 < npix;
+        uint4 xa[N1], xb[N1], ya[N2], yb[N2];
+#pragma unroll
+        for (int m = 0; m < N1; ++m) {
+            xa[m] = ok0 ? __ldg(x1 + p0 * CV1 + m * 4 + t) : make_uint4(0, 0, 0, 0);
+            xb[m] = ok1 ? __ldg(x1 + p1 * CV1 + m * 4 + t) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int m = 0; m < N2; ++m) {
+            ya[m] = ok0 ? __ldg(x2 + p0 * CV2 + m * 4 + t) : make_uint4(0, 0, 0, 0);
+            yb[m] = ok1 ? __ldg(x2 + p1 * CV2 + m * 4 + t) : make_uint4(0, 0, 0, 0);
+        }
+        const float g0 = ok0 ? gate_at(p0) : 0.0f, g1 = ok1 ? gate_at(p1) : 0.0f;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, acs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < N1; ++m) {
+            mma_16816(acc, xa[m].x, xb[m].x, xa[m].y, xb[m].y, wa[m][0], wa[m][1]);
+            mma_16816(acc, xa[m].z, xb[m].z, xa[m].w, xb[m].w, wa[m][2], wa[m][3]);
+        }
+#pragma unroll
+        for (int m = 0; m < N2; ++m) {
+            mma_16816(acs, ya[m].x, yb[m].x, ya[m].y, yb[m].y, wb[m][0], wb[m][1]);
+            mma_16816(acs, ya[m].z, yb[m].z, ya[m].w, yb[m].w, wb[m][2], wb[m][3]);
+        }
+        if (ok0) heads_store(t, fmaf(g0, acs[0], acc[0]) + b0, fmaf(g0, acs[1], acc[1]) + b1, p0, HW, seg, rbox, angle);
+        if (ok1) heads_store(t, fmaf(g1, acs[2], acc[2]) + b0, fmaf(g1, acs[3], acc[3]) + b1, p1, HW, seg, rbox, angle);
     }
 }
 
@@ -140,6 +226,27 @@ extern "C" int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, co
         else (void)pdl::launch(heads_kernel<512, 1>, dim3(g), dim3(256), 0, stream, xp, wp, bias, o, (float*)nullptr, (float*)nullptr, npix, H * W);
     }
     const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
+
+// The three heads on  (w1 . x1) + upsample(gate_prob) * (w2 . x2) + bias  (see heads_dual_kernel): x1 bf16 [B, H, W, 256],
+// x2 bf16 [B, H, W, 64], w1 bf16 [8, 256], w2 bf16 [8, 64] (8-row head layout), gate_prob bf16 [B, gh, gw], bias fp32 [8].
+extern "C" int fots_b200_heads_merged_nhwc_bf16(const void* x1, const void* w1, const void* x2, const void* w2, const void* gate_prob,
+                                                const float* bias, float* seg, float* rbox, float* angle, int B, int H, int W, int C1,
+                                                int C2, int gh, int gw, cudaStream_t stream) {
+    if (!x1 || !w1 || !x2 || !w2 || !gate_prob || !bias || !seg || !rbox || !angle || B <= 0 || H <= 0 || W <= 0 || gh <= 0 || gw <= 0)
+        return RROI_B200_ERR_INVALID_ARG;
+    if (C1 != 256 || C2 != 64) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(w2)) & 15)
+        return RROI_B200_ERR_INVALID_ARG;
+    const long long npix = (long long)B * H * W;
+    const long long tiles = (npix + 15) / 16;
+    long long ctas = (tiles + 7) / 8;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    const cudaError_t e = pdl::launch(heads_dual_kernel<256, 64>, dim3((unsigned)ctas), dim3(256), 0, stream, static_cast<const uint4*>(x1),
+                                      static_cast<const __nv_bfloat16*>(w1), static_cast<const uint4*>(x2), static_cast<const __nv_bfloat16*>(w2),
+                                      static_cast<const __nv_bfloat16*>(gate_prob), bias, seg, rbox, angle, npix, H, W, gh, gw);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
 }

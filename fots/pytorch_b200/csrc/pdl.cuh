@@ -8,8 +8,12 @@
 //   * pdl::trigger() first (lets ITS successor be scheduled as soon as all of this grid's CTAs are resident),
 //   * pdl::wait() before the first access to anything another kernel of the stream may have written or may still read
 //     (activations, statistics workspaces, outputs) -- constant weights may be read before it.
-// Stream capture records these launches as programmatic edges of the CUDA graph.  FOTS_B200_PDL=0 launches everything
-// with full stream serialisation (A/B switch; the in-kernel instructions are then no-ops).
+// Stream capture records these launches as programmatic edges of the CUDA graph.
+// MEASURED on B200 (tools/step_time.py, CUDA-graph replay of the end-to-end step): no gain -- graph replay already hides the
+// launch latency, what a small launch costs is its own chain of DRAM round trips -- and a LOSS on large batches, where the
+// early-resident waiting CTAs get in the way of the running grid: 8-image step 3.787 (on) vs 3.805 ms (off), 32-image
+// micro-batch 14.28 (on) vs 13.74 ms (off).  So it is OFF by default (launches are fully stream-serialised and the in-kernel
+// instructions are no-ops); FOTS_B200_PDL=1 switches it on (eager, launch-bound callers).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -20,7 +24,7 @@ __device__ __forceinline__ void wait() { asm volatile("griddepcontrol.wait;" :::
 __device__ __forceinline__ void trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 inline bool enabled() {
-    static const bool on = [] { const char* e = getenv("FOTS_B200_PDL"); return !(e && e[0] == '0'); }();
+    static const bool on = [] { const char* e = getenv("FOTS_B200_PDL"); return e && e[0] == '1'; }();
     return on;
 }
 

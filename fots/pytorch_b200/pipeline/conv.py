@@ -28,6 +28,8 @@ STATS_MAX_MB = float(os.environ.get("FOTS_B200_TC_STATS_MAX_MB", "0"))
 LEVEL = int(os.environ.get("FOTS_B200_TC_LEVEL", "2"))
 # A/B switch: compute the 2x upsampling of the top-down merge inside the depthwise kernel (1) or as its own kernel (0)
 DW_UP = os.environ.get("FOTS_B200_DW_UP", "1") != "0"
+# A/B switch: fold the last top-down level into the heads when the caller does not need the 256-channel map (inference)
+MERGED_HEADS = os.environ.get("FOTS_B200_MERGED_HEADS", "1") != "0"
 
 
 def _lib():
@@ -338,6 +340,45 @@ def maxpool(x, kernel, stride, padding):
                                            torch.cuda.current_stream(x.device).cuda_stream)
     _cabi.check(rc, "fots_b200_maxpool_nhwc_bf16")
     return y
+
+
+def pack_merged_heads(act, rbox, angle, pw_conv, lateral_conv):
+    """Fold the last level of the top-down merge into the heads (fots_b200_heads_merged_nhwc_bf16): with the head block
+    Wh [8, 256] (pack_heads layout), x = pw_conv(d) + lateral_conv(s) * gate gives logits = (Wh Wpw) d + gate * (Wh Wlat) s + bh.
+    Returns (w1 bf16 [8, 256], w2 bf16 [8, Cs], bias fp32 [8]) or None when a convolution carries a bias (it would need the gate)."""
+    if pw_conv.bias is not None or lateral_conv.bias is not None:
+        return None
+    C = act.in_channels
+    wh = torch.zeros((8, C), dtype=torch.float32, device=act.weight.device)
+    bh = torch.zeros((8,), dtype=torch.float32, device=act.weight.device)
+    wh[0] = act.weight.detach().float()[0, :, 0, 0]
+    wh[2:6] = rbox.weight.detach().float()[:, :, 0, 0]
+    wh[6:8] = angle.weight.detach().float()[:, :, 0, 0]
+    bh[0] = act.bias.detach().float()[0]
+    bh[2:6] = rbox.bias.detach().float()
+    bh[6:8] = angle.bias.detach().float()
+    w1 = wh @ pw_conv.weight.detach().float()[:, :, 0, 0]                     # [8, 256]
+    w2 = wh @ lateral_conv.weight.detach().float()[:, :, 0, 0]                # [8, Cs]
+    return w1.to(torch.bfloat16).contiguous(), w2.to(torch.bfloat16).contiguous(), bh.contiguous()
+
+
+def heads_merged(d, s, gate_prob, packed):
+    """(seg, rbox, angle) fp32 from d bf16 [B, 256, H, W], s bf16 [B, 64, H, W] (both channels-last) and the low-resolution
+    gate probabilities bf16 [B, 1, gh, gw] in one pass over d and s (see pack_merged_heads)."""
+    B, C1, H, W = d.shape
+    C2 = s.size(1)
+    seg = torch.empty((B, 1, H, W), dtype=torch.float32, device=d.device)
+    rbox = torch.empty((B, 4, H, W), dtype=torch.float32, device=d.device)
+    ang = torch.empty((B, 2, H, W), dtype=torch.float32, device=d.device)
+    L = _lib()
+    L.fots_b200_heads_merged_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_heads_merged_nhwc_bf16.argtypes = [ctypes.c_void_p] * 9 + [ctypes.c_int] * 7 + [ctypes.c_void_p]
+    with torch.cuda.device(d.device):
+        rc = L.fots_b200_heads_merged_nhwc_bf16(d.data_ptr(), packed[0].data_ptr(), s.data_ptr(), packed[1].data_ptr(), gate_prob.data_ptr(),
+                                                packed[2].data_ptr(), seg.data_ptr(), rbox.data_ptr(), ang.data_ptr(), B, H, W, C1, C2,
+                                                gate_prob.size(2), gate_prob.size(3), torch.cuda.current_stream(d.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_heads_merged_nhwc_bf16")
+    return seg, rbox, ang
 
 
 def stem_eligible(x, conv):

@@ -59,7 +59,8 @@ class FOTSPipeline:
         b, R, _ = quads.shape
         x = images.contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
-            seg, rbox, angle, feats = self.net(x)
+            # inference needs the full-resolution heads and the recogniser's map only
+            seg, rbox, angle, feats = self.net(x, need_features=False) if getattr(self.net, "HEADS_ONLY_FORWARD", False) else self.net(x)
         bidx = torch.arange(b, device=quads.device, dtype=torch.int32).repeat_interleave(R)
         rois = boxes_to_rois(quads.reshape(b * R, 9), bidx)
         focr = feats[1]
@@ -161,7 +162,7 @@ class FOTSPipeline:
         def head_part(i):
             x = images[i * micro:(i + 1) * micro].contiguous(memory_format=torch.channels_last)
             with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
-                seg, rbox, angle, feats = self.net(x)
+                seg, rbox, angle, feats = self.net(x, need_features=False) if getattr(self.net, "HEADS_ONLY_FORWARD", False) else self.net(x)
             s0, r0, a0 = seg[0].float().contiguous(), rbox[0].float().contiguous(), angle[0].float().contiguous()
             if override_maps is not None:                      # planted maps overwrite what the heads produced
                 s0.copy_(override_maps[0][i * micro:(i + 1) * micro])

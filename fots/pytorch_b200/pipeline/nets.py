@@ -150,6 +150,7 @@ class FOTSNet(nn.Module):
     """
 
     STAGES = ((_ResIN, 64, 3, 1), (_ResIN, 128, 4, 2), (_ResSepIN, 256, 6, 2), (_ResSepIN, 512, 4, 2))
+    HEADS_ONLY_FORWARD = True          # forward(x, need_features=False) exists (FOTSPipeline asks for it)
 
     def __init__(self, attention=False, multi_scale=True, nclass=7500):
         super().__init__()
@@ -220,15 +221,18 @@ class FOTSNet(nn.Module):
         ang = ang / torch.sqrt((ang * ang).sum(1, keepdim=True))
         return seg, rbox, ang
 
-    def forward(self, x):
+    def forward(self, x, need_features=True):
+        """need_features=False (inference): the caller only wants the full-resolution heads and the recogniser's map --
+        returns ([seg], [rbox], [angle], [None, focr]) and, on the B200 fast path, folds the last top-down level into the heads
+        (conv.pack_merged_heads: the 256-channel map at 1/4 scale and the 1/8-scale auxiliary heads are never computed)."""
         focr = self.forward_features(x)
         s3 = self.layer1(self.drop1(focr))
         s2 = self.layer2(s3)
         s1 = self.layer3(s2)
         pw = lambda conv, t: tc.apply(conv, t, 1.0, level=2)              # 1x1 laterals
-        f1, f2, f3 = pw(self.feature1, s3), pw(self.feature2, s2), pw(self.feature3, s1)
+        f2, f3 = pw(self.feature2, s2), pw(self.feature3, s1)
         f4 = pw(self.feature4, self.drop1(self.layer4(s1)))
-        if fused.merge_eligible(f1, f2, f3, f4):
+        if fused.merge_eligible(f2, f3, f4) and fused.merge_eligible(s3):
             # inference fast path: each merge step is one fused kernel (upsample + attention gate + add)
             apack = getattr(self, "_att_pack", None)
             if self.attention and apack is not None and tc.LEVEL >= 2 and f4.size(1) in (128, 256, 512):
@@ -247,8 +251,24 @@ class FOTSNet(nn.Module):
                     return pw(seq[1], tc.dwconv_up(seq[0], lo, size))
                 return pw(seq[1], tc.dwconv(seq[0], fused.fpn_merge(a_lo=lo, size=size)))
             f2 = fused.fpn_merge(c_hi=up(self.upconv1, x, f2.shape[2:]), b_hi=f2, **gate(x))
-            x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, **gate(f2))
-        elif self.attention:
+            mh = getattr(self, "_merged_heads", None)
+            g2 = gate(f2)
+            if (not need_features and mh is not None and tc.MERGED_HEADS and tc.LEVEL >= 2 and not self.training and "gate_prob_lo" in g2
+                    and tc.DW_UP and tc.dw_eligible(f2, self.upconv2[0]) and f2.size(1) == 256 and s3.size(1) == 64):
+                d = tc.dwconv_up(self.upconv2[0], f2, s3.shape[2:])
+                seg, rbox, ang = tc.heads_merged(d, s3, g2["gate_prob_lo"], mh)
+                return [seg], [rbox], [ang], [None, focr]
+            f1 = pw(self.feature1, s3)
+            x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, **g2)
+            if not need_features:
+                seg, rbox, ang = self._heads(x)
+                return [seg], [rbox], [ang], [None, focr]
+            seg2, rbox2, ang2 = self._heads(f2)
+            x = self.drop1(x)
+            seg, rbox, ang = self._heads(x)
+            return [seg, seg2], [rbox, rbox2], [ang, ang2], [x, focr]
+        f1 = pw(self.feature1, s3)
+        if self.attention:
             # (the reference upsamples the gate expanded to all channels; upsampling the one-channel gate and broadcasting is
             # the same arithmetic per element)
             x = _up(f4, f3) + f3 * self._gate(f4, f3)
@@ -297,7 +317,7 @@ class FOTSNet(nn.Module):
         re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
         batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
         self.to(device=device, memory_format=torch.channels_last)
-        self._conv11_pad = self._heads_pack = self._l0c1_pairs = self._att_pack = None
+        self._conv11_pad = self._heads_pack = self._l0c1_pairs = self._att_pack = self._merged_heads = None
         if inference:
             for m in self.modules():
                 if isinstance(m, nn.Conv2d):
@@ -314,6 +334,8 @@ class FOTSNet(nn.Module):
             self._heads_pack = tc.pack_heads(self.act, self.rbox, self.angle)
             if self.attention:
                 self._att_pack = tc.pack_to1(self.conv_attenton)
+                # the last top-down level folded into the heads (forward(..., need_features=False))
+                self._merged_heads = tc.pack_merged_heads(self.act, self.rbox, self.angle, self.upconv2[1], self.feature1)
             c01 = self.layer0[2]
             if c01.in_channels == 32 and c01.out_channels == 32 and c01.bias is None:
                 self._l0c1_pairs = tc.pack_pixel_pairs_s2(c01.weight.detach())

@@ -252,6 +252,16 @@ int fots_b200_instnorm_crelu_bwd_nhwc_bf16(const void* x, const void* y, const v
 /* Backward of the align_corners bilinear upsampling of the top-down merge (the a_lo-only form of fots_b200_fpn_merge_nhwc_bf16;
  * tools/models.py:411-438 F.interpolate under autograd): dlo bf16 [B, h, w, C] = U^T dhi bf16 [B, H, W, C].  Gather form, no atomics. */
 int fots_b200_upsample_bilinear_bwd_nhwc_bf16(const void* dhi, void* dlo, int B, int h, int w, int H, int W, int C, cudaStream_t stream);
+/* The last level of the top-down merge collapsed into the detection heads (inference; tools/models.py:430-456).  There
+ *     x = upconv2_pw(d) + feature1(s) * upsample(sigmoid(conv_attenton(f2))),   heads = squash(Wh x + bh)
+ * and x feeds nothing but the heads, so with the products Wh Wpw (8 x 256) and Wh Wf1 (8 x 64) folded by the caller
+ *     logits = w1 . x1 + upsample(gate_prob) * (w2 . x2) + bias
+ * x1 = d bf16 [B, H, W, 256] (the depthwise half of upconv2), x2 = s bf16 [B, H, W, 64] (the stage-1 output), gate_prob bf16
+ * [B, gh, gw]; w1 / w2 in the 8-row head layout of fots_b200_heads_nhwc_bf16, outputs as there.  The pointwise 256 -> 256 and
+ * lateral 64 -> 256 convolutions, the merge kernel and the 256-channel map x are never computed. */
+int fots_b200_heads_merged_nhwc_bf16(const void* x1, const void* w1, const void* x2, const void* w2, const void* gate_prob,
+                                     const float* bias, float* seg, float* rbox, float* angle, int B, int H, int W, int C1, int C2,
+                                     int gh, int gw, cudaStream_t stream);
 /* Consumer B's first layer (tools/models.py:853-897, CRNN.cnn conv0 + relu0 + pooling0): 3 input channels cannot fill a
  * k-block of the tcgen05 kernel.  x fp32 NCHW [N, 3, H, W] (RoIRotate of the raw image, src/utils.py:430-436), w bf16
  * [Cout, 3, 3, 3] contiguous, bias fp32 [Cout] or NULL -> y bf16 NHWC = maxpool2x2(relu(conv3x3_pad1(x) + bias)) when

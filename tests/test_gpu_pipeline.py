@@ -434,6 +434,42 @@ def test_general_maxpool_kernel_equals_torch(cuda, N, C, H, W, k, s, p):
     assert torch.equal(torch.nan_to_num(got.float(), nan=12345.0), torch.nan_to_num(ref, nan=12345.0))
 
 
+def test_last_merge_level_folded_into_the_heads(cuda):
+    """FOTSNet.forward(x, need_features=False) on the B200 inference path folds upconv2's pointwise convolution, the feature1
+    lateral and the last merge into the head weights (fots_b200_heads_merged_nhwc_bf16): the full-resolution heads must agree with
+    the materialised path (same bf16 kernels, the 256-channel map written and re-read) to bf16 noise, and with the fp32 torch
+    network as closely as that path does."""
+    from fots.pytorch_b200.pipeline import FOTSNet
+    from fots.pytorch_b200.pipeline import conv as TC
+    torch.manual_seed(3)
+    net = FOTSNet(attention=True, nclass=89).to(cuda).eval()
+    x = torch.randn(2, 3, 192, 320, device=cuda)
+    with torch.no_grad():
+        ref = net(x)                                                    # fp32, torch ops
+        net.to_b200(cuda, inference=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            full = net(x.contiguous(memory_format=torch.channels_last))
+            fold = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
+    assert net._merged_heads is not None and len(fold[0]) == 1 and fold[3][0] is None
+    assert torch.equal(fold[3][1], full[3][1])                           # the recogniser's map is the same tensor
+    for k, name, scale in ((0, "seg", 1.0), (1, "rbox", 128.0), (2, "angle", 1.0)):
+        a, b, r = fold[k][0].float(), full[k][0].float(), ref[k][0].float()
+        assert a.shape == b.shape == r.shape
+        # vs the materialised bf16 path: one bf16 rounding of x (and of the folded weights) apart
+        assert float((a - b).abs().mean()) <= 4e-3 * scale, (name, float((a - b).abs().mean()))
+        # vs fp32: not worse than the materialised path by more than noise
+        ea, eb = float((a - r).abs().mean()), float((b - r).abs().mean())
+        assert ea <= 1.25 * eb + 2e-3 * scale, (name, ea, eb)
+    # the switch keeps the materialised path reachable
+    TC.MERGED_HEADS = False
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            plain = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
+    finally:
+        TC.MERGED_HEADS = True
+    assert torch.equal(plain[0][0], full[0][0]) and torch.equal(plain[1][0], full[1][0])
+
+
 def test_step_with_detector_postprocessing_in_the_loop(cuda):
     """FOTSPipeline.capture_with_detection: backbone + heads -> planted maps overwrite the head outputs -> GPU decode ->
     host merge (thread pool) -> RoIs -> RoIRotate -> recogniser, two CUDA graphs per micro-batch.  The boxes the merge
