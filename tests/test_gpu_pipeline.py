@@ -451,7 +451,10 @@ def test_last_merge_level_folded_into_the_heads(cuda):
             full = net(x.contiguous(memory_format=torch.channels_last))
             fold = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
     assert net._merged_heads is not None and len(fold[0]) == 1 and fold[3][0] is None
-    assert torch.equal(fold[3][1], full[3][1])                           # the recogniser's map is the same tensor
+    # the recogniser's map comes from the same kernels in both calls; the InstanceNorm statistics are fp64 atomic sums whose
+    # order varies between launches, so a value may land on the other side of a bf16 rounding boundary
+    fa, fb = fold[3][1].float(), full[3][1].float()
+    assert float((fa - fb).abs().max()) <= 2.0 ** -7 * float(fb.abs().max())
     for k, name, scale in ((0, "seg", 1.0), (1, "rbox", 128.0), (2, "angle", 1.0)):
         a, b, r = fold[k][0].float(), full[k][0].float(), ref[k][0].float()
         assert a.shape == b.shape == r.shape
@@ -467,7 +470,7 @@ def test_last_merge_level_folded_into_the_heads(cuda):
             plain = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
     finally:
         TC.MERGED_HEADS = True
-    assert torch.equal(plain[0][0], full[0][0]) and torch.equal(plain[1][0], full[1][0])
+    assert float((plain[0][0] - full[0][0]).abs().max()) <= 2e-2 and float((plain[1][0] - full[1][0]).abs().max()) <= 2e-2 * 128
 
 
 def test_step_with_detector_postprocessing_in_the_loop(cuda):
