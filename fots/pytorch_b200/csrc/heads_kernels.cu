@@ -23,6 +23,24 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// 32-byte load (sm_100 LDG.256): the four lanes of a pixel row then cover one whole 128-byte line per instruction -- with 16-byte
+// loads a warp-level load touched 16 lines for 1 KB and the kernels were bound by L1 wavefronts (3.8 TB/s), not by HBM.
+struct U8 { uint32_t r[8]; };
+__device__ __forceinline__ U8 ldg256(const void* p) {
+    U8 v;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7]) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ U8 zero256() { U8 v; for (int i = 0; i < 8; ++i) v.r[i] = 0u; return v; }
+// acc += A(16 channels of rows g, g + 8) . B(the same 16 channels of head g): four k16 steps' worth of register pairs
+__device__ __forceinline__ void mma_u8(float (&acc)[4], const U8& a, const U8& b, const U8& w) {
+    mma_16816(acc, a.r[0], b.r[0], a.r[1], b.r[1], w.r[0], w.r[1]);
+    mma_16816(acc, a.r[2], b.r[2], a.r[3], b.r[3], w.r[2], w.r[3]);
+    mma_16816(acc, a.r[4], b.r[4], a.r[5], b.r[5], w.r[4], w.r[5]);
+    mma_16816(acc, a.r[6], b.r[6], a.r[7], b.r[7], w.r[6], w.r[7]);
+}
+
 // Squashing + store of one pixel's two columns (2t, 2t + 1) of the 8-column head block {act, 0, rbox0..3, angle0, angle1}.
 __device__ __forceinline__ void heads_store(int t, float v0, float v1, long long p, int HW, float* __restrict__ seg, float* __restrict__ rbox,
                                             float* __restrict__ angle) {
@@ -42,10 +60,10 @@ __device__ __forceinline__ void heads_store(int t, float v0, float v1, long long
     }
 }
 
-// Logical k of the MMA <-> physical channel.  Lane (g = lane / 4, t = lane % 4) loads, for load m, the 8 channels
-// 32 m + 8 t .. + 7 of pixel rows g and g + 8 (the four t-lanes of a pixel read 64 contiguous bytes); k-step 2m consumes
-// the first four of them (k = 2t, 2t+1 | 2t+8, 2t+9), k-step 2m+1 the last four.  The B fragment of lane (g, t) is head g at
-// the same channels, so the permutation cancels in the dot product.
+// Logical k of the MMA <-> physical channel.  Lane (g = lane / 4, t = lane % 4) loads, for load m, the 16 channels
+// 64 m + 16 t .. + 15 of pixel rows g and g + 8 (the four t-lanes of a pixel read 128 contiguous bytes = one line); four k-steps
+// consume them four channels at a time (k = 2t, 2t+1 | 2t+8, 2t+9).  The B fragment of lane (g, t) is head g at the same
+// channels, so the permutation cancels in the dot product.
 // wq: [8 heads][C] bf16, column order {act, 0, rbox0..3, angle0, angle1};  bias: [8] fp32 in the same order.
 // RAW: a 1x1 convolution to ONE output channel (the attention gate of the top-down merge, tools/models.py:405-438:
 // conv_attenton = Conv2d(256, 1, 1)): column 0 + bias, no squashing, written as bf16 [npix] -- the logits
@@ -54,37 +72,31 @@ template <int C, int RAW>
 __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ wq,
                                                     const float* __restrict__ bias, float* __restrict__ seg, float* __restrict__ rbox,
                                                     float* __restrict__ angle, long long npix, int HW) {
-    constexpr int NL = C / 32;                        // 16-byte loads per pixel row and lane
+    constexpr int NL = C / 64;                        // 32-byte loads per pixel row and lane
     pdl::trigger();                                   // the weights / bias below are constants: loaded before pdl::wait()
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    // this lane's weights: head g, channels 32 m + 8 t .. + 7 -> four 32-bit registers per m
-    uint32_t wb[NL][4];
+    // this lane's weights: head g, channels 64 m + 16 t .. + 15 -> eight 32-bit registers per m
+    U8 wb[NL];
 #pragma unroll
-    for (int m = 0; m < NL; ++m) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(wq + (size_t)g * C + m * 32 + t * 8));
-        wb[m][0] = v.x; wb[m][1] = v.y; wb[m][2] = v.z; wb[m][3] = v.w;
-    }
+    for (int m = 0; m < NL; ++m) wb[m] = ldg256(wq + (size_t)g * C + m * 64 + t * 16);
     const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
     pdl::wait();
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long ntiles = (npix + 15) / 16;
-    constexpr int CV = C / 8;
+    const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(x);
     for (long long tile = warp0; tile < ntiles; tile += nwarps) {
         const long long p0 = tile * 16 + g, p1 = p0 + 8;
         const bool ok0 = p0 < npix, ok1 = p1 < npix;
-        uint4 xa[NL], xb[NL];
+        U8 xa[NL], xb[NL];
 #pragma unroll
         for (int m = 0; m < NL; ++m) {
-            xa[m] = ok0 ? __ldg(x + p0 * CV + m * 4 + t) : make_uint4(0, 0, 0, 0);
-            xb[m] = ok1 ? __ldg(x + p1 * CV + m * 4 + t) : make_uint4(0, 0, 0, 0);
+            xa[m] = ok0 ? ldg256(xe + p0 * C + m * 64 + t * 16) : zero256();
+            xb[m] = ok1 ? ldg256(xe + p1 * C + m * 64 + t * 16) : zero256();
         }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < NL; ++m) {
-            mma_16816(acc, xa[m].x, xb[m].x, xa[m].y, xb[m].y, wb[m][0], wb[m][1]);
-            mma_16816(acc, xa[m].z, xb[m].z, xa[m].w, xb[m].w, wb[m][2], wb[m][3]);
-        }
+        for (int m = 0; m < NL; ++m) mma_u8(acc, xa[m], xb[m], wb[m]);
         // acc[0], acc[1] = (pixel p0, columns 2t, 2t+1); acc[2], acc[3] = (pixel p1, same columns)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -115,20 +127,14 @@ __global__ void __launch_bounds__(256) heads_dual_kernel(const uint4* __restrict
                                                          const __nv_bfloat16* __restrict__ gate, const float* __restrict__ bias,
                                                          float* __restrict__ seg, float* __restrict__ rbox, float* __restrict__ angle,
                                                          long long npix, int H, int W, int gh, int gw) {
-    constexpr int N1 = C1 / 32, N2 = C2 / 32;
+    constexpr int N1 = C1 / 64, N2 = C2 / 64;
     pdl::trigger();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    uint32_t wa[N1][4], wb[N2][4];
+    U8 wa[N1], wb[N2];
 #pragma unroll
-    for (int m = 0; m < N1; ++m) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w1 + (size_t)g * C1 + m * 32 + t * 8));
-        wa[m][0] = v.x; wa[m][1] = v.y; wa[m][2] = v.z; wa[m][3] = v.w;
-    }
+    for (int m = 0; m < N1; ++m) wa[m] = ldg256(w1 + (size_t)g * C1 + m * 64 + t * 16);
 #pragma unroll
-    for (int m = 0; m < N2; ++m) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w2 + (size_t)g * C2 + m * 32 + t * 8));
-        wb[m][0] = v.x; wb[m][1] = v.y; wb[m][2] = v.z; wb[m][3] = v.w;
-    }
+    for (int m = 0; m < N2; ++m) wb[m] = ldg256(w2 + (size_t)g * C2 + m * 64 + t * 16);
     const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
     pdl::wait();
     const int HW = H * W;
@@ -148,33 +154,28 @@ __global__ void __launch_bounds__(256) heads_dual_kernel(const uint4* __restrict
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long ntiles = (npix + 15) / 16;
-    constexpr int CV1 = C1 / 8, CV2 = C2 / 8;
+    const __nv_bfloat16* x1e = reinterpret_cast<const __nv_bfloat16*>(x1);
+    const __nv_bfloat16* x2e = reinterpret_cast<const __nv_bfloat16*>(x2);
     for (long long tile = warp0; tile < ntiles; tile += nwarps) {
         const long long p0 = tile * 16 + g, p1 = p0 + 8;
         const bool ok0 = p0 < npix, ok1 = p1 < npix;
-        uint4 xa[N1], xb[N1], ya[N2], yb[N2];
+        U8 xa[N1], xb[N1], ya[N2], yb[N2];
 #pragma unroll
         for (int m = 0; m < N1; ++m) {
-            xa[m] = ok0 ? __ldg(x1 + p0 * CV1 + m * 4 + t) : make_uint4(0, 0, 0, 0);
-            xb[m] = ok1 ? __ldg(x1 + p1 * CV1 + m * 4 + t) : make_uint4(0, 0, 0, 0);
+            xa[m] = ok0 ? ldg256(x1e + p0 * C1 + m * 64 + t * 16) : zero256();
+            xb[m] = ok1 ? ldg256(x1e + p1 * C1 + m * 64 + t * 16) : zero256();
         }
 #pragma unroll
         for (int m = 0; m < N2; ++m) {
-            ya[m] = ok0 ? __ldg(x2 + p0 * CV2 + m * 4 + t) : make_uint4(0, 0, 0, 0);
-            yb[m] = ok1 ? __ldg(x2 + p1 * CV2 + m * 4 + t) : make_uint4(0, 0, 0, 0);
+            ya[m] = ok0 ? ldg256(x2e + p0 * C2 + m * 64 + t * 16) : zero256();
+            yb[m] = ok1 ? ldg256(x2e + p1 * C2 + m * 64 + t * 16) : zero256();
         }
         const float g0 = ok0 ? gate_at(p0) : 0.0f, g1 = ok1 ? gate_at(p1) : 0.0f;
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, acs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < N1; ++m) {
-            mma_16816(acc, xa[m].x, xb[m].x, xa[m].y, xb[m].y, wa[m][0], wa[m][1]);
-            mma_16816(acc, xa[m].z, xb[m].z, xa[m].w, xb[m].w, wa[m][2], wa[m][3]);
-        }
+        for (int m = 0; m < N1; ++m) mma_u8(acc, xa[m], xb[m], wa[m]);
 #pragma unroll
-        for (int m = 0; m < N2; ++m) {
-            mma_16816(acs, ya[m].x, yb[m].x, ya[m].y, yb[m].y, wb[m][0], wb[m][1]);
-            mma_16816(acs, ya[m].z, yb[m].z, ya[m].w, yb[m].w, wb[m][2], wb[m][3]);
-        }
+        for (int m = 0; m < N2; ++m) mma_u8(acs, ya[m], yb[m], wb[m]);
         if (ok0) heads_store(t, fmaf(g0, acs[0], acc[0]) + b0, fmaf(g0, acs[1], acc[1]) + b1, p0, HW, seg, rbox, angle);
         if (ok1) heads_store(t, fmaf(g1, acs[2], acc[2]) + b0, fmaf(g1, acs[3], acc[3]) + b1, p1, HW, seg, rbox, angle);
     }
@@ -186,7 +187,7 @@ extern "C" int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const fl
                                          int B, int H, int W, int C, cudaStream_t stream) {
     if (!x || !wq || !bias || !seg || !rbox || !angle || B <= 0 || H <= 0 || W <= 0) return RROI_B200_ERR_INVALID_ARG;
     if (C != 128 && C != 256 && C != 512) return RROI_B200_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 31) return RROI_B200_ERR_INVALID_ARG;      // 32-byte loads
     const long long npix = (long long)B * H * W;
     const long long tiles = (npix + 15) / 16;
     long long ctas = (tiles + 7) / 8;
@@ -207,7 +208,7 @@ extern "C" int fots_b200_conv1x1_to1_nhwc_bf16(const void* x, const void* wq, co
                                                int sigmoid, cudaStream_t stream) {
     if (!x || !wq || !bias || !out || B <= 0 || H <= 0 || W <= 0) return RROI_B200_ERR_INVALID_ARG;
     if (C != 128 && C != 256 && C != 512) return RROI_B200_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 15) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wq)) & 31) return RROI_B200_ERR_INVALID_ARG;      // 32-byte loads
     const long long npix = (long long)B * H * W;
     const long long tiles = (npix + 15) / 16;
     long long ctas = (tiles + 7) / 8;
@@ -238,7 +239,7 @@ extern "C" int fots_b200_heads_merged_nhwc_bf16(const void* x1, const void* w1, 
     if (!x1 || !w1 || !x2 || !w2 || !gate_prob || !bias || !seg || !rbox || !angle || B <= 0 || H <= 0 || W <= 0 || gh <= 0 || gw <= 0)
         return RROI_B200_ERR_INVALID_ARG;
     if (C1 != 256 || C2 != 64) return RROI_B200_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(w2)) & 15)
+    if ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(w2)) & 31)
         return RROI_B200_ERR_INVALID_ARG;
     const long long npix = (long long)B * H * W;
     const long long tiles = (npix + 15) / 16;
