@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint4* __restrict__ x,
 // merge kernel and the 236 MB map x itself (written once, read twice per 8 images) disappear: this kernel reads d and s once.
 // Same fragment scheme as heads_kernel; the gate is interpolated per pixel with the merge kernel's arithmetic.
 template <int C1, int C2>
-__global__ void __launch_bounds__(256) heads_dual_kernel(const uint4* __restrict__ x1, const __nv_bfloat16* __restrict__ w1,
+__global__ void __launch_bounds__(256, 2) heads_dual_kernel(const uint4* __restrict__ x1, const __nv_bfloat16* __restrict__ w1,
                                                          const uint4* __restrict__ x2, const __nv_bfloat16* __restrict__ w2,
                                                          const __nv_bfloat16* __restrict__ gate, const float* __restrict__ bias,
                                                          float* __restrict__ seg, float* __restrict__ rbox, float* __restrict__ angle,
@@ -130,11 +130,16 @@ __global__ void __launch_bounds__(256) heads_dual_kernel(const uint4* __restrict
     constexpr int N1 = C1 / 64, N2 = C2 / 64;
     pdl::trigger();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    U8 wa[N1], wb[N2];
+    // weight fragments of every lane in shared memory ([m][lane] x 32 bytes, read back as two LDS.128 right before the MMAs):
+    // kept in registers they push the kernel to 156 registers = one CTA per SM, too few warps for a streaming kernel
+    __shared__ __align__(32) U8 wsm[(N1 + N2) * 32];
+    if (threadIdx.x < 32) {
 #pragma unroll
-    for (int m = 0; m < N1; ++m) wa[m] = ldg256(w1 + (size_t)g * C1 + m * 64 + t * 16);
+        for (int m = 0; m < N1; ++m) wsm[m * 32 + lane] = ldg256(w1 + (size_t)g * C1 + m * 64 + t * 16);
 #pragma unroll
-    for (int m = 0; m < N2; ++m) wb[m] = ldg256(w2 + (size_t)g * C2 + m * 64 + t * 16);
+        for (int m = 0; m < N2; ++m) wsm[(N1 + m) * 32 + lane] = ldg256(w2 + (size_t)g * C2 + m * 64 + t * 16);
+    }
+    __syncthreads();
     const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
     pdl::wait();
     const int HW = H * W;
@@ -173,9 +178,9 @@ __global__ void __launch_bounds__(256) heads_dual_kernel(const uint4* __restrict
         const float g0 = ok0 ? gate_at(p0) : 0.0f, g1 = ok1 ? gate_at(p1) : 0.0f;
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, acs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < N1; ++m) mma_u8(acc, xa[m], xb[m], wa[m]);
+        for (int m = 0; m < N1; ++m) mma_u8(acc, xa[m], xb[m], wsm[m * 32 + lane]);
 #pragma unroll
-        for (int m = 0; m < N2; ++m) mma_u8(acs, ya[m], yb[m], wb[m]);
+        for (int m = 0; m < N2; ++m) mma_u8(acs, ya[m], yb[m], wsm[(N1 + m) * 32 + lane]);
         if (ok0) heads_store(t, fmaf(g0, acs[0], acc[0]) + b0, fmaf(g0, acs[1], acc[1]) + b1, p0, HW, seg, rbox, angle);
         if (ok1) heads_store(t, fmaf(g1, acs[2], acc[2]) + b0, fmaf(g1, acs[3], acc[3]) + b1, p1, HW, seg, rbox, angle);
     }
