@@ -86,3 +86,28 @@ def test_shapes_and_channels_last():
         assert torch.allclose(lp.exp().sum(1), torch.ones(2, 40), atol=1e-4)
     with pytest.raises(ValueError):
         CRNN(nclass=10)(torch.randn(1, 3, 48, 64))
+
+
+def test_folded_head_weights_reproduce_the_last_merge_level():
+    """conv.pack_merged_heads (host algebra behind fots_b200_heads_merged_nhwc_bf16): with x = upconv2_pw(d) + feature1(s) * gate
+    (tools/models.py:430-438) the head logits Wh x + bh equal (Wh Wpw) d + gate * (Wh Wf1) s + bh.  Checked on the CPU in fp32
+    against the modules themselves; the packed weights are bf16, hence the tolerance."""
+    from fots.pytorch_b200.pipeline import conv as TC
+    torch.manual_seed(5)
+    net = FOTSNet(attention=True, nclass=20).eval()
+    d, s = torch.randn(2, 256, 6, 10), torch.randn(2, 64, 6, 10)
+    gate = torch.rand(2, 1, 6, 10)
+    with torch.no_grad():
+        x = net.upconv2[1](d) + net.feature1(s) * gate
+        want = torch.cat((net.act(x), torch.zeros_like(net.act(x)), net.rbox(x), net.angle(x)), 1)       # the kernel's 8-column block
+        w1, w2, b = TC.pack_merged_heads(net.act, net.rbox, net.angle, net.upconv2[1], net.feature1)
+        got = (torch.einsum("jc,bchw->bjhw", w1.float(), d) + gate * torch.einsum("jc,bchw->bjhw", w2.float(), s)
+               + b.view(1, 8, 1, 1))
+    assert w1.shape == (8, 256) and w2.shape == (8, 64) and b.shape == (8,)
+    live = [0, 2, 3, 4, 5, 6, 7]
+    err = (got[:, live] - want[:, live]).abs().max()
+    assert float(err) <= 2.0 ** -7 * float(want.abs().max()) + 1e-3, float(err)
+    assert float(got[:, 1].abs().max()) == 0.0                                                           # the padding column stays empty
+    # a convolution with a bias cannot be folded behind the gate: the packer declines
+    biased = torch.nn.Conv2d(64, 256, 1, bias=True)
+    assert TC.pack_merged_heads(net.act, net.rbox, net.angle, net.upconv2[1], biased) is None
