@@ -421,17 +421,136 @@ rroi_fwd_nchw_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap 
 //      same 4-FFMA chain, and stores 32 consecutive pw per warp (128-byte coalesced).
 // Tiles whose footprint does not fit (more than 96 rows or 20 KB per channel) or planes whose rows are not 16-byte
 // aligned take the gather loop inside the same kernel.  Bit-identical to the gather kernel (and to the reference kernel, see tests/).
+// Template: S stages of SF floats each (dynamic shared memory); RING = S-deep ring with ONE barrier per stage (stage
+// st + S - 1 is issued right after the barrier that publishes stage st) instead of the two-barrier double buffer.
 constexpr int kRowsMax = 96;                      // image rows a tile's footprint may span
-constexpr int kStageFloats = 5120;                // floats per stage (20 KB); two stages
-constexpr int kGranMax = kStageFloats / 4;        // granules of one channel
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+struct RowsStageArgs {
+    float* stage0;            // S stages of SF floats
+    const int* gsrc;          // plane offset (floats) of every granule of the footprint
+    const float* plane0;      // channel 0 of the RoI's image
+    float* dst;               // this thread's bin in channel 0 of the RoI's output
+    size_t HW, bins;
+    int C, gtot;
+    bool live;
+    int o_lt, o_rt, o_lb, o_rb;       // float offsets of the four taps inside a channel slot (gtot * 4 = the zero granule)
+    float wlt, wrt, wrb, wlb;
+};
+
+// The staged channel loop for CGS channels per stage.  A stage is CGS slots of SF / CGS floats, so every shared-memory
+// address of the blend is (per-thread tap address of the stage) + (compile-time channel offset): LDS with an immediate,
+// no address arithmetic per channel.  Copies: warp w owns channel slot w % CGS and, with the 8 / CGS - 1 other warps of
+// that slot, walks the slot's granules 32 * (8 / CGS) apart -- consecutive lanes copy consecutive granules of one plane
+// (coalesced), the plane offsets of a thread's <= KP granules are loaded once, the destination of granule k is the
+// thread's first destination + a compile-time step, and the source plane advances by CGS planes per stage.
+template <int S, int SF, bool RING, int CGS>
+__device__ __forceinline__ void rows_stage_loop(const RowsStageArgs& a) {
+    constexpr int STRIDE = SF / CGS;                          // floats per channel slot
+    constexpr int WPC = 8 / CGS;                              // warps that share a slot
+    constexpr int KP = (SF / 4 - CGS + 255) / 256;            // granules per thread: ceil((STRIDE / 4 - 1) / (32 * WPC))
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nst = (a.C + CGS - 1) / CGS;
+    for (int i = threadIdx.x; i < S * CGS * 4; i += 256)      // the zero granule of every slot of every stage
+        a.stage0[(i >> 2) / CGS * SF + ((i >> 2) % CGS) * STRIDE + a.gtot * 4 + (i & 3)] = 0.0f;
+    const int ch = warp % CGS, g0 = (warp / CGS) * 32 + lane;
+    uint32_t soff[KP];
+    int nk = 0;                                               // granules this thread copies per stage
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int gi = g0 + k * 32 * WPC;
+        soff[k] = gi < a.gtot ? (uint32_t)a.gsrc[gi] : 0u;
+        nk += gi < a.gtot;
+    }
+    const uint32_t sbase = smem_addr(a.stage0);
+    const uint32_t cdst = sbase + (uint32_t)(ch * STRIDE + g0 * 4) * 4u;
+    const float* csrc = a.plane0 + (size_t)ch * a.HW;         // this warp's plane of stage 0; + CGS planes per issued stage
+    int issued = 0;
+    auto issue = [&]() {                                      // stages are issued in order: stage `issued` into buffer issued % S
+        if (issued * CGS + ch < a.C) {                        // warp-uniform (the last stage may hold fewer channels)
+            const uint32_t db = cdst + (uint32_t)(issued % S) * (uint32_t)(SF * 4);
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < nk) cp_async_16(db + k * (32 * WPC * 16), csrc + soff[k]);
+        }
+        csrc += (size_t)CGS * a.HW;
+        ++issued;
+    };
+    float* d = a.dst;
+    auto blend = [&](int st) {
+        const float* sb = a.stage0 + (st % S) * SF;
+        const float* q_lt = sb + a.o_lt; const float* q_rt = sb + a.o_rt;
+        const float* q_rb = sb + a.o_rb; const float* q_lb = sb + a.o_lb;
+        const int cn = min(CGS, a.C - st * CGS);
+        if (a.live) {
+            if (cn == CGS) {
+                float x[CGS][4];
+#pragma unroll
+                for (int ci = 0; ci < CGS; ++ci) {
+                    x[ci][0] = q_lt[ci * STRIDE]; x[ci][1] = q_rt[ci * STRIDE];
+                    x[ci][2] = q_rb[ci * STRIDE]; x[ci][3] = q_lb[ci * STRIDE];
+                }
+#pragma unroll
+                for (int ci = 0; ci < CGS; ++ci) {
+                    float v = __fmaf_rn(x[ci][0], a.wlt, 0.0f);
+                    v = __fmaf_rn(x[ci][1], a.wrt, v);
+                    v = __fmaf_rn(a.wrb, x[ci][2], v);
+                    v = __fmaf_rn(x[ci][3], a.wlb, v);
+                    d[ci * a.bins] = v;
+                }
+            } else {
+                for (int ci = 0; ci < cn; ++ci) {
+                    float v = __fmaf_rn(q_lt[ci * STRIDE], a.wlt, 0.0f);
+                    v = __fmaf_rn(q_rt[ci * STRIDE], a.wrt, v);
+                    v = __fmaf_rn(a.wrb, q_rb[ci * STRIDE], v);
+                    v = __fmaf_rn(q_lb[ci * STRIDE], a.wlb, v);
+                    d[ci * a.bins] = v;
+                }
+            }
+        }
+        d += (size_t)cn * a.bins;
+    };
+    __syncthreads();                                          // zero granules written before anybody blends
+    if (RING) {
+        // S-deep ring, one barrier per stage: the barrier of stage st says "everybody's copies of stage st have landed"
+        // AND "everybody has finished blending stage st - 1", so buffer (st - 1) % S = (st + S - 1) % S may be refilled.
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) {
+            if (k < nst) issue();
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int st = 0; st < nst; ++st) {
+            cp_async_wait<S - 2>();
+            __syncthreads();
+            if (st + S - 1 < nst) issue();
+            asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty: keeps the group count uniform)
+            blend(st);
+        }
+    } else {
+        issue();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int st = 0; st < nst; ++st) {
+            if (st + 1 < nst) { issue(); asm volatile("cp.async.commit_group;" ::: "memory"); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();                                  // everybody's copies of this stage have landed
+            blend(st);
+            __syncthreads();                                  // the buffer may be refilled (stage st + 2)
+        }
+    }
+}
+
+template <int S, int SF, bool RING>
 __global__ void __launch_bounds__(256) rroi_fwd_nchw_rows_kernel(const FwdParams p) {
-    __shared__ __align__(16) float stage[2][kStageFloats];
-    __shared__ int gsrc[kGranMax];                // plane offset (in floats) of every granule of the footprint
+    constexpr int kStageFloats = SF;              // floats per stage
+    constexpr int kGranMax = SF / 4;              // granules of one channel
+    static_assert(SF % 1024 == 0 && (RING || S == 2), "stage = whole rounds of 256 granules; the double buffer has two stages");
+    extern __shared__ __align__(16) unsigned char rows_smem[];
+    float (*stage)[kStageFloats] = reinterpret_cast<float (*)[kStageFloats]>(rows_smem);
+    int* gsrc = reinterpret_cast<int*>(rows_smem + (size_t)S * SF * 4);   // plane offset (in floats) of every granule of the footprint
     __shared__ int rlo[kRowsMax], rhi[kRowsMax], goff[kRowsMax + 1];
     __shared__ int ylim[2];                       // first / last image row of the footprint
     __shared__ RoiXform sX;
@@ -495,7 +614,7 @@ __global__ void __launch_bounds__(256) rroi_fwd_nchw_rows_kernel(const FwdParams
     __syncthreads();
     const int y0 = ylim[0], nrows = ylim[1] >= ylim[0] ? ylim[1] - ylim[0] + 1 : 0;
     const bool aligned = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.feat) & 15) == 0);
-    bool staged = aligned && nrows > 0 && nrows <= kRowsMax;                      // CTA-uniform
+    bool staged = aligned && nrows > 0 && nrows <= kRowsMax && (size_t)p.H * p.W <= (1u << 28);   // CTA-uniform (32-bit copy offsets)
     if (staged) {
         // ---- 2. per-row spans of the loaded taps
         if (top_used) {
@@ -552,14 +671,7 @@ __global__ void __launch_bounds__(256) rroi_fwd_nchw_rows_kernel(const FwdParams
 
     if (staged) {
         // Every staged channel is followed by one granule of zeros; a tap that is not loaded (border test, coinciding tap,
-        // bin outside the RoI) reads that zero, so the blend loop is branch-free: 4 LDS + 4 FFMA + 1 STG per channel.
-        const int chf = gtot * 4 + 4;                                             // floats per staged channel incl. the zero granule
-        const int cgs = min(8, kStageFloats / chf);                               // channels per stage (>= 1: gtot < kGranMax)
-        const int nst = (p.C + cgs - 1) / cgs;
-        for (int i = threadIdx.x; i < 2 * cgs * 4; i += 256) {
-            const int buf = i / (cgs * 4), rem = i - buf * cgs * 4;
-            stage[buf][(rem >> 2) * chf + gtot * 4 + (rem & 3)] = 0.0f;
-        }
+        // bin outside the RoI) reads that zero, so the blend is branch-free: 4 LDS + 4 FFMA + 1 STG per channel.
         const int zero = gtot * 4;
         int o_lt = zero, o_rt = zero, o_lb = zero, o_rb = zero;
         if (top_used) {
@@ -572,55 +684,16 @@ __global__ void __launch_bounds__(256) rroi_fwd_nchw_rows_kernel(const FwdParams
             if (code & C_LB) o_lb = o;
             if (code & C_RB) o_rb = o + 1;
         }
-        // The stage's (channel, granule) pairs are dealt to the threads 256 apart (consecutive threads copy consecutive
-        // granules of one plane: coalesced).  A stage holds at most kStageFloats / 4 = 1280 granules, i.e. at most 5 pairs
-        // per thread, and the pairs are the same for every stage -- so their shared-memory offset and their plane offset
-        // are computed once and kept in registers; issuing a stage is then <= 5 x (add, add, LDGSTS).
-        constexpr int kPairs = kStageFloats / 4 / 256;                            // 5
-        uint32_t pair_dst[kPairs];
-        long long pair_src[kPairs];
-        int pair_ci[kPairs];
-        {
-            int gi = threadIdx.x, ci = 0;
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) {
-                while (gi >= gtot && ci < cgs) { gi -= gtot; ++ci; }
-                pair_ci[k] = ci < cgs ? ci : 0x7fffffff;                           // past the stage: never issued
-                pair_dst[k] = (uint32_t)((ci * chf + gi * 4) * 4);
-                pair_src[k] = ci < cgs ? (long long)ci * (long long)HW + gsrc[gi] : 0;
-                gi += 256;
-            }
-        }
-        auto issue = [&](int st) {
-            const int c0 = st * cgs, cn = min(cgs, p.C - c0);
-            const uint32_t sb = smem_addr(stage[st & 1]);
-            const float* pl0 = plane0 + (size_t)c0 * HW;
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k)
-                if (pair_ci[k] < cn) cp_async_16(sb + pair_dst[k], pl0 + pair_src[k]);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        __syncthreads();                                                           // zero granules written before anybody blends
-        issue(0);
-        float* d = dst;
-        for (int st = 0; st < nst; ++st) {
-            if (st + 1 < nst) { issue(st + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();                                                       // everybody's copies of this stage have landed
-            const int cn = min(cgs, p.C - st * cgs);
-            if (live) {
-                const float* sc = stage[st & 1];
-#pragma unroll 2
-                for (int ci = 0; ci < cn; ++ci, sc += chf, d += bins) {
-                    float v = __fmaf_rn(sc[o_lt], wlt, 0.0f);
-                    v = __fmaf_rn(sc[o_rt], wrt, v);
-                    v = __fmaf_rn(wrb, sc[o_rb], v);
-                    v = __fmaf_rn(sc[o_lb], wlb, v);
-                    *d = v;
-                }
-            }
-            __syncthreads();                                                       // the buffer may be refilled (stage st + 2)
-        }
+        RowsStageArgs a;
+        a.stage0 = &stage[0][0]; a.gsrc = gsrc; a.plane0 = plane0; a.dst = dst; a.HW = HW; a.bins = (size_t)bins;
+        a.C = p.C; a.gtot = gtot; a.live = live;
+        a.o_lt = o_lt; a.o_rt = o_rt; a.o_lb = o_lb; a.o_rb = o_rb; a.wlt = wlt; a.wrt = wrt; a.wrb = wrb; a.wlb = wlb;
+        // channels per stage: the largest power of two whose slot (SF / cgs floats) holds the footprint + its zero granule
+        const int need = gtot * 4 + 4;                                             // <= SF: gtot < kGranMax
+        if (need <= SF / 8) rows_stage_loop<S, SF, RING, 8>(a);
+        else if (need <= SF / 4) rows_stage_loop<S, SF, RING, 4>(a);
+        else if (need <= SF / 2) rows_stage_loop<S, SF, RING, 2>(a);
+        else rows_stage_loop<S, SF, RING, 1>(a);
         if (full_idx && live) {                                                    // legacy [N,C,PH,PW] centre tensors
             for (int c = 0; c < p.C; ++c) {
                 p.idx_x[((size_t)n * p.C + c) * bins + obin] = ccx;
@@ -714,6 +787,34 @@ static cudaError_t tma_kernel_smem_optin() {
     return e;
 }
 
+// Row-segment kernel: dynamic shared memory (stages + granule table), opted in per device ordinal like the TMA kernel.
+template <int S, int SF, bool RING>
+static cudaError_t launch_rows(long long grid, const FwdParams& p, cudaStream_t s, bool pdl) {
+    constexpr int kSmem = S * SF * 4 + SF;                                          // stages + int gsrc[SF / 4]
+    static bool done[64] = {};
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!(dev >= 0 && dev < 64 && done[dev])) {
+        e = cudaFuncSetAttribute(rroi_fwd_nchw_rows_kernel<S, SF, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, rroi_fwd_nchw_rows_kernel<S, SF, RING>, p);
+}
+
 cudaError_t launch_fwd_nchw(const FwdParams& p0, const Opts& o, cudaStream_t s) {
     FwdParams p = p0;
     p.tiles = ((p.PH + kPatch - 1) / kPatch) * ((p.PW + kPatch - 1) / kPatch);
@@ -753,9 +854,13 @@ cudaError_t launch_fwd_nchw(const FwdParams& p0, const Opts& o, cudaStream_t s) 
         const long long rtiles = (long long)p.N * ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
         const bool staged = o.variant == 2 || (o.variant == 0 && o.nchw_cg == 0 && p.idx_mode != IDX_FULL &&
                                                rtiles * (o.concurrency > 1 ? o.concurrency : 1) >= 148 * 4);
+        if (o.variant == 3 || o.variant == 4) {       // ring forms kept for the sweep (profiles/r02_sweep_nchw3.txt): no gain
+            p.tiles = ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
+            return o.variant == 3 ? launch_rows<3, 4096, true>(rtiles, p, s, pdl) : launch_rows<4, 3072, true>(rtiles, p, s, pdl);
+        }
         if (staged) {
             p.tiles = ((p.PH + 7) / 8) * ((p.PW + 31) / 32);
-            return launch_1d(rroi_fwd_nchw_rows_kernel, rtiles, 256, p, s, pdl);
+            return launch_rows<2, 5120, false>(rtiles, p, s, pdl);
         }
     }
     switch (o.nchw_cg) {     // channels in flight per lane

@@ -420,7 +420,8 @@ def test_nchw_tma_staged_forward_equals_gather_kernel_and_oracle(oracle, cuda, C
     (5, 33, 50, 0.5, 5, 13, None),                                             # W % 4 != 0: gather fallback; ragged block
     (40, 45, 80, 0.25, 8, 64, "stress"),
 ])
-def test_nchw_row_segment_staged_forward_equals_oracle(oracle, cuda, C, H, W, scale, ph, pw, rois):
+@pytest.mark.parametrize("variant", [2, 3, 4])
+def test_nchw_row_segment_staged_forward_equals_oracle(oracle, cuda, C, H, W, scale, ph, pw, rois, variant):
     """The NCHW forward that stages exactly the row segments a tile touches (rroi_fwd_nchw_rows_kernel, opts.variant = 2)
     agrees bit for bit with the oracle and the gather kernel, centres included, also through the legacy [N,C,PH,PW] centres."""
     from fots.pytorch_b200 import _cabi
@@ -436,11 +437,11 @@ def test_nchw_row_segment_staged_forward_equals_oracle(oracle, cuda, C, H, W, sc
     else:
         r = np.array(rois, np.float32)
     want, wx, wy = oracle.forward(feats, r, ph, pw, scale, threads=0)
-    got, ix, iy = Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(variant=2))
+    got, ix, iy = Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(variant=variant))
     Hh.assert_bit_equal(got, want, "row-staged NCHW forward")
     Hh.assert_bit_equal(ix, wx[:, 0], "idx_x")
     Hh.assert_bit_equal(iy, wy[:, 0], "idx_y")
-    got2, _, _ = Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(variant=2, rois_ready=True, pdl=True))
+    got2, _, _ = Hh.run_new_forward(feats, r, ph, pw, scale, cuda, channels_last=False, opts=_cabi.opts(variant=variant, rois_ready=True, pdl=True))
     Hh.assert_bit_equal(got2, want, "row-staged NCHW forward, RoIs ready")
 
 

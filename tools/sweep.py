@@ -103,6 +103,14 @@ def sweep_bf16():
                 point(C=C, images=images, streams=S, dtype="bf16", variant=v, rois_ready=True, concurrency=S)
 
 
+def sweep_nchw2():
+    """Row-segment kernel: ring depth / stage size / L2 policy hints (variants 3-12 of launch_fwd_nchw)."""
+    vs = [int(v) for v in os.environ.get("SWEEP_VARIANTS", "2,3,4").split(",")]
+    for images, S in ((32, 1), (1, 8)):
+        for v in vs:
+            point(layout="nchw", images=images, streams=S, variant=v, rois_ready=True)
+
+
 def sweep_nchw():
     for images, S in ((1, 1), (1, 8), (32, 1)):
         for cg in (2, 4, 8):
@@ -114,7 +122,7 @@ def sweep_nchw():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fwd"]
     for w in which:
-        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw}[w]()
+        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw, "nchw2": sweep_nchw2}[w]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "sweep_%s.json" % "_".join(which)), "w") as f:
         json.dump(RECS, f, indent=1)
