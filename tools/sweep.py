@@ -22,6 +22,8 @@ import bench  # noqa: E402
 from fots.pytorch_b200 import _cabi  # noqa: E402
 
 RECS = []
+if os.environ.get("SWEEP_LIB"):        # A/B against another build of the library on the same box (development only)
+    _cabi.LIB_PATH = os.environ["SWEEP_LIB"]
 
 
 def point(layout="nhwc", C=64, images=1, streams=1, backward=False, dtype="fp32", xform=False, target=2000, steps=8, **opts):
@@ -111,6 +113,13 @@ def sweep_nchw2():
             point(layout="nchw", images=images, streams=S, variant=v, rois_ready=True)
 
 
+def sweep_nchw_ab():
+    """Default NCHW forward at the bench's points (for alternating runs of two library builds, SWEEP_LIB)."""
+    point(layout="nchw", images=32, streams=1)
+    point(layout="nchw", images=32, streams=1, rois_ready=True)
+    point(layout="nchw", images=1, streams=8, concurrency=8, rois_ready=True)
+
+
 def sweep_nchw():
     for images, S in ((1, 1), (1, 8), (32, 1)):
         for cg in (2, 4, 8):
@@ -122,7 +131,7 @@ def sweep_nchw():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fwd"]
     for w in which:
-        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw, "nchw2": sweep_nchw2}[w]()
+        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw, "nchw2": sweep_nchw2, "nchw_ab": sweep_nchw_ab}[w]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "sweep_%s.json" % "_".join(which)), "w") as f:
         json.dump(RECS, f, indent=1)
