@@ -113,11 +113,36 @@ def sweep_nchw2():
             point(layout="nchw", images=images, streams=S, variant=v, rois_ready=True)
 
 
+def set_l2_fetch_granularity(nbytes):
+    """cudaLimitMaxL2FetchGranularity (a device-wide hint, experiment only): 32 / 64 / 128 bytes fetched from DRAM per L2 miss."""
+    import ctypes
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    rt = ctypes.CDLL("libcudart.so.12") if not os.path.exists("/usr/local/cuda/lib64/libcudart.so") else ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    got = ctypes.c_size_t(0)
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(nbytes))
+    rt.cudaDeviceGetLimit(ctypes.byref(got), 5)
+    print("# cudaLimitMaxL2FetchGranularity <- %d: rc %d, now %d" % (nbytes, rc, got.value), flush=True)
+
+
 def sweep_nchw_ab():
     """Default NCHW forward at the bench's points (for alternating runs of two library builds, SWEEP_LIB)."""
+    if os.environ.get("SWEEP_L2_FETCH"):
+        set_l2_fetch_granularity(int(os.environ["SWEEP_L2_FETCH"]))
+    point(layout="nhwc", images=32, streams=1)
     point(layout="nchw", images=32, streams=1)
     point(layout="nchw", images=32, streams=1, rois_ready=True)
     point(layout="nchw", images=1, streams=8, concurrency=8, rois_ready=True)
+
+
+def sweep_cfg4():
+    """cfg4's per-GPU batch (2 048 RoIs, one launch), channels-last: every forward variant on one box."""
+    for v in (5, 7, 8, 9, 10, 16, 5, 7, 8, 9, 10):
+        point(layout="nhwc", images=32, streams=1, variant=v)
+    for v in (5, 7, 8, 9, 10):
+        point(layout="nhwc", images=1, streams=8, variant=v, concurrency=8, rois_ready=True)
+    for v in (5, 7, 8):
+        point(layout="nhwc", images=32, C=256, streams=1, variant=v)
 
 
 def sweep_nchw():
@@ -131,7 +156,7 @@ def sweep_nchw():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fwd"]
     for w in which:
-        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw, "nchw2": sweep_nchw2, "nchw_ab": sweep_nchw_ab}[w]()
+        {"fwd": sweep_fwd, "bwd": sweep_bwd, "bwd_nchw": sweep_bwd_nchw, "bf16": sweep_bf16, "nchw": sweep_nchw, "nchw2": sweep_nchw2, "nchw_ab": sweep_nchw_ab, "cfg4": sweep_cfg4}[w]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "sweep_%s.json" % "_".join(which)), "w") as f:
         json.dump(RECS, f, indent=1)
