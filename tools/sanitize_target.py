@@ -62,5 +62,16 @@ for (H, W) in ((45, 80), (45, 79)):
     gt = torch.randn_like(out)
     backward_raw(gt, r, ix, iy, feats.shape, 0.25, _cabi.LAYOUT_NCHW, opts=_cabi.opts(bwd_mode=4))
     backward_raw(gt, r, None, None, feats.shape, 0.25, _cabi.LAYOUT_NCHW, opts=_cabi.opts(bwd_mode=4))
+# NCHW forward, row segments in fixed-stride channel slots: double buffer and both ring forms; RoI heights chosen so that
+# tiles take 8, 4, 2 and 1 channels per stage; C = 7 leaves a partial last stage; W = 79 takes the gather fallback
+for (C, H, W) in ((16, 90, 160), (7, 90, 160), (16, 45, 79)):
+    feats = WL.features(5, 2, C, H, W)
+    rois = np.concatenate([WL.stress_rois(41, 24, 2, W * 4, H * 4),
+                           np.array([[0, 320, 180, 40, 300, 10], [1, 300, 200, 90, 600, -25], [0, 320, 180, 160, 640, 40],
+                                     [1, 320, 180, 250, 640, 75]], np.float32)], 0)
+    f, r = torch.from_numpy(feats).to(dev), torch.from_numpy(rois).to(dev)
+    for v in (2, 3, 4):
+        forward_raw(f, r, 8, 64, 0.25, opts=_cabi.opts(variant=v))
+        forward_raw(f, r, 8, 64, 0.25, want_idx=True, opts=_cabi.opts(variant=v, rois_ready=True))
 torch.cuda.synchronize()
 print("sanitize target done")
