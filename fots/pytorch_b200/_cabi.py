@@ -59,7 +59,7 @@ EXPORTS = (
     "fots_b200_instnorm_apply_nhwc_bf16", "fots_b200_instnorm_bwd_nhwc_bf16", "fots_b200_instnorm_crelu_bwd_nhwc_bf16", "fots_b200_upsample_bilinear_bwd_nhwc_bf16", "fots_b200_instnorm_set_single_pass", "fots_b200_merge_candidates_host", "fots_b200_merge_candidates_host_batch",
     "fots_b200_stem_conv3x3_c3_c16", "fots_b200_stem_conv3x3_c3_c16_u8", "fots_b200_maxpool_h2_nhwc_bf16",
     "fots_b200_gemm_bf16w", "fots_b200_bilstm_recurrent", "fots_b200_dwconv3x3_nhwc_bf16", "fots_b200_dwconv3x3_norm_nhwc_bf16", "fots_b200_dwconv3x3_up_nhwc_bf16", "fots_b200_instnorm_stats_nhwc_bf16",
-    "fots_b200_heads_nhwc_bf16", "fots_b200_heads_merged_nhwc_bf16", "fots_b200_conv1x1_to1_nhwc_bf16", "fots_b200_conv3x3_c3_pool_nhwc_bf16", "fots_b200_maxpool_nhwc_bf16",
+    "fots_b200_heads_nhwc_bf16", "fots_b200_heads_merged_nhwc_bf16", "fots_b200_heads_gather_nhwc_bf16", "fots_b200_conv1x1_to1_nhwc_bf16", "fots_b200_conv3x3_c3_pool_nhwc_bf16", "fots_b200_maxpool_nhwc_bf16",
 )
 
 _lib = None

@@ -186,6 +186,118 @@ __global__ void __launch_bounds__(256, 2) heads_dual_kernel(const uint4* __restr
     }
 }
 
+
+// ---- ... and the depthwise half of upconv2 and its 2x upsampling folded in as well -------------------------------------------
+// d = dw3x3(up(f2)) is linear too, and the bilinear upsampling (spatial, per channel) commutes with any per-pixel channel
+// mix.  With M = Wh Wpw [8, 256] and the depthwise taps w_dw[c, tap]:
+//     (M d)(p) = sum_tap  up(T_tap)(p + tap),     T_tap = (M . diag(w_dw[:, tap])) f2          (zero outside the map: the padding)
+// T = [9 taps][8 heads] = 72 channels at the LOW resolution comes out of one 1x1 convolution on f2 (the tcgen05 kernel, 72
+// padded to TC output channels, bf16); this kernel then gathers, per full-resolution pixel, 9 taps x 4 bilinear samples of
+// 16 bytes (its eight head columns of one tap at one low-resolution pixel; served by L1 / L2) instead of reading 512 bytes
+// of d.  The 256-channel map d at 1/4 scale (944 MB per 32 images, written once and read once) and the upsample-on-load
+// depthwise kernel disappear.
+// Phase 1: lane = pixel (32 consecutive pixels of a row per warp: neighbouring lanes share their low-resolution samples), the
+// eight sums and the gate go to the warp's slice of shared memory.  Phase 2: the s-part on tensor cores in heads_dual_kernel's
+// fragment scheme (two 16-pixel MMA tiles), gate, bias, squashing, stores.
+template <int C2, int MINB>
+__global__ void __launch_bounds__(256, MINB) heads_gather_kernel(const uint4* __restrict__ T, int TC, const uint4* __restrict__ x2,
+                                                        const __nv_bfloat16* __restrict__ w2, const __nv_bfloat16* __restrict__ gate,
+                                                        const float* __restrict__ bias, float* __restrict__ seg, float* __restrict__ rbox,
+                                                        float* __restrict__ angle, long long npix, int H, int W, int h, int w) {
+    constexpr int N2 = C2 / 64;
+    __shared__ float dsm[8][32][9];                          // [warp][pixel][8 sums + gate]
+    pdl::trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    U8 wb[N2];
+#pragma unroll
+    for (int m = 0; m < N2; ++m) wb[m] = ldg256(w2 + (size_t)g * C2 + m * 64 + t * 16);
+    const float b0 = __ldg(bias + 2 * t), b1 = __ldg(bias + 2 * t + 1);
+    pdl::wait();
+    const int HW = H * W;
+    const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
+    const int rec = TC / 8;                                  // uint4 per low-resolution pixel
+    // CTA tile = 8 consecutive rows (one per warp) x 32 pixels: the rows share their low-resolution samples, so T is read
+    // from L2 once per tile (~17 KB) and from L1 otherwise -- with one row segment per warp anywhere in the batch the kernel
+    // was bound by L2 -> L1 sector traffic (1.1 GB per 32 images)
+    const int xb = (W + 31) / 32, yb = (H + 7) / 8;
+    const long long ntiles = (long long)(npix / HW) * yb * xb;
+    const __nv_bfloat16* x2e = reinterpret_cast<const __nv_bfloat16*>(x2);
+    float (*my)[9] = dsm[warp];
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long b = tile / ((long long)yb * xb);
+        const int rem = (int)(tile - b * yb * xb), Y = (rem / xb) * 8 + warp, X0 = (rem % xb) * 32, X = X0 + lane;
+        const bool row_ok = Y < H;
+        const long long prow = (b * H + Y) * (long long)W;   // pixel index of (b, Y, 0)
+        // ---- phase 1: this lane's pixel
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gt = 0.0f;
+        if (row_ok && X < W) {
+            int ro[3][2], co[3][2];                          // low-resolution row offsets (* w) / columns of the three taps
+            float rl[3], cl[3];                              // interpolation fractions; < 0: the tap lies in the padding
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int qy = Y + k - 1, qx = X + k - 1;
+                const float fy = sy * (float)qy, fx = sx * (float)qx;
+                const int y0 = (int)fy, x0 = (int)fx;
+                ro[k][0] = y0 * w; ro[k][1] = (y0 + (y0 < h - 1 ? 1 : 0)) * w;
+                co[k][0] = x0;     co[k][1] = x0 + (x0 < w - 1 ? 1 : 0);
+                rl[k] = (qy >= 0 && qy < H) ? fy - (float)y0 : -1.0f;
+                cl[k] = (qx >= 0 && qx < W) ? fx - (float)x0 : -1.0f;
+            }
+            {                                                // gate at (Y, X) = tap (1, 1)'s sample position
+                const __nv_bfloat16* gp = gate + b * (long long)h * w;
+                const float ly1 = rl[1], lx1 = cl[1], ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+                const float s00 = __bfloat162float(gp[ro[1][0] + co[1][0]]), s01 = __bfloat162float(gp[ro[1][0] + co[1][1]]);
+                const float s10 = __bfloat162float(gp[ro[1][1] + co[1][0]]), s11 = __bfloat162float(gp[ro[1][1] + co[1][1]]);
+                gt = ly0 * (lx0 * s00 + lx1 * s01) + ly1 * (lx0 * s10 + lx1 * s11);
+            }
+            const uint4* Tb = T + (size_t)b * h * w * rec;
+            auto acc8 = [&](const uint4 v, float wgt) {
+                a[0] = fmaf(wgt, __uint_as_float(v.x << 16), a[0]); a[1] = fmaf(wgt, __uint_as_float(v.x & 0xffff0000u), a[1]);
+                a[2] = fmaf(wgt, __uint_as_float(v.y << 16), a[2]); a[3] = fmaf(wgt, __uint_as_float(v.y & 0xffff0000u), a[3]);
+                a[4] = fmaf(wgt, __uint_as_float(v.z << 16), a[4]); a[5] = fmaf(wgt, __uint_as_float(v.z & 0xffff0000u), a[5]);
+                a[6] = fmaf(wgt, __uint_as_float(v.w << 16), a[6]); a[7] = fmaf(wgt, __uint_as_float(v.w & 0xffff0000u), a[7]);
+            };
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (rl[r] < 0.0f) continue;
+                const float ly1 = rl[r], ly0 = 1.0f - ly1;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (cl[c] < 0.0f) continue;
+                    const float lx1 = cl[c], lx0 = 1.0f - lx1;
+                    const uint4* q = Tb + (r * 3 + c);
+                    const uint4 v00 = __ldg(q + (size_t)(ro[r][0] + co[c][0]) * rec), v01 = __ldg(q + (size_t)(ro[r][0] + co[c][1]) * rec);
+                    const uint4 v10 = __ldg(q + (size_t)(ro[r][1] + co[c][0]) * rec), v11 = __ldg(q + (size_t)(ro[r][1] + co[c][1]) * rec);
+                    acc8(v00, ly0 * lx0); acc8(v01, ly0 * lx1); acc8(v10, ly1 * lx0); acc8(v11, ly1 * lx1);
+                }
+            }
+        }
+        __syncwarp();                                        // the previous tile's phase 2 has read the slice
+#pragma unroll
+        for (int k = 0; k < 8; ++k) my[lane][k] = a[k];
+        my[lane][8] = gt;
+        __syncwarp();
+        // ---- phase 2: two 16-pixel MMA tiles of this warp's row segment
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int l0 = half * 16 + g, l1 = l0 + 8;
+            const bool ok0 = row_ok && X0 + l0 < W, ok1 = row_ok && X0 + l1 < W;
+            const long long p0 = prow + X0 + l0, p1 = prow + X0 + l1;
+            U8 ya[N2], yb2[N2];
+#pragma unroll
+            for (int m = 0; m < N2; ++m) {
+                ya[m] = ok0 ? ldg256(x2e + p0 * C2 + m * 64 + t * 16) : zero256();
+                yb2[m] = ok1 ? ldg256(x2e + p1 * C2 + m * 64 + t * 16) : zero256();
+            }
+            float acs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int m = 0; m < N2; ++m) mma_u8(acs, ya[m], yb2[m], wb[m]);
+            if (ok0) heads_store(t, fmaf(my[l0][8], acs[0], my[l0][2 * t]) + b0, fmaf(my[l0][8], acs[1], my[l0][2 * t + 1]) + b1, p0, HW, seg, rbox, angle);
+            if (ok1) heads_store(t, fmaf(my[l1][8], acs[2], my[l1][2 * t]) + b0, fmaf(my[l1][8], acs[3], my[l1][2 * t + 1]) + b1, p1, HW, seg, rbox, angle);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int fots_b200_heads_nhwc_bf16(const void* x, const void* wq, const float* bias, float* seg, float* rbox, float* angle,
@@ -253,6 +365,30 @@ extern "C" int fots_b200_heads_merged_nhwc_bf16(const void* x1, const void* w1, 
     const cudaError_t e = pdl::launch(heads_dual_kernel<256, 64>, dim3((unsigned)ctas), dim3(256), 0, stream, static_cast<const uint4*>(x1),
                                       static_cast<const __nv_bfloat16*>(w1), static_cast<const uint4*>(x2), static_cast<const __nv_bfloat16*>(w2),
                                       static_cast<const __nv_bfloat16*>(gate_prob), bias, seg, rbox, angle, npix, H, W, gh, gw);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
+    return RROI_B200_OK;
+}
+
+// The three heads on  sum_tap up(T_tap)(p + tap) + upsample(gate_prob) * (w2 . x2) + bias  (see heads_gather_kernel):
+// T bf16 [B, h, w, TC] at the low resolution (channel tap * 8 + head column; TC >= 72, TC % 8 == 0: the 1x1 convolution that
+// produces it pads its output channels), x2 bf16 [B, H, W, 64], w2 bf16 [8, 64], gate_prob bf16 [B, h, w], bias fp32 [8].
+// Upsampling = bilinear, align_corners (what fots_b200_dwconv3x3_up_nhwc_bf16 computes).
+extern "C" int fots_b200_heads_gather_nhwc_bf16(const void* T, int TC, const void* x2, const void* w2, const void* gate_prob,
+                                                const float* bias, float* seg, float* rbox, float* angle, int B, int H, int W, int h,
+                                                int w, int C2, cudaStream_t stream) {
+    if (!T || !x2 || !w2 || !gate_prob || !bias || !seg || !rbox || !angle || B <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0)
+        return RROI_B200_ERR_INVALID_ARG;
+    if (C2 != 64 || TC < 72 || TC % 8 != 0) return RROI_B200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(w2)) & 31) return RROI_B200_ERR_INVALID_ARG;       // 32-byte loads
+    if (reinterpret_cast<uintptr_t>(T) & 15) return RROI_B200_ERR_INVALID_ARG;
+    const long long npix = (long long)B * H * W;
+    long long ctas = (long long)B * ((H + 7) / 8) * ((W + 31) / 32);      // CTA tiles of 8 rows x 32 pixels, grid-strided
+    if (ctas > 148 * 16) ctas = 148 * 16;
+    // 4 CTAs per SM (64 registers, a few spilled): the kernel waits on L1 / L2 loads, measured 209 us per 32 images against
+    // 262 us at 2 CTAs per SM (113 registers)
+    const cudaError_t e = pdl::launch(heads_gather_kernel<64, 4>, dim3((unsigned)ctas), dim3(256), 0, stream, static_cast<const uint4*>(T), TC,
+                                      static_cast<const uint4*>(x2), static_cast<const __nv_bfloat16*>(w2),
+                                      static_cast<const __nv_bfloat16*>(gate_prob), bias, seg, rbox, angle, npix, H, W, h, w);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return RROI_B200_ERR_CUDA; }
     return RROI_B200_OK;
 }

@@ -30,6 +30,7 @@ LEVEL = int(os.environ.get("FOTS_B200_TC_LEVEL", "2"))
 DW_UP = os.environ.get("FOTS_B200_DW_UP", "1") != "0"
 # A/B switch: fold the last top-down level into the heads when the caller does not need the 256-channel map (inference)
 MERGED_HEADS = os.environ.get("FOTS_B200_MERGED_HEADS", "1") != "0"
+GATHER_HEADS = os.environ.get("FOTS_B200_GATHER_HEADS", "1") != "0"    # ... and the depthwise half of upconv2 (heads_gather)
 
 
 def _lib():
@@ -378,6 +379,47 @@ def heads_merged(d, s, gate_prob, packed):
                                                 packed[2].data_ptr(), seg.data_ptr(), rbox.data_ptr(), ang.data_ptr(), B, H, W, C1, C2,
                                                 gate_prob.size(2), gate_prob.size(3), torch.cuda.current_stream(d.device).cuda_stream)
     _cabi.check(rc, "fots_b200_heads_merged_nhwc_bf16")
+    return seg, rbox, ang
+
+
+def pack_gather_heads(act, rbox, angle, pw_conv, dw_conv):
+    """Fold the depthwise half of upconv2 into the heads as well (fots_b200_heads_gather_nhwc_bf16): with M = Wh Wpw [8, 256]
+    and the depthwise taps w_dw [256, 9], filter tap * 8 + o of the returned 1x1 convolution weight (bf16 [128, 256, 1, 1],
+    filters 72.. are zero: the tcgen05 kernel's output tiles are 64 wide) is M[o, :] * w_dw[:, tap] -- it turns the
+    low-resolution map f2 into the tap map T.  None when a bias is in the way."""
+    if pw_conv.bias is not None or dw_conv.bias is not None or tuple(dw_conv.weight.shape[1:]) != (1, 3, 3):
+        return None
+    C = act.in_channels
+    wh = torch.zeros((8, C), dtype=torch.float32, device=act.weight.device)
+    wh[0] = act.weight.detach().float()[0, :, 0, 0]
+    wh[2:6] = rbox.weight.detach().float()[:, :, 0, 0]
+    wh[6:8] = angle.weight.detach().float()[:, :, 0, 0]
+    m = wh @ pw_conv.weight.detach().float()[:, :, 0, 0]                      # [8, 256]
+    wdw = dw_conv.weight.detach().float().reshape(-1, 9)                      # [256, 9]
+    a = torch.zeros((128, m.size(1)), dtype=torch.float32, device=m.device)
+    a[:72] = (m[None, :, :] * wdw.t()[:, None, :]).reshape(72, -1)            # [9, 8, 256]
+    return a.to(torch.bfloat16).reshape(128, -1, 1, 1).contiguous(memory_format=torch.channels_last)
+
+
+def heads_gather(f2, s, gate_prob, a72, packed):
+    """(seg, rbox, angle) fp32 at s's resolution from the LOW-resolution map f2 bf16 [B, 256, h, w], s bf16 [B, 64, H, W]
+    (channels-last) and the gate probabilities bf16 [B, 1, h, w]: T = conv1x1(f2, a72) on the tcgen05 kernel (bf16
+    [B, h, w, 128]), then the 9-tap x 4-sample gather per pixel.  packed = pack_merged_heads(...) (its w2 and bias),
+    a72 = pack_gather_heads(...)."""
+    B, C1, h, w = f2.shape
+    _, C2, H, W = s.shape
+    T = conv2d(f2, a72)
+    seg = torch.empty((B, 1, H, W), dtype=torch.float32, device=f2.device)
+    rbox = torch.empty((B, 4, H, W), dtype=torch.float32, device=f2.device)
+    ang = torch.empty((B, 2, H, W), dtype=torch.float32, device=f2.device)
+    L = _lib()
+    L.fots_b200_heads_gather_nhwc_bf16.restype = ctypes.c_int
+    L.fots_b200_heads_gather_nhwc_bf16.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    with torch.cuda.device(f2.device):
+        rc = L.fots_b200_heads_gather_nhwc_bf16(T.data_ptr(), T.size(1), s.data_ptr(), packed[1].data_ptr(), gate_prob.data_ptr(),
+                                                packed[2].data_ptr(), seg.data_ptr(), rbox.data_ptr(), ang.data_ptr(), B, H, W, h, w, C2,
+                                                torch.cuda.current_stream(f2.device).cuda_stream)
+    _cabi.check(rc, "fots_b200_heads_gather_nhwc_bf16")
     return seg, rbox, ang
 
 

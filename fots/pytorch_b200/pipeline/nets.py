@@ -255,8 +255,13 @@ class FOTSNet(nn.Module):
             g2 = gate(f2)
             if (not need_features and mh is not None and tc.MERGED_HEADS and tc.LEVEL >= 2 and not self.training and "gate_prob_lo" in g2
                     and tc.DW_UP and tc.dw_eligible(f2, self.upconv2[0]) and f2.size(1) == 256 and s3.size(1) == 64):
-                d = tc.dwconv_up(self.upconv2[0], f2, s3.shape[2:])
-                seg, rbox, ang = tc.heads_merged(d, s3, g2["gate_prob_lo"], mh)
+                a72 = getattr(self, "_gather_heads", None)
+                if a72 is not None and tc.GATHER_HEADS and f2.is_contiguous(memory_format=torch.channels_last):
+                    # the depthwise half of upconv2 and its upsampling folded in too: a 256 -> 72 GEMM at 1/8 scale + a gather
+                    seg, rbox, ang = tc.heads_gather(f2, s3, g2["gate_prob_lo"], a72, mh)
+                else:
+                    d = tc.dwconv_up(self.upconv2[0], f2, s3.shape[2:])
+                    seg, rbox, ang = tc.heads_merged(d, s3, g2["gate_prob_lo"], mh)
                 return [seg], [rbox], [ang], [None, focr]
             f1 = pw(self.feature1, s3)
             x = fused.fpn_merge(c_hi=up(self.upconv2, f2, f1.shape[2:]), b_hi=f1, **g2)
@@ -317,7 +322,7 @@ class FOTSNet(nn.Module):
         re-cast ~100 fp32 weight tensors on every forward (norm parameters stay fp32: the fused kernels and
         batch_norm read them as such).  Keep inference=False for training (fp32 master weights)."""
         self.to(device=device, memory_format=torch.channels_last)
-        self._conv11_pad = self._heads_pack = self._l0c1_pairs = self._att_pack = self._merged_heads = None
+        self._conv11_pad = self._heads_pack = self._l0c1_pairs = self._att_pack = self._merged_heads = self._gather_heads = None
         if inference:
             for m in self.modules():
                 if isinstance(m, nn.Conv2d):
@@ -336,6 +341,7 @@ class FOTSNet(nn.Module):
                 self._att_pack = tc.pack_to1(self.conv_attenton)
                 # the last top-down level folded into the heads (forward(..., need_features=False))
                 self._merged_heads = tc.pack_merged_heads(self.act, self.rbox, self.angle, self.upconv2[1], self.feature1)
+                self._gather_heads = tc.pack_gather_heads(self.act, self.rbox, self.angle, self.upconv2[1], self.upconv2[0])
             c01 = self.layer0[2]
             if c01.in_channels == 32 and c01.out_channels == 32 and c01.bias is None:
                 self._l0c1_pairs = tc.pack_pixel_pairs_s2(c01.weight.detach())

@@ -262,6 +262,16 @@ int fots_b200_upsample_bilinear_bwd_nhwc_bf16(const void* dhi, void* dlo, int B,
 int fots_b200_heads_merged_nhwc_bf16(const void* x1, const void* w1, const void* x2, const void* w2, const void* gate_prob,
                                      const float* bias, float* seg, float* rbox, float* angle, int B, int H, int W, int C1, int C2,
                                      int gh, int gw, cudaStream_t stream);
+/* ... with the depthwise half of upconv2 and its 2x upsampling folded in as well (both linear; the bilinear upsampling
+ * commutes with a per-pixel channel mix):  (Wh Wpw) dw3x3(up(f2)) (p) = sum_tap up(T_tap)(p + tap),  T_tap = (Wh Wpw) diag(w_dw[:, tap]) f2,
+ * zero where p + tap leaves the map.  T bf16 [B, h, w, TC] (channel tap * 8 + head column, TC >= 72 and a multiple of 8) is one
+ * 1x1 convolution of the low-resolution map f2 with the caller-folded weight (fots_b200_conv2d_nhwc_bf16, output channels
+ * padded with zero filters); this entry point gathers 9 taps x 4 bilinear samples (align_corners) per full-resolution pixel.
+ * The upsample-on-load depthwise convolution and its 256-channel output at 1/4 scale are never computed.  x2, w2, gate_prob
+ * [B, h, w], bias, outputs: as above. */
+int fots_b200_heads_gather_nhwc_bf16(const void* T, int TC, const void* x2, const void* w2, const void* gate_prob, const float* bias,
+                                     float* seg, float* rbox, float* angle, int B, int H, int W, int h, int w, int C2,
+                                     cudaStream_t stream);
 /* Consumer B's first layer (tools/models.py:853-897, CRNN.cnn conv0 + relu0 + pooling0): 3 input channels cannot fill a
  * k-block of the tcgen05 kernel.  x fp32 NCHW [N, 3, H, W] (RoIRotate of the raw image, src/utils.py:430-436), w bf16
  * [Cout, 3, 3, 3] contiguous, bias fp32 [Cout] or NULL -> y bf16 NHWC = maxpool2x2(relu(conv3x3_pad1(x) + bias)) when

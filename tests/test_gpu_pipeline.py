@@ -463,6 +463,16 @@ def test_last_merge_level_folded_into_the_heads(cuda):
         # vs fp32: not worse than the materialised path by more than noise
         ea, eb = float((a - r).abs().mean()), float((b - r).abs().mean())
         assert ea <= 1.25 * eb + 2e-3 * scale, (name, ea, eb)
+    # the depthwise half folded in as well (the default) vs the heads on the materialised d
+    assert net._gather_heads is not None
+    TC.GATHER_HEADS = False
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            merged = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
+    finally:
+        TC.GATHER_HEADS = True
+    for k, scale in ((0, 1.0), (1, 128.0), (2, 1.0)):
+        assert float((fold[k][0] - merged[k][0]).abs().mean()) <= 4e-3 * scale
     # the switch keeps the materialised path reachable
     TC.MERGED_HEADS = False
     try:
@@ -471,6 +481,53 @@ def test_last_merge_level_folded_into_the_heads(cuda):
     finally:
         TC.MERGED_HEADS = True
     assert float((plain[0][0] - full[0][0]).abs().max()) <= 2e-2 and float((plain[1][0] - full[1][0]).abs().max()) <= 2e-2 * 128
+
+
+@pytest.mark.parametrize("B,h,w,H,W", [(2, 12, 20, 24, 40), (1, 7, 9, 13, 17), (3, 23, 40, 45, 80)])
+def test_heads_gather_kernel_matches_fp32_reference(cuda, B, h, w, H, W):
+    """fots_b200_heads_gather_nhwc_bf16 (the depthwise half of upconv2 + its upsampling folded into the heads): against an fp32
+    torch restatement on the same bf16-rounded operands -- T = f2 . a72^T, every tap map upsampled (bilinear, align_corners),
+    shifted by its tap with zero padding and summed (on the bf16 T the kernel reads), + gate * (w2 . s) + bias, squashed like tools/models.py:440-456 -- and,
+    loosely, against the materialised path (fots_b200_dwconv3x3_up_nhwc_bf16 -> fots_b200_heads_merged_nhwc_bf16)."""
+    import torch.nn.functional as F
+    from fots.pytorch_b200.pipeline import conv as TC
+    g = torch.Generator(device=cuda).manual_seed(B * 100 + h)
+    cl = lambda *s: torch.randn(*s, device=cuda, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    f2, s3 = cl(B, 256, h, w), cl(B, 64, H, W)
+    gate = torch.rand(B, 1, h, w, device=cuda, generator=g).to(torch.bfloat16)
+    act, rbox, angle = torch.nn.Conv2d(256, 1, 1).to(cuda), torch.nn.Conv2d(256, 4, 1).to(cuda), torch.nn.Conv2d(256, 2, 1).to(cuda)
+    pw, lat = torch.nn.Conv2d(256, 256, 1, bias=False).to(cuda), torch.nn.Conv2d(64, 256, 1, bias=False).to(cuda)
+    dw = torch.nn.Conv2d(256, 256, 3, 1, 1, groups=256, bias=False).to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    mh = TC.pack_merged_heads(act, rbox, angle, pw, lat)
+    a72 = TC.pack_gather_heads(act, rbox, angle, pw, dw)
+    assert a72.shape == (128, 256, 1, 1) and float(a72[72:].abs().max()) == 0.0
+    seg, rb, ang = TC.heads_gather(f2, s3, gate, a72, mh)
+    # the tap map: the tcgen05 1x1 convolution against an fp32 product of the same bf16 operands, to bf16 rounding
+    Tc = TC.conv2d(f2, a72)                                                   # bf16 [B, 128, h, w] channels-last (deterministic)
+    Tf = (f2.float().permute(0, 2, 3, 1).reshape(-1, 256) @ a72.float().reshape(128, 256).t()).reshape(B, h, w, 128).permute(0, 3, 1, 2)
+    assert float((Tc.float() - Tf).abs().max()) <= 2.0 ** -8 * float(Tf.abs().max()) + 1e-6
+    assert float(Tc[:, 72:].abs().max()) == 0.0
+    # fp32 restatement of the gather on exactly the T the kernel reads
+    T = Tc.float()[:, :72].reshape(B, 9, 8, h, w)
+    up = F.interpolate(T.reshape(B, 72, h, w), size=(H, W), mode="bilinear", align_corners=True).reshape(B, 9, 8, H, W)
+    logit = torch.zeros(B, 8, H, W, device=cuda)
+    padded = F.pad(up, (1, 1, 1, 1))
+    for r in range(3):
+        for c in range(3):
+            logit += padded[:, r * 3 + c, :, r:r + H, c:c + W]
+    gate_up = F.interpolate(gate.float(), size=(H, W), mode="bilinear", align_corners=True)
+    logit += gate_up * torch.einsum("oc,bchw->bohw", mh[1].float(), s3.float()) + mh[2][None, :, None, None]
+    want_seg = torch.sigmoid(logit[:, 0:1])
+    want_rb = torch.sigmoid(logit[:, 2:6]) * 128
+    a2 = torch.sigmoid(logit[:, 6:8]) * 2 - 1
+    want_ang = a2 / a2.norm(dim=1, keepdim=True)
+    assert float((seg - want_seg).abs().max()) <= 2e-4
+    assert float((rb - want_rb).abs().max()) <= 2e-4 * 128
+    assert float((ang - want_ang).abs().max()) <= 1e-3
+    # the materialised path rounds d to bf16 and the folded [8, 256] matrix to bf16: loose agreement only
+    d = TC.dwconv_up(dw, f2, (H, W))
+    seg2, rb2, ang2 = TC.heads_merged(d, s3, gate, mh)
+    assert float((seg - seg2).abs().mean()) <= 4e-3 and float((rb - rb2).abs().mean()) <= 4e-3 * 128
 
 
 def test_step_with_detector_postprocessing_in_the_loop(cuda):
