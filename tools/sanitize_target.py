@@ -44,6 +44,14 @@ with torch.no_grad():
     fused.fpn_merge(a_lo=a_lo, b_hi=b_hi, gate_prob_lo=gate)
     fused.fpn_merge(c_hi=c_hi, b_hi=b_hi, gate_prob_lo=gate)
     fused.fpn_merge(c_hi=c_hi, b_hi=b_hi, gate_logits_lo=gate)
+    # the last top-down level folded into the heads: tap map (tcgen05 1x1 convolution) + gather, odd sizes and a ragged tile
+    for (B_, h_, w_, H_, W_) in ((2, 12, 20, 24, 40), (1, 7, 9, 13, 17)):
+        f2, s3 = cl(B_, 256, h_, w_), cl(B_, 64, H_, W_)
+        gp = torch.rand(B_, 1, h_, w_, device=dev).to(torch.bfloat16)
+        hd = [torch.nn.Conv2d(256, k, 1).to(dev) for k in (1, 4, 2)]
+        pw_, lat_ = torch.nn.Conv2d(256, 256, 1, bias=False).to(dev), torch.nn.Conv2d(64, 256, 1, bias=False).to(dev)
+        dw_ = torch.nn.Conv2d(256, 256, 3, 1, 1, groups=256, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        TC.heads_gather(f2, s3, gp, TC.pack_gather_heads(hd[0], hd[1], hd[2], pw_, dw_), TC.pack_merged_heads(hd[0], hd[1], hd[2], pw_, lat_))
     # CRNN front end
     w = (torch.randn(64, 3, 3, 3, device=dev) / 5).to(torch.bfloat16)
     y = TC.conv3x3_c3_pool(torch.randn(3, 3, 32, 100, device=dev), w, torch.randn(64, device=dev), True)
