@@ -111,3 +111,33 @@ def test_folded_head_weights_reproduce_the_last_merge_level():
     # a convolution with a bias cannot be folded behind the gate: the packer declines
     biased = torch.nn.Conv2d(64, 256, 1, bias=True)
     assert TC.pack_merged_heads(net.act, net.rbox, net.angle, net.upconv2[1], biased) is None
+
+
+def test_gather_head_weights_reproduce_upsample_depthwise_and_pointwise():
+    """conv.pack_gather_heads (host algebra behind fots_b200_heads_gather_nhwc_bf16): the head logits of
+    upconv2(upsample(f2)) -- tools/models.py:436-438, F.interpolate(bilinear, align_corners=True) -> depthwise 3x3 -> 1x1 --
+    equal  sum_tap shift_tap(upsample(T_tap)),  T = conv1x1(f2, A),  A[tap * 8 + o] = (Wh Wpw)[o, :] * w_dw[:, tap]:
+    the upsampling commutes with the channel mix and the depthwise taps become shifts with zero padding.  CPU, fp32, against
+    the modules themselves, on an odd size; the packed weights are bf16, hence the tolerance."""
+    import torch.nn.functional as F
+    from fots.pytorch_b200.pipeline import conv as TC
+    torch.manual_seed(6)
+    net = FOTSNet(attention=True, nclass=20).eval()
+    B, h, w, H, W = 2, 5, 7, 9, 13
+    f2 = torch.randn(B, 256, h, w)
+    with torch.no_grad():
+        x = net.upconv2(F.interpolate(f2, size=(H, W), mode="bilinear", align_corners=True))
+        want = torch.cat((net.act(x) - net.act.bias.view(1, -1, 1, 1), torch.zeros(B, 1, H, W), net.rbox(x) - net.rbox.bias.view(1, -1, 1, 1),
+                          net.angle(x) - net.angle.bias.view(1, -1, 1, 1)), 1)                           # 8-column block without the bias
+        a = TC.pack_gather_heads(net.act, net.rbox, net.angle, net.upconv2[1], net.upconv2[0])
+        assert a.shape == (128, 256, 1, 1) and float(a[72:].abs().max()) == 0.0
+        T = F.conv2d(f2, a.float())[:, :72]                                                              # [B, 72, h, w]
+        up = F.pad(F.interpolate(T, size=(H, W), mode="bilinear", align_corners=True), (1, 1, 1, 1)).reshape(B, 9, 8, H + 2, W + 2)
+        got = sum(up[:, r * 3 + c, :, r:r + H, c:c + W] for r in range(3) for c in range(3))
+    live = [0, 2, 3, 4, 5, 6, 7]
+    err = (got[:, live] - want[:, live]).abs().max()
+    assert float(err) <= 2.0 ** -7 * float(want.abs().max()) + 1e-3, float(err)
+    assert float(got[:, 1].abs().max()) == 0.0
+    # a depthwise convolution with a bias is not folded
+    biased = torch.nn.Conv2d(256, 256, 3, 1, 1, groups=256, bias=True)
+    assert TC.pack_gather_heads(net.act, net.rbox, net.angle, net.upconv2[1], biased) is None
