@@ -56,7 +56,9 @@ typedef struct rroi_b200_opts {
                                /* one small launch alone wants many small CTAs, overlapping launches want fewer,    */
                                /* larger ones.                                                                      */
     int variant;               /* 0 = automatic (grid size + concurrency); > 0 forces a forward kernel variant      */
-                               /* (sweeps and parity tests; see launch_fwd_nhwc / launch_fwd_nchw)                  */
+                               /* (sweeps and parity tests; see launch_fwd_nhwc / launch_fwd_nchw).  NCHW: 1 = gather */
+                               /* kernel, 2 = row segments staged in a double buffer (what automatic takes for        */
+                               /* launches that fill the GPU), 3 / 4 = the same in a 3- / 4-deep ring (no gain).      */
     int nchw_cg;               /* NCHW kernels: channels in flight per lane / per CTA: 1,2,4,8,16 (0 = default)     */
     int bwd_mode;              /* backward: 0 = automatic; 2 = generic (non-packed) channels-last kernel;            */
                                /* NCHW: 4 = row segments + per-granule gather (= automatic), 1 = one reduction per  */
