@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
+from fots.pytorch_b200 import _cabi  # noqa: E402
+if os.environ.get("SWEEP_LIB"):        # A/B against another build of the library on the same box (development only)
+    _cabi.LIB_PATH = os.environ["SWEEP_LIB"]
+
 from fots.pytorch_b200.pipeline import FOTSNet, FOTSPipeline  # noqa: E402
 from fots.pytorch_b200.pipeline import conv as TC  # noqa: E402
 from fots.pytorch_b200.pipeline.infer import planted_quads  # noqa: E402
