@@ -23,6 +23,7 @@
 #include "../../../include/fots_b200_pipeline.h"
 #include "pdl.cuh"
 #include <cuda.h>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -686,21 +687,23 @@ cudaError_t launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
     return pdl::launch(conv_tc_kernel<MT, BN, STAGES, PAIR, HALO, WRES>, dim3(grid), dim3(kThreads), smem, stream, mx, mw, my, P);
 }
 
-int g_force_bn = 0;        // 0 = automatic; set through fots_b200_conv_set_tile for sweeps
-int g_halo = -1;           // -1 = automatic, 0 = never, 1 = whenever the shape allows, 2 = same but always the three-copy form
+// A/B switches for sweeps and parity tests (process-wide; atomics so that a concurrent launch reads a whole value, and every
+// launch reads each switch ONCE -- a switch flipped mid-call cannot produce an inconsistent tile choice)
+std::atomic<int> g_force_bn_sw{0};   // 0 = automatic; set through fots_b200_conv_set_tile for sweeps
+std::atomic<int> g_halo_sw{-1};      // -1 = automatic, 0 = never, 1 = whenever the shape allows, 2 = same but always the three-copy form
                            // (fots_b200_conv_set_halo; sweeps / tests)
 
 }  // namespace
 
 extern "C" int fots_b200_conv_set_halo(int mode) {
     if (mode < -1 || mode > 2) return RROI_B200_ERR_INVALID_ARG;
-    g_halo = mode;
+    g_halo_sw.store(mode, std::memory_order_relaxed);
     return RROI_B200_OK;
 }
 
 extern "C" int fots_b200_conv_set_tile(int bn) {
     if (bn != 0 && bn != 64 && bn != 128 && bn != 256 && bn != 512) return RROI_B200_ERR_INVALID_ARG;   // 512 = 256 on a CTA pair
-    g_force_bn = bn;
+    g_force_bn_sw.store(bn, std::memory_order_relaxed);
     return RROI_B200_OK;
 }
 
@@ -719,6 +722,7 @@ static int conv2d_impl(const void* x, const void* w, const float* bias, void* y,
     // CTA pairs (cta_group::2) for 256-wide cout tiles: forced with tile = 512, automatic when there are enough pixel tiles
     // to keep all 74 clusters busy for several rounds (measured: conv8/9 1351 -> 1425 TF/s, conv7 1228 -> 1326; the
     // 256-tile conv10_s is better off with single CTAs)
+    const int g_force_bn = g_force_bn_sw.load(std::memory_order_relaxed), g_halo = g_halo_sw.load(std::memory_order_relaxed);
     const long long px_tiles = ((long long)N * Ho * Wo + BM - 1) / BM;
     bool pair = Cout % 256 == 0 && stats == nullptr && (g_force_bn == 512 || (g_force_bn == 0 && px_tiles >= 4 * 148));
     int bn = pair ? 256 : (g_force_bn && g_force_bn != 512) ? g_force_bn : (Cout % 256 == 0 ? 256 : Cout % 128 == 0 ? 128 : 64);

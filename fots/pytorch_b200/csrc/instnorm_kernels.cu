@@ -4,6 +4,7 @@
 #include "../../../include/fots_b200_pipeline.h"
 #include "pdl.cuh"
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -822,10 +823,10 @@ extern "C" int fots_b200_fpn_merge_prob_nhwc_bf16(const void* a_lo, const void* 
 }
 
 // A/B switch for sweeps and tests (fots_b200_instnorm_set_single_pass): the single-pass kernel is the default
-static int g_in_single_pass = 1;          // 0 = never, 1 = automatic (small instances), 2 = whenever the instance fits
+static std::atomic<int> g_in_single_pass_sw{1};   // 0 = never, 1 = automatic (small instances), 2 = whenever the instance fits
 extern "C" int fots_b200_instnorm_set_single_pass(int mode) {
     if (mode < 0 || mode > 2) return RROI_B200_ERR_INVALID_ARG;
-    g_in_single_pass = mode;
+    g_in_single_pass_sw.store(mode, std::memory_order_relaxed);
     return RROI_B200_OK;
 }
 
@@ -837,6 +838,7 @@ static int instnorm_impl(const void* x, void* y, const float* gamma, const float
         return RROI_B200_ERR_INVALID_ARG;
     // small instances: one launch, x read once (single-pass cluster kernel); B >= 65536 exceeds gridDim.y
     FusedPlan pl;
+    const int g_in_single_pass = g_in_single_pass_sw.load(std::memory_order_relaxed);
     if (!have_stats && !crelu && B < 65536 && g_in_single_pass && plan_fused(HW, C, &pl, g_in_single_pass == 2)) {
         const cudaError_t ef = residual ? launch_fused<true>(pl, x, y, gamma, beta, residual, B, HW, C, eps, slope, stream)
                                         : launch_fused<false>(pl, x, y, gamma, beta, nullptr, B, HW, C, eps, slope, stream);
