@@ -24,7 +24,7 @@ for n in names:
     seen[fam(n)] += 1
 shown = set()
 for name, blk in zip(names, blocks):
-    ins = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", blk)
+    ins = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Za-z0-9_.]*)", blk)
     cnt = collections.Counter()
     for m in ins:
         for k in KEYS:
