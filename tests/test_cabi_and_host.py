@@ -70,6 +70,27 @@ def test_argument_errors_without_gpu():
     assert b"invalid" in L.rroi_b200_strerror(_cabi.ERR_INVALID_ARG)
 
 
+def test_folded_heads_entry_points_reject_bad_arguments_without_gpu():
+    """fots_b200_heads_merged / _gather_nhwc_bf16: argument checks run before anything touches CUDA."""
+    from fots.pytorch_b200 import _cabi
+    L = _cabi.lib()
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.fots_b200_heads_gather_nhwc_bf16.restype = i
+    L.fots_b200_heads_gather_nhwc_bf16.argtypes = [vp, i] + [vp] * 7 + [i] * 6 + [vp]
+    L.fots_b200_heads_merged_nhwc_bf16.restype = i
+    L.fots_b200_heads_merged_nhwc_bf16.argtypes = [vp] * 9 + [i] * 7 + [vp]
+    a = ctypes.c_void_p(64)                                                    # aligned, never dereferenced
+    bad = _cabi.ERR_INVALID_ARG
+    assert L.fots_b200_heads_gather_nhwc_bf16(None, 128, a, a, a, a, a, a, a, 1, 8, 8, 4, 4, 64, None) == bad      # no tap map
+    assert L.fots_b200_heads_gather_nhwc_bf16(a, 64, a, a, a, a, a, a, a, 1, 8, 8, 4, 4, 64, None) == bad         # fewer than 72 tap channels
+    assert L.fots_b200_heads_gather_nhwc_bf16(a, 76, a, a, a, a, a, a, a, 1, 8, 8, 4, 4, 64, None) == bad         # not whole 16-byte vectors
+    assert L.fots_b200_heads_gather_nhwc_bf16(a, 128, a, a, a, a, a, a, a, 1, 8, 8, 4, 4, 32, None) == bad        # s must have 64 channels
+    assert L.fots_b200_heads_gather_nhwc_bf16(a, 128, ctypes.c_void_p(16), a, a, a, a, a, a, 1, 8, 8, 4, 4, 64, None) == bad   # 32-byte loads of s
+    assert L.fots_b200_heads_gather_nhwc_bf16(a, 128, a, a, a, a, a, a, a, 0, 8, 8, 4, 4, 64, None) == bad        # empty batch
+    assert L.fots_b200_heads_merged_nhwc_bf16(a, a, a, a, a, a, a, a, a, 1, 8, 8, 128, 64, 4, 4, None) == bad     # d must have 256 channels
+    assert L.fots_b200_heads_merged_nhwc_bf16(a, a, a, a, None, a, a, a, a, 1, 8, 8, 256, 64, 4, 4, None) == bad  # no gate
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from fots.pytorch_b200 import _cabi
     monkeypatch.setattr(_cabi, "_lib", None)
