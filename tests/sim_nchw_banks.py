@@ -3,7 +3,7 @@
 the compact row-segment layout the kernel uses, for a dense x + S*y placement with the narrowest odd stride, and with the best of 33 strides per tile
 (compact 2.40, odd stride 2.17, best stride 1.33).  Uses the oracle for the sample centres (development tool)."""
 import sys, numpy as np
-sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
 import workloads as WL
 from oracle import rroi_oracle as O
 H,W,PH,PW=180,320,8,64
